@@ -1,0 +1,221 @@
+"""TEST INFRASTRUCTURE — ctypes front end for the two CPU checkers under oracle/.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline leg and the
+``--impl reference`` arm) may import this module.  The product package
+(lofreq_b200) never does.
+
+  kind="reference": oracle/_ref/libsnpref.so — the unmodified reference sources
+                    (/root/reference/src/lofreq/{snpcaller,utils,log}.c) plus
+                    oracle/ref_harness.c.  Built only where /root/reference is
+                    mounted; the built .so travels with the repo snapshot.
+  kind="port":      oracle/libsnvoracle.so — oracle/snv_oracle.c, the from-scratch
+                    C restatement (buildable anywhere with gcc).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libsnpref.so")
+BINOM_SO = os.path.join(HERE, "_ref", "libbinomref.so")
+PORT_SO = os.path.join(HERE, "libsnvoracle.so")
+
+VARCALL_USE_BAQ, VARCALL_USE_MQ, VARCALL_USE_SQ, VARCALL_USE_IDAQ = 1, 2, 4, 8   # defaults.h:76-80
+LDBL_MAX = np.finfo(np.longdouble).max
+LDBL_MIN = np.finfo(np.longdouble).tiny
+
+
+def build(quiet=True):
+    """Compile the checkers (gcc). The reference half is skipped when
+    /root/reference is not mounted (the GPU box): the prebuilt .so is kept."""
+    out = subprocess.run(["make", "-C", HERE], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if not quiet:
+        print(out.stdout)
+
+
+class _Conf(C.Structure):
+    _fields_ = [("min_bq", C.c_int), ("min_alt_bq", C.c_int), ("def_alt_bq", C.c_int),
+                ("min_jq", C.c_int), ("min_alt_jq", C.c_int), ("def_alt_jq", C.c_int),
+                ("min_cov", C.c_int), ("bonf_dynamic", C.c_int), ("flag", C.c_int),
+                ("sig", C.c_float), ("bonf_subst", C.c_longlong), ("num_snv_tests", C.c_longlong)]
+
+
+class _Batch(C.Structure):
+    _fields_ = [("n_cols", C.c_longlong), ("col_off", C.c_void_p), ("nt_cnt", C.c_void_p),
+                ("ref_base", C.c_void_p), ("coverage", C.c_void_p),
+                ("bq", C.c_void_p), ("mq", C.c_void_p), ("baq", C.c_void_p), ("sq", C.c_void_p)]
+
+
+class _Out(C.Structure):
+    _fields_ = [("alt_counts", C.c_void_p), ("alt_raw_counts", C.c_void_p), ("tested", C.c_void_p),
+                ("bonf_used", C.c_void_p), ("pvalues", C.c_void_p), ("called", C.c_void_p),
+                ("qual", C.c_void_p)]
+
+
+def default_conf(**over):
+    """init_varcall_conf defaults (snpcaller.c:626-651)."""
+    d = dict(min_bq=6, min_alt_bq=6, def_alt_bq=0, min_jq=0, min_alt_jq=0, def_alt_jq=0,
+             min_cov=1, bonf_dynamic=1, flag=VARCALL_USE_MQ | VARCALL_USE_BAQ | VARCALL_USE_IDAQ,
+             sig=0.01, bonf_subst=1, num_snv_tests=0)
+    d.update(over)
+    return d
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    def __init__(self, kind="port"):
+        self.kind = kind
+        path = REF_SO if kind == "reference" else PORT_SO
+        if not os.path.exists(path):
+            build()
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = lib = C.CDLL(path)
+        self.libc = C.CDLL(None)
+        self.libc.free.argtypes = [C.c_void_p]
+        pre = "lfref_" if kind == "reference" else "lfo_"
+        self._call_columns = getattr(lib, pre + "call_columns")
+        self._call_columns.restype = C.c_int
+        self._call_columns.argtypes = [C.POINTER(_Conf), C.POINTER(_Batch), C.POINTER(_Out)]
+        self._errprobs = getattr(lib, pre + "column_errprobs")
+        self._errprobs.restype = C.c_int
+        self._errprobs.argtypes = [C.POINTER(_Conf), C.POINTER(_Batch), C.c_longlong,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        if kind == "reference":
+            names = dict(snpcaller="snpcaller", poissbin="poissbin", merge="merge_srcq_mapq_baq_and_bq",
+                         log_sum="log_sum", tailsum="probvec_tailsum", dp="pruned_calc_prob_dist",
+                         p2q="lfref_prob_to_phredqual", p2q_safe="lfref_prob_to_phredqual_safe",
+                         q2p="lfref_phredqual_to_prob")
+        else:
+            names = dict(snpcaller="lfo_snpcaller", poissbin="lfo_poissbin", merge="lfo_merge_quals",
+                         log_sum="lfo_log_sum", tailsum="lfo_tailsum", dp="lfo_pruned_dp",
+                         p2q="lfo_prob_to_phred", p2q_safe="lfo_prob_to_phred_safe", q2p="lfo_phred_to_prob")
+        f = getattr(lib, names["snpcaller"])
+        f.restype = C.c_int
+        if kind == "reference":   # snpcaller.h:97-102 has the trailing approx_threshold_n
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_double, C.c_int]
+        else:
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_double]
+        self._snpcaller = f
+        f = getattr(lib, names["poissbin"])
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_double]
+        self._poissbin = f
+        f = getattr(lib, names["merge"]); f.restype = C.c_double; f.argtypes = [C.c_int] * 4
+        self._merge = f
+        f = getattr(lib, names["log_sum"]); f.restype = C.c_double; f.argtypes = [C.c_double] * 2
+        self.log_sum = f
+        f = getattr(lib, names["tailsum"]); f.restype = C.c_double; f.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self._tailsum = f
+        f = getattr(lib, names["p2q"]); f.restype = C.c_int; f.argtypes = [C.c_longdouble]
+        self.prob_to_phred = f
+        f = getattr(lib, names["p2q_safe"]); f.restype = C.c_int; f.argtypes = [C.c_double]
+        self.prob_to_phred_safe = f
+        f = getattr(lib, names["q2p"]); f.restype = C.c_double; f.argtypes = [C.c_int]
+        self.phred_to_prob = f
+
+    # -- scalar/vector entry points -------------------------------------
+    def merge(self, sq, mq, baq, bq):
+        return self._merge(int(sq), int(mq), int(baq), int(bq))
+
+    def snpcaller(self, err_probs, counts, bonf, sig):
+        ep = np.ascontiguousarray(err_probs, dtype=np.float64)
+        cn = np.ascontiguousarray(counts, dtype=np.int32)
+        pv = np.empty(3, dtype=np.longdouble)
+        args = [_ptr(pv), _ptr(ep), len(ep), _ptr(cn), int(bonf), float(sig)]
+        if self.kind == "reference":
+            args.append(-1)
+        rc = self._snpcaller(*args)
+        if rc:
+            raise RuntimeError("snpcaller returned %d" % rc)
+        return pv
+
+    def poissbin(self, err_probs, k, bonf, sig):
+        """returns (pvalue longdouble, row float64[k+1]) — row is the malloc'd
+        vector the reference hands back (may be partial after an early exit)."""
+        ep = np.ascontiguousarray(err_probs, dtype=np.float64)
+        pv = np.empty(1, dtype=np.longdouble)
+        p = self._poissbin(_ptr(pv), _ptr(ep), len(ep), int(k), int(bonf), float(sig))
+        row = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(k + 1,)).copy()
+        self.libc.free(p)
+        return pv[0], row
+
+    def tailsum(self, row, start):
+        r = np.ascontiguousarray(row, dtype=np.float64)
+        return self._tailsum(_ptr(r), int(start), len(r))
+
+    # -- batch entry points ---------------------------------------------
+    @staticmethod
+    def _mk_batch(b):
+        keep = []
+
+        def arr(x, dt):
+            if x is None:
+                return None
+            a = np.ascontiguousarray(x, dtype=dt)
+            keep.append(a)
+            return _ptr(a)
+        n = len(b["ref_base"])
+        s = _Batch(n, arr(b["col_off"], np.int64), arr(b["nt_cnt"], np.int32), arr(b["ref_base"], np.uint8),
+                   arr(b.get("coverage"), np.int32), arr(b["bq"], np.uint8), arr(b.get("mq"), np.uint8),
+                   arr(b.get("baq"), np.uint8), arr(b.get("sq"), np.uint8))
+        return s, keep, n
+
+    def call_columns(self, batch, conf=None):
+        """Run the whole per-column path over a packed batch (dict of numpy
+        arrays, see oracle/column_batch.h). Returns dict of outputs plus the
+        final bonf_subst / num_snv_tests."""
+        conf = default_conf() if conf is None else conf
+        cf = _Conf(**conf)
+        sb, keep, n = self._mk_batch(batch)
+        out = dict(alt_counts=np.zeros((n, 3), np.int32), alt_raw_counts=np.zeros((n, 3), np.int32),
+                   tested=np.zeros(n, np.uint8), bonf_used=np.zeros(n, np.int64),
+                   pvalues=np.zeros((n, 3), np.longdouble), called=np.zeros((n, 3), np.uint8),
+                   qual=np.zeros((n, 3), np.int32))
+        so = _Out(*[_ptr(out[k]) for k in ("alt_counts", "alt_raw_counts", "tested", "bonf_used",
+                                            "pvalues", "called", "qual")])
+        rc = self._call_columns(C.byref(cf), C.byref(sb), C.byref(so))
+        if rc:
+            raise RuntimeError("call_columns returned %d" % rc)
+        out["bonf_subst"] = cf.bonf_subst
+        out["num_snv_tests"] = cf.num_snv_tests
+        return out
+
+    def column_errprobs(self, batch, c, conf=None):
+        conf = default_conf() if conf is None else conf
+        cf = _Conf(**conf)
+        sb, keep, n = self._mk_batch(batch)
+        depth = int(np.asarray(batch["nt_cnt"]).reshape(-1, 4)[c].sum())
+        ep = np.zeros(max(depth, 1), np.float64)
+        ab = np.zeros(3, np.int32); ac = np.zeros(3, np.int32); ar = np.zeros(3, np.int32)
+        m = self._errprobs(C.byref(cf), C.byref(sb), int(c), _ptr(ep), _ptr(ab), _ptr(ac), _ptr(ar))
+        return ep[:m].copy(), ab, ac, ar
+
+
+class BinomRef:
+    """binom() of the reference (src/lofreq/binom.c:52-93 over cdflib90)."""
+
+    def __init__(self):
+        if not os.path.exists(BINOM_SO):
+            build()
+        self.lib = C.CDLL(BINOM_SO)
+        self.lib.binom.restype = C.c_int
+        self.lib.binom.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_double]
+
+    def cdf_sf(self, num_trials, num_success, prob):
+        p, q = C.c_double(), C.c_double()
+        rc = self.lib.binom(C.byref(p), C.byref(q), int(num_trials), int(num_success), float(prob))
+        if rc:
+            raise RuntimeError("binom status %d" % rc)
+        return p.value, q.value
+
+
+def have_reference():
+    return os.path.exists(REF_SO)
