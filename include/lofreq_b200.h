@@ -1,0 +1,182 @@
+/* lofreq_b200 — C ABI of the B200-native per-pileup-column SNV test.
+ *
+ * This is the boundary a LoFreq maintainer binds to.  Plain C types only (no
+ * torch, no C++), one shared library: lofreq_b200/lib/liblofreq_b200.so.
+ * Every entry point names the reference interface it stands in for; paths are
+ * relative to the reference tree (src/lofreq/...).
+ *
+ * The test itself (quality merge -> error probabilities -> Poisson-binomial
+ * tail -> per-allele p-values) runs in hand-written sm_100a CUDA kernels.
+ * There is no CPU implementation behind these calls: without a CUDA device
+ * lfb200_create() fails and every compute entry point returns an error.
+ *
+ * Host-side work that stays on the CPU, because it needs x87 long double to
+ * make the same decisions as the reference: expl() of the natural-log
+ * p-values, the FE-exception clamp of snpcaller.c:1174-1188, the comparison
+ * `pvalue * bonf < sig` (lofreq_call.c:832) and PROB_TO_PHREDQUAL
+ * (utils.h:45).  It runs only on the few columns the device could not rule
+ * out ("sites").
+ */
+#ifndef LOFREQ_B200_H
+#define LOFREQ_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFB200_NUM_NONCONS 3          /* NUM_NONCONS_BASES, defaults.h:38 */
+
+/* varcall_conf_t.flag bits (defaults.h:76-80) */
+#define LFB200_USE_BAQ  1
+#define LFB200_USE_MQ   2
+#define LFB200_USE_SQ   4
+#define LFB200_USE_IDAQ 8
+
+/* per-allele result status */
+#define LFB200_ST_VALUE   0           /* ln p / pvalue hold a computed value              */
+#define LFB200_ST_LDBLMAX 1           /* reference returns LDBL_MAX: not computed / pruned / clamped high */
+#define LFB200_ST_LDBLMIN 2           /* reference returns LDBL_MIN: clamped low (snpcaller.c:1177)      */
+
+/* The fields of varcall_conf_t (snpcaller.h:38-63) this path reads, same names
+ * and meaning; defaults = init_varcall_conf (snpcaller.c:626-651) via
+ * lfb200_init_conf().  bonf_subst and num_snv_tests are in/out: the running
+ * Bonferroni factor (lofreq_call.c:794-800) and the global test counter
+ * (lofreq_call.c:84,801). */
+typedef struct {
+    int min_bq, min_alt_bq, def_alt_bq;
+    int min_jq, min_alt_jq, def_alt_jq;
+    int min_cov;
+    int bonf_dynamic;
+    int flag;
+    float sig;
+    long long bonf_subst;
+    long long num_snv_tests;
+} lfb200_conf_t;
+
+/* A batch of pileup columns = the packed form of the plp_col_t objects
+ * (plp.h:73-145) the reference hands to its per-column callback
+ * (plp.c:1443).  For column c the reads are grouped by called base in A,C,G,T
+ * order (the order plp_to_errprobs walks base_quals[], snpcaller.c:383-388),
+ * group sizes in nt_cnt[4c..4c+3]; the quality bytes of its reads start at
+ * plane[col_off[c]].  Bytes between the end of a column and col_off[c+1] are
+ * padding.  mq / baq / sq may be NULL (quality absent).  Byte 255 in mq, baq
+ * and sq means "not available" (-1 in the reference; mq==255 is mapped to -1
+ * by snpcaller.c:451-453 itself).  coverage may be NULL (= reads in the
+ * column); it is plp_col_t.coverage_plp.
+ * Device variants: every pointer is a device pointer, planes 16-byte aligned
+ * and readable up to the next multiple of 16 bytes past the last read. */
+typedef struct {
+    long long n_cols;
+    const long long *col_off;          /* n_cols + 1 */
+    const int *nt_cnt;                 /* 4 * n_cols */
+    const char *ref_base;              /* n_cols, uppercase */
+    const int *coverage;               /* n_cols or NULL */
+    const unsigned char *bq, *mq, *baq, *sq;
+} lfb200_batch_t;
+
+/* One column the device could not rule out (a candidate variant site), after
+ * host finishing.  pvalue[] are what snpcaller() would have written to
+ * snp_pvalues[] (snpcaller.h:97-102) including the LDBL_MAX / LDBL_MIN
+ * sentinels; called[] is the test of lofreq_call.c:832; qual[] is
+ * PROB_TO_PHREDQUAL(pvalue) where called, else -1 (lofreq_call.c:863). */
+typedef struct {
+    long long col;                     /* index into the batch */
+    long long bonf;                    /* Bonferroni factor handed to the test */
+    double lnp[LFB200_NUM_NONCONS];    /* natural log of the tail probability from the device */
+    long double pvalue[LFB200_NUM_NONCONS];
+    int alt_count[LFB200_NUM_NONCONS]; /* filtered counts, A,C,G,T-minus-ref order (snpcaller.c:489) */
+    int alt_raw_count[LFB200_NUM_NONCONS];
+    int qual[LFB200_NUM_NONCONS];
+    unsigned char status[LFB200_NUM_NONCONS];
+    unsigned char called[LFB200_NUM_NONCONS];
+} lfb200_site_t;
+
+/* Optional dense per-column outputs of the host entry point; any pointer may
+ * be NULL.  Layout [n_cols] or [n_cols][3]. */
+typedef struct {
+    int *alt_counts;                   /* plp_to_errprobs alt_counts  (snpcaller.h:72-75) */
+    int *alt_raw_counts;               /* plp_to_errprobs alt_raw_counts */
+    unsigned char *tested;             /* column reached snpcaller() (lofreq_call.c:794-807) */
+    long long *bonf_used;              /* bonf_subst passed to snpcaller(), 0 if untested */
+    double *lnp;                       /* ln p where status == LFB200_ST_VALUE */
+    unsigned char *status;
+    long double *pvalues;              /* snpcaller() snp_pvalues[] */
+    unsigned char *called;
+    int *qual;
+} lfb200_dense_out_t;
+
+typedef struct {
+    long long n_cols, n_tested, n_sites, n_heavy;   /* n_heavy: columns that needed the O(depth*K) kernel */
+    long long bonf_subst_final, num_snv_tests;
+} lfb200_summary_t;
+
+typedef struct lfb200_ctx lfb200_ctx;
+
+/* ---- life cycle ------------------------------------------------------- */
+int lfb200_create(lfb200_ctx **ctx, int device);     /* 0 = ok; fails without a CUDA device */
+void lfb200_destroy(lfb200_ctx *ctx);
+const char *lfb200_last_error(void);
+/* init_varcall_conf (snpcaller.c:626-651) */
+void lfb200_init_conf(lfb200_conf_t *conf);
+
+/* ---- the batched door (new; replaces one call_vars() per column,
+ *      lofreq_call.c:886-935 / 734-879, minus the VCF writing) ------------ */
+/* Host buffers in, sites out (sorted by column).  conf->bonf_subst and
+ * conf->num_snv_tests are advanced exactly as call_snvs() would over the same
+ * columns in order.  Returns 0, or non-zero with lfb200_last_error() set;
+ * if more than max_sites sites exist the call fails with that message. */
+int lfb200_call_columns(lfb200_ctx *ctx, lfb200_conf_t *conf, const lfb200_batch_t *host_batch,
+                        const lfb200_dense_out_t *dense, lfb200_site_t *sites, long long max_sites,
+                        lfb200_summary_t *summary);
+
+/* Device-resident batch, two phases so that region shards on several GPUs can
+ * exchange their tested-column counts in between (the running Bonferroni of a
+ * shard starts where the previous shard's ends; lofreq2_call_pparallel.py
+ * instead restarts it per region and sums the counts at the end, :131-161).
+ * stream is a cudaStream_t (or NULL).
+ *   screen : gates, alt counts, tested flags, exact tails for columns with
+ *            max alt count <= 8 — one streaming pass over the quality planes
+ *   ntested: number of tested columns found by screen (synchronises)
+ *   test   : running Bonferroni from conf->bonf_subst, significance screen,
+ *            O(depth*K) kernel for the remaining columns, site compaction
+ *   sites  : copy the sites back and finish them on the host (synchronises) */
+int lfb200_screen_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, const lfb200_batch_t *dev_batch, void *stream);
+int lfb200_ntested_device(lfb200_ctx *ctx, void *stream, long long *n_tested);
+int lfb200_test_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *stream);
+int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites,
+                        long long max_sites, lfb200_summary_t *summary);
+/* device pointers of the per-column results of the last screen/test (valid
+ * until the next screen on this ctx): int[3n], int[3n], u8[n], i64[n] */
+int lfb200_device_results(lfb200_ctx *ctx, const int **alt_counts, const int **alt_raw_counts,
+                          const unsigned char **tested, const long long **bonf_used);
+
+/* ---- link-compatible single-column symbols ----------------------------- */
+/* snpcaller() of snpcaller.h:97-102 (callers: lofreq_call.c:319,384,807,
+ * lofreq_uniq.c:311): same arguments, same sentinels, returns 0 on success.
+ * A batch of one through the same kernels, on a lazily created default ctx.
+ * approx_threshold_n > 0 is refused like a reference build without GSL
+ * (snpcaller.c:1118-1125) but by returning 1 instead of exit(1). */
+int lfb200_snpcaller(long double *snp_pvalues, const double *err_probs, const int num_err_probs,
+                     const int *noncons_counts, const long long int bonf_factor,
+                     const double sig_level, const int approx_threshold_n);
+/* many independent snpcaller() problems in one launch: problem i owns
+ * err_probs[ep_off[i] .. ep_off[i+1]), noncons_counts[3i..], bonf[i]; writes
+ * snp_pvalues[3i..], lnp[3i..] (nullable), status[3i..] (nullable). */
+int lfb200_snpcaller_batch(lfb200_ctx *ctx, long long n, const double *err_probs, const long long *ep_off,
+                           const int *noncons_counts, const long long *bonf, double sig_level,
+                           long double *snp_pvalues, double *lnp, unsigned char *status);
+
+/* ---- synthetic pileup columns on the device (benchmark input,
+ *      bit-identical to oracle/synth_np.py) --------------- */
+/* workload: 2..5 = C2..C5.  Writes columns [c0, c0+n_cols) with the given
+ * per-column pitch into device buffers; col_off must already hold the
+ * offsets (n_cols+1).  baq may be NULL. */
+int lfb200_synth_depths(int workload, long long c0, long long n_cols, int *depth_dev, void *stream);
+int lfb200_synth_columns(int workload, long long c0, long long n_cols, const long long *col_off_dev,
+                         int *nt_cnt_dev, char *ref_base_dev, unsigned char *bq_dev, unsigned char *mq_dev,
+                         unsigned char *baq_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

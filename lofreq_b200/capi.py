@@ -1,0 +1,106 @@
+"""ctypes binding of include/lofreq_b200.h — the same C ABI a LoFreq maintainer
+would bind from C.  Loading fails loudly when the library has not been built;
+creating a context fails loudly when there is no CUDA device (no CPU path)."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+NUM_NONCONS = 3
+USE_BAQ, USE_MQ, USE_SQ, USE_IDAQ = 1, 2, 4, 8
+ST_VALUE, ST_LDBLMAX, ST_LDBLMIN = 0, 1, 2
+
+
+class Conf(C.Structure):
+    _fields_ = [("min_bq", C.c_int), ("min_alt_bq", C.c_int), ("def_alt_bq", C.c_int),
+                ("min_jq", C.c_int), ("min_alt_jq", C.c_int), ("def_alt_jq", C.c_int),
+                ("min_cov", C.c_int), ("bonf_dynamic", C.c_int), ("flag", C.c_int),
+                ("sig", C.c_float), ("bonf_subst", C.c_longlong), ("num_snv_tests", C.c_longlong)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_cols", C.c_longlong), ("col_off", C.c_void_p), ("nt_cnt", C.c_void_p),
+                ("ref_base", C.c_void_p), ("coverage", C.c_void_p),
+                ("bq", C.c_void_p), ("mq", C.c_void_p), ("baq", C.c_void_p), ("sq", C.c_void_p)]
+
+
+class Site(C.Structure):
+    _fields_ = [("col", C.c_longlong), ("bonf", C.c_longlong), ("lnp", C.c_double * 3),
+                ("pvalue", C.c_longdouble * 3), ("alt_count", C.c_int * 3), ("alt_raw_count", C.c_int * 3),
+                ("qual", C.c_int * 3), ("status", C.c_ubyte * 3), ("called", C.c_ubyte * 3)]
+
+
+class DenseOut(C.Structure):
+    _fields_ = [("alt_counts", C.c_void_p), ("alt_raw_counts", C.c_void_p), ("tested", C.c_void_p),
+                ("bonf_used", C.c_void_p), ("lnp", C.c_void_p), ("status", C.c_void_p),
+                ("pvalues", C.c_void_p), ("called", C.c_void_p), ("qual", C.c_void_p)]
+
+
+class Summary(C.Structure):
+    _fields_ = [("n_cols", C.c_longlong), ("n_tested", C.c_longlong), ("n_sites", C.c_longlong),
+                ("n_heavy", C.c_longlong), ("bonf_subst_final", C.c_longlong), ("num_snv_tests", C.c_longlong)]
+
+
+# every symbol include/lofreq_b200.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_conf", "lfb200_call_columns",
+           "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_sites_device",
+           "lfb200_device_results", "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_synth_depths",
+           "lfb200_synth_columns"]
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """dlopen liblofreq_b200.so and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.LIB):
+        raise RuntimeError("liblofreq_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                           " (there is no CPU fallback)")
+    lib = C.CDLL(_build.LIB)
+    vp, ll = C.c_void_p, C.c_longlong
+    lib.lfb200_create.restype = C.c_int
+    lib.lfb200_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.lfb200_destroy.restype = None
+    lib.lfb200_destroy.argtypes = [vp]
+    lib.lfb200_last_error.restype = C.c_char_p
+    lib.lfb200_last_error.argtypes = []
+    lib.lfb200_init_conf.restype = None
+    lib.lfb200_init_conf.argtypes = [C.POINTER(Conf)]
+    lib.lfb200_call_columns.restype = C.c_int
+    lib.lfb200_call_columns.argtypes = [vp, C.POINTER(Conf), C.POINTER(Batch), C.POINTER(DenseOut),
+                                        C.POINTER(Site), ll, C.POINTER(Summary)]
+    lib.lfb200_screen_device.restype = C.c_int
+    lib.lfb200_screen_device.argtypes = [vp, C.POINTER(Conf), C.POINTER(Batch), vp]
+    lib.lfb200_ntested_device.restype = C.c_int
+    lib.lfb200_ntested_device.argtypes = [vp, vp, C.POINTER(ll)]
+    lib.lfb200_test_device.restype = C.c_int
+    lib.lfb200_test_device.argtypes = [vp, C.POINTER(Conf), vp]
+    lib.lfb200_sites_device.restype = C.c_int
+    lib.lfb200_sites_device.argtypes = [vp, C.POINTER(Conf), vp, C.POINTER(Site), ll, C.POINTER(Summary)]
+    lib.lfb200_device_results.restype = C.c_int
+    lib.lfb200_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.lfb200_snpcaller.restype = C.c_int
+    lib.lfb200_snpcaller.argtypes = [vp, vp, C.c_int, vp, ll, C.c_double, C.c_int]
+    lib.lfb200_snpcaller_batch.restype = C.c_int
+    lib.lfb200_snpcaller_batch.argtypes = [vp, ll, vp, vp, vp, vp, C.c_double, vp, vp, vp]
+    lib.lfb200_synth_depths.restype = C.c_int
+    lib.lfb200_synth_depths.argtypes = [C.c_int, ll, ll, vp, vp]
+    lib.lfb200_synth_columns.restype = C.c_int
+    lib.lfb200_synth_columns.argtypes = [C.c_int, ll, ll, vp, vp, vp, vp, vp, vp, vp]
+    _lib = lib
+    return lib
+
+
+class Lfb200Error(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise Lfb200Error(load().lfb200_last_error().decode() or "lofreq_b200 call failed (rc=%d)" % rc)

@@ -1,0 +1,592 @@
+// Host side of liblofreq_b200.so: context and workspace management, the C ABI of
+// include/lofreq_b200.h, and the long double finishing of the few columns the device keeps
+// ("sites").  No SNV arithmetic happens here except what needs x87 long double to decide exactly
+// like the reference: expl(), the FE-exception clamp, pvalue*bonf < sig, PROB_TO_PHREDQUAL.
+#include <algorithm>
+#include <cerrno>
+#include <cfenv>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/lofreq_b200.h"
+#include "internal.h"
+
+using namespace lfb;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) return fail("CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *lfb200_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct lfb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;       // used by the host entry points
+    Lut *d_lut = nullptr;
+    // workspace of the current batch
+    DevBuf w_cnt6, w_tested, w_tails, w_bonf, w_blocksum, w_jobs, w_cand, w_counters;
+    Workspace ws{};
+    // device copies of host batches (host entry point)
+    DevBuf in_off, in_cnt, in_ref, in_cov, in_bq, in_mq, in_baq, in_sq;
+    // single problems
+    DevBuf p_ep, p_off, p_cnt, p_bonf, p_out;
+    // pinned scratch for small D2H transfers
+    Counters *h_counters = nullptr;
+    std::vector<Cand> h_cand;
+    // state of the last screen
+    DevBatch cur{};
+    bool have_batch = false;
+    long long n_tested = -1;
+};
+
+static void build_lut(Lut &l)
+{
+    for (int q = 0; q < 256; ++q) {
+        const double p = pow(10.0, -1.0 * q / 10.0);     // PHREDQUAL_TO_PROB, utils.h:42
+        l.bq[q] = p;
+        l.mq[q] = p;
+        l.aq[q] = p;
+    }
+    l.mq[0] = 0.5;      // MQ0_ERRPROB, snpcaller.c:64,315
+    l.mq[255] = 0.0;    // unknown -> -1 -> probability 0, snpcaller.c:451-453,311
+    l.aq[255] = 0.0;    // -1: quality not available (plp.c:961)
+}
+
+// PROB_TO_PHREDQUAL_SAFE (utils.h:46)
+static int prob_to_phred_safe(double p)
+{
+    if (p <= 0.0) return INT_MAX;
+    return (int)(-10.0 * log10l(p));
+}
+
+// Smallest double jp for which the reference's filter `merged_qual < min_q` (snpcaller.c:469,480) fires,
+// found by bisection on the bit pattern with the reference's own expression, so that the device can
+// filter with one comparison and still agree at every integer boundary of log10l.
+static double jq_cut(int min_q)
+{
+    if (min_q <= 0) return INFINITY;          // merged_qual >= 0 always (jp <= 1)
+    if (!(prob_to_phred_safe(1.0) < min_q)) return INFINITY;
+    unsigned long long lo = 1, hi;            // lo: predicate false (tiny jp, huge quality); hi: true
+    double one = 1.0;
+    memcpy(&hi, &one, 8);
+    double dlo;
+    memcpy(&dlo, &lo, 8);
+    if (prob_to_phred_safe(dlo) < min_q) return dlo;
+    while (hi - lo > 1) {
+        const unsigned long long mid = lo + (hi - lo) / 2;
+        double d;
+        memcpy(&d, &mid, 8);
+        if (prob_to_phred_safe(d) < min_q) hi = mid; else lo = mid;
+    }
+    double d;
+    memcpy(&d, &hi, 8);
+    return d;
+}
+
+static int make_devconf(const lfb200_conf_t *c, const lfb200_batch_t *b, DevConf &d)
+{
+    memset(&d, 0, sizeof(d));
+    d.min_bq = c->min_bq;
+    d.min_alt_bq = c->min_alt_bq;
+    if (c->def_alt_bq == -1) d.alt_bq_mode = 2;
+    else if (c->def_alt_bq != 0) {
+        d.alt_bq_mode = 1;
+        d.alt_bq_prob = pow(10.0, -1.0 * c->def_alt_bq / 10.0);
+    }
+    d.min_cov = c->min_cov;
+    d.use_mq = (c->flag & LFB200_USE_MQ) && b->mq;
+    d.use_baq = (c->flag & LFB200_USE_BAQ) && b->baq;
+    d.use_sq = (c->flag & LFB200_USE_SQ) && b->sq;
+    d.skip_jp = jq_cut(c->min_jq);
+    d.skip_alt_jp = jq_cut(c->min_alt_jq);
+    d.jq_filters = std::isfinite(d.skip_jp) || std::isfinite(d.skip_alt_jp);
+    if (c->def_alt_jq == -1) return fail("def_alt_jq = -1 is not implemented (neither in the reference, snpcaller.c:482-484)");
+    d.def_alt_jq_on = c->def_alt_jq != 0;
+    d.def_alt_jq_prob = d.def_alt_jq_on ? pow(10.0, -1.0 * c->def_alt_jq / 10.0) : 0.0;
+    d.sig = (double)c->sig;
+    d.bonf_dynamic = c->bonf_dynamic;
+    d.bonf_start = c->bonf_subst;
+    return 0;
+}
+
+extern "C" void lfb200_init_conf(lfb200_conf_t *c)
+{
+    // init_varcall_conf, snpcaller.c:626-651 with defaults.h:40-80
+    memset(c, 0, sizeof(*c));
+    c->min_bq = 6;
+    c->min_alt_bq = 6;
+    c->def_alt_bq = 0;
+    c->min_jq = 0;
+    c->min_alt_jq = 0;
+    c->def_alt_jq = 0;
+    c->min_cov = 1;
+    c->bonf_dynamic = 1;
+    c->flag = LFB200_USE_MQ | LFB200_USE_BAQ | LFB200_USE_IDAQ;
+    c->sig = 0.01f;
+    c->bonf_subst = 1;
+    c->num_snv_tests = 0;
+}
+
+extern "C" int lfb200_create(lfb200_ctx **out, int device)
+{
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail("no CUDA device: lofreq_b200 has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    lfb200_ctx *ctx = new lfb200_ctx();
+    ctx->device = device;
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    Lut l;
+    build_lut(l);
+    CU(cudaMalloc(&ctx->d_lut, sizeof(Lut)));
+    CU(cudaMemcpy(ctx->d_lut, &l, sizeof(Lut), cudaMemcpyHostToDevice));
+    CU(cudaMallocHost(&ctx->h_counters, sizeof(Counters)));
+    if (ctx->w_counters.ensure(sizeof(Counters))) return fail("out of device memory");
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void lfb200_destroy(lfb200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_tails, &ctx->w_bonf, &ctx->w_blocksum, &ctx->w_jobs,
+                      &ctx->w_cand, &ctx->w_counters, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov,
+                      &ctx->in_bq, &ctx->in_mq, &ctx->in_baq, &ctx->in_sq, &ctx->p_ep, &ctx->p_off, &ctx->p_cnt,
+                      &ctx->p_bonf, &ctx->p_out};
+    for (DevBuf *b : bufs) b->release();
+    if (ctx->d_lut) cudaFree(ctx->d_lut);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static int ensure_workspace(lfb200_ctx *ctx, long long n)
+{
+    const size_t nn = (size_t)std::max<long long>(n, 1);
+    int bad = 0;
+    bad |= ctx->w_cnt6.ensure(nn * 6 * sizeof(int));
+    bad |= ctx->w_tested.ensure(nn + 1024);
+    bad |= ctx->w_tails.ensure(nn * 4 * sizeof(double));
+    bad |= ctx->w_bonf.ensure(nn * sizeof(long long));
+    bad |= ctx->w_blocksum.ensure(((nn + 1023) / 1024 + 1) * sizeof(long long));
+    bad |= ctx->w_jobs.ensure(nn * NCLASS * sizeof(int));
+    bad |= ctx->w_cand.ensure(nn * sizeof(Cand));
+    if (bad) return fail("out of device memory for a batch of %lld columns", n);
+    Workspace &w = ctx->ws;
+    w.cap_cols = n;
+    w.cnt6 = (int *)ctx->w_cnt6.p;
+    w.tested = (unsigned char *)ctx->w_tested.p;
+    w.tails = (double *)ctx->w_tails.p;
+    w.bonf_used = (long long *)ctx->w_bonf.p;
+    w.blocksum = (long long *)ctx->w_blocksum.p;
+    w.jobs = (int *)ctx->w_jobs.p;
+    w.cand = (Cand *)ctx->w_cand.p;
+    w.counters = (Counters *)ctx->w_counters.p;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// long double finishing of one site: snpcaller.c:1144-1196 + lofreq_call.c:832,863
+// ------------------------------------------------------------------------------------------------
+static const double LN_EXP_UNDERFLOW = 708.3964185322641;   // glibc exp() raises FE_UNDERFLOW below -this
+
+// expl() with the reference's clamp (snpcaller.c:1047-1059, 1169-1188); `pre_flag` = an exp() inside the
+// preceding probvec_tailsum would already have raised FE_UNDERFLOW
+static long double expl_clamped(double t, bool pre_flag)
+{
+    errno = 0;
+    feclearexcept(FE_ALL_EXCEPT);
+    long double p = expl((long double)t);
+    const bool flagged = pre_flag || errno || fetestexcept(FE_INVALID | FE_DIVBYZERO | FE_OVERFLOW | FE_UNDERFLOW);
+    if (flagged) p = (p < DBL_EPSILON) ? LDBL_MIN : LDBL_MAX;
+    errno = 0;
+    feclearexcept(FE_ALL_EXCEPT);
+    return p;
+}
+
+static void finish_site(const Cand &cd, double sig, lfb200_site_t &s)
+{
+    s.col = cd.col;
+    s.bonf = cd.bonf;
+    int K = 0, imax = 0;
+    for (int i = 0; i < 3; ++i) {
+        s.lnp[i] = cd.lnp[i];
+        s.pvalue[i] = LDBL_MAX;
+        s.alt_count[i] = cd.cnt[i];
+        s.alt_raw_count[i] = cd.raw[i];
+        s.qual[i] = -1;
+        s.status[i] = LFB200_ST_LDBLMAX;
+        s.called[i] = 0;
+        if (cd.cnt[i] > K) { K = cd.cnt[i]; imax = i; }
+    }
+    if (K == 0 || (cd.flags & CF_INSIG)) return;
+    // poissbin: pvalue = expl(probvec[K]) with clamp, then the significance gate (snpcaller.c:1155)
+    const long double pK = expl_clamped(cd.lnp[imax], false);
+    if (pK * (double)cd.bonf > sig) return;
+    for (int i = 0; i < 3; ++i) {
+        const int c = cd.cnt[i];
+        if (c == 0) continue;
+        const double t = cd.lnp[i];
+        // probvec_tailsum folds row[c..K] with log_sum; its exp() underflows exactly when the running sum
+        // and the next term are more than 708.396 nats apart.  The row is log-concave, so the widest gap is
+        // against the last two entries, min(row[K-1], row[K]) = ln_floor.
+        const bool pre = (c < K) && (t - cd.ln_floor > LN_EXP_UNDERFLOW);
+        const long double p = expl_clamped(t, pre);
+        s.pvalue[i] = p;
+        s.status[i] = (p == LDBL_MAX) ? LFB200_ST_LDBLMAX : (p == LDBL_MIN) ? LFB200_ST_LDBLMIN : LFB200_ST_VALUE;
+        if (p * (double)cd.bonf < sig) {                 // lofreq_call.c:832
+            s.called[i] = 1;
+            s.qual[i] = (int)(-10.0 * log10l(p));        // PROB_TO_PHREDQUAL, lofreq_call.c:863
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident batches
+// ------------------------------------------------------------------------------------------------
+static void to_devbatch(const lfb200_batch_t *b, DevBatch &d)
+{
+    d.n_cols = b->n_cols;
+    d.col_off = b->col_off;
+    d.nt_cnt = b->nt_cnt;
+    d.ref_base = b->ref_base;
+    d.coverage = b->coverage;
+    d.bq = b->bq;
+    d.mq = b->mq;
+    d.baq = b->baq;
+    d.sq = b->sq;
+}
+
+extern "C" int lfb200_screen_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, const lfb200_batch_t *b, void *stream)
+{
+    if (!ctx) return fail("no context");
+    if (b->n_cols < 0 || b->n_cols > 2000000000ll) return fail("n_cols %lld out of range", b->n_cols);
+    if (!b->bq) return fail("the bq plane is required");
+    CU(cudaSetDevice(ctx->device));
+    DevConf dc;
+    if (make_devconf(conf, b, dc)) return 1;
+    if (ensure_workspace(ctx, b->n_cols)) return 1;
+    to_devbatch(b, ctx->cur);
+    ctx->have_batch = true;
+    ctx->n_tested = -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_screen(dc, ctx->cur, ctx->d_lut, ctx->ws, st);
+    launch_scan(ctx->cur, ctx->ws, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lfb200_ntested_device(lfb200_ctx *ctx, void *stream, long long *n_tested)
+{
+    if (!ctx || !ctx->have_batch) return fail("no screened batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->cur.n_cols == 0) { *n_tested = ctx->n_tested = 0; return 0; }
+    CU(cudaMemcpyAsync(ctx->h_counters, ctx->ws.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_tested = ctx->n_tested = (long long)ctx->h_counters->n_tested;
+    return 0;
+}
+
+extern "C" int lfb200_test_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *stream)
+{
+    if (!ctx || !ctx->have_batch) return fail("no screened batch");
+    lfb200_batch_t hb;
+    memset(&hb, 0, sizeof(hb));
+    hb.mq = ctx->cur.mq; hb.baq = ctx->cur.baq; hb.sq = ctx->cur.sq;
+    DevConf dc;
+    if (make_devconf(conf, &hb, dc)) return 1;
+    launch_test(dc, ctx->cur, ctx->d_lut, ctx->ws, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static long long final_bonf(const lfb200_conf_t *conf, long long n_tested)
+{
+    if (!conf->bonf_dynamic || n_tested == 0) return conf->bonf_subst;
+    return (conf->bonf_subst == 1 ? 0 : conf->bonf_subst) + 3 * n_tested;     // lofreq_call.c:794-800
+}
+
+extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites,
+                                   long long max_sites, lfb200_summary_t *summary)
+{
+    if (!ctx || !ctx->have_batch) return fail("no screened batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    lfb200_summary_t sm;
+    memset(&sm, 0, sizeof(sm));
+    sm.n_cols = ctx->cur.n_cols;
+    long long n_cand = 0;
+    if (ctx->cur.n_cols > 0) {
+        CU(cudaMemcpyAsync(ctx->h_counters, ctx->ws.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const Counters &c = *ctx->h_counters;
+        if (c.err_flags & CF_UNSUPPORTED)
+            return fail("a column has an alt count above %d: not supported by this build", MAXK_WARP);
+        sm.n_tested = (long long)c.n_tested;
+        n_cand = c.n_cand;
+        for (int i = 0; i < NCLASS; ++i) sm.n_heavy += c.n_jobs[i];
+    }
+    if (n_cand > max_sites) return fail("%lld sites but room for %lld", n_cand, max_sites);
+    ctx->h_cand.resize((size_t)n_cand);
+    if (n_cand) {
+        CU(cudaMemcpyAsync(ctx->h_cand.data(), ctx->ws.cand, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    std::sort(ctx->h_cand.begin(), ctx->h_cand.end(), [](const Cand &a, const Cand &b) { return a.col < b.col; });
+    const double sig = (double)conf->sig;
+    for (long long i = 0; i < n_cand; ++i) {
+        if (ctx->h_cand[(size_t)i].flags & CF_RANGE)
+            return fail("column %lld: tail outside the representable range", ctx->h_cand[(size_t)i].col);
+        finish_site(ctx->h_cand[(size_t)i], sig, sites[i]);
+    }
+    sm.n_sites = n_cand;
+    sm.bonf_subst_final = final_bonf(conf, sm.n_tested);
+    conf->bonf_subst = sm.bonf_subst_final;
+    conf->num_snv_tests += 3 * sm.n_tested;       // lofreq_call.c:801
+    sm.num_snv_tests = conf->num_snv_tests;
+    if (summary) *summary = sm;
+    return 0;
+}
+
+extern "C" int lfb200_device_results(lfb200_ctx *ctx, const int **alt_counts, const int **alt_raw_counts,
+                                     const unsigned char **tested, const long long **bonf_used)
+{
+    if (!ctx || !ctx->have_batch) return fail("no screened batch");
+    // cnt6 is [n][6]: callers index alt_counts[6c+i], alt_raw_counts = alt_counts + 3 with the same stride
+    if (alt_counts) *alt_counts = ctx->ws.cnt6;
+    if (alt_raw_counts) *alt_raw_counts = ctx->ws.cnt6 + 3;
+    if (tested) *tested = ctx->ws.tested;
+    if (bonf_used) *bonf_used = ctx->ws.bonf_used;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host buffers in, sites out
+// ------------------------------------------------------------------------------------------------
+static int upload(DevBuf &buf, const void *src, size_t bytes, size_t pad, cudaStream_t st, const void **dev)
+{
+    if (!src) { *dev = nullptr; return 0; }
+    if (buf.ensure(bytes + pad)) return fail("out of device memory (%zu bytes)", bytes + pad);
+    if (bytes) CU(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st));
+    *dev = buf.p;
+    return 0;
+}
+
+extern "C" int lfb200_call_columns(lfb200_ctx *ctx, lfb200_conf_t *conf, const lfb200_batch_t *hb,
+                                   const lfb200_dense_out_t *dense, lfb200_site_t *sites, long long max_sites,
+                                   lfb200_summary_t *summary)
+{
+    if (!ctx) return fail("no context");
+    CU(cudaSetDevice(ctx->device));
+    const long long n = hb->n_cols;
+    if (n < 0) return fail("negative n_cols");
+    cudaStream_t st = ctx->stream;
+    lfb200_batch_t db = *hb;
+    const size_t plane_bytes = n ? (size_t)hb->col_off[n] : 0;
+    const void *d;
+    if (upload(ctx->in_off, hb->col_off, (size_t)(n + 1) * 8, 0, st, &d)) return 1;
+    db.col_off = (const long long *)d;
+    if (upload(ctx->in_cnt, hb->nt_cnt, (size_t)n * 16, 0, st, &d)) return 1;
+    db.nt_cnt = (const int *)d;
+    if (upload(ctx->in_ref, hb->ref_base, (size_t)n, 0, st, &d)) return 1;
+    db.ref_base = (const char *)d;
+    if (upload(ctx->in_cov, hb->coverage, (size_t)n * 4, 0, st, &d)) return 1;
+    db.coverage = (const int *)d;
+    if (upload(ctx->in_bq, hb->bq, plane_bytes, 32, st, &d)) return 1;
+    db.bq = (const unsigned char *)d;
+    // planes the flags switch off are not needed on the device
+    if (upload(ctx->in_mq, (conf->flag & LFB200_USE_MQ) ? hb->mq : nullptr, plane_bytes, 32, st, &d)) return 1;
+    db.mq = (const unsigned char *)d;
+    if (upload(ctx->in_baq, (conf->flag & LFB200_USE_BAQ) ? hb->baq : nullptr, plane_bytes, 32, st, &d)) return 1;
+    db.baq = (const unsigned char *)d;
+    if (upload(ctx->in_sq, (conf->flag & LFB200_USE_SQ) ? hb->sq : nullptr, plane_bytes, 32, st, &d)) return 1;
+    db.sq = (const unsigned char *)d;
+
+    if (lfb200_screen_device(ctx, conf, &db, st)) return 1;
+    if (lfb200_test_device(ctx, conf, st)) return 1;
+    lfb200_summary_t sm;
+    const lfb200_conf_t conf_in = *conf;
+    if (lfb200_sites_device(ctx, conf, st, sites, max_sites, &sm)) return 1;
+
+    if (dense) {
+        const size_t nn = (size_t)n;
+        if (dense->alt_counts || dense->alt_raw_counts) {
+            std::vector<int> c6(nn * 6);
+            if (nn) CU(cudaMemcpyAsync(c6.data(), ctx->ws.cnt6, nn * 24, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (size_t c = 0; c < nn; ++c)
+                for (int i = 0; i < 3; ++i) {
+                    if (dense->alt_counts) dense->alt_counts[3 * c + i] = c6[6 * c + i];
+                    if (dense->alt_raw_counts) dense->alt_raw_counts[3 * c + i] = c6[6 * c + 3 + i];
+                }
+        }
+        if (dense->tested && nn) CU(cudaMemcpyAsync(dense->tested, ctx->ws.tested, nn, cudaMemcpyDeviceToHost, st));
+        if (dense->bonf_used && nn) CU(cudaMemcpyAsync(dense->bonf_used, ctx->ws.bonf_used, nn * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (size_t c = 0; c < nn * 3; ++c) {
+            if (dense->lnp) dense->lnp[c] = 0.0;
+            if (dense->status) dense->status[c] = LFB200_ST_LDBLMAX;
+            if (dense->pvalues) dense->pvalues[c] = LDBL_MAX;
+            if (dense->called) dense->called[c] = 0;
+            if (dense->qual) dense->qual[c] = -1;
+        }
+        for (long long k = 0; k < sm.n_sites; ++k) {
+            const lfb200_site_t &s = sites[k];
+            for (int i = 0; i < 3; ++i) {
+                const size_t at = (size_t)s.col * 3 + i;
+                if (dense->lnp) dense->lnp[at] = s.lnp[i];
+                if (dense->status) dense->status[at] = s.status[i];
+                if (dense->pvalues) dense->pvalues[at] = s.pvalue[i];
+                if (dense->called) dense->called[at] = s.called[i];
+                if (dense->qual) dense->qual[at] = s.qual[i];
+            }
+        }
+    }
+    (void)conf_in;
+    if (summary) *summary = sm;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// link-compatible single problems
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfb200_snpcaller_batch(lfb200_ctx *ctx, long long n, const double *err_probs, const long long *ep_off,
+                                      const int *noncons_counts, const long long *bonf, double sig_level,
+                                      long double *snp_pvalues, double *lnp, unsigned char *status)
+{
+    if (!ctx) return fail("no context");
+    if (n <= 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n_ep = (size_t)ep_off[n];
+    const void *d;
+    ProbBatch pb;
+    pb.n = n;
+    pb.sig = sig_level;
+    if (upload(ctx->p_ep, err_probs, n_ep * 8, 8, st, &d)) return 1;
+    pb.err_probs = (const double *)d;
+    if (upload(ctx->p_off, ep_off, (size_t)(n + 1) * 8, 0, st, &d)) return 1;
+    pb.ep_off = (const long long *)d;
+    if (upload(ctx->p_cnt, noncons_counts, (size_t)n * 12, 0, st, &d)) return 1;
+    pb.counts = (const int *)d;
+    if (upload(ctx->p_bonf, bonf, (size_t)n * 8, 0, st, &d)) return 1;
+    pb.bonf = (const long long *)d;
+    if (ctx->p_out.ensure((size_t)n * sizeof(Cand))) return fail("out of device memory");
+    launch_prob_jobs(pb, (Cand *)ctx->p_out.p, st);
+    CU(cudaGetLastError());
+    ctx->h_cand.resize((size_t)n);
+    CU(cudaMemcpyAsync(ctx->h_cand.data(), ctx->p_out.p, (size_t)n * sizeof(Cand), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (long long i = 0; i < n; ++i) {
+        const Cand &cd = ctx->h_cand[(size_t)i];
+        if (cd.flags & CF_UNSUPPORTED) return fail("problem %lld: alt count above %d or above the number of reads", i, MAXK_WARP);
+        if (cd.flags & CF_RANGE) return fail("problem %lld: tail outside the representable range", i);
+        lfb200_site_t s;
+        finish_site(cd, sig_level, s);
+        for (int a = 0; a < 3; ++a) {
+            snp_pvalues[3 * i + a] = s.pvalue[a];
+            if (lnp) lnp[3 * i + a] = s.lnp[a];
+            if (status) status[3 * i + a] = s.status[a];
+        }
+    }
+    return 0;
+}
+
+static lfb200_ctx *g_default_ctx = nullptr;
+
+extern "C" int lfb200_snpcaller(long double *snp_pvalues, const double *err_probs, const int num_err_probs,
+                                const int *noncons_counts, const long long int bonf_factor, const double sig_level,
+                                const int approx_threshold_n)
+{
+    if (approx_threshold_n > 0) {
+        // a reference build without GSL exits here (snpcaller.c:1118-1125); we refuse without killing the caller
+        fprintf(stderr, "FATAL(lofreq_b200): --approx-threshold needs the GSL Poisson pre-test, which this path does not provide\n");
+        return 1;
+    }
+    if (!g_default_ctx && lfb200_create(&g_default_ctx, 0)) {
+        fprintf(stderr, "FATAL(lofreq_b200): %s\n", g_err);
+        return 1;
+    }
+    const long long off[2] = {0, num_err_probs};
+    const long long bonf[1] = {bonf_factor};
+    if (lfb200_snpcaller_batch(g_default_ctx, 1, err_probs, off, noncons_counts, bonf, sig_level, snp_pvalues, nullptr, nullptr)) {
+        fprintf(stderr, "FATAL(lofreq_b200): %s\n", g_err);
+        return 1;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic columns
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfb200_synth_depths(int workload, long long c0, long long n_cols, int *depth_dev, void *stream)
+{
+    if (workload < 2 || workload > 5) return fail("workload must be 2..5");
+    launch_synth_depths(workload, c0, n_cols, depth_dev, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lfb200_synth_columns(int workload, long long c0, long long n_cols, const long long *col_off_dev,
+                                    int *nt_cnt_dev, char *ref_base_dev, unsigned char *bq_dev, unsigned char *mq_dev,
+                                    unsigned char *baq_dev, void *stream)
+{
+    if (workload < 2 || workload > 5) return fail("workload must be 2..5");
+    launch_synth_columns(workload, c0, n_cols, col_off_dev, nt_cnt_dev, ref_base_dev, bq_dev, mq_dev, baq_dev,
+                         (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,99 @@
+// Internal declarations shared by the CUDA translation units and the host side
+// of liblofreq_b200.so.  Not part of the public ABI (that is include/lofreq_b200.h).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace lfb {
+
+constexpr int KS = 8;              // columns whose largest alt count is <= KS are finished by the screen kernel
+constexpr int NCLASS = 8;          // register-tile classes of the O(depth*K) kernel: R = 1,2,4,..,64 cells per lane, then XL
+constexpr int MAXK_WARP = 2048;    // 32 lanes * 64 cells
+
+// what the kernels need from varcall_conf_t, pre-digested on the host
+struct DevConf {
+    int min_bq, min_alt_bq;
+    int alt_bq_mode;               // 0 keep, 1 constant (def_alt_bq > 0), 2 median of the ref-base qualities (def_alt_bq == -1)
+    double alt_bq_prob;            // pow(10, -def_alt_bq/10) for mode 1
+    int min_cov;
+    int use_mq, use_baq, use_sq;   // flag bit set AND plane present
+    int jq_filters;                // min_jq or min_alt_jq can reject a read
+    double skip_jp, skip_alt_jp;   // a read is dropped when its merged probability is >= this (see host_api.cpp: jq_cut)
+    int def_alt_jq_on;
+    double def_alt_jq_prob;
+    double sig;                    // (double)conf->sig, as call_snvs passes it (lofreq_call.c:807)
+    int bonf_dynamic;
+    long long bonf_start;          // conf->bonf_subst on entry
+};
+
+struct DevBatch {
+    long long n_cols;
+    const long long *col_off;
+    const int *nt_cnt;
+    const char *ref_base;
+    const int *coverage;
+    const unsigned char *bq, *mq, *baq, *sq;
+};
+
+// pow(10,-q/10) tables built on the host with glibc pow() so that the device
+// works on bit-identical probabilities (utils.h:42)
+struct Lut {
+    double bq[256];                // plain phred
+    double mq[256];                // [0] = 0.5 (MQ0_ERRPROB, snpcaller.c:64), [255] = 0 (unknown -> -1 -> prob 0)
+    double aq[256];                // baq / sq: [255] = 0 (-1: not available)
+};
+
+// a column (or a stand-alone snpcaller problem) the device could not rule out
+struct Cand {
+    long long col;
+    long long bonf;
+    double lnp[3];                 // ln P(X >= count_i)
+    double ln_floor;               // min(ln P(X = K-1), ln P(X >= K)), K = max count: input of the clamp rule
+    int cnt[3];
+    int raw[3];
+    int flags;
+    int pad;
+};
+enum { CF_INSIG = 1, CF_RANGE = 2, CF_UNSUPPORTED = 4 };
+
+struct Counters {
+    unsigned long long n_tested;   // written by the block-sum scan
+    unsigned int n_cand;
+    unsigned int n_jobs[NCLASS];
+    unsigned int next_job[NCLASS];
+    unsigned int err_flags;
+};
+
+struct Workspace {
+    long long cap_cols;
+    int *cnt6;                     // [n][6]: alt_counts[3], alt_raw_counts[3]
+    unsigned char *tested;         // [n]
+    double *tails;                 // [n][4]: linear P(X>=c_i) for the three alleles, min(P[K-1], P(>=K))
+    long long *bonf_used;          // [n]
+    long long *blocksum;           // [ceil(n/1024)]
+    int *jobs;                     // [NCLASS][n]
+    Cand *cand;                    // [n]
+    Counters *counters;
+};
+
+// stand-alone snpcaller problems (link-compatible path)
+struct ProbBatch {
+    long long n;
+    const double *err_probs;
+    const long long *ep_off;
+    const int *counts;             // [n][3]
+    const long long *bonf;         // [n]
+    double sig;
+};
+
+// launchers (snv_kernels.cu)
+void launch_screen(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
+void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st);
+void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
+void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st);
+// synth.cu
+void launch_synth_depths(int workload, long long c0, long long n, int *depth, cudaStream_t st);
+void launch_synth_columns(int workload, long long c0, long long n, const long long *col_off, int *nt_cnt, char *ref,
+                          unsigned char *bq, unsigned char *mq, unsigned char *baq, cudaStream_t st);
+
+}  // namespace lfb

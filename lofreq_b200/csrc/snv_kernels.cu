@@ -1,0 +1,961 @@
+// sm_100a kernels of the per-pileup-column SNV test.
+//
+// What the reference does per column (lofreq_call.c:734-879 -> snpcaller.c):
+//   plp_to_errprobs (snpcaller.c:345-498)  quality bytes -> merged error probabilities, alt counts
+//   qsort                                   (order only changes rounding and where pruning fires)
+//   snpcaller -> poissbin -> pruned_calc_prob_dist (snpcaller.c:830-1204)
+//                                           Poisson-binomial DP in log space, tail p-value per allele
+//
+// What runs here:
+//   k_screen    one warp per column, ONE streaming pass over the quality planes with 128-bit loads:
+//               gates, alt counts, and — when the largest alt count K <= 8, i.e. almost every column —
+//               the exact distribution truncated at K, evaluated in linear space on 32 disjoint read
+//               subsets and merged by truncated convolution over warp shuffles.  HBM-bound.
+//   k_block_counts / k_scan_blocks / k_finalize
+//               running Bonferroni factor = prefix sum over the tested flags (lofreq_call.c:794-800),
+//               significance screen, compaction of the surviving columns ("sites"), job lists.
+//   k_heavy<R>  one warp per remaining column (K > 8): the O(depth*K) recurrence in fp64, K cells tiled
+//               over lanes x R registers, one shuffle per read for the lane boundary.  Odds form
+//               E[k] += E[k-1]*o (one DFMA per cell), exact power-of-two rescaling, exponential tilting
+//               when the tail is further out than fp64 can hold.  fp64-pipe-bound.
+//   k_prob_jobs the same routines fed with ready-made double error probabilities (snpcaller() symbol).
+//
+// All sums are over positive terms, so the relative error of a tail is O(depth * 2^-53); the reference's
+// log-space arithmetic (exp + log1p per cell) is not reproduced, its results are (tests/test_parity_gpu.py).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+#include "internal.h"
+
+namespace lfb {
+
+#define FULL 0xffffffffu
+static constexpr double LN2 = 0.69314718055994530942;
+static constexpr double DEPS = 2.220446049250313e-16;   // DBL_EPSILON
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
+    return v;
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// merge_srcq_mapq_baq_and_bq (snpcaller.c:334), same association, no contraction
+__device__ __forceinline__ double merge4(double sp, double mp, double bap, double bp)
+{
+    const double om = __dsub_rn(1.0, mp);
+    const double os = __dsub_rn(1.0, sp);
+    const double oa = __dsub_rn(1.0, bap);
+    double acc = __dadd_rn(mp, __dmul_rn(om, sp));
+    const double oms = __dmul_rn(om, os);
+    acc = __dadd_rn(acc, __dmul_rn(oms, bap));
+    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(oms, oa), bp));
+    return acc;
+}
+
+// DBL_EPSILON guards of pruned_calc_prob_dist (snpcaller.c:872-881), in linear space
+__device__ __forceinline__ void guard_pq(double jp, double &p, double &q)
+{
+    p = (fabs(jp) < DEPS) ? DEPS : jp;
+    q = (fabs(jp - 1.0) < DEPS) ? (1.0 - jp + DEPS) : (1.0 - jp);
+}
+
+struct Geom {            // one column of a batch
+    long long off;       // first read in the planes
+    int n;               // reads in the column
+    int b1, b2, b3;      // group boundaries: A [0,b1) C [b1,b2) G [b2,b3) T [b3,n)
+    int ref_idx;         // 0..3, -1 = not A/C/G/T
+    double alt_bp;       // base-quality probability forced on alt reads (alt_bq_mode != 0)
+};
+
+__device__ __forceinline__ int ref_index(char r)
+{
+    return r == 'A' ? 0 : r == 'C' ? 1 : r == 'G' ? 2 : r == 'T' ? 3 : -1;
+}
+
+// plp_to_errprobs for one read (snpcaller.c:399-491).  Returns false when the read is filtered out.
+// lut points at the shared-memory copy of Lut (bq | mq | aq).
+template <bool NEEDP>
+__device__ __forceinline__ bool eval_read(const DevConf &cf, const double *lut, const Geom &g, int pos, int bq, int mq,
+                                          int baq, int sq, bool &is_alt, int &slot, double &jp)
+{
+    const int grp = (pos >= g.b1) + (pos >= g.b2) + (pos >= g.b3);
+    is_alt = grp != g.ref_idx;
+    slot = grp - (grp > g.ref_idx);
+    if (bq < cf.min_bq) return false;
+    if (is_alt && bq < cf.min_alt_bq) return false;
+    if (!NEEDP && !cf.jq_filters) return true;
+    double bp = lut[bq];
+    if (is_alt && cf.alt_bq_mode) bp = g.alt_bp;
+    const double mp = cf.use_mq ? lut[256 + mq] : 0.0;
+    const double bap = cf.use_baq ? lut[512 + baq] : 0.0;
+    const double sp = cf.use_sq ? lut[512 + sq] : 0.0;
+    jp = merge4(sp, mp, bap, bp);
+    if (cf.jq_filters) {
+        if (jp >= cf.skip_jp) return false;
+        if (is_alt && jp >= cf.skip_alt_jp) return false;
+    }
+    if (is_alt && cf.def_alt_jq_on) jp = cf.def_alt_jq_prob;
+    return true;
+}
+
+__device__ __forceinline__ void load_lut(double *s_lut, const Lut *lut)
+{
+    const double *src = reinterpret_cast<const double *>(lut);
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = src[i];
+    __syncthreads();
+}
+
+// median of the reference-base qualities (int_median, utils.c:435-458) for def_alt_bq == -1.
+// hist: 256 ints of shared memory owned by this warp.
+__device__ int warp_ref_median(const unsigned char *bqp, long long off, int lo, int hi, int *hist)
+{
+    const int lane = lane_id();
+    for (int i = lane; i < 256; i += 32) hist[i] = 0;
+    __syncwarp();
+    for (int i = lo + lane; i < hi; i += 32) atomicAdd(&hist[bqp[off + i]], 1);
+    __syncwarp();
+    int med = -1;
+    const int n = hi - lo;
+    if (n > 0 && lane == 0) {
+        // order statistics n/2 and n/2-1 of the sorted values
+        const int r_hi = n / 2, r_lo = n / 2 - 1;
+        int acc = 0, v_hi = -1, v_lo = -1;
+        for (int v = 0; v < 256; ++v) {
+            const int nxt = acc + hist[v];
+            if (v_lo < 0 && r_lo >= 0 && r_lo < nxt) v_lo = v;
+            if (v_hi < 0 && r_hi < nxt) v_hi = v;
+            acc = nxt;
+        }
+        med = (n & 1) ? v_hi : (int)((v_hi + v_lo) / 2.0);
+    }
+    med = __shfl_sync(FULL, med, 0);
+    __syncwarp();
+    return med;
+}
+
+__device__ __forceinline__ bool load_geom(const DevBatch &b, long long c, Geom &g, int &cov)
+{
+    const int4 cnt = reinterpret_cast<const int4 *>(b.nt_cnt)[c];
+    g.off = b.col_off[c];
+    g.b1 = cnt.x;
+    g.b2 = g.b1 + cnt.y;
+    g.b3 = g.b2 + cnt.z;
+    g.n = g.b3 + cnt.w;
+    g.ref_idx = ref_index(b.ref_base[c]);
+    g.alt_bp = 0.0;
+    cov = b.coverage ? b.coverage[c] : g.n;
+    return true;
+}
+
+__device__ __forceinline__ void setup_alt_bq(const DevConf &cf, const DevBatch &b, const double *s_lut, Geom &g, int *hist)
+{
+    if (cf.alt_bq_mode == 1) {
+        g.alt_bp = cf.alt_bq_prob;
+    } else if (cf.alt_bq_mode == 2) {
+        const int lo = g.ref_idx == 0 ? 0 : g.ref_idx == 1 ? g.b1 : g.ref_idx == 2 ? g.b2 : g.b3;
+        const int hi = g.ref_idx == 0 ? g.b1 : g.ref_idx == 1 ? g.b2 : g.ref_idx == 2 ? g.b3 : g.n;
+        const int med = warp_ref_median(b.bq, g.off, lo, hi, hist);
+        g.alt_bp = med < 0 ? 0.0 : s_lut[med];      // empty ref group: bq = -1 -> probability 0 (snpcaller.c:435, 331)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// distribution truncated at K (K <= KS): P[k] = P(k errors), k < K; T = P(>= K errors)
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void lane_update(double (&P)[K], double &T, double p, double q)
+{
+    T = fma(P[K - 1], p, T);
+#pragma unroll
+    for (int k = K - 1; k >= 1; --k) P[k] = fma(P[k - 1], p, P[k] * q);
+    P[0] = P[0] * q;
+}
+
+// butterfly merge of the 32 per-lane distributions; every lane ends with the distribution of all reads
+template <int K>
+__device__ __forceinline__ void tree_merge(double (&P)[K], double &T)
+{
+#pragma unroll 1
+    for (int m = 1; m < 32; m <<= 1) {
+        double b[K], c[K];
+        const double tb = __shfl_xor_sync(FULL, T, m);
+        double sum_a = 0.0, sum_b = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            b[k] = __shfl_xor_sync(FULL, P[k], m);
+            sum_a += P[k];
+            sum_b += b[k];
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i <= k; ++i) acc = fma(P[i], b[k - i], acc);
+            c[k] = acc;
+        }
+        double t = T * (sum_b + tb) + tb * sum_a;
+        double asuf = 0.0;
+#pragma unroll
+        for (int j = 1; j < K; ++j) {
+            asuf += P[K - j];
+            t = fma(b[j], asuf, t);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) P[k] = c[k];
+        T = t;
+    }
+}
+
+// tails[i] = P(X >= cnt[i]) (0 when cnt[i] == 0), tails[3] = min(P[K-1], T)
+template <int K>
+__device__ __forceinline__ void small_tails(const double (&P)[K], double T, const int (&cnt)[3], double (&tails)[4])
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double s = T;
+#pragma unroll
+        for (int k = K - 1; k >= 0; --k)
+            if (k >= cnt[i]) s += P[k];
+        tails[i] = cnt[i] > 0 ? s : 0.0;
+    }
+    tails[3] = fmin(P[K - 1], T);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_screen
+// ------------------------------------------------------------------------------------------------
+struct Chunk {          // 16 consecutive bytes of each plane
+    uint4 bq, mq, baq, sq;
+};
+
+__device__ __forceinline__ int byte_of(const uint4 &v, int j)
+{
+    const unsigned w = j < 4 ? v.x : j < 8 ? v.y : j < 12 ? v.z : v.w;
+    return (w >> (8 * (j & 3))) & 0xff;
+}
+
+__device__ __forceinline__ uint4 ldg16(const unsigned char *p)
+{
+    return __ldg(reinterpret_cast<const uint4 *>(p));
+}
+
+template <int K>
+__device__ __noinline__ void screen_small(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &g,
+                                          const int (&cnt)[3], long long abase, int lead, int nchunks, double (&tails)[4])
+{
+    const int lane = lane_id();
+    double P[K], T = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) P[k] = (k == 0) ? 1.0 : 0.0;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < nchunks; i += 32) {
+        const long long a = abase + 16ll * i;
+        Chunk ch;
+        ch.bq = ldg16(b.bq + a);
+        ch.mq = cf.use_mq ? ldg16(b.mq + a) : zero;
+        ch.baq = cf.use_baq ? ldg16(b.baq + a) : zero;
+        ch.sq = cf.use_sq ? ldg16(b.sq + a) : zero;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int pos = 16 * i + j - lead;
+            if (pos < 0 || pos >= g.n) continue;
+            bool is_alt;
+            int slot;
+            double jp;
+            if (!eval_read<true>(cf, s_lut, g, pos, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j),
+                                 byte_of(ch.sq, j), is_alt, slot, jp))
+                continue;
+            double p, q;
+            guard_pq(jp, p, q);
+            lane_update<K>(P, T, p, q);
+        }
+    }
+    tree_merge<K>(P, T);
+    small_tails<K>(P, T, cnt, tails);
+}
+
+__global__ void __launch_bounds__(256) k_screen(const DevConf cf, const DevBatch b, const Lut *lut, const Workspace ws)
+{
+    __shared__ double s_lut[768];
+    __shared__ int s_hist[8][256];
+    load_lut(s_lut, lut);
+    const int lane = lane_id();
+    const int wib = threadIdx.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+
+    for (long long c = warp0; c < b.n_cols; c += nwarps) {
+        Geom g;
+        int cov;
+        load_geom(b, c, g, cov);
+        int cnt[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
+        bool gate = g.ref_idx >= 0 && !(g.n * 2 < cov) && !(g.n < cf.min_cov);   // lofreq_call.c:892,931,747,754
+        const long long abase = g.off & ~15ll;
+        const int lead = (int)(g.off - abase);
+        const int nchunks = (lead + g.n + 15) >> 4;
+        if (gate) {
+            setup_alt_bq(cf, b, s_lut, g, s_hist[wib]);
+            const uint4 zero = make_uint4(0, 0, 0, 0);
+            for (int i = lane; i < nchunks; i += 32) {
+                const long long a = abase + 16ll * i;
+                Chunk ch;
+                ch.bq = ldg16(b.bq + a);
+                ch.mq = ch.baq = ch.sq = zero;
+                if (cf.jq_filters) {
+                    if (cf.use_mq) ch.mq = ldg16(b.mq + a);
+                    if (cf.use_baq) ch.baq = ldg16(b.baq + a);
+                    if (cf.use_sq) ch.sq = ldg16(b.sq + a);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int pos = 16 * i + j - lead;
+                    if (pos < 0 || pos >= g.n) continue;
+                    bool is_alt;
+                    int slot;
+                    double jp;
+                    const bool ok = eval_read<false>(cf, s_lut, g, pos, byte_of(ch.bq, j), byte_of(ch.mq, j),
+                                                     byte_of(ch.baq, j), byte_of(ch.sq, j), is_alt, slot, jp);
+                    if (is_alt) {     // raw counts precede every filter (snpcaller.c:418-420)
+                        raw[0] += slot == 0;
+                        raw[1] += slot == 1;
+                        raw[2] += slot == 2;
+                        if (ok) {
+                            cnt[0] += slot == 0;
+                            cnt[1] += slot == 1;
+                            cnt[2] += slot == 2;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                cnt[i] = __reduce_add_sync(FULL, cnt[i]);
+                raw[i] = __reduce_add_sync(FULL, raw[i]);
+            }
+        }
+        const int K = max(cnt[0], max(cnt[1], cnt[2]));
+        const bool tested = gate && K > 0;     // lofreq_call.c:768-780: no alt left -> not a test
+        if (lane < 6) ws.cnt6[6 * c + lane] = lane < 3 ? cnt[lane] : raw[lane - 3];
+        if (lane == 0) ws.tested[c] = tested ? 1 : 0;
+        if (tested && K <= KS) {
+            double tails[4];
+            switch (K) {
+                case 1: screen_small<1>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
+                case 2: screen_small<2>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
+                case 3: screen_small<3>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
+                case 4: screen_small<4>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
+                case 5: screen_small<5>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
+                case 6: screen_small<6>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
+                case 7: screen_small<7>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
+                default: screen_small<8>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
+            }
+            if (lane < 4) ws.tails[4 * c + lane] = tails[lane];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// running Bonferroni: prefix sum over tested flags, then the significance screen
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_block_counts(const unsigned char *tested, long long n, long long *blocksum)
+{
+    const long long c = (long long)blockIdx.x * 1024 + threadIdx.x;
+    const int t = (c < n) ? tested[c] : 0;
+    const int total = __syncthreads_count(t);
+    if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
+}
+
+// exclusive scan of blocksum in place, one block
+__global__ void __launch_bounds__(1024) k_scan_blocks(long long *blocksum, int nb, Counters *ctr)
+{
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const long long v = (i < nb) ? blocksum[i] : 0;
+        long long x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long y = __shfl_up_sync(FULL, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) s_warp[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            long long z = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long y = __shfl_up_sync(FULL, z, d);
+                if (lane >= d) z += y;
+            }
+            s_warp[lane] = z;
+        }
+        __syncthreads();
+        const long long carry = s_carry;
+        const long long incl = x + (w ? s_warp[w - 1] : 0) + carry;
+        if (i < nb) blocksum[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ctr->n_tested = (unsigned long long)s_carry;
+}
+
+__device__ __forceinline__ int class_of(int K)
+{
+    const int need = (K + 31) >> 5;          // cells per lane
+    if (need > 64) return NCLASS - 1;        // XL
+    int cls = 0;
+    while ((1 << cls) < need) ++cls;
+    return cls;
+}
+
+__global__ void __launch_bounds__(1024) k_finalize(const DevConf cf, const long long n, const Workspace ws)
+{
+    __shared__ int s_warp[32];
+    const long long c = (long long)blockIdx.x * 1024 + threadIdx.x;
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    const int t = (c < n) ? ws.tested[c] : 0;
+    const unsigned bal = __ballot_sync(FULL, t);
+    if (lane == 0) s_warp[w] = __popc(bal);
+    __syncthreads();
+    if (w == 0) {
+        int z = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(FULL, z, d);
+            if (lane >= d) z += y;
+        }
+        s_warp[lane] = z;
+    }
+    __syncthreads();
+    if (c >= n) return;
+    long long bonf = 0;
+    if (t) {
+        // 1-based rank of this column among the tested columns of the batch
+        const long long rank = ws.blocksum[blockIdx.x] + (w ? s_warp[w - 1] : 0) + __popc(bal & ((2u << lane) - 1u));
+        // lofreq_call.c:794-800: first tested column sets 3 when bonf_subst was 1, else += 3
+        bonf = cf.bonf_dynamic ? ((cf.bonf_start == 1 ? 0 : cf.bonf_start) + 3 * rank) : cf.bonf_start;
+    }
+    ws.bonf_used[c] = bonf;
+    if (!t) return;
+    int cnt[3], raw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        cnt[i] = ws.cnt6[6 * c + i];
+        raw[i] = ws.cnt6[6 * c + 3 + i];
+    }
+    const int K = max(cnt[0], max(cnt[1], cnt[2]));
+    if (K > KS) {
+        const int cls = class_of(K);
+        const unsigned slot = atomicAdd(&ws.counters->n_jobs[cls], 1u);
+        ws.jobs[(long long)cls * ws.cap_cols + slot] = (int)c;
+        return;
+    }
+    const double4 tl = reinterpret_cast<const double4 *>(ws.tails)[c];
+    const double tails[3] = {tl.x, tl.y, tl.z};
+    const double tK = cnt[0] == K ? tails[0] : cnt[1] == K ? tails[1] : tails[2];
+    // clearly insignificant -> snpcaller() leaves LDBL_MAX everywhere (snpcaller.c:1155); the margin keeps
+    // borderline columns for the host, which repeats the comparison in long double
+    if (tK * (double)bonf > cf.sig * (1.0 + 1e-9)) return;
+    const unsigned slot = atomicAdd(&ws.counters->n_cand, 1u);
+    Cand cd;
+    cd.col = c;
+    cd.bonf = bonf;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        cd.lnp[i] = cnt[i] > 0 ? log(tails[i]) : 0.0;
+        cd.cnt[i] = cnt[i];
+        cd.raw[i] = raw[i];
+    }
+    cd.ln_floor = log(tl.w);
+    cd.flags = 0;
+    cd.pad = 0;
+    ws.cand[slot] = cd;
+}
+
+// ------------------------------------------------------------------------------------------------
+// read sources for the O(depth*K) routines
+// ------------------------------------------------------------------------------------------------
+struct ByteSrc {
+    const DevConf *cf;
+    const DevBatch *b;
+    const double *lut;
+    Geom g;
+    __device__ __forceinline__ int size() const { return g.n; }
+    __device__ __forceinline__ bool get(int pos, double &jp) const
+    {
+        const long long a = g.off + pos;
+        bool is_alt;
+        int slot;
+        return eval_read<true>(*cf, lut, g, pos, b->bq[a], cf->use_mq ? b->mq[a] : 0, cf->use_baq ? b->baq[a] : 0,
+                               cf->use_sq ? b->sq[a] : 0, is_alt, slot, jp);
+    }
+};
+
+struct ProbSrc {
+    const double *ep;
+    int n;
+    __device__ __forceinline__ int size() const { return n; }
+    __device__ __forceinline__ bool get(int pos, double &jp) const
+    {
+        jp = ep[pos];
+        return true;
+    }
+};
+
+// distribution truncated at K <= KS from a generic source (secondary alleles of heavy columns, small
+// stand-alone problems); lanes stride over the reads
+template <int K, class Src>
+__device__ __noinline__ void src_small(const Src &src, double (&P8)[KS], double &T)
+{
+    double P[K];
+    T = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) P[k] = (k == 0) ? 1.0 : 0.0;
+    const int n = src.size();
+    for (int pos = lane_id(); pos < n; pos += 32) {
+        double jp;
+        if (!src.get(pos, jp)) continue;
+        double p, q;
+        guard_pq(jp, p, q);
+        lane_update<K>(P, T, p, q);
+    }
+    tree_merge<K>(P, T);
+#pragma unroll
+    for (int k = 0; k < KS; ++k) P8[k] = (k < K) ? P[k < K ? k : 0] : 0.0;
+}
+
+template <class Src>
+__device__ void src_small_dispatch(const Src &src, int K, double (&P8)[KS], double &T)
+{
+    switch (K) {
+        case 1: src_small<1>(src, P8, T); break;
+        case 2: src_small<2>(src, P8, T); break;
+        case 3: src_small<3>(src, P8, T); break;
+        case 4: src_small<4>(src, P8, T); break;
+        case 5: src_small<5>(src, P8, T); break;
+        case 6: src_small<6>(src, P8, T); break;
+        case 7: src_small<7>(src, P8, T); break;
+        default: src_small<8>(src, P8, T); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the O(depth*K) recurrence, K cells over 32 lanes x R registers
+// ------------------------------------------------------------------------------------------------
+template <int R>
+struct Row {
+    double E[R];       // odds-form cells: lane l, register r holds k = K - 32R + l*R + r (k < 0: padding, always 0)
+    double T;          // absorbing state P(>= K) in the same scaling (valid on lane 31)
+    int e2;            // power-of-two exponent taken out so far
+    double sum_lq;     // sum over reads of ln q (whole warp)
+    double ln_s;       // tilt
+};
+
+template <int R>
+__device__ __forceinline__ void rescale(Row<R> &row, bool force)
+{
+    int hi = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) hi = max(hi, __double2hiint(row.E[r]));
+    if (lane_id() == 31) hi = max(hi, __double2hiint(row.T));
+    hi = __reduce_max_sync(FULL, hi);
+    const int ex = (hi >> 20) - 1023;
+    if (force ? (ex != 0) : (ex > 200 || ex < -200)) {
+        const double f = __hiloint2double((1023 - ex) << 20, 0);
+#pragma unroll
+        for (int r = 0; r < R; ++r) row.E[r] *= f;
+        row.T *= f;
+        row.e2 += ex;
+    }
+}
+
+// Runs the recurrence over every read of src with tilt exp(ln_s).  sm: 32 double2 of shared memory per warp.
+template <int R, class Src>
+__device__ __forceinline__ void dp_run(const Src &src, int K, double ln_s, double2 *sm, Row<R> &row)
+{
+    const int lane = lane_id();
+    const double s = (ln_s == 0.0) ? 1.0 : exp(ln_s);
+    const int k0 = K - 32 * R + lane * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) row.E[r] = (k0 + r == 0) ? 1.0 : 0.0;
+    row.T = 0.0;
+    row.e2 = 0;
+    row.ln_s = ln_s;
+    double lq_acc = 0.0;
+    const int n = src.size();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int n0 = 0; n0 < n; n0 += 32) {
+        const int pos = n0 + lane;
+        double jp = 0.0, o = 0.0, rq = 1.0;
+        const bool ok = pos < n && src.get(pos, jp);
+        if (ok) {
+            double p, q;
+            guard_pq(jp, p, q);
+            o = p * s / q;
+            rq = 1.0 / q;
+            lq_acc += log(q);
+        }
+        const unsigned m = __ballot_sync(FULL, ok);
+        const int cnt = __popc(m);
+        const bool slow = __any_sync(FULL, ok && (o > 1048576.0 || rq > 1048576.0));
+        __syncwarp();
+        if (ok) sm[__popc(m & lt_mask)] = make_double2(o, rq);
+        __syncwarp();
+        for (int j = 0; j < cnt; ++j) {
+            const double2 c = sm[j];
+            const double top = row.E[R - 1];
+            double in = __shfl_up_sync(FULL, top, 1);
+            if (lane == 0) in = 0.0;
+            row.T = fma(top, c.x, row.T * c.y);
+#pragma unroll
+            for (int r = R - 1; r >= 1; --r) row.E[r] = fma(row.E[r - 1], c.x, row.E[r]);
+            row.E[0] = fma(in, c.x, row.E[0]);
+            if (slow) rescale<R>(row, true);
+        }
+        if (!slow) rescale<R>(row, false);
+    }
+    row.sum_lq = warp_sum(lq_acc);
+}
+
+// saddlepoint tilt: ln s with sum_n o_n/(1+o_n) = min(K, N-1/2), o_n = p_n s / q_n
+template <class Src>
+__device__ double newton_tilt(const Src &src, int K, int N, double lam)
+{
+    const int lane = lane_id();
+    const double kt = fmin((double)K, (double)N - 0.5);
+    const double s0 = kt * fmax((double)N - lam, 1e-300) / (fmax(lam, 1e-300) * ((double)N - kt));
+    double ls = log(fmax(s0, 1.0));
+    double lo = 0.0, hi = 60.0;
+    ls = fmin(ls, hi);
+    const int n = src.size();
+    for (int it = 0; it < 40; ++it) {
+        const double s = exp(ls);
+        double g = 0.0, d = 0.0;
+        for (int pos = lane; pos < n; pos += 32) {
+            double jp;
+            if (!src.get(pos, jp)) continue;
+            double p, q;
+            guard_pq(jp, p, q);
+            const double o = p * s / q;
+            const double w = o / (1.0 + o);
+            g += w;
+            d += w / (1.0 + o);
+        }
+        g = warp_sum(g) - kt;
+        d = warp_sum(d);
+        g = __shfl_sync(FULL, g, 0);
+        d = __shfl_sync(FULL, d, 0);
+        if (g > 0.0) hi = fmin(hi, ls); else lo = fmax(lo, ls);
+        double nl = d > 0.0 ? ls - g / d : 0.5 * (lo + hi);
+        if (!(nl > lo && nl < hi)) nl = 0.5 * (lo + hi);
+        const bool done = fabs(nl - ls) < 1e-3;
+        ls = nl;
+        if (done) break;
+    }
+    return ls;
+}
+
+struct TailOut {
+    double lnT;        // ln P(X >= K)
+    double lnKm1;      // ln P(X == K-1)
+    int flags;
+};
+
+// ln P(X >= K) for K > KS, choosing the tilt; leaves the final row in `row`
+template <int R, class Src>
+__device__ TailOut heavy_tail(const Src &src, int K, int N, double lam, double2 *sm, Row<R> &row)
+{
+    TailOut out;
+    out.flags = 0;
+    // Chernoff exponent of the tail: beyond ~300 nats the untilted cells of interest drift out of fp64 range
+    const double cher = ((double)K > lam) ? ((double)K * log((double)K / lam) - (double)K + lam) : 0.0;
+    double ln_s = 0.0;
+    if (cher > 300.0) ln_s = newton_tilt(src, K, N, lam);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        dp_run<R>(src, K, ln_s, sm, row);
+        // how far below the largest cell does the absorbing state sit?
+        int hi = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) hi = max(hi, __double2hiint(row.E[r]));
+        hi = __reduce_max_sync(FULL, hi);
+        const int hiT = __shfl_sync(FULL, __double2hiint(row.T), 31);
+        const int gap = ((max(hi, hiT)) >> 20) - (hiT >> 20);
+        if (gap > 580 && ln_s == 0.0 && attempt == 0) {
+            ln_s = newton_tilt(src, K, N, lam);
+            continue;
+        }
+        if (gap > 900) out.flags |= CF_RANGE;
+        break;
+    }
+    const double T = __shfl_sync(FULL, row.T, 31);
+    const double top = __shfl_sync(FULL, row.E[R - 1], 31);
+    const double base = (double)row.e2 * LN2 + row.sum_lq;
+    out.lnT = log(T) + base - (double)K * row.ln_s;
+    out.lnKm1 = log(top) + base - (double)(K - 1) * row.ln_s;
+    return out;
+}
+
+// sum over cells k >= c of an untilted final row plus the absorbing state -> ln P(X >= c)
+template <int R>
+__device__ double row_tail(const Row<R> &row, int K, int c)
+{
+    const int lane = lane_id();
+    const int k0 = K - 32 * R + lane * R;
+    double s = (lane == 31) ? row.T : 0.0;
+#pragma unroll
+    for (int r = R - 1; r >= 0; --r)
+        if (k0 + r >= c) s += row.E[r];
+    s = warp_sum(s);
+    s = __shfl_sync(FULL, s, 0);
+    return log(s) + (double)row.e2 * LN2 + row.sum_lq;
+}
+
+// The whole snpcaller() arithmetic for one column / problem with K = max count.
+// Returns false when the column is clearly insignificant (no site).
+template <int R, class Src>
+__device__ bool run_problem(const Src &src, const int (&cnt)[3], long long bonf, double sig, double2 *sm, Cand &cd)
+{
+    const int lane = lane_id();
+    const int K = max(cnt[0], max(cnt[1], cnt[2]));
+    cd.flags = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cd.lnp[i] = 0.0;
+    cd.ln_floor = 0.0;
+
+    if (K <= KS) {
+        double P[KS], T;
+        src_small_dispatch(src, K, P, T);
+        if (T * (double)bonf > sig * (1.0 + 1e-9)) return false;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (cnt[i] == 0) continue;
+            double s = T;
+#pragma unroll
+            for (int k = KS - 1; k >= 0; --k)
+                if (k >= cnt[i] && k < K) s += P[k];
+            cd.lnp[i] = log(s);
+        }
+        double pk1 = P[0];
+#pragma unroll
+        for (int k = 1; k < KS; ++k)
+            if (k == K - 1) pk1 = P[k];
+        cd.ln_floor = log(fmin(pk1, T));
+        return true;
+    }
+
+    // N = reads that survive the filters, lam = sum of their error probabilities
+    int N = 0;
+    double lam = 0.0;
+    for (int pos = lane; pos < src.size(); pos += 32) {
+        double jp;
+        if (!src.get(pos, jp)) continue;
+        double p, q;
+        guard_pq(jp, p, q);
+        lam += p;
+        ++N;
+    }
+    N = __reduce_add_sync(FULL, N);
+    lam = __shfl_sync(FULL, warp_sum(lam), 0);
+
+    Row<R> row;
+    const TailOut main_t = heavy_tail<R>(src, K, N, lam, sm, row);
+    cd.flags |= main_t.flags;
+    if (main_t.lnT > -700.0 && exp(main_t.lnT) * (double)bonf > sig * (1.0 + 1e-9)) return false;
+    cd.ln_floor = fmin(main_t.lnT, main_t.lnKm1);
+    const bool untilted = (row.ln_s == 0.0);
+    double sec[3] = {0.0, 0.0, 0.0};
+    // alleles below K that can reuse the untilted row
+    if (untilted) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (cnt[i] > 0 && cnt[i] < K) sec[i] = row_tail<R>(row, K, cnt[i]);
+    }
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {
+        const int c = cnt[i];
+        if (c == 0) continue;
+        if (c == K) { cd.lnp[i] = main_t.lnT; continue; }
+        if (untilted) { cd.lnp[i] = sec[i]; continue; }
+        if (i == 2 && c == cnt[1]) { cd.lnp[i] = cd.lnp[1]; continue; }
+        if (i >= 1 && c == cnt[0]) { cd.lnp[i] = cd.lnp[0]; continue; }
+        if (c <= KS) {
+            double P[KS], T;
+            src_small_dispatch(src, c, P, T);
+            cd.lnp[i] = log(T);
+        } else {
+            const TailOut t2 = heavy_tail<R>(src, c, N, lam, sm, row);
+            cd.flags |= t2.flags;
+            cd.lnp[i] = t2.lnT;
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_heavy<R>: persistent warps pull columns of one register-tile class from a job list
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(128) k_heavy(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, const Lut *lut,
+                                               const Workspace ws, int cls)
+{
+    __shared__ double s_lut[768];
+    __shared__ double2 s_par[4][32];
+    __shared__ int s_hist[4][256];
+    load_lut(s_lut, lut);
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    const unsigned njobs = ws.counters->n_jobs[cls];
+    const int *jobs = ws.jobs + (long long)cls * ws.cap_cols;
+    for (;;) {
+        unsigned j = 0;
+        if (lane == 0) j = atomicAdd(&ws.counters->next_job[cls], 1u);
+        j = __shfl_sync(FULL, j, 0);
+        if (j >= njobs) break;
+        const long long c = jobs[j];
+        ByteSrc src;
+        src.cf = &cf;
+        src.b = &b;
+        src.lut = s_lut;
+        int cov;
+        load_geom(b, c, src.g, cov);
+        setup_alt_bq(cf, b, s_lut, src.g, s_hist[wib]);
+        int cnt[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
+        const long long bonf = ws.bonf_used[c];
+        Cand cd;
+        const bool site = run_problem<R>(src, cnt, bonf, cf.sig, s_par[wib], cd);
+        if (site && lane == 0) {
+            cd.col = c;
+            cd.bonf = bonf;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                cd.cnt[i] = cnt[i];
+                cd.raw[i] = ws.cnt6[6 * c + 3 + i];
+            }
+            cd.pad = 0;
+            const unsigned slot = atomicAdd(&ws.counters->n_cand, 1u);
+            ws.cand[slot] = cd;
+        }
+    }
+}
+
+// columns with K > 2048 are not implemented yet: report loudly instead of computing something else
+__global__ void k_heavy_xl(const Workspace ws, int cls)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0 && ws.counters->n_jobs[cls] > 0) atomicOr(&ws.counters->err_flags, (unsigned)CF_UNSUPPORTED);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_prob_jobs<R>: stand-alone snpcaller() problems on ready-made error probabilities
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(128) k_prob_jobs(const ProbBatch pb, Cand *out, int cls)
+{
+    __shared__ double2 s_par[4][32];
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * 4 + wib, nwarps = (long long)gridDim.x * 4;
+    for (long long i = warp0; i < pb.n; i += nwarps) {
+        int cnt[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) cnt[a] = pb.counts[3 * i + a];
+        const int K = max(cnt[0], max(cnt[1], cnt[2]));
+        const int my_cls = K <= KS ? 0 : class_of(K);
+        if (my_cls != cls) continue;
+        ProbSrc src;
+        src.ep = pb.err_probs + pb.ep_off[i];
+        src.n = (int)(pb.ep_off[i + 1] - pb.ep_off[i]);
+        Cand cd;
+        bool site = false;
+        if (K > 0 && K <= src.n && cls < NCLASS - 1) site = run_problem<R>(src, cnt, pb.bonf[i], pb.sig, s_par[wib], cd);
+        else { cd.flags = 0; cd.ln_floor = 0.0; cd.lnp[0] = cd.lnp[1] = cd.lnp[2] = 0.0; }
+        if (lane == 0) {
+            if (!site) cd.flags |= CF_INSIG;
+            if (K > MAXK_WARP || K > src.n) cd.flags |= CF_UNSUPPORTED;
+            cd.col = i;
+            cd.bonf = pb.bonf[i];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { cd.cnt[a] = cnt[a]; cd.raw[a] = cnt[a]; }
+            cd.pad = 0;
+            out[i] = cd;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static int sm_count()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+void launch_screen(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st)
+{
+    if (b.n_cols <= 0) return;
+    const long long want = (b.n_cols + 7) / 8;
+    const int grid = (int)(want < (long long)sm_count() * 8 ? want : (long long)sm_count() * 8);
+    k_screen<<<grid, 256, 0, st>>>(cf, b, lut, ws);
+}
+
+void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st)
+{
+    if (b.n_cols <= 0) return;
+    const int nb = (int)((b.n_cols + 1023) / 1024);
+    k_block_counts<<<nb, 1024, 0, st>>>(ws.tested, b.n_cols, ws.blocksum);
+    k_scan_blocks<<<1, 1024, 0, st>>>(ws.blocksum, nb, ws.counters);
+}
+
+void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st)
+{
+    if (b.n_cols <= 0) return;
+    const int nb = (int)((b.n_cols + 1023) / 1024);
+    // n_tested (first 8 bytes) belongs to the scan; everything after it is per-test state
+    cudaMemsetAsync(reinterpret_cast<char *>(ws.counters) + 8, 0, sizeof(Counters) - 8, st);
+    k_finalize<<<nb, 1024, 0, st>>>(cf, b.n_cols, ws);
+    const int g = sm_count() * 4;
+    // largest tiles first: they are the long poles
+    k_heavy_xl<<<1, 32, 0, st>>>(ws, 7);
+    k_heavy<64><<<g, 128, 0, st>>>(cf, b, lut, ws, 6);
+    k_heavy<32><<<g, 128, 0, st>>>(cf, b, lut, ws, 5);
+    k_heavy<16><<<g, 128, 0, st>>>(cf, b, lut, ws, 4);
+    k_heavy<8><<<g, 128, 0, st>>>(cf, b, lut, ws, 3);
+    k_heavy<4><<<g, 128, 0, st>>>(cf, b, lut, ws, 2);
+    k_heavy<2><<<g, 128, 0, st>>>(cf, b, lut, ws, 1);
+    k_heavy<1><<<g, 128, 0, st>>>(cf, b, lut, ws, 0);
+}
+
+void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st)
+{
+    if (pb.n <= 0) return;
+    const long long want = (pb.n + 3) / 4;
+    const int g = (int)(want < (long long)sm_count() * 4 ? want : (long long)sm_count() * 4);
+    k_prob_jobs<1><<<g, 128, 0, st>>>(pb, out, 0);
+    k_prob_jobs<2><<<g, 128, 0, st>>>(pb, out, 1);
+    k_prob_jobs<4><<<g, 128, 0, st>>>(pb, out, 2);
+    k_prob_jobs<8><<<g, 128, 0, st>>>(pb, out, 3);
+    k_prob_jobs<16><<<g, 128, 0, st>>>(pb, out, 4);
+    k_prob_jobs<32><<<g, 128, 0, st>>>(pb, out, 5);
+    k_prob_jobs<64><<<g, 128, 0, st>>>(pb, out, 6);
+    k_prob_jobs<64><<<g, 128, 0, st>>>(pb, out, 7);   // XL: only marks CF_UNSUPPORTED
+}
+
+}  // namespace lfb

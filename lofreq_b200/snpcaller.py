@@ -1,0 +1,150 @@
+"""Host-side mirror of the reference's per-column interface (snpcaller.h:72-102,
+lofreq_call.c:734-935), over the C ABI.  Names and argument meaning follow the reference:
+
+  varcall_conf(**over)                       init_varcall_conf (snpcaller.c:626-651)
+  Caller.snpcaller(err_probs, counts, bonf, sig)          snpcaller() (snpcaller.h:97-102)
+  Caller.call_columns(batch, conf)           one call_vars() per column (lofreq_call.c:886-935), batched
+
+Everything is computed on the GPU; a missing library or device raises."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import ST_VALUE, ST_LDBLMAX, ST_LDBLMIN  # noqa: F401
+
+LDBL_MAX = np.finfo(np.longdouble).max
+LDBL_MIN = np.finfo(np.longdouble).tiny
+
+
+def varcall_conf(**over):
+    lib = capi.load()
+    c = capi.Conf()
+    lib.lfb200_init_conf(C.byref(c))
+    for k, v in over.items():
+        if not hasattr(c, k):
+            raise KeyError(k)
+        setattr(c, k, v)
+    return c
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def conf_from(conf):
+    if conf is None:
+        return varcall_conf()
+    if isinstance(conf, capi.Conf):
+        return conf
+    return varcall_conf(**conf)
+
+
+class Caller:
+    """Owns one lfb200_ctx on one GPU."""
+
+    def __init__(self, device=0):
+        self.lib = capi.load()
+        self._ctx = C.c_void_p()
+        capi.check(self.lib.lfb200_create(C.byref(self._ctx), int(device)))
+        self.device = int(device)
+
+    def close(self):
+        if self._ctx:
+            self.lib.lfb200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- snpcaller(): one problem or many ------------------------------------------------
+    def snpcaller(self, err_probs, noncons_counts, bonf_factor, sig_level):
+        pv, _, _ = self.snpcaller_batch([np.asarray(err_probs, np.float64)], [noncons_counts], [bonf_factor], sig_level)
+        return pv[0]
+
+    def snpcaller_batch(self, err_probs_list, counts, bonf, sig_level):
+        n = len(err_probs_list)
+        off = np.zeros(n + 1, np.int64)
+        off[1:] = np.cumsum([len(e) for e in err_probs_list])
+        ep = np.ascontiguousarray(np.concatenate([np.asarray(e, np.float64) for e in err_probs_list])
+                                  if n else np.zeros(0), np.float64)
+        cn = np.ascontiguousarray(counts, np.int32).reshape(n, 3)
+        bf = np.ascontiguousarray(bonf, np.int64).reshape(n)
+        pv = np.zeros((n, 3), np.longdouble)
+        lnp = np.zeros((n, 3), np.float64)
+        st = np.zeros((n, 3), np.uint8)
+        capi.check(self.lib.lfb200_snpcaller_batch(self._ctx, n, _ptr(ep), _ptr(off), _ptr(cn), _ptr(bf),
+                                                    float(sig_level), _ptr(pv), _ptr(lnp), _ptr(st)))
+        return pv, lnp, st
+
+    # ---- host batch -----------------------------------------------------------------------
+    def call_columns(self, batch, conf=None, dense=True, max_sites=None):
+        """batch: dict of numpy arrays (col_off, nt_cnt, ref_base, bq, mq, baq, sq, coverage), the packed
+        form of plp_col_t described in include/lofreq_b200.h.  Returns a dict with the dense per-column
+        arrays (when dense=True), 'sites' (structured array) and the advanced counters."""
+        cf = conf_from(conf)
+        keep = []
+
+        def arr(x, dt):
+            if x is None:
+                return None
+            a = np.ascontiguousarray(x, dtype=dt)
+            keep.append(a)
+            return _ptr(a)
+        n = len(batch["ref_base"])
+        hb = capi.Batch(n, arr(batch["col_off"], np.int64), arr(batch["nt_cnt"], np.int32),
+                        arr(batch["ref_base"], np.uint8), arr(batch.get("coverage"), np.int32),
+                        arr(batch["bq"], np.uint8), arr(batch.get("mq"), np.uint8),
+                        arr(batch.get("baq"), np.uint8), arr(batch.get("sq"), np.uint8))
+        max_sites = n if max_sites is None else max_sites
+        sites = (capi.Site * max(max_sites, 1))()
+        sm = capi.Summary()
+        out = {}
+        dptr = None
+        if dense:
+            out = dict(alt_counts=np.zeros((n, 3), np.int32), alt_raw_counts=np.zeros((n, 3), np.int32),
+                       tested=np.zeros(n, np.uint8), bonf_used=np.zeros(n, np.int64),
+                       lnp=np.zeros((n, 3), np.float64), status=np.zeros((n, 3), np.uint8),
+                       pvalues=np.zeros((n, 3), np.longdouble), called=np.zeros((n, 3), np.uint8),
+                       qual=np.zeros((n, 3), np.int32))
+            d = capi.DenseOut(*[_ptr(out[k]) for k in ("alt_counts", "alt_raw_counts", "tested", "bonf_used",
+                                                       "lnp", "status", "pvalues", "called", "qual")])
+            dptr = C.byref(d)
+        capi.check(self.lib.lfb200_call_columns(self._ctx, C.byref(cf), C.byref(hb), dptr, sites, max_sites,
+                                                 C.byref(sm)))
+        out["sites"] = np.ctypeslib.as_array(sites)[: sm.n_sites].copy() if sm.n_sites else np.zeros(0, dtype=[("col", "i8")])
+        out["n_sites"] = sm.n_sites
+        out["n_tested"] = sm.n_tested
+        out["n_heavy"] = sm.n_heavy
+        out["bonf_subst"] = cf.bonf_subst
+        out["num_snv_tests"] = cf.num_snv_tests
+        return out
+
+    # ---- device-resident batch (torch tensors or raw pointers) -----------------------------
+    @staticmethod
+    def device_batch(t):
+        """t: dict of CUDA torch tensors (see lofreq_b200.synth.generate_device)."""
+        def p(x):
+            return None if x is None else C.c_void_p(x.data_ptr())
+        return capi.Batch(int(t["ref_base"].numel()), p(t["col_off"]), p(t["nt_cnt"]), p(t["ref_base"]),
+                          p(t.get("coverage")), p(t["bq"]), p(t.get("mq")), p(t.get("baq")), p(t.get("sq")))
+
+    def screen(self, dev_batch, conf, stream=None):
+        capi.check(self.lib.lfb200_screen_device(self._ctx, C.byref(conf), C.byref(dev_batch), stream))
+
+    def ntested(self, stream=None):
+        n = C.c_longlong()
+        capi.check(self.lib.lfb200_ntested_device(self._ctx, stream, C.byref(n)))
+        return n.value
+
+    def test(self, conf, stream=None):
+        capi.check(self.lib.lfb200_test_device(self._ctx, C.byref(conf), stream))
+
+    def sites(self, conf, max_sites, stream=None):
+        sites = (capi.Site * max(max_sites, 1))()
+        sm = capi.Summary()
+        capi.check(self.lib.lfb200_sites_device(self._ctx, C.byref(conf), stream, sites, max_sites, C.byref(sm)))
+        return sites, sm

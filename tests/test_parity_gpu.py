@@ -1,0 +1,271 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (lofreq_b200/capi.py ->
+liblofreq_b200.so), against the CPU oracle and the golden fixtures generated from the
+unmodified reference.
+
+Bars (BASELINE.json north_star / SURVEY.md §8d):
+  * tested flags, Bonferroni factors and counters, alt counts, LDBL_MAX/LDBL_MIN sentinel status,
+    called (pos, alt) set, integer QUAL: bit-exact
+  * ln p: |d ln p| <= 1e-10 * max(|ln p|, 1)   (1e-10 relative on log(p); absolute below |ln p| = 1,
+    where p > 0.37 can never be called)
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import synth_np
+from oracle.pyoracle import default_conf
+from test_oracle import GOLD, ld_from_bytes, load_conf
+
+LNP_RTOL = 1e-10
+
+
+def status_of(pv):
+    st = np.zeros(pv.shape, np.uint8)
+    st[pv == np.finfo(np.longdouble).max] = 1
+    st[pv == np.finfo(np.longdouble).tiny] = 2
+    return st
+
+
+def assert_lnp_close(got_pv, want_pv, st, what=""):
+    m = st == 0
+    if not m.any():
+        return 0.0
+    with np.errstate(all="ignore"):
+        a = np.log(got_pv[m]).astype(np.float64)
+        b = np.log(want_pv[m]).astype(np.float64)
+    err = np.abs(a - b) / np.maximum(np.abs(b), 1.0)
+    assert err.max() <= LNP_RTOL, (what, float(err.max()))
+    return float(err.max())
+
+
+@pytest.fixture(scope="module")
+def caller():
+    import lofreq_b200
+    c = lofreq_b200.Caller(0)
+    yield c
+    c.close()
+
+
+def compare_batch(got, want, what=""):
+    for k in ("alt_counts", "alt_raw_counts", "tested", "bonf_used"):
+        assert np.array_equal(got[k], want[k]), (what, k)
+    want_st = status_of(want["pvalues"])
+    assert np.array_equal(got["status"], want_st), (what, "status",
+                                                     np.argwhere(got["status"] != want_st)[:5].tolist())
+    assert np.array_equal(status_of(got["pvalues"]), want_st), (what, "sentinels")
+    assert np.array_equal(got["called"], want["called"]), (what, "called")
+    assert np.array_equal(got["qual"], want["qual"]), (what, "qual")
+    assert got["bonf_subst"] == want["bonf_subst"] and got["num_snv_tests"] == want["num_snv_tests"], what
+    return assert_lnp_close(got["pvalues"], want["pvalues"], want_st, what)
+
+
+def test_snpcaller_golden_grid(caller):
+    z = np.load(os.path.join(GOLD, "snpcaller_grid.npz"))
+    want = ld_from_bytes(z["pvalue_ld"])
+    offs = z["offsets"]
+    eps = [z["err_probs"][offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+    sig = float(z["sig"][0])
+    sel = np.nonzero(z["sig"] == sig)[0]
+    pv, lnp, st = caller.snpcaller_batch([eps[i] for i in sel], z["counts"][sel], z["bonf"][sel], sig)
+    names = z["names"][sel]
+    bad = np.argwhere(st != z["status"][sel])
+    assert len(bad) == 0, [(names[i], st[i].tolist(), z["status"][sel][i].tolist()) for i, _ in bad[:5]]
+    assert np.array_equal(status_of(pv), z["status"][sel])
+    assert_lnp_close(pv, want[sel], z["status"][sel], "grid")
+    # the remaining cases (sig = 1: the known-answer value of snpcaller.c:1222-1232) one by one
+    for i in np.nonzero(z["sig"] != sig)[0]:
+        got = caller.snpcaller(eps[i], z["counts"][i], int(z["bonf"][i]), float(z["sig"][i]))
+        assert np.array_equal(status_of(got), z["status"][i]), z["names"][i]
+        assert_lnp_close(got, want[i], z["status"][i], str(z["names"][i]))
+    kat = caller.snpcaller(np.full(10, 0.001), (1, 0, 0), 1, 1.0)
+    assert abs(float(kat[0]) - 0.00995512) < 5e-9
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "batch_*.npz"))))
+def test_batch_golden(caller, path):
+    z = np.load(path)
+    b = synth_np.generate(str(z["workload"]), int(z["c0"]), int(z["n_cols"]), with_baq=bool(z["with_baq"]))
+    got = caller.call_columns(b, load_conf(z))
+    want = {k: z[k] for k in ("alt_counts", "alt_raw_counts", "tested", "bonf_used", "called", "qual")}
+    want["pvalues"] = ld_from_bytes(z["pvalue_ld"])
+    want["bonf_subst"] = int(z["bonf_subst"])
+    want["num_snv_tests"] = int(z["num_snv_tests"])
+    compare_batch(got, want, os.path.basename(path))
+
+
+@pytest.mark.parametrize("wl,c0,n,baq", [("C2", 31337, 4000, True), ("C3", 20000, 600, False),
+                                        ("C4", 999000, 5000, True), ("C5", 4100, 400, False)])
+def test_batch_vs_oracle(caller, port_oracle, wl, c0, n, baq):
+    b = synth_np.generate(wl, c0, n, with_baq=baq)
+    conf = default_conf(bonf_subst=1)
+    want = port_oracle.call_columns(b, dict(conf))
+    got = caller.call_columns(b, dict(conf))
+    compare_batch(got, want, wl)
+    assert got["n_sites"] >= int(want["called"].any(axis=1).sum())
+
+
+def test_running_bonferroni_carries_over_batches(caller, port_oracle):
+    """two consecutive batches with the conf carried over == one batch (lofreq_call.c:794-801)"""
+    b_all = synth_np.generate("C2", 0, 3000)
+    want = port_oracle.call_columns(b_all, default_conf())
+    import lofreq_b200
+    cf = lofreq_b200.varcall_conf()
+    first = synth_np.generate("C2", 0, 1200)
+    second = synth_np.generate("C2", 1200, 1800)
+    g1 = caller.call_columns(first, cf)
+    g2 = caller.call_columns(second, cf)
+    assert np.array_equal(np.r_[g1["bonf_used"], g2["bonf_used"]], want["bonf_used"])
+    assert np.array_equal(np.r_[g1["called"], g2["called"]], want["called"])
+    assert np.array_equal(np.r_[g1["qual"], g2["qual"]], want["qual"])
+    assert cf.bonf_subst == want["bonf_subst"] and cf.num_snv_tests == want["num_snv_tests"]
+
+
+def _custom_batch(cols, pad=1, with_baq=True):
+    """cols: list of dict(ref=, groups=[(bq, mq, baq) arrays per A,C,G,T], coverage=optional)"""
+    col_off = [0]
+    bq, mq, baq, nt, ref, cov = [], [], [], [], [], []
+    for c in cols:
+        n = 0
+        for g in range(4):
+            q = c["groups"][g]
+            nt.append(len(q[0]))
+            bq.extend(q[0]); mq.extend(q[1]); baq.extend(q[2])
+            n += len(q[0])
+        padn = (-n) % pad + c.get("gap", 0)
+        bq.extend([0] * padn); mq.extend([0] * padn); baq.extend([0] * padn)
+        col_off.append(col_off[-1] + n + padn)
+        ref.append(ord(c["ref"]))
+        cov.append(c.get("coverage", n))
+    tail = 64
+    return dict(col_off=np.array(col_off, np.int64), nt_cnt=np.array(nt, np.int32).reshape(-1, 4),
+                ref_base=np.array(ref, np.uint8), coverage=np.array(cov, np.int32),
+                bq=np.array(bq + [0] * tail, np.uint8), mq=np.array(mq + [0] * tail, np.uint8),
+                baq=np.array(baq + [0] * tail, np.uint8) if with_baq else None, sq=None)
+
+
+def test_edge_columns(caller, port_oracle):
+    rng = np.random.default_rng(5)
+
+    def grp(n, qlo=20, qhi=41, mqv=None, baqv=None):
+        return (rng.integers(qlo, qhi, n), rng.integers(0, 256, n) if mqv is None else np.full(n, mqv),
+                rng.integers(0, 94, n) if baqv is None else np.full(n, baqv))
+    e = (np.zeros(0, int),) * 3
+    cols = [
+        dict(ref="A", groups=[e, e, e, e]),                                   # empty column
+        dict(ref="N", groups=[grp(30), grp(3), e, e]),                        # ref N: skipped (lofreq_call.c:892)
+        dict(ref="C", groups=[grp(2), grp(40), grp(1), grp(5)], gap=7),       # ragged, unaligned next column
+        dict(ref="G", groups=[grp(9), e, grp(100), e], coverage=500),         # num_bases*2 < coverage: skipped
+        dict(ref="T", groups=[grp(13), grp(1), grp(1), grp(333)], gap=3),
+        dict(ref="A", groups=[e, grp(50), e, e]),                             # no ref reads at all, K == N
+        dict(ref="A", groups=[grp(60, mqv=255), grp(8, mqv=255), e, e]),      # mq unknown
+        dict(ref="A", groups=[grp(60, mqv=0), grp(8, mqv=0), e, e]),          # mq 0 -> 0.5
+        dict(ref="C", groups=[grp(4, baqv=255), grp(200, baqv=255), grp(3, baqv=255), e]),   # baq not available
+        dict(ref="G", groups=[grp(5, 0, 6), grp(5, 0, 6), grp(90, 0, 12), grp(7, 0, 12)]),   # around min_bq = 6
+        dict(ref="T", groups=[grp(1), e, e, e]),                              # N == 1, alt only
+        dict(ref="T", groups=[e, e, e, grp(1)]),                              # N == 1, ref only
+        dict(ref="A", groups=[grp(700), grp(300), grp(120), grp(15)]),        # tri-allelic, large counts
+        dict(ref="C", groups=[grp(9, 60, 94), grp(2500, 60, 94, 60, 93), grp(1200, 60, 94, 60, 93), grp(1, 60, 94)]),
+    ]
+    for pad in (1, 16):
+        b = _custom_batch(cols, pad=pad)
+        for conf in (default_conf(), default_conf(min_cov=10), default_conf(flag=0), default_conf(def_alt_bq=-1),
+                     default_conf(min_bq=3, min_alt_bq=20, min_jq=15, min_alt_jq=25, def_alt_jq=35)):
+            want = port_oracle.call_columns(b, dict(conf))
+            got = caller.call_columns(b, dict(conf))
+            compare_batch(got, want, "edge pad=%d %s" % (pad, conf))
+    empty = _custom_batch([])
+    got = caller.call_columns(empty, default_conf())
+    assert got["n_sites"] == 0 and got["num_snv_tests"] == 0 and got["bonf_subst"] == 1
+
+
+def test_random_snpcaller_problems(caller, port_oracle):
+    rng = np.random.default_rng(77)
+    sig = float(np.float32(0.01))
+    eps, cnts, bonfs = [], [], []
+    for it in range(300):
+        n = int(rng.integers(1, 2500))
+        mode = rng.integers(0, 4)
+        if mode == 0:
+            q = rng.integers(20, 41, n)
+        elif mode == 1:
+            q = rng.integers(6, 60, n)
+        elif mode == 2:
+            q = np.full(n, int(rng.integers(10, 45)))
+        else:
+            q = np.where(rng.random(n) < 0.3, 3, rng.integers(20, 41, n))
+        ep = np.sort(10.0 ** (-q / 10.0))
+        k1 = int(rng.integers(1, n + 1)) if rng.random() < 0.7 else int(rng.integers(1, min(n, 20) + 1))
+        k2 = int(rng.integers(0, min(k1, n - k1) + 1)) if rng.random() < 0.7 else 0
+        k3 = int(rng.integers(0, min(5, n - k1 - k2) + 1))
+        c = [k1, k2, k3]
+        rng.shuffle(c)
+        eps.append(ep); cnts.append(c); bonfs.append(int(rng.integers(1, 10 ** 7)))
+    pv, lnp, st = caller.snpcaller_batch(eps, cnts, bonfs, sig)
+    want = np.array([port_oracle.snpcaller(e, c, b, sig) for e, c, b in zip(eps, cnts, bonfs)])
+    wst = status_of(want)
+    bad = np.argwhere(st != wst)
+    assert len(bad) == 0, [(len(eps[i]), cnts[i], bonfs[i], st[i].tolist(), wst[i].tolist()) for i, _ in bad[:5]]
+    assert_lnp_close(pv, want, wst, "random problems")
+
+
+@pytest.mark.parametrize("wl,c0,n,baq", [("C2", 0, 3000, True), ("C3", 123456, 300, True), ("C4", 5, 3000, False),
+                                        ("C5", 1000, 500, True)])
+def test_synth_matches_numpy(wl, c0, n, baq):
+    import torch
+    from lofreq_b200 import synth
+    t = synth.generate_device(wl, c0, n, with_baq=baq)
+    torch.cuda.synchronize()
+    b = synth_np.generate(wl, c0, n, with_baq=baq)
+    assert np.array_equal(t["col_off"].cpu().numpy(), b["col_off"])
+    assert np.array_equal(t["nt_cnt"].cpu().numpy(), b["nt_cnt"])
+    assert np.array_equal(t["ref_base"].cpu().numpy(), b["ref_base"])
+    tot = int(b["col_off"][-1])
+    assert np.array_equal(t["bq"].cpu().numpy()[:tot], b["bq"])
+    assert np.array_equal(t["mq"].cpu().numpy()[:tot], b["mq"])
+    if baq:
+        assert np.array_equal(t["baq"].cpu().numpy()[:tot], b["baq"])
+
+
+def test_full_size_c2_properties(caller, port_oracle):
+    """BASELINE.json configs[1]: 1M columns at depth 500, Q30, generated on the device.
+    Size-independent properties + a sampled comparison against the oracle."""
+    import lofreq_b200
+    from lofreq_b200 import synth
+    n = 1_000_000
+    t = synth.generate_device("C2", 0, n)
+    db = caller.device_batch(t)
+    cf = lofreq_b200.varcall_conf()
+    caller.screen(db, cf)
+    n_tested = caller.ntested()
+    caller.test(cf)
+    sites, sm = caller.sites(cf, n)
+    assert sm.n_tested == n_tested and sm.num_snv_tests == 3 * n_tested and cf.bonf_subst == 3 * n_tested
+    # the same columns through the host entry point on a slice, against the oracle
+    sel0, sel1 = 250_000, 262_000
+    b = synth_np.generate("C2", sel0, sel1 - sel0)
+    conf = default_conf(bonf_subst=1)
+    want = port_oracle.call_columns(b, dict(conf))
+    got = caller.call_columns(b, dict(conf))
+    compare_batch(got, want, "C2 slice")
+    # sites of the full run restricted to the slice must be the called columns of the slice, with the
+    # full-run Bonferroni factors being larger (running factor) -> subset relation
+    s = np.ctypeslib.as_array(sites)[: sm.n_sites]
+    assert np.all(np.diff(s["col"]) > 0)                      # sorted, unique
+    in_slice = s[(s["col"] >= sel0) & (s["col"] < sel1)]
+    full_called = set(int(c) - sel0 for c, cl in zip(in_slice["col"], in_slice["called"]) if cl.any())
+    slice_called = set(np.nonzero(want["called"].any(axis=1))[0].tolist())
+    assert full_called <= slice_called
+    # idempotence: a second pass over the same resident batch gives identical sites
+    cf2 = lofreq_b200.varcall_conf()
+    caller.screen(db, cf2)
+    caller.test(cf2)
+    sites2, sm2 = caller.sites(cf2, n)
+    s2 = np.ctypeslib.as_array(sites2)[: sm2.n_sites]
+    assert sm2.n_sites == sm.n_sites and np.array_equal(s["col"], s2["col"]) and np.array_equal(s["lnp"], s2["lnp"])
+    assert np.array_equal(s["qual"], s2["qual"])
+    # 1 % of the columns are variant sites, nearly all of them significant
+    assert 0.005 * n < sm.n_sites < 0.02 * n
