@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — pileup-columns/sec of the per-column SNV test (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cols M] [--workload C2]
+
+A step = one pass of the hot path over one batch of synthetic pileup columns (workload C2 of
+BASELINE.json: 1M columns, depth 500, uniform Q30, MQ60; 1 % variant columns).  Per rank the batch is
+resident in HBM for `value`; `e2e` goes through the host entry point of the C ABI with pinned host
+buffers (H2D of the planes + D2H of the sites inside the timed region).
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/libsnpref.so: the
+unmodified snpcaller.c driven like call_snvs; falls back to the C restatement when it was not built)
+on all host cores over disjoint column ranges, the way lofreq2_call_pparallel.py shards regions.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pileup_columns_per_sec"
+UNIT = "columns/s"
+DEPTH = {"C2": 500, "C3": 2000, "C4": 300}
+
+
+def workload_desc(wl, cols):
+    return {"C2": "C2: %d synthetic pileup columns, depth 500, uniform Q30, MQ60, 1%% variant sites" % cols,
+            "C3": "C3: %d synthetic columns, depth 2000, Q20-40" % cols,
+            "C4": "C4: %d synthetic columns, depth 300, mixed Q" % cols,
+            "C5": "C5: %d synthetic columns, depth 50-10000 log-uniform, Q20-40" % cols}[wl]
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the reference (or the port) over column ranges, one process per core
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, wl, c0, n = args
+    from oracle import synth_np
+    from oracle.pyoracle import Oracle, default_conf
+    orc = Oracle(kind)
+    conf = default_conf()
+    dt, tested, chunk = 0.0, 0, 10_000          # generate in chunks (numpy generator memory), time only the test
+    for s0 in range(0, n, chunk):
+        b = synth_np.generate(wl, c0 + s0, min(chunk, n - s0))
+        t0 = time.perf_counter()
+        out = orc.call_columns(b, conf)
+        dt += time.perf_counter() - t0
+        conf["bonf_subst"], conf["num_snv_tests"] = out["bonf_subst"], out["num_snv_tests"]   # running Bonferroni
+        tested += int(out["tested"].sum())
+    return dt, tested
+
+
+def cpu_kind():
+    from oracle.pyoracle import have_reference
+    return "reference" if have_reference() else "port"
+
+
+def cpu_run(wl, cols_per_proc, procs, c0=0, pool=None):
+    """returns (columns/s over all procs, seconds of the slowest worker, kind)"""
+    kind = cpu_kind()
+    jobs = [(kind, wl, c0 + i * cols_per_proc, cols_per_proc) for i in range(procs)]
+    if procs == 1 or pool is None:
+        res = [_cpu_worker(j) for j in jobs]
+        slow = sum(r[0] for r in res)
+    else:
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
+        slow = max(r[0] for r in res)
+    return cols_per_proc * procs / slow, slow, kind
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes_per_column(wl, with_baq=False):
+    """planes the configuration merges (bq, mq[, baq]) over the column's reads +
+    per-column metadata in (col_off 8, nt_cnt 16, ref_base 1) + per-column results out (alt counts and
+    raw counts 24, tested 1, bonf 8)."""
+    d = DEPTH[wl]
+    return d * (3 if with_baq else 2) + 25 + 33
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    procs = max(1, cores)
+    # bounded sample: ~1.5 s of CPU work per process and step
+    cols_per_proc = args.ref_cols_per_proc
+    import multiprocessing as mp
+    pool = mp.get_context("spawn").Pool(procs) if procs > 1 else None
+    for _ in range(args.warmup):
+        cpu_run(args.workload, max(cols_per_proc // 8, 256), procs, pool=pool)
+    vals, secs = [], []
+    for k in range(args.steps):
+        v, s, kind = cpu_run(args.workload, cols_per_proc, procs, c0=k * cols_per_proc * procs, pool=pool)
+        vals.append(v); secs.append(s)
+    if pool:
+        pool.close()
+    value = sum(vals) / len(vals)
+    sample = "%d columns per step (%d per process x %d processes), %s" % (cols_per_proc * procs, cols_per_proc, procs,
+                                                                          workload_desc(args.workload, args.cols))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_desc(args.workload, args.cols), "cpu_path": kind_desc(kind)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def kind_desc(kind):
+    return ("unmodified reference snpcaller.c/utils.c compiled into oracle/_ref/libsnpref.so, driven like call_snvs"
+            if kind == "reference" else "C restatement oracle/snv_oracle.c (reference not built here)")
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import lofreq_b200
+    from lofreq_b200 import capi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    wl, n = args.workload, args.cols
+    caller = lofreq_b200.Caller(local)
+    lib = caller.lib
+    stream = torch.cuda.current_stream()
+    st = C.c_void_p(stream.cuda_stream)
+
+    # this rank's region shard: columns [rank*n, (rank+1)*n)
+    t = synth.generate_device(wl, rank * n, n, with_baq=False, device=str(dev))
+    torch.cuda.synchronize()
+    db = caller.device_batch(t)
+    max_sites = n
+    sites_buf = (capi.Site * max_sites)()
+    sm = capi.Summary()
+    counts_dev = torch.zeros(world, dtype=torch.int64, device=dev)
+
+    def step_device(profile=False):
+        """screen -> (exchange tested counts) -> test -> sites; returns summary"""
+        cf = lofreq_b200.varcall_conf()
+        capi.check(lib.lfb200_screen_device(caller._ctx, C.byref(cf), C.byref(db), st))
+        if world > 1:
+            nt = C.c_longlong()
+            capi.check(lib.lfb200_ntested_device(caller._ctx, st, C.byref(nt)))
+            mine = torch.tensor([nt.value], dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(counts_dev, mine)
+            before = int(counts_dev[:rank].sum().item())
+            if before:
+                cf.bonf_subst = 3 * before          # the running factor of the shards before this one
+        capi.check(lib.lfb200_test_device(caller._ctx, C.byref(cf), st))
+        capi.check(lib.lfb200_sites_device(caller._ctx, C.byref(cf), st, sites_buf, max_sites, C.byref(sm)))
+        if world > 1:
+            # the final per-region variant-count gather (north_star): 1 x int64 per rank
+            mine = torch.tensor([sm.n_sites], dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(counts_dev, mine)
+        return sm
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: resident inputs -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    capi.check(lib.lfb200_set_profiling(caller._ctx, 1))
+    prof = np.zeros((args.steps, 4), np.float32)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_device()
+        row = (C.c_float * 4)()
+        capi.check(lib.lfb200_get_profile(caller._ctx, row))
+        prof[k] = list(row)
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    capi.check(lib.lfb200_set_profiling(caller._ctx, 0))
+    n_sites, n_tested, n_heavy = sm.n_sites, sm.n_tested, sm.n_heavy
+    el = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    ms_step = float(el.item()) / args.steps
+    value = world * n / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers through lfb200_call_columns ----------------------------------------
+    total = t["total_bytes"]
+    hb_t = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in
+            (("col_off", t["col_off"]), ("nt_cnt", t["nt_cnt"]), ("ref_base", t["ref_base"]),
+             ("bq", t["bq"][: total + 16]), ("mq", t["mq"][: total + 16]))}
+    torch.cuda.synchronize()
+    hb = capi.Batch(n, hb_t["col_off"].data_ptr(), hb_t["nt_cnt"].data_ptr(), hb_t["ref_base"].data_ptr(), None,
+                    hb_t["bq"].data_ptr(), hb_t["mq"].data_ptr(), None, None)
+    h2d = 8 * (n + 1) + 16 * n + n + 2 * total
+
+    def step_e2e():
+        cf = lofreq_b200.varcall_conf()
+        capi.check(lib.lfb200_call_columns(caller._ctx, C.byref(cf), C.byref(hb), None, sites_buf, max_sites, C.byref(sm)))
+        return sm
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    el = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    e2e_value = world * n / float(el.item())
+    d2h = 128 + int(sm.n_sites) * 80
+
+    # ---- roofline of the dominant kernel (k_screen) ---------------------------------------------
+    peak, peak_src = measured_peaks()
+    t_screen = float(prof[:, 0].mean()) * 1e-3
+    bytes_algo = algorithmic_bytes_per_column(wl) * n
+    achieved = bytes_algo / t_screen / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_screen", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_algo, "kernel_ms": t_screen * 1e3,
+                "phase_ms": {"k_screen": float(prof[:, 0].mean()), "prefix_sum": float(prof[:, 1].mean()),
+                             "k_finalize": float(prof[:, 2].mean()), "k_heavy": float(prof[:, 3].mean())}}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            procs = 1
+            v, s, kind = cpu_run(wl, args.cpu_sample, procs)
+            cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": kind,
+                   "sample": "first %d columns of the same workload, %.1f s, single thread (the reference is "
+                             "single-threaded; all-core number: --impl reference)" % (args.cpu_sample, s)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_desc(wl, n) + " per GPU (region shard = rank*cols)",
+                           "cols_per_gpu": n, "depth": DEPTH.get(wl), "l2": "inputs larger than L2 (%.2f GB per step)" % (2 * total / 1e9),
+                           "value_region": "screen + prefix sum + significance test + O(depth*K) kernel + D2H of sites + long double finishing, inputs resident in HBM",
+                           "tested_columns": int(n_tested), "sites": int(n_sites), "heavy_columns": int(n_heavy)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+                "gpu_launches": 12 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "wall_ms_per_step": wall * 1e3 / args.steps}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    caller.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4"])
+    ap.add_argument("--cols", type=int, default=1_000_000, help="columns per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=200_000, help="columns of the single-thread cpu_baseline sample")
+    ap.add_argument("--ref-cols-per-proc", type=int, default=30_000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -145,8 +145,13 @@ int lfb200_ntested_device(lfb200_ctx *ctx, void *stream, long long *n_tested);
 int lfb200_test_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *stream);
 int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites,
                         long long max_sites, lfb200_summary_t *summary);
+/* optional per-phase device timing with CUDA events on the launching stream (benchmark / roofline):
+ * ms4 = { k_screen, prefix-sum kernels, k_finalize, k_heavy<*> } of the last screen + test */
+int lfb200_set_profiling(lfb200_ctx *ctx, int on);
+int lfb200_get_profile(lfb200_ctx *ctx, float *ms4);
 /* device pointers of the per-column results of the last screen/test (valid
- * until the next screen on this ctx): int[3n], int[3n], u8[n], i64[n] */
+ * until the next screen on this ctx): alt_counts and alt_raw_counts are interleaved, stride 6 ints per
+ * column (alt_raw_counts = alt_counts + 3); tested u8[n]; bonf_used i64[n] */
 int lfb200_device_results(lfb200_ctx *ctx, const int **alt_counts, const int **alt_raw_counts,
                           const unsigned char **tested, const long long **bonf_used);
 

@@ -30,6 +30,27 @@ class Site(C.Structure):
                 ("qual", C.c_int * 3), ("status", C.c_ubyte * 3), ("called", C.c_ubyte * 3)]
 
 
+def _site_dtype():
+    import numpy as np
+    names, formats, offsets = [], [], []
+    for name, np_fmt in (("col", "<i8"), ("bonf", "<i8"), ("lnp", ("<f8", (3,))), ("pvalue", (np.longdouble, (3,))),
+                         ("alt_count", ("<i4", (3,))), ("alt_raw_count", ("<i4", (3,))), ("qual", ("<i4", (3,))),
+                         ("status", ("u1", (3,))), ("called", ("u1", (3,)))):
+        names.append(name)
+        formats.append(np_fmt)
+        offsets.append(getattr(Site, name).offset)
+    return np.dtype(dict(names=names, formats=formats, offsets=offsets, itemsize=C.sizeof(Site)))
+
+
+def sites_to_numpy(sites, n):
+    """structured numpy copy of the first n entries of a (Site * m) ctypes array"""
+    import numpy as np
+    dt = _site_dtype()
+    if n <= 0:
+        return np.zeros(0, dtype=dt)
+    return np.frombuffer(sites, dtype=dt, count=n).copy()
+
+
 class DenseOut(C.Structure):
     _fields_ = [("alt_counts", C.c_void_p), ("alt_raw_counts", C.c_void_p), ("tested", C.c_void_p),
                 ("bonf_used", C.c_void_p), ("lnp", C.c_void_p), ("status", C.c_void_p),
@@ -44,7 +65,7 @@ class Summary(C.Structure):
 # every symbol include/lofreq_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_conf", "lfb200_call_columns",
            "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_sites_device",
-           "lfb200_device_results", "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_synth_depths",
+           "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_synth_depths",
            "lfb200_synth_columns"]
 
 _lib = None
@@ -85,6 +106,10 @@ def load():
     lib.lfb200_sites_device.argtypes = [vp, C.POINTER(Conf), vp, C.POINTER(Site), ll, C.POINTER(Summary)]
     lib.lfb200_device_results.restype = C.c_int
     lib.lfb200_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.lfb200_set_profiling.restype = C.c_int
+    lib.lfb200_set_profiling.argtypes = [vp, C.c_int]
+    lib.lfb200_get_profile.restype = C.c_int
+    lib.lfb200_get_profile.argtypes = [vp, C.POINTER(C.c_float)]
     lib.lfb200_snpcaller.restype = C.c_int
     lib.lfb200_snpcaller.argtypes = [vp, vp, C.c_int, vp, ll, C.c_double, C.c_int]
     lib.lfb200_snpcaller_batch.restype = C.c_int

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -81,6 +82,9 @@ struct lfb200_ctx {
     // pinned scratch for small D2H transfers
     Counters *h_counters = nullptr;
     std::vector<Cand> h_cand;
+    // optional per-phase timing (lfb200_set_profiling): events on the launching stream
+    bool profiling = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // state of the last screen
     DevBatch cur{};
     bool have_batch = false;
@@ -324,8 +328,11 @@ extern "C" int lfb200_screen_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, 
     ctx->have_batch = true;
     ctx->n_tested = -1;
     cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
     launch_screen(dc, ctx->cur, ctx->d_lut, ctx->ws, st);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
     launch_scan(ctx->cur, ctx->ws, st);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
     CU(cudaGetLastError());
     return 0;
 }
@@ -349,7 +356,9 @@ extern "C" int lfb200_test_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, vo
     hb.mq = ctx->cur.mq; hb.baq = ctx->cur.baq; hb.sq = ctx->cur.sq;
     DevConf dc;
     if (make_devconf(conf, &hb, dc)) return 1;
-    launch_test(dc, ctx->cur, ctx->d_lut, ctx->ws, (cudaStream_t)stream);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[3], (cudaStream_t)stream);
+    launch_test(dc, ctx->cur, ctx->d_lut, ctx->ws, (cudaStream_t)stream, ctx->profiling ? ctx->ev[4] : nullptr);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[5], (cudaStream_t)stream);
     CU(cudaGetLastError());
     return 0;
 }
@@ -387,10 +396,29 @@ extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *s
     }
     std::sort(ctx->h_cand.begin(), ctx->h_cand.end(), [](const Cand &a, const Cand &b) { return a.col < b.col; });
     const double sig = (double)conf->sig;
-    for (long long i = 0; i < n_cand; ++i) {
+    for (long long i = 0; i < n_cand; ++i)
         if (ctx->h_cand[(size_t)i].flags & CF_RANGE)
             return fail("column %lld: tail outside the representable range", ctx->h_cand[(size_t)i].col);
-        finish_site(ctx->h_cand[(size_t)i], sig, sites[i]);
+    // long double finishing: independent per site (FE flags and errno are per thread)
+    {
+        const Cand *cands = ctx->h_cand.data();
+        unsigned nthr = std::thread::hardware_concurrency();
+        nthr = std::max(1u, std::min(nthr, 16u));
+        if (n_cand < 2048) nthr = 1;
+        auto work = [&](long long lo, long long hi) {
+            for (long long i = lo; i < hi; ++i) finish_site(cands[i], sig, sites[i]);
+        };
+        if (nthr == 1) {
+            work(0, n_cand);
+        } else {
+            std::vector<std::thread> pool;
+            const long long per = (n_cand + nthr - 1) / nthr;
+            for (unsigned t = 0; t < nthr; ++t) {
+                const long long lo = t * per, hi = std::min<long long>(n_cand, lo + per);
+                if (lo < hi) pool.emplace_back(work, lo, hi);
+            }
+            for (auto &th : pool) th.join();
+        }
     }
     sm.n_sites = n_cand;
     sm.bonf_subst_final = final_bonf(conf, sm.n_tested);
@@ -398,6 +426,26 @@ extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *s
     conf->num_snv_tests += 3 * sm.n_tested;       // lofreq_call.c:801
     sm.num_snv_tests = conf->num_snv_tests;
     if (summary) *summary = sm;
+    return 0;
+}
+
+extern "C" int lfb200_set_profiling(lfb200_ctx *ctx, int on)
+{
+    if (!ctx) return fail("no context");
+    if (on && !ctx->ev[0])
+        for (int i = 0; i < 6; ++i) CU(cudaEventCreate(&ctx->ev[i]));
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+extern "C" int lfb200_get_profile(lfb200_ctx *ctx, float *ms4)
+{
+    if (!ctx || !ctx->profiling) return fail("profiling is off");
+    CU(cudaEventSynchronize(ctx->ev[5]));
+    CU(cudaEventElapsedTime(&ms4[0], ctx->ev[0], ctx->ev[1]));   // k_screen
+    CU(cudaEventElapsedTime(&ms4[1], ctx->ev[1], ctx->ev[2]));   // k_block_counts + k_scan_blocks
+    CU(cudaEventElapsedTime(&ms4[2], ctx->ev[3], ctx->ev[4]));   // k_finalize
+    CU(cudaEventElapsedTime(&ms4[3], ctx->ev[4], ctx->ev[5]));   // k_heavy<*>
     return 0;
 }
 

@@ -89,7 +89,8 @@ struct ProbBatch {
 // launchers (snv_kernels.cu)
 void launch_screen(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
 void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st);
-void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
+void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
+                 cudaEvent_t after_finalize);
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st);
 // synth.cu
 void launch_synth_depths(int workload, long long c0, long long n, int *depth, cudaStream_t st);

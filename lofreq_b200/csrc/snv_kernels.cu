@@ -231,10 +231,6 @@ __device__ __forceinline__ void small_tails(const double (&P)[K], double T, cons
 // ------------------------------------------------------------------------------------------------
 // k_screen
 // ------------------------------------------------------------------------------------------------
-struct Chunk {          // 16 consecutive bytes of each plane
-    uint4 bq, mq, baq, sq;
-};
-
 __device__ __forceinline__ int byte_of(const uint4 &v, int j)
 {
     const unsigned w = j < 4 ? v.x : j < 8 ? v.y : j < 12 ? v.z : v.w;
@@ -246,42 +242,82 @@ __device__ __forceinline__ uint4 ldg16(const unsigned char *p)
     return __ldg(reinterpret_cast<const uint4 *>(p));
 }
 
+// [lo, hi) of the reads showing the reference base
+__device__ __forceinline__ void ref_range(const Geom &g, int &lo, int &hi)
+{
+    lo = g.ref_idx == 0 ? 0 : g.ref_idx == 1 ? g.b1 : g.ref_idx == 2 ? g.b2 : g.b3;
+    hi = g.ref_idx == 0 ? g.b1 : g.ref_idx == 1 ? g.b2 : g.ref_idx == 2 ? g.b3 : g.n;
+}
+
+// merged error probability of a read that shows the reference base and passed the bq filter
+// (merge_srcq_mapq_baq_and_bq with the terms of absent planes dropped: x*0, +0 and *1 are exact)
+__device__ __forceinline__ double ref_read_prob(const DevConf &cf, const double *lut, int bq, int mq, int baq, int sq)
+{
+    const double bp = lut[bq];
+    if (cf.use_baq | cf.use_sq)
+        return merge4(cf.use_sq ? lut[512 + sq] : 0.0, cf.use_mq ? lut[256 + mq] : 0.0, cf.use_baq ? lut[512 + baq] : 0.0, bp);
+    if (!cf.use_mq) return bp;
+    const double mp = lut[256 + mq];
+    return __dadd_rn(mp, __dmul_rn(__dsub_rn(1.0, mp), bp));
+}
+
+// Second sweep of a tested column with K <= KS: every lane folds the reads of its 16-byte chunks into
+// a distribution truncated at K, then the 32 distributions are merged.
 template <int K>
-__device__ __noinline__ void screen_small(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &g,
-                                          const int (&cnt)[3], long long abase, int lead, int nchunks, double (&tails)[4])
+__device__ __forceinline__ void screen_small(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &g,
+                                          const int (&cnt)[3], double (&tails)[4])
 {
     const int lane = lane_id();
     double P[K], T = 0.0;
 #pragma unroll
     for (int k = 0; k < K; ++k) P[k] = (k == 0) ? 1.0 : 0.0;
+    const long long abase = g.off & ~15ll;
+    const int lead = (int)(g.off - abase);
+    const int nchunks = (lead + g.n + 15) >> 4;
+    int ref_lo, ref_hi;
+    ref_range(g, ref_lo, ref_hi);
     const uint4 zero = make_uint4(0, 0, 0, 0);
     for (int i = lane; i < nchunks; i += 32) {
         const long long a = abase + 16ll * i;
-        Chunk ch;
-        ch.bq = ldg16(b.bq + a);
-        ch.mq = cf.use_mq ? ldg16(b.mq + a) : zero;
-        ch.baq = cf.use_baq ? ldg16(b.baq + a) : zero;
-        ch.sq = cf.use_sq ? ldg16(b.sq + a) : zero;
+        const uint4 vbq = ldg16(b.bq + a);
+        const uint4 vmq = cf.use_mq ? ldg16(b.mq + a) : zero;
+        const uint4 vbaq = cf.use_baq ? ldg16(b.baq + a) : zero;
+        const uint4 vsq = cf.use_sq ? ldg16(b.sq + a) : zero;
+        const int pos0 = 16 * i - lead;
+        if (pos0 >= ref_lo && pos0 + 16 <= ref_hi) {
+            // the whole chunk shows the reference base: no alt bookkeeping
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int pos = 16 * i + j - lead;
-            if (pos < 0 || pos >= g.n) continue;
-            bool is_alt;
-            int slot;
-            double jp;
-            if (!eval_read<true>(cf, s_lut, g, pos, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j),
-                                 byte_of(ch.sq, j), is_alt, slot, jp))
-                continue;
-            double p, q;
-            guard_pq(jp, p, q);
-            lane_update<K>(P, T, p, q);
+            for (int j = 0; j < 16; ++j) {
+                const int bq = byte_of(vbq, j);
+                if (bq < cf.min_bq) continue;
+                const double jp = ref_read_prob(cf, s_lut, bq, byte_of(vmq, j), byte_of(vbaq, j), byte_of(vsq, j));
+                if (cf.jq_filters && jp >= cf.skip_jp) continue;
+                double p, q;
+                guard_pq(jp, p, q);
+                lane_update<K>(P, T, p, q);
+            }
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < 16; ++j) {
+                const int pos = pos0 + j;
+                if (pos < 0 || pos >= g.n) continue;
+                bool is_alt;
+                int slot;
+                double jp;
+                if (!eval_read<true>(cf, s_lut, g, pos, byte_of(vbq, j), byte_of(vmq, j), byte_of(vbaq, j),
+                                     byte_of(vsq, j), is_alt, slot, jp))
+                    continue;
+                double p, q;
+                guard_pq(jp, p, q);
+                lane_update<K>(P, T, p, q);
+            }
         }
     }
     tree_merge<K>(P, T);
     small_tails<K>(P, T, cnt, tails);
 }
 
-__global__ void __launch_bounds__(256) k_screen(const DevConf cf, const DevBatch b, const Lut *lut, const Workspace ws)
+__global__ void __launch_bounds__(256, 4) k_screen(const DevConf cf, const DevBatch b, const Lut *lut, const Workspace ws)
 {
     __shared__ double s_lut[768];
     __shared__ int s_hist[8][256];
@@ -296,42 +332,35 @@ __global__ void __launch_bounds__(256) k_screen(const DevConf cf, const DevBatch
         int cov;
         load_geom(b, c, g, cov);
         int cnt[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
-        bool gate = g.ref_idx >= 0 && !(g.n * 2 < cov) && !(g.n < cf.min_cov);   // lofreq_call.c:892,931,747,754
-        const long long abase = g.off & ~15ll;
-        const int lead = (int)(g.off - abase);
-        const int nchunks = (lead + g.n + 15) >> 4;
-        if (gate) {
+        const bool gate = g.ref_idx >= 0 && !(g.n * 2 < cov) && !(g.n < cf.min_cov);   // lofreq_call.c:892,931,747,754
+        int ref_lo, ref_hi;
+        ref_range(g, ref_lo, ref_hi);
+        const int n_alt = g.n - (ref_hi - ref_lo);
+        if (gate && n_alt > 0) {
+            // First sweep: only reads that show a non-reference base decide whether the column is tested
+            // and what K is, so only those are looked at (alt counts, snpcaller.c:418-420,489).
             setup_alt_bq(cf, b, s_lut, g, s_hist[wib]);
-            const uint4 zero = make_uint4(0, 0, 0, 0);
-            for (int i = lane; i < nchunks; i += 32) {
-                const long long a = abase + 16ll * i;
-                Chunk ch;
-                ch.bq = ldg16(b.bq + a);
-                ch.mq = ch.baq = ch.sq = zero;
+            for (int i = lane; i < n_alt; i += 32) {
+                const int pos = i < ref_lo ? i : i - ref_lo + ref_hi;
+                const long long a = g.off + pos;
+                const int bq = b.bq[a];
+                int mq = 0, baq = 0, sq = 0;
                 if (cf.jq_filters) {
-                    if (cf.use_mq) ch.mq = ldg16(b.mq + a);
-                    if (cf.use_baq) ch.baq = ldg16(b.baq + a);
-                    if (cf.use_sq) ch.sq = ldg16(b.sq + a);
+                    if (cf.use_mq) mq = b.mq[a];
+                    if (cf.use_baq) baq = b.baq[a];
+                    if (cf.use_sq) sq = b.sq[a];
                 }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int pos = 16 * i + j - lead;
-                    if (pos < 0 || pos >= g.n) continue;
-                    bool is_alt;
-                    int slot;
-                    double jp;
-                    const bool ok = eval_read<false>(cf, s_lut, g, pos, byte_of(ch.bq, j), byte_of(ch.mq, j),
-                                                     byte_of(ch.baq, j), byte_of(ch.sq, j), is_alt, slot, jp);
-                    if (is_alt) {     // raw counts precede every filter (snpcaller.c:418-420)
-                        raw[0] += slot == 0;
-                        raw[1] += slot == 1;
-                        raw[2] += slot == 2;
-                        if (ok) {
-                            cnt[0] += slot == 0;
-                            cnt[1] += slot == 1;
-                            cnt[2] += slot == 2;
-                        }
-                    }
+                bool is_alt;
+                int slot;
+                double jp;
+                const bool ok = eval_read<false>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp);
+                raw[0] += slot == 0;              // raw counts precede every filter (snpcaller.c:418-420)
+                raw[1] += slot == 1;
+                raw[2] += slot == 2;
+                if (ok) {
+                    cnt[0] += slot == 0;
+                    cnt[1] += slot == 1;
+                    cnt[2] += slot == 2;
                 }
             }
 #pragma unroll
@@ -342,21 +371,25 @@ __global__ void __launch_bounds__(256) k_screen(const DevConf cf, const DevBatch
         }
         const int K = max(cnt[0], max(cnt[1], cnt[2]));
         const bool tested = gate && K > 0;     // lofreq_call.c:768-780: no alt left -> not a test
-        if (lane < 6) ws.cnt6[6 * c + lane] = lane < 3 ? cnt[lane] : raw[lane - 3];
+        {
+            const int v = lane == 0 ? cnt[0] : lane == 1 ? cnt[1] : lane == 2 ? cnt[2] : lane == 3 ? raw[0] : lane == 4 ? raw[1] : raw[2];
+            if (lane < 6) ws.cnt6[6 * c + lane] = v;
+        }
         if (lane == 0) ws.tested[c] = tested ? 1 : 0;
         if (tested && K <= KS) {
             double tails[4];
             switch (K) {
-                case 1: screen_small<1>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
-                case 2: screen_small<2>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
-                case 3: screen_small<3>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
-                case 4: screen_small<4>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
-                case 5: screen_small<5>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
-                case 6: screen_small<6>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
-                case 7: screen_small<7>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
-                default: screen_small<8>(cf, b, s_lut, g, cnt, abase, lead, nchunks, tails); break;
+                case 1: screen_small<1>(cf, b, s_lut, g, cnt, tails); break;
+                case 2: screen_small<2>(cf, b, s_lut, g, cnt, tails); break;
+                case 3: screen_small<3>(cf, b, s_lut, g, cnt, tails); break;
+                case 4: screen_small<4>(cf, b, s_lut, g, cnt, tails); break;
+                case 5: screen_small<5>(cf, b, s_lut, g, cnt, tails); break;
+                case 6: screen_small<6>(cf, b, s_lut, g, cnt, tails); break;
+                case 7: screen_small<7>(cf, b, s_lut, g, cnt, tails); break;
+                default: screen_small<8>(cf, b, s_lut, g, cnt, tails); break;
             }
-            if (lane < 4) ws.tails[4 * c + lane] = tails[lane];
+            const double tv = lane == 0 ? tails[0] : lane == 1 ? tails[1] : lane == 2 ? tails[2] : tails[3];
+            if (lane < 4) ws.tails[4 * c + lane] = tv;
         }
     }
 }
@@ -924,13 +957,15 @@ void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st)
     k_scan_blocks<<<1, 1024, 0, st>>>(ws.blocksum, nb, ws.counters);
 }
 
-void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st)
+void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
+                 cudaEvent_t after_finalize)
 {
     if (b.n_cols <= 0) return;
     const int nb = (int)((b.n_cols + 1023) / 1024);
     // n_tested (first 8 bytes) belongs to the scan; everything after it is per-test state
     cudaMemsetAsync(reinterpret_cast<char *>(ws.counters) + 8, 0, sizeof(Counters) - 8, st);
     k_finalize<<<nb, 1024, 0, st>>>(cf, b.n_cols, ws);
+    if (after_finalize) cudaEventRecord(after_finalize, st);
     const int g = sm_count() * 4;
     // largest tiles first: they are the long poles
     k_heavy_xl<<<1, 32, 0, st>>>(ws, 7);

@@ -115,7 +115,7 @@ class Caller:
             dptr = C.byref(d)
         capi.check(self.lib.lfb200_call_columns(self._ctx, C.byref(cf), C.byref(hb), dptr, sites, max_sites,
                                                  C.byref(sm)))
-        out["sites"] = np.ctypeslib.as_array(sites)[: sm.n_sites].copy() if sm.n_sites else np.zeros(0, dtype=[("col", "i8")])
+        out["sites"] = capi.sites_to_numpy(sites, sm.n_sites)
         out["n_sites"] = sm.n_sites
         out["n_tested"] = sm.n_tested
         out["n_heavy"] = sm.n_heavy
@@ -147,4 +147,4 @@ class Caller:
         sites = (capi.Site * max(max_sites, 1))()
         sm = capi.Summary()
         capi.check(self.lib.lfb200_sites_device(self._ctx, C.byref(conf), stream, sites, max_sites, C.byref(sm)))
-        return sites, sm
+        return capi.sites_to_numpy(sites, sm.n_sites), sm
