@@ -213,19 +213,24 @@ __device__ __forceinline__ void tree_merge(double (&P)[K], double &T)
     }
 }
 
-// tails[i] = P(X >= cnt[i]) (0 when cnt[i] == 0), tails[3] = min(P[K-1], T)
-template <int K>
-__device__ __forceinline__ void small_tails(const double (&P)[K], double T, const int (&cnt)[3], double (&tails)[4])
+// The distribution was truncated at KV >= K = max count.  tails[i] = P(X >= cnt[i]) (0 when cnt[i] == 0),
+// tails[3] = min(P(X = K-1), P(X >= K)).
+template <int KV>
+__device__ __forceinline__ void small_tails(const double (&P)[KV], double T, const int (&cnt)[3], int K, double (&tails)[4])
 {
+    double t0 = T, t1 = T, t2 = T, tk = T, pk1 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        double s = T;
-#pragma unroll
-        for (int k = K - 1; k >= 0; --k)
-            if (k >= cnt[i]) s += P[k];
-        tails[i] = cnt[i] > 0 ? s : 0.0;
+    for (int k = KV - 1; k >= 0; --k) {      // small terms first
+        if (k >= cnt[0]) t0 += P[k];
+        if (k >= cnt[1]) t1 += P[k];
+        if (k >= cnt[2]) t2 += P[k];
+        if (k >= K) tk += P[k];
+        if (k == K - 1) pk1 = P[k];
     }
-    tails[3] = fmin(P[K - 1], T);
+    tails[0] = cnt[0] > 0 ? t0 : 0.0;
+    tails[1] = cnt[1] > 0 ? t1 : 0.0;
+    tails[2] = cnt[2] > 0 ? t2 : 0.0;
+    tails[3] = fmin(pk1, tk);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,63 +266,98 @@ __device__ __forceinline__ double ref_read_prob(const DevConf &cf, const double 
     return __dadd_rn(mp, __dmul_rn(__dsub_rn(1.0, mp), bp));
 }
 
-// Second sweep of a tested column with K <= KS: every lane folds the reads of its 16-byte chunks into
-// a distribution truncated at K, then the 32 distributions are merged.
-template <int K>
+struct Chunk16 {        // 16 consecutive bytes of each plane, one lane's share of a 512-read stripe
+    uint4 bq, mq, baq, sq;
+};
+
+__device__ __forceinline__ void load_chunk(const DevConf &cf, const DevBatch &b, long long a, Chunk16 &ch)
+{
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    ch.bq = ldg16(b.bq + a);
+    ch.mq = cf.use_mq ? ldg16(b.mq + a) : zero;
+    ch.baq = cf.use_baq ? ldg16(b.baq + a) : zero;
+    ch.sq = cf.use_sq ? ldg16(b.sq + a) : zero;
+}
+
+// fold the reads of one 16-byte chunk into the lane's truncated distribution.  One code path for
+// reference and alt reads (divergence between lanes would execute both anyway).
+template <int KV>
+__device__ __forceinline__ void fold_chunk(const DevConf &cf, const double *s_lut, const Geom &g, int ref_lo, int ref_hi,
+                                           int pos0, const Chunk16 &ch, double (&P)[KV], double &T)
+{
+    const bool general_merge = cf.use_baq | cf.use_sq;
+#pragma unroll 1
+    for (int w = 0; w < 4; ++w) {
+        unsigned wbq = w == 0 ? ch.bq.x : w == 1 ? ch.bq.y : w == 2 ? ch.bq.z : ch.bq.w;
+        unsigned wmq = w == 0 ? ch.mq.x : w == 1 ? ch.mq.y : w == 2 ? ch.mq.z : ch.mq.w;
+        unsigned wbaq = w == 0 ? ch.baq.x : w == 1 ? ch.baq.y : w == 2 ? ch.baq.z : ch.baq.w;
+        unsigned wsq = w == 0 ? ch.sq.x : w == 1 ? ch.sq.y : w == 2 ? ch.sq.z : ch.sq.w;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j, wbq >>= 8, wmq >>= 8, wbaq >>= 8, wsq >>= 8) {
+            const int pos = pos0 + 4 * w + j;
+            const int bq = wbq & 0xff;
+            const bool is_alt = pos < ref_lo || pos >= ref_hi;
+            if (pos < 0 || pos >= g.n || bq < (is_alt ? max(cf.min_bq, cf.min_alt_bq) : cf.min_bq)) continue;
+            double bp = s_lut[bq];
+            if (is_alt && cf.alt_bq_mode) bp = g.alt_bp;
+            const double mp = cf.use_mq ? s_lut[256 + (wmq & 0xff)] : 0.0;
+            double jp;
+            if (general_merge)
+                jp = merge4(cf.use_sq ? s_lut[512 + (wsq & 0xff)] : 0.0, mp, cf.use_baq ? s_lut[512 + (wbaq & 0xff)] : 0.0, bp);
+            else
+                jp = __dadd_rn(mp, __dmul_rn(__dsub_rn(1.0, mp), bp));   // sp = bap = 0: the dropped terms are exact
+            if (jp >= (is_alt ? fmin(cf.skip_jp, cf.skip_alt_jp) : cf.skip_jp)) continue;   // +inf unless min_jq/min_alt_jq > 0
+            if (is_alt && cf.def_alt_jq_on) jp = cf.def_alt_jq_prob;
+            double q = 1.0 - jp;
+            if (jp < DEPS || fabs(q) < DEPS) guard_pq(jp, jp, q);
+            lane_update<KV>(P, T, jp, q);
+        }
+    }
+}
+
+// Second sweep of a tested column with K <= KS: every lane folds the reads of its 16-byte chunks into a
+// distribution truncated at KV >= K, then the 32 distributions are merged.  The first chunk of every lane
+// was loaded before the alt counts were known (one memory round trip per column instead of two).
+template <int KV>
 __device__ __forceinline__ void screen_small(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &g,
-                                          const int (&cnt)[3], double (&tails)[4])
+                                             const int (&cnt)[3], int K, const Chunk16 &first, double (&tails)[4])
 {
     const int lane = lane_id();
-    double P[K], T = 0.0;
+    double P[KV], T = 0.0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) P[k] = (k == 0) ? 1.0 : 0.0;
+    for (int k = 0; k < KV; ++k) P[k] = (k == 0) ? 1.0 : 0.0;
     const long long abase = g.off & ~15ll;
     const int lead = (int)(g.off - abase);
     const int nchunks = (lead + g.n + 15) >> 4;
     int ref_lo, ref_hi;
     ref_range(g, ref_lo, ref_hi);
-    const uint4 zero = make_uint4(0, 0, 0, 0);
+    Chunk16 ch = first;
+#pragma unroll 1
     for (int i = lane; i < nchunks; i += 32) {
-        const long long a = abase + 16ll * i;
-        const uint4 vbq = ldg16(b.bq + a);
-        const uint4 vmq = cf.use_mq ? ldg16(b.mq + a) : zero;
-        const uint4 vbaq = cf.use_baq ? ldg16(b.baq + a) : zero;
-        const uint4 vsq = cf.use_sq ? ldg16(b.sq + a) : zero;
-        const int pos0 = 16 * i - lead;
-        if (pos0 >= ref_lo && pos0 + 16 <= ref_hi) {
-            // the whole chunk shows the reference base: no alt bookkeeping
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int bq = byte_of(vbq, j);
-                if (bq < cf.min_bq) continue;
-                const double jp = ref_read_prob(cf, s_lut, bq, byte_of(vmq, j), byte_of(vbaq, j), byte_of(vsq, j));
-                if (cf.jq_filters && jp >= cf.skip_jp) continue;
-                double p, q;
-                guard_pq(jp, p, q);
-                lane_update<K>(P, T, p, q);
-            }
-        } else {
-#pragma unroll 4
-            for (int j = 0; j < 16; ++j) {
-                const int pos = pos0 + j;
-                if (pos < 0 || pos >= g.n) continue;
-                bool is_alt;
-                int slot;
-                double jp;
-                if (!eval_read<true>(cf, s_lut, g, pos, byte_of(vbq, j), byte_of(vmq, j), byte_of(vbaq, j),
-                                     byte_of(vsq, j), is_alt, slot, jp))
-                    continue;
-                double p, q;
-                guard_pq(jp, p, q);
-                lane_update<K>(P, T, p, q);
-            }
-        }
+        if (i != lane) load_chunk(cf, b, abase + 16ll * i, ch);
+        fold_chunk<KV>(cf, s_lut, g, ref_lo, ref_hi, 16 * i - lead, ch, P, T);
     }
-    tree_merge<K>(P, T);
-    small_tails<K>(P, T, cnt, tails);
+    tree_merge<KV>(P, T);
+    small_tails<KV>(P, T, cnt, K, tails);
 }
 
-__global__ void __launch_bounds__(256, 4) k_screen(const DevConf cf, const DevBatch b, const Lut *lut, const Workspace ws)
+struct RawGeom {        // the per-column metadata as loaded, one column ahead of its use
+    long long off;
+    int4 cnt;
+    int cov;
+    char ref;
+};
+
+__device__ __forceinline__ void load_raw(const DevBatch &b, long long c, RawGeom &r)
+{
+    r.cnt = __ldg(reinterpret_cast<const int4 *>(b.nt_cnt) + c);
+    r.off = __ldg(b.col_off + c);
+    r.ref = __ldg(b.ref_base + c);
+    r.cov = b.coverage ? __ldg(b.coverage + c) : -1;
+}
+
+__global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
+                                                   const Lut *lut, const Workspace ws)
 {
     __shared__ double s_lut[768];
     __shared__ int s_hist[8][256];
@@ -327,16 +367,31 @@ __global__ void __launch_bounds__(256, 4) k_screen(const DevConf cf, const DevBa
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
 
+    RawGeom nxt;
+    if (warp0 < b.n_cols) load_raw(b, warp0, nxt);
     for (long long c = warp0; c < b.n_cols; c += nwarps) {
+        const RawGeom cur = nxt;
+        if (c + nwarps < b.n_cols) load_raw(b, c + nwarps, nxt);     // metadata of the next column: in flight during this one
         Geom g;
-        int cov;
-        load_geom(b, c, g, cov);
+        g.off = cur.off;
+        g.b1 = cur.cnt.x;
+        g.b2 = g.b1 + cur.cnt.y;
+        g.b3 = g.b2 + cur.cnt.z;
+        g.n = g.b3 + cur.cnt.w;
+        g.ref_idx = ref_index(cur.ref);
+        g.alt_bp = 0.0;
+        const int cov = cur.cov < 0 ? g.n : cur.cov;
         int cnt[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
         const bool gate = g.ref_idx >= 0 && !(g.n * 2 < cov) && !(g.n < cf.min_cov);   // lofreq_call.c:892,931,747,754
         int ref_lo, ref_hi;
         ref_range(g, ref_lo, ref_hi);
         const int n_alt = g.n - (ref_hi - ref_lo);
+        Chunk16 first;
+        first.bq = first.mq = first.baq = first.sq = make_uint4(0, 0, 0, 0);
         if (gate && n_alt > 0) {
+            // issue this lane's share of the first 512-read stripe now; it is consumed after the alt counts
+            const long long abase = g.off & ~15ll;
+            if (16 * lane < (int)(g.off - abase) + g.n) load_chunk(cf, b, abase + 16ll * lane, first);
             // First sweep: only reads that show a non-reference base decide whether the column is tested
             // and what K is, so only those are looked at (alt counts, snpcaller.c:418-420,489).
             setup_alt_bq(cf, b, s_lut, g, s_hist[wib]);
@@ -378,16 +433,10 @@ __global__ void __launch_bounds__(256, 4) k_screen(const DevConf cf, const DevBa
         if (lane == 0) ws.tested[c] = tested ? 1 : 0;
         if (tested && K <= KS) {
             double tails[4];
-            switch (K) {
-                case 1: screen_small<1>(cf, b, s_lut, g, cnt, tails); break;
-                case 2: screen_small<2>(cf, b, s_lut, g, cnt, tails); break;
-                case 3: screen_small<3>(cf, b, s_lut, g, cnt, tails); break;
-                case 4: screen_small<4>(cf, b, s_lut, g, cnt, tails); break;
-                case 5: screen_small<5>(cf, b, s_lut, g, cnt, tails); break;
-                case 6: screen_small<6>(cf, b, s_lut, g, cnt, tails); break;
-                case 7: screen_small<7>(cf, b, s_lut, g, cnt, tails); break;
-                default: screen_small<8>(cf, b, s_lut, g, cnt, tails); break;
-            }
+            if (K == 1) screen_small<1>(cf, b, s_lut, g, cnt, K, first, tails);
+            else if (K == 2) screen_small<2>(cf, b, s_lut, g, cnt, K, first, tails);
+            else if (K <= 4) screen_small<4>(cf, b, s_lut, g, cnt, K, first, tails);
+            else screen_small<8>(cf, b, s_lut, g, cnt, K, first, tails);
             const double tv = lane == 0 ? tails[0] : lane == 1 ? tails[1] : lane == 2 ? tails[2] : tails[3];
             if (lane < 4) ws.tails[4 * c + lane] = tv;
         }
