@@ -12,7 +12,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -43,6 +48,69 @@ static int fail(const char *fmt, ...)
 extern "C" const char *lfb200_last_error(void) { return g_err; }
 
 // ------------------------------------------------------------------------------------------------
+// A few persistent worker threads for the long double finishing (FE flags and errno are per thread).
+class WorkerPool {
+public:
+    explicit WorkerPool(unsigned n) : stop_(false), gen_(0), pending_(0)
+    {
+        for (unsigned i = 0; i < n; ++i) threads_.emplace_back([this, i] { loop(i); });
+    }
+    ~WorkerPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    unsigned size() const { return (unsigned)threads_.size(); }
+    // runs fn(part, nparts) on every worker and on the caller; returns when all are done
+    void run(const std::function<void(unsigned, unsigned)> &fn)
+    {
+        const unsigned parts = size() + 1;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn;
+            pending_ = size();
+            ++gen_;
+        }
+        cv_.notify_all();
+        fn(parts - 1, parts);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    void loop(unsigned id)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(unsigned, unsigned)> *fn;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            (*fn)(id, size() + 1);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(unsigned, unsigned)> *fn_ = nullptr;
+    bool stop_;
+    unsigned long long gen_;
+    unsigned pending_;
+};
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -81,7 +149,22 @@ struct lfb200_ctx {
     DevBuf p_ep, p_off, p_cnt, p_bonf, p_out;
     // pinned scratch for small D2H transfers
     Counters *h_counters = nullptr;
-    std::vector<Cand> h_cand;
+    Cand *h_cand = nullptr;              // pinned
+    size_t h_cand_cap = 0;
+    std::vector<lfb200_site_t> h_sites;  // finished in device order, then emitted sorted by column
+    std::vector<std::pair<long long, unsigned>> h_order;
+    std::unique_ptr<WorkerPool> pool;
+    int ensure_cand(size_t n)
+    {
+        if (n <= h_cand_cap) return 0;
+        if (h_cand) cudaFreeHost(h_cand);
+        h_cand = nullptr;
+        h_cand_cap = 0;
+        const size_t want = n + n / 4 + 1024;
+        if (cudaMallocHost(&h_cand, want * sizeof(Cand)) != cudaSuccess) { cudaGetLastError(); return 1; }
+        h_cand_cap = want;
+        return 0;
+    }
     // optional per-phase timing (lfb200_set_profiling): events on the launching stream
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -214,6 +297,8 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     for (DevBuf *b : bufs) b->release();
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_cand) cudaFreeHost(ctx->h_cand);
+    ctx->pool.reset();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -389,36 +474,33 @@ extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *s
         for (int i = 0; i < NCLASS; ++i) sm.n_heavy += c.n_jobs[i];
     }
     if (n_cand > max_sites) return fail("%lld sites but room for %lld", n_cand, max_sites);
-    ctx->h_cand.resize((size_t)n_cand);
+    if (ctx->ensure_cand((size_t)n_cand)) return fail("out of pinned host memory");
     if (n_cand) {
-        CU(cudaMemcpyAsync(ctx->h_cand.data(), ctx->ws.cand, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_cand, ctx->ws.cand, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
-    std::sort(ctx->h_cand.begin(), ctx->h_cand.end(), [](const Cand &a, const Cand &b) { return a.col < b.col; });
-    const double sig = (double)conf->sig;
+    const Cand *cands = ctx->h_cand;
     for (long long i = 0; i < n_cand; ++i)
-        if (ctx->h_cand[(size_t)i].flags & CF_RANGE)
-            return fail("column %lld: tail outside the representable range", ctx->h_cand[(size_t)i].col);
-    // long double finishing: independent per site (FE flags and errno are per thread)
-    {
-        const Cand *cands = ctx->h_cand.data();
-        unsigned nthr = std::thread::hardware_concurrency();
-        nthr = std::max(1u, std::min(nthr, 16u));
-        if (n_cand < 2048) nthr = 1;
-        auto work = [&](long long lo, long long hi) {
-            for (long long i = lo; i < hi; ++i) finish_site(cands[i], sig, sites[i]);
-        };
-        if (nthr == 1) {
-            work(0, n_cand);
-        } else {
-            std::vector<std::thread> pool;
-            const long long per = (n_cand + nthr - 1) / nthr;
-            for (unsigned t = 0; t < nthr; ++t) {
-                const long long lo = t * per, hi = std::min<long long>(n_cand, lo + per);
-                if (lo < hi) pool.emplace_back(work, lo, hi);
-            }
-            for (auto &th : pool) th.join();
+        if (cands[i].flags & CF_RANGE) return fail("column %lld: tail outside the representable range", cands[i].col);
+    // long double finishing, independent per site; then emit in column order (device order is arbitrary)
+    const double sig = (double)conf->sig;
+    ctx->h_order.resize((size_t)n_cand);
+    for (long long i = 0; i < n_cand; ++i) ctx->h_order[(size_t)i] = std::make_pair(cands[i].col, (unsigned)i);
+    std::sort(ctx->h_order.begin(), ctx->h_order.end());
+    const std::pair<long long, unsigned> *order = ctx->h_order.data();
+    auto work = [&](unsigned part, unsigned parts) {
+        const long long per = (n_cand + parts - 1) / parts;
+        const long long lo = (long long)part * per, hi = std::min<long long>(n_cand, lo + per);
+        for (long long i = lo; i < hi; ++i) finish_site(cands[order[i].second], sig, sites[i]);
+    };
+    if (n_cand < 1024) {
+        work(0, 1);
+    } else {
+        if (!ctx->pool) {
+            unsigned hw = std::thread::hardware_concurrency();
+            ctx->pool.reset(new WorkerPool(std::max(1u, std::min(hw, 16u)) - 1));
         }
+        ctx->pool->run(work);
     }
     sm.n_sites = n_cand;
     sm.bonf_subst_final = final_bonf(conf, sm.n_tested);
@@ -575,8 +657,8 @@ extern "C" int lfb200_snpcaller_batch(lfb200_ctx *ctx, long long n, const double
     if (ctx->p_out.ensure((size_t)n * sizeof(Cand))) return fail("out of device memory");
     launch_prob_jobs(pb, (Cand *)ctx->p_out.p, st);
     CU(cudaGetLastError());
-    ctx->h_cand.resize((size_t)n);
-    CU(cudaMemcpyAsync(ctx->h_cand.data(), ctx->p_out.p, (size_t)n * sizeof(Cand), cudaMemcpyDeviceToHost, st));
+    if (ctx->ensure_cand((size_t)n)) return fail("out of pinned host memory");
+    CU(cudaMemcpyAsync(ctx->h_cand, ctx->p_out.p, (size_t)n * sizeof(Cand), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     for (long long i = 0; i < n; ++i) {
         const Cand &cd = ctx->h_cand[(size_t)i];

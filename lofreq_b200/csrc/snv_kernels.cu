@@ -675,7 +675,7 @@ __device__ __forceinline__ void dp_run(const Src &src, int K, double ln_s, doubl
     row.T = 0.0;
     row.e2 = 0;
     row.ln_s = ln_s;
-    double lq_acc = 0.0;
+    double lq_acc = 0.0, q_prod = 1.0;      // sum of ln q = lq_acc + ln(q_prod); the log is taken once per ~hundreds of reads
     const int n = src.size();
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int n0 = 0; n0 < n; n0 += 32) {
@@ -685,9 +685,13 @@ __device__ __forceinline__ void dp_run(const Src &src, int K, double ln_s, doubl
         if (ok) {
             double p, q;
             guard_pq(jp, p, q);
-            o = p * s / q;
             rq = 1.0 / q;
-            lq_acc += log(q);
+            o = p * s * rq;
+            q_prod *= q;
+            if (q_prod < 1e-200) {
+                lq_acc += log(q_prod);
+                q_prod = 1.0;
+            }
         }
         const unsigned m = __ballot_sync(FULL, ok);
         const int cnt = __popc(m);
@@ -708,6 +712,7 @@ __device__ __forceinline__ void dp_run(const Src &src, int K, double ln_s, doubl
         }
         if (!slow) rescale<R>(row, false);
     }
+    lq_acc += log(q_prod);
     row.sum_lq = warp_sum(lq_acc);
 }
 
@@ -730,10 +735,10 @@ __device__ double newton_tilt(const Src &src, int K, int N, double lam)
             if (!src.get(pos, jp)) continue;
             double p, q;
             guard_pq(jp, p, q);
-            const double o = p * s / q;
-            const double w = o / (1.0 + o);
+            const double ps = p * s;
+            const double w = ps / (q + ps);        // o/(1+o)
             g += w;
-            d += w / (1.0 + o);
+            d += w * (1.0 - w);                    // derivative with respect to ln s = variance of the tilted sum
         }
         g = warp_sum(g) - kt;
         d = warp_sum(d);
@@ -742,7 +747,8 @@ __device__ double newton_tilt(const Src &src, int K, int N, double lam)
         if (g > 0.0) hi = fmin(hi, ls); else lo = fmax(lo, ls);
         double nl = d > 0.0 ? ls - g / d : 0.5 * (lo + hi);
         if (!(nl > lo && nl < hi)) nl = 0.5 * (lo + hi);
-        const bool done = fabs(nl - ls) < 1e-3;
+        // an error e in ln s costs about d*e^2/2 nats of head-room (of ~700): stop once that is negligible
+        const bool done = fabs(nl - ls) * sqrt(fmax(d, 1.0)) < 0.5;
         ls = nl;
         if (done) break;
     }
@@ -1015,16 +1021,32 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
     cudaMemsetAsync(reinterpret_cast<char *>(ws.counters) + 8, 0, sizeof(Counters) - 8, st);
     k_finalize<<<nb, 1024, 0, st>>>(cf, b.n_cols, ws);
     if (after_finalize) cudaEventRecord(after_finalize, st);
+    // The register-tile classes are independent: run them side by side so that their warps share the SMs
+    // (each class alone has too few columns to hide its own latencies).
+    static cudaStream_t side[NCLASS] = {nullptr};
+    static cudaEvent_t ev_fork = nullptr, ev_join[NCLASS] = {nullptr};
+    if (!ev_fork) {
+        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+        for (int i = 0; i < NCLASS; ++i) {
+            cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
+        }
+    }
     const int g = sm_count() * 4;
-    // largest tiles first: they are the long poles
-    k_heavy_xl<<<1, 32, 0, st>>>(ws, 7);
-    k_heavy<64><<<g, 128, 0, st>>>(cf, b, lut, ws, 6);
-    k_heavy<32><<<g, 128, 0, st>>>(cf, b, lut, ws, 5);
-    k_heavy<16><<<g, 128, 0, st>>>(cf, b, lut, ws, 4);
-    k_heavy<8><<<g, 128, 0, st>>>(cf, b, lut, ws, 3);
-    k_heavy<4><<<g, 128, 0, st>>>(cf, b, lut, ws, 2);
-    k_heavy<2><<<g, 128, 0, st>>>(cf, b, lut, ws, 1);
-    k_heavy<1><<<g, 128, 0, st>>>(cf, b, lut, ws, 0);
+    cudaEventRecord(ev_fork, st);
+    for (int i = 0; i < NCLASS; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
+    k_heavy_xl<<<1, 32, 0, side[7]>>>(ws, 7);
+    k_heavy<64><<<g, 128, 0, side[6]>>>(cf, b, lut, ws, 6);
+    k_heavy<32><<<g, 128, 0, side[5]>>>(cf, b, lut, ws, 5);
+    k_heavy<16><<<g, 128, 0, side[4]>>>(cf, b, lut, ws, 4);
+    k_heavy<8><<<g, 128, 0, side[3]>>>(cf, b, lut, ws, 3);
+    k_heavy<4><<<g, 128, 0, side[2]>>>(cf, b, lut, ws, 2);
+    k_heavy<2><<<g, 128, 0, side[1]>>>(cf, b, lut, ws, 1);
+    k_heavy<1><<<g, 128, 0, side[0]>>>(cf, b, lut, ws, 0);
+    for (int i = 0; i < NCLASS; ++i) {
+        cudaEventRecord(ev_join[i], side[i]);
+        cudaStreamWaitEvent(st, ev_join[i], 0);
+    }
 }
 
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st)
