@@ -4,6 +4,7 @@
 // like the reference: expl(), the FE-exception clamp, pvalue*bonf < sig, PROB_TO_PHREDQUAL.
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
 #include <cfenv>
 #include <cfloat>
 #include <climits>
@@ -152,7 +153,7 @@ struct lfb200_ctx {
     Cand *h_cand = nullptr;              // pinned
     size_t h_cand_cap = 0;
     std::vector<lfb200_site_t> h_sites;  // finished in device order, then emitted sorted by column
-    std::vector<std::pair<long long, unsigned>> h_order;
+    std::vector<std::pair<long long, unsigned>> h_order, h_order2;
     std::unique_ptr<WorkerPool> pool;
     int ensure_cand(size_t n)
     {
@@ -463,6 +464,10 @@ extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *s
     memset(&sm, 0, sizeof(sm));
     sm.n_cols = ctx->cur.n_cols;
     long long n_cand = 0;
+    static const bool dbg = getenv("LFB200_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = dbg ? now() : 0.0;
+    double t1 = 0, t2 = 0, t3 = 0;
     if (ctx->cur.n_cols > 0) {
         CU(cudaMemcpyAsync(ctx->h_counters, ctx->ws.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -473,21 +478,37 @@ extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *s
         n_cand = c.n_cand;
         for (int i = 0; i < NCLASS; ++i) sm.n_heavy += c.n_jobs[i];
     }
+    if (dbg) t1 = now();
     if (n_cand > max_sites) return fail("%lld sites but room for %lld", n_cand, max_sites);
     if (ctx->ensure_cand((size_t)n_cand)) return fail("out of pinned host memory");
     if (n_cand) {
         CU(cudaMemcpyAsync(ctx->h_cand, ctx->ws.cand, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
+    if (dbg) t2 = now();
     const Cand *cands = ctx->h_cand;
     for (long long i = 0; i < n_cand; ++i)
         if (cands[i].flags & CF_RANGE) return fail("column %lld: tail outside the representable range", cands[i].col);
     // long double finishing, independent per site; then emit in column order (device order is arbitrary)
     const double sig = (double)conf->sig;
+    // column order: LSD radix sort of (col, index) pairs, 3 passes of 11 bits (n_cols < 2^31)
     ctx->h_order.resize((size_t)n_cand);
+    ctx->h_order2.resize((size_t)n_cand);
     for (long long i = 0; i < n_cand; ++i) ctx->h_order[(size_t)i] = std::make_pair(cands[i].col, (unsigned)i);
-    std::sort(ctx->h_order.begin(), ctx->h_order.end());
+    {
+        std::pair<long long, unsigned> *a = ctx->h_order.data(), *b2 = ctx->h_order2.data();
+        for (int pass = 0; pass < 3; ++pass) {
+            unsigned hist[2049] = {0};
+            const int sh = 11 * pass;
+            for (long long i = 0; i < n_cand; ++i) ++hist[((a[i].first >> sh) & 2047) + 1];
+            for (int d = 0; d < 2048; ++d) hist[d + 1] += hist[d];
+            for (long long i = 0; i < n_cand; ++i) b2[hist[(a[i].first >> sh) & 2047]++] = a[i];
+            std::swap(a, b2);
+        }
+        if (a != ctx->h_order.data()) ctx->h_order.swap(ctx->h_order2);
+    }
     const std::pair<long long, unsigned> *order = ctx->h_order.data();
+    if (dbg) t3 = now();
     auto work = [&](unsigned part, unsigned parts) {
         const long long per = (n_cand + parts - 1) / parts;
         const long long lo = (long long)part * per, hi = std::min<long long>(n_cand, lo + per);
@@ -502,6 +523,9 @@ extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *s
         }
         ctx->pool->run(work);
     }
+    if (dbg)
+        fprintf(stderr, "[lfb200] sites: wait+counters %.0f us, cand D2H %.0f us, sort %.0f us, finish %.0f us (%lld sites)\n",
+                t1 - t0, t2 - t1, t3 - t2, now() - t3, n_cand);
     sm.n_sites = n_cand;
     sm.bonf_subst_final = final_bonf(conf, sm.n_tested);
     conf->bonf_subst = sm.bonf_subst_final;
