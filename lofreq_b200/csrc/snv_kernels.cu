@@ -279,47 +279,100 @@ __device__ __forceinline__ void load_chunk(const DevConf &cf, const DevBatch &b,
     ch.sq = cf.use_sq ? ldg16(b.sq + a) : zero;
 }
 
-// fold the reads of one 16-byte chunk into the lane's truncated distribution.  One code path for
-// reference and alt reads (divergence between lanes would execute both anyway).
-template <int KV>
-__device__ __forceinline__ void fold_chunk(const DevConf &cf, const double *s_lut, const Geom &g, int ref_lo, int ref_hi,
-                                           int pos0, const Chunk16 &ch, double (&P)[KV], double &T)
+__device__ __forceinline__ double lds_f64(unsigned saddr)
 {
-    const bool general_merge = cf.use_baq | cf.use_sq;
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+    return v;
+}
+
+// What the per-read loop needs from DevConf, hoisted into registers once per column.
+struct ReadRules {
+    int min_bq, min_alt;           // bq thresholds for reference / alt reads
+    double skip, skip_alt;         // merged-probability cut-offs (+inf when the jq filters are off)
+    bool use_mq, general_merge, use_baq, use_sq, alt_bq, alt_jq;
+    double alt_bp, alt_jp;
+};
+
+// Fold the reads of one 16-byte chunk into the lane's truncated distribution.
+// UNIFORM: the configuration treats reference and alt reads alike in this sweep (defaults: min_alt_bq <=
+// min_bq, no def_alt_bq / def_alt_jq, no jq filters, min_bq >= 1) — bytes outside the column were zeroed by
+// the caller, so the bq filter drops them and no position bookkeeping is needed.  With bq >= 1 every
+// probability is <= 0.96, so the q-guard of snpcaller.c:877 cannot fire and the p-guard is max(p, DBL_EPSILON).
+template <int KV, bool UNIFORM>
+__device__ __forceinline__ void fold_chunk(const ReadRules &rr, unsigned lut_sa, int n, int ref_lo, int ref_hi, int pos0,
+                                           const Chunk16 &ch, double (&P)[KV], double &T)
+{
 #pragma unroll 1
     for (int w = 0; w < 4; ++w) {
         unsigned wbq = w == 0 ? ch.bq.x : w == 1 ? ch.bq.y : w == 2 ? ch.bq.z : ch.bq.w;
         unsigned wmq = w == 0 ? ch.mq.x : w == 1 ? ch.mq.y : w == 2 ? ch.mq.z : ch.mq.w;
-        unsigned wbaq = w == 0 ? ch.baq.x : w == 1 ? ch.baq.y : w == 2 ? ch.baq.z : ch.baq.w;
-        unsigned wsq = w == 0 ? ch.sq.x : w == 1 ? ch.sq.y : w == 2 ? ch.sq.z : ch.sq.w;
+        if (UNIFORM) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int bq = (wbq >> (8 * j)) & 0xff;
+                if (bq < rr.min_bq) continue;
+                const double bp = lds_f64(lut_sa + 8 * bq);
+                double jp = bp;
+                if (rr.use_mq) {
+                    const double mp = lds_f64(lut_sa + 2048 + 8 * ((wmq >> (8 * j)) & 0xff));
+                    jp = __dadd_rn(mp, __dmul_rn(__dsub_rn(1.0, mp), bp));   // sp = bap = 0: the dropped terms are exact
+                }
+                const double q = 1.0 - jp;
+                if (jp < DEPS) jp = DEPS;
+                lane_update<KV>(P, T, jp, q);
+            }
+        } else {
+            unsigned wbaq = w == 0 ? ch.baq.x : w == 1 ? ch.baq.y : w == 2 ? ch.baq.z : ch.baq.w;
+            unsigned wsq = w == 0 ? ch.sq.x : w == 1 ? ch.sq.y : w == 2 ? ch.sq.z : ch.sq.w;
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j, wbq >>= 8, wmq >>= 8, wbaq >>= 8, wsq >>= 8) {
-            const int pos = pos0 + 4 * w + j;
-            const int bq = wbq & 0xff;
-            const bool is_alt = pos < ref_lo || pos >= ref_hi;
-            if (pos < 0 || pos >= g.n || bq < (is_alt ? max(cf.min_bq, cf.min_alt_bq) : cf.min_bq)) continue;
-            double bp = s_lut[bq];
-            if (is_alt && cf.alt_bq_mode) bp = g.alt_bp;
-            const double mp = cf.use_mq ? s_lut[256 + (wmq & 0xff)] : 0.0;
-            double jp;
-            if (general_merge)
-                jp = merge4(cf.use_sq ? s_lut[512 + (wsq & 0xff)] : 0.0, mp, cf.use_baq ? s_lut[512 + (wbaq & 0xff)] : 0.0, bp);
-            else
-                jp = __dadd_rn(mp, __dmul_rn(__dsub_rn(1.0, mp), bp));   // sp = bap = 0: the dropped terms are exact
-            if (jp >= (is_alt ? fmin(cf.skip_jp, cf.skip_alt_jp) : cf.skip_jp)) continue;   // +inf unless min_jq/min_alt_jq > 0
-            if (is_alt && cf.def_alt_jq_on) jp = cf.def_alt_jq_prob;
-            double q = 1.0 - jp;
-            if (jp < DEPS || fabs(q) < DEPS) guard_pq(jp, jp, q);
-            lane_update<KV>(P, T, jp, q);
+            for (int j = 0; j < 4; ++j, wbq >>= 8, wmq >>= 8, wbaq >>= 8, wsq >>= 8) {
+                const int pos = pos0 + 4 * w + j;
+                const int bq = wbq & 0xff;
+                const bool is_alt = pos < ref_lo || pos >= ref_hi;
+                if (pos < 0 || pos >= n || bq < (is_alt ? rr.min_alt : rr.min_bq)) continue;
+                double bp = lds_f64(lut_sa + 8 * bq);
+                if (is_alt && rr.alt_bq) bp = rr.alt_bp;
+                const double mp = rr.use_mq ? lds_f64(lut_sa + 2048 + 8 * (wmq & 0xff)) : 0.0;
+                double jp;
+                if (rr.general_merge)
+                    jp = merge4(rr.use_sq ? lds_f64(lut_sa + 4096 + 8 * (wsq & 0xff)) : 0.0, mp,
+                                rr.use_baq ? lds_f64(lut_sa + 4096 + 8 * (wbaq & 0xff)) : 0.0, bp);
+                else
+                    jp = __dadd_rn(mp, __dmul_rn(__dsub_rn(1.0, mp), bp));
+                if (jp >= (is_alt ? rr.skip_alt : rr.skip)) continue;
+                if (is_alt && rr.alt_jq) jp = rr.alt_jp;
+                double q = 1.0 - jp;
+                if (jp < DEPS || fabs(q) < DEPS) guard_pq(jp, jp, q);
+                lane_update<KV>(P, T, jp, q);
+            }
         }
     }
+}
+
+// zero the bytes of a chunk that lie outside [0, n) of the column (UNIFORM path: bq 0 is filtered out)
+__device__ __forceinline__ void mask_chunk(uint4 &v, int pos0, int n)
+{
+    if (pos0 >= 0 && pos0 + 16 <= n) return;
+    unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        unsigned m = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pos = pos0 + 4 * k + j;
+            if (pos >= 0 && pos < n) m |= 0xffu << (8 * j);
+        }
+        w[k] &= m;
+    }
+    v = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // Second sweep of a tested column with K <= KS: every lane folds the reads of its 16-byte chunks into a
 // distribution truncated at KV >= K, then the 32 distributions are merged.  The first chunk of every lane
 // was loaded before the alt counts were known (one memory round trip per column instead of two).
 template <int KV>
-__device__ __forceinline__ void screen_small(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &g,
+__device__ __forceinline__ void screen_small(const DevConf &cf, const DevBatch &b, unsigned lut_sa, const Geom &g,
                                              const int (&cnt)[3], int K, const Chunk16 &first, double (&tails)[4])
 {
     const int lane = lane_id();
@@ -331,11 +384,32 @@ __device__ __forceinline__ void screen_small(const DevConf &cf, const DevBatch &
     const int nchunks = (lead + g.n + 15) >> 4;
     int ref_lo, ref_hi;
     ref_range(g, ref_lo, ref_hi);
+    ReadRules rr;
+    rr.min_bq = cf.min_bq;
+    rr.min_alt = max(cf.min_bq, cf.min_alt_bq);
+    rr.skip = cf.skip_jp;
+    rr.skip_alt = fmin(cf.skip_jp, cf.skip_alt_jp);
+    rr.use_mq = cf.use_mq;
+    rr.use_baq = cf.use_baq;
+    rr.use_sq = cf.use_sq;
+    rr.general_merge = cf.use_baq | cf.use_sq;
+    rr.alt_bq = cf.alt_bq_mode != 0;
+    rr.alt_bp = g.alt_bp;
+    rr.alt_jq = cf.def_alt_jq_on != 0;
+    rr.alt_jp = cf.def_alt_jq_prob;
+    const bool uniform = cf.min_bq >= 1 && cf.min_alt_bq <= cf.min_bq && !rr.alt_bq && !rr.alt_jq && !cf.jq_filters &&
+                         !rr.general_merge;
     Chunk16 ch = first;
 #pragma unroll 1
     for (int i = lane; i < nchunks; i += 32) {
         if (i != lane) load_chunk(cf, b, abase + 16ll * i, ch);
-        fold_chunk<KV>(cf, s_lut, g, ref_lo, ref_hi, 16 * i - lead, ch, P, T);
+        const int pos0 = 16 * i - lead;
+        if (uniform) {
+            mask_chunk(ch.bq, pos0, g.n);
+            fold_chunk<KV, true>(rr, lut_sa, g.n, ref_lo, ref_hi, pos0, ch, P, T);
+        } else {
+            fold_chunk<KV, false>(rr, lut_sa, g.n, ref_lo, ref_hi, pos0, ch, P, T);
+        }
     }
     tree_merge<KV>(P, T);
     small_tails<KV>(P, T, cnt, K, tails);
@@ -356,45 +430,70 @@ __device__ __forceinline__ void load_raw(const DevBatch &b, long long c, RawGeom
     r.cov = b.coverage ? __ldg(b.coverage + c) : -1;
 }
 
+// Work distribution: a warp takes 32 consecutive columns at a time.  Metadata, gates and the "does this
+// column show any non-reference base at all" test run lane-per-column (most columns stop here and cost a
+// fraction of an instruction per lane); the columns that do are then processed one by one by the whole warp.
 __global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
                                                    const Lut *lut, const Workspace ws)
 {
     __shared__ double s_lut[768];
     __shared__ int s_hist[8][256];
     load_lut(s_lut, lut);
+    unsigned lut_sa = (unsigned)__cvta_generic_to_shared(s_lut);
+    asm volatile("" : "+r"(lut_sa));          // keep the shared-window address in a register
     const int lane = lane_id();
     const int wib = threadIdx.x >> 5;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
 
     RawGeom nxt;
-    if (warp0 < b.n_cols) load_raw(b, warp0, nxt);
-    for (long long c = warp0; c < b.n_cols; c += nwarps) {
+    nxt.off = 0; nxt.cnt = make_int4(0, 0, 0, 0); nxt.cov = -1; nxt.ref = 'N';
+    if (warp0 * 32 + lane < b.n_cols) load_raw(b, warp0 * 32 + lane, nxt);
+    for (long long base = warp0 * 32; base < b.n_cols; base += nwarps * 32) {
+        const long long c_mine = base + lane;
         const RawGeom cur = nxt;
-        if (c + nwarps < b.n_cols) load_raw(b, c + nwarps, nxt);     // metadata of the next column: in flight during this one
-        Geom g;
-        g.off = cur.off;
-        g.b1 = cur.cnt.x;
-        g.b2 = g.b1 + cur.cnt.y;
-        g.b3 = g.b2 + cur.cnt.z;
-        g.n = g.b3 + cur.cnt.w;
-        g.ref_idx = ref_index(cur.ref);
-        g.alt_bp = 0.0;
-        const int cov = cur.cov < 0 ? g.n : cur.cov;
-        int cnt[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
-        const bool gate = g.ref_idx >= 0 && !(g.n * 2 < cov) && !(g.n < cf.min_cov);   // lofreq_call.c:892,931,747,754
-        int ref_lo, ref_hi;
-        ref_range(g, ref_lo, ref_hi);
-        const int n_alt = g.n - (ref_hi - ref_lo);
-        Chunk16 first;
-        first.bq = first.mq = first.baq = first.sq = make_uint4(0, 0, 0, 0);
-        if (gate && n_alt > 0) {
+        if (c_mine + nwarps * 32 < b.n_cols) load_raw(b, c_mine + nwarps * 32, nxt);   // next group's metadata in flight
+        // ---- lane per column ----
+        const int m_b1 = cur.cnt.x, m_b2 = m_b1 + cur.cnt.y, m_b3 = m_b2 + cur.cnt.z, m_n = m_b3 + cur.cnt.w;
+        const int m_ref = ref_index(cur.ref);
+        const int m_cov = cur.cov < 0 ? m_n : cur.cov;
+        const bool m_gate = c_mine < b.n_cols && m_ref >= 0 && !(m_n * 2 < m_cov) && !(m_n < cf.min_cov);   // lofreq_call.c:892,931,747,754
+        const int m_refcnt = m_ref == 0 ? cur.cnt.x : m_ref == 1 ? cur.cnt.y : m_ref == 2 ? cur.cnt.z : cur.cnt.w;
+        const bool m_need = m_gate && (m_n - m_refcnt) > 0;
+        if (c_mine < b.n_cols && !m_need) {
+            // no non-reference base (or gated out): not a test (lofreq_call.c:768-780), all counts zero
+            int2 *o = reinterpret_cast<int2 *>(ws.cnt6 + 6 * c_mine);
+            o[0] = make_int2(0, 0);
+            o[1] = make_int2(0, 0);
+            o[2] = make_int2(0, 0);
+            ws.tested[c_mine] = 0;
+        }
+        // ---- whole warp per remaining column ----
+        unsigned todo = __ballot_sync(FULL, m_need);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long long c = base + src;
+            Geom g;
+            g.off = __shfl_sync(FULL, cur.off, src);
+            g.b1 = __shfl_sync(FULL, m_b1, src);
+            g.b2 = __shfl_sync(FULL, m_b2, src);
+            g.b3 = __shfl_sync(FULL, m_b3, src);
+            g.n = __shfl_sync(FULL, m_n, src);
+            g.ref_idx = __shfl_sync(FULL, m_ref, src);
+            g.alt_bp = 0.0;
+            int ref_lo, ref_hi;
+            ref_range(g, ref_lo, ref_hi);
+            const int n_alt = g.n - (ref_hi - ref_lo);
             // issue this lane's share of the first 512-read stripe now; it is consumed after the alt counts
+            Chunk16 first;
+            first.bq = first.mq = first.baq = first.sq = make_uint4(0, 0, 0, 0);
             const long long abase = g.off & ~15ll;
             if (16 * lane < (int)(g.off - abase) + g.n) load_chunk(cf, b, abase + 16ll * lane, first);
             // First sweep: only reads that show a non-reference base decide whether the column is tested
             // and what K is, so only those are looked at (alt counts, snpcaller.c:418-420,489).
             setup_alt_bq(cf, b, s_lut, g, s_hist[wib]);
+            int cnt[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
             for (int i = lane; i < n_alt; i += 32) {
                 const int pos = i < ref_lo ? i : i - ref_lo + ref_hi;
                 const long long a = g.off + pos;
@@ -423,22 +522,27 @@ __global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevCo
                 cnt[i] = __reduce_add_sync(FULL, cnt[i]);
                 raw[i] = __reduce_add_sync(FULL, raw[i]);
             }
-        }
-        const int K = max(cnt[0], max(cnt[1], cnt[2]));
-        const bool tested = gate && K > 0;     // lofreq_call.c:768-780: no alt left -> not a test
-        {
-            const int v = lane == 0 ? cnt[0] : lane == 1 ? cnt[1] : lane == 2 ? cnt[2] : lane == 3 ? raw[0] : lane == 4 ? raw[1] : raw[2];
-            if (lane < 6) ws.cnt6[6 * c + lane] = v;
-        }
-        if (lane == 0) ws.tested[c] = tested ? 1 : 0;
-        if (tested && K <= KS) {
-            double tails[4];
-            if (K == 1) screen_small<1>(cf, b, s_lut, g, cnt, K, first, tails);
-            else if (K == 2) screen_small<2>(cf, b, s_lut, g, cnt, K, first, tails);
-            else if (K <= 4) screen_small<4>(cf, b, s_lut, g, cnt, K, first, tails);
-            else screen_small<8>(cf, b, s_lut, g, cnt, K, first, tails);
-            const double tv = lane == 0 ? tails[0] : lane == 1 ? tails[1] : lane == 2 ? tails[2] : tails[3];
-            if (lane < 4) ws.tails[4 * c + lane] = tv;
+            const int K = max(cnt[0], max(cnt[1], cnt[2]));
+            const bool tested = K > 0;     // lofreq_call.c:768-780: no alt left after filtering -> not a test
+            if (lane == 0) {
+                int2 *o = reinterpret_cast<int2 *>(ws.cnt6 + 6 * c);
+                o[0] = make_int2(cnt[0], cnt[1]);
+                o[1] = make_int2(cnt[2], raw[0]);
+                o[2] = make_int2(raw[1], raw[2]);
+                ws.tested[c] = tested ? 1 : 0;
+            }
+            if (tested && K <= KS) {
+                double tails[4];
+                if (K == 1) screen_small<1>(cf, b, lut_sa, g, cnt, K, first, tails);
+                else if (K == 2) screen_small<2>(cf, b, lut_sa, g, cnt, K, first, tails);
+                else if (K <= 4) screen_small<4>(cf, b, lut_sa, g, cnt, K, first, tails);
+                else screen_small<8>(cf, b, lut_sa, g, cnt, K, first, tails);
+                if (lane == 0) {
+                    double2 *o = reinterpret_cast<double2 *>(ws.tails + 4 * c);
+                    o[0] = make_double2(tails[0], tails[1]);
+                    o[1] = make_double2(tails[2], tails[3]);
+                }
+            }
         }
     }
 }
@@ -999,8 +1103,9 @@ static int sm_count()
 void launch_screen(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st)
 {
     if (b.n_cols <= 0) return;
-    const long long want = (b.n_cols + 7) / 8;
-    const int grid = (int)(want < (long long)sm_count() * 8 ? want : (long long)sm_count() * 8);
+    // one resident wave: 4 CTAs of 8 warps per SM, every warp strides over groups of 32 columns
+    const long long want = (b.n_cols + 255) / 256;
+    const int grid = (int)(want < (long long)sm_count() * 4 ? want : (long long)sm_count() * 4);
     k_screen<<<grid, 256, 0, st>>>(cf, b, lut, ws);
 }
 
