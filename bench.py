@@ -97,7 +97,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -195,7 +195,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import lofreq_b200
-    from lofreq_b200 import capi, synth
+    from lofreq_b200 import capi, shard, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,7 +226,6 @@ def run_ours(args):
     sms = [capi.Summary(), capi.Summary()]
     sm = sms[0]
     confs = [None, None]
-    counts_dev = torch.zeros(world, dtype=torch.int64, device=dev)
 
     def launch(i):
         """screen -> (exchange tested counts) -> test for context i, asynchronous"""
@@ -236,11 +235,8 @@ def run_ours(args):
         if world > 1:
             nt = C.c_longlong()
             capi.check(lib.lfb200_ntested_device(ctx, sts[i], C.byref(nt)))
-            mine = torch.tensor([nt.value], dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(counts_dev, mine)
-            before = int(counts_dev[:rank].sum().item())
-            if before:
-                cf.bonf_subst = 3 * before          # the running factor of the shards before this one
+            counts = shard.gather_counts(nt.value, device=dev)       # 1 x int64 per rank over NCCL
+            cf.bonf_subst = shard.bonf_start_for_rank(counts, rank)  # running factor of the shards before this one
         capi.check(lib.lfb200_test_device(ctx, C.byref(cf), sts[i]))
         confs[i] = cf
 
@@ -249,9 +245,7 @@ def run_ours(args):
         capi.check(lib.lfb200_sites_device(callers[i]._ctx, C.byref(confs[i]), sts[i], sites_bufs[i], max_sites,
                                            C.byref(sms[i])))
         if world > 1:
-            # the final per-region variant-count gather (north_star): 1 x int64 per rank
-            mine = torch.tensor([sms[i].n_sites], dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(counts_dev, mine)
+            shard.gather_counts(sms[i].n_sites, device=dev)   # the final per-region variant-count gather (north_star)
         return sms[i]
 
     def run_steps(k_steps, prof=None):
@@ -319,7 +313,7 @@ def run_ours(args):
              ("bq", t["bq"][: total + 16]), ("mq", t["mq"][: total + 16]))}
     torch.cuda.synchronize()
     hb = capi.Batch(n, hb_t["col_off"].data_ptr(), hb_t["nt_cnt"].data_ptr(), hb_t["ref_base"].data_ptr(), None,
-                    hb_t["bq"].data_ptr(), hb_t["mq"].data_ptr(), None, None)
+                    hb_t["bq"].data_ptr(), hb_t["mq"].data_ptr(), None, None, None)
     h2d = 8 * (n + 1) + 16 * n + n + 2 * total
 
     def step_e2e():

@@ -72,6 +72,8 @@ typedef struct {
     const char *ref_base;              /* n_cols, uppercase */
     const int *coverage;               /* n_cols or NULL */
     const unsigned char *bq, *mq, *baq, *sq;
+    const int *num_bases;              /* n_cols or NULL (= reads in the column): plp_col_t.num_bases, which also
+                                        * counts reads showing N (plp.c:1019-1022); only the gates use it */
 } lfb200_batch_t;
 
 /* One column the device could not rule out (a candidate variant site), after
@@ -154,6 +156,34 @@ int lfb200_get_profile(lfb200_ctx *ctx, float *ms4);
  * column (alt_raw_counts = alt_counts + 3); tested u8[n]; bonf_used i64[n] */
 int lfb200_device_results(lfb200_ctx *ctx, const int **alt_counts, const int **alt_raw_counts,
                           const unsigned char **tested, const long long **bonf_used);
+
+/* ---- the per-column callback surface ---------------------------------------
+ * The reference hands one plp_col_t at a time to a callback
+ *   void (*plp_proc_func)(const plp_col_t *, void *)      (plp.h:159-163, plp.c:1443)
+ * and the pointer is only valid during the call (plp.c:1445).  A column
+ * builder copies what the SNV test needs out of the plp_col_t, batches
+ * batch_cols columns, runs them through lfb200_call_columns() and reports
+ * every site through on_site in input order — call_vars() (lofreq_call.c:886)
+ * becomes lfb200_builder_add_column(), and one lfb200_builder_flush() goes
+ * after mpileup() returns (lofreq_call.c:1477).  INTEGRATION.md has the adapter.
+ * conf is kept by reference: bonf_subst / num_snv_tests advance at each flush.
+ *
+ * add_column arguments, per nt4 index A,C,G,T (NUM_NT4 minus N):
+ *   quals[i] = plp_col_t.base_quals[i].data, n[i] = plp_col_t.base_quals[i].n   (plp.h:89, utils.h:60-66)
+ *   map_quals / baq_quals / source_quals likewise; the array pointer or any
+ *   entry may be NULL when that varray is empty (snpcaller.c:444-463 then
+ *   treats the quality as absent); a stored -1 means "not available".
+ * num_bases = plp_col_t.num_bases (gates of lofreq_call.c:747,931); tag is returned with the site
+ * (e.g. plp_col_t.pos). */
+typedef void (*lfb200_site_fn)(const lfb200_site_t *site, long long tag, char ref_base, int coverage_plp, void *user);
+typedef struct lfb200_builder lfb200_builder;
+int lfb200_builder_create(lfb200_builder **bld, lfb200_ctx *ctx, lfb200_conf_t *conf, long long batch_cols,
+                          lfb200_site_fn on_site, void *user);
+int lfb200_builder_add_column(lfb200_builder *bld, long long tag, char ref_base, int coverage_plp, int num_bases,
+                              const int *const base_quals[4], const int *const map_quals[4],
+                              const int *const baq_quals[4], const int *const source_quals[4], const int n[4]);
+int lfb200_builder_flush(lfb200_builder *bld);
+void lfb200_builder_destroy(lfb200_builder *bld);
 
 /* ---- link-compatible single-column symbols ----------------------------- */
 /* snpcaller() of snpcaller.h:97-102 (callers: lofreq_call.c:319,384,807,

@@ -21,7 +21,8 @@ class Conf(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("n_cols", C.c_longlong), ("col_off", C.c_void_p), ("nt_cnt", C.c_void_p),
                 ("ref_base", C.c_void_p), ("coverage", C.c_void_p),
-                ("bq", C.c_void_p), ("mq", C.c_void_p), ("baq", C.c_void_p), ("sq", C.c_void_p)]
+                ("bq", C.c_void_p), ("mq", C.c_void_p), ("baq", C.c_void_p), ("sq", C.c_void_p),
+                ("num_bases", C.c_void_p)]
 
 
 class Site(C.Structure):
@@ -62,10 +63,13 @@ class Summary(C.Structure):
                 ("n_heavy", C.c_longlong), ("bonf_subst_final", C.c_longlong), ("num_snv_tests", C.c_longlong)]
 
 
+SITE_FN = C.CFUNCTYPE(None, C.POINTER(Site), C.c_longlong, C.c_char, C.c_int, C.c_void_p)
+
 # every symbol include/lofreq_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_conf", "lfb200_call_columns",
            "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_sites_device",
-           "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_synth_depths",
+           "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
+           "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_synth_depths",
            "lfb200_synth_columns"]
 
 _lib = None
@@ -110,6 +114,14 @@ def load():
     lib.lfb200_set_profiling.argtypes = [vp, C.c_int]
     lib.lfb200_get_profile.restype = C.c_int
     lib.lfb200_get_profile.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.lfb200_builder_create.restype = C.c_int
+    lib.lfb200_builder_create.argtypes = [C.POINTER(vp), vp, C.POINTER(Conf), ll, SITE_FN, vp]
+    lib.lfb200_builder_add_column.restype = C.c_int
+    lib.lfb200_builder_add_column.argtypes = [vp, ll, C.c_char, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    lib.lfb200_builder_flush.restype = C.c_int
+    lib.lfb200_builder_flush.argtypes = [vp]
+    lib.lfb200_builder_destroy.restype = None
+    lib.lfb200_builder_destroy.argtypes = [vp]
     lib.lfb200_snpcaller.restype = C.c_int
     lib.lfb200_snpcaller.argtypes = [vp, vp, C.c_int, vp, ll, C.c_double, C.c_int]
     lib.lfb200_snpcaller_batch.restype = C.c_int

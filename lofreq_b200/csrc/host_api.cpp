@@ -145,7 +145,7 @@ struct lfb200_ctx {
     DevBuf w_cnt6, w_tested, w_tails, w_bonf, w_blocksum, w_jobs, w_cand, w_counters;
     Workspace ws{};
     // device copies of host batches (host entry point)
-    DevBuf in_off, in_cnt, in_ref, in_cov, in_bq, in_mq, in_baq, in_sq;
+    DevBuf in_off, in_cnt, in_ref, in_cov, in_nb, in_bq, in_mq, in_baq, in_sq;
     // single problems
     DevBuf p_ep, p_off, p_cnt, p_bonf, p_out;
     // pinned scratch for small D2H transfers
@@ -292,7 +292,7 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_tails, &ctx->w_bonf, &ctx->w_blocksum, &ctx->w_jobs,
-                      &ctx->w_cand, &ctx->w_counters, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov,
+                      &ctx->w_cand, &ctx->w_counters, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
                       &ctx->in_bq, &ctx->in_mq, &ctx->in_baq, &ctx->in_sq, &ctx->p_ep, &ctx->p_off, &ctx->p_cnt,
                       &ctx->p_bonf, &ctx->p_out};
     for (DevBuf *b : bufs) b->release();
@@ -399,6 +399,7 @@ static void to_devbatch(const lfb200_batch_t *b, DevBatch &d)
     d.mq = b->mq;
     d.baq = b->baq;
     d.sq = b->sq;
+    d.num_bases = b->num_bases;
 }
 
 extern "C" int lfb200_screen_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, const lfb200_batch_t *b, void *stream)
@@ -599,6 +600,8 @@ extern "C" int lfb200_call_columns(lfb200_ctx *ctx, lfb200_conf_t *conf, const l
     db.ref_base = (const char *)d;
     if (upload(ctx->in_cov, hb->coverage, (size_t)n * 4, 0, st, &d)) return 1;
     db.coverage = (const int *)d;
+    if (upload(ctx->in_nb, hb->num_bases, (size_t)n * 4, 0, st, &d)) return 1;
+    db.num_bases = (const int *)d;
     if (upload(ctx->in_bq, hb->bq, plane_bytes, 32, st, &d)) return 1;
     db.bq = (const unsigned char *)d;
     // planes the flags switch off are not needed on the device
@@ -653,6 +656,124 @@ extern "C" int lfb200_call_columns(lfb200_ctx *ctx, lfb200_conf_t *conf, const l
     if (summary) *summary = sm;
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// column builder: the per-column callback surface (plp.h:159-163) in front of the batched door
+// ------------------------------------------------------------------------------------------------
+struct lfb200_builder {
+    lfb200_ctx *ctx;
+    lfb200_conf_t *conf;
+    long long batch_cols;
+    lfb200_site_fn on_site;
+    void *user;
+    std::vector<long long> col_off, tags;
+    std::vector<int> nt_cnt, coverage, num_bases;
+    std::vector<char> ref;
+    std::vector<unsigned char> bq, mq, baq, sq;
+    bool any_mq = false, any_baq = false, any_sq = false;
+    std::vector<lfb200_site_t> sites;
+};
+
+extern "C" int lfb200_builder_create(lfb200_builder **out, lfb200_ctx *ctx, lfb200_conf_t *conf, long long batch_cols,
+                                     lfb200_site_fn on_site, void *user)
+{
+    *out = nullptr;
+    if (!ctx || !conf || !on_site) return fail("builder needs a context, a conf and a site callback");
+    if (batch_cols <= 0) return fail("batch_cols must be positive");
+    lfb200_builder *b = new lfb200_builder();
+    b->ctx = ctx;
+    b->conf = conf;
+    b->batch_cols = batch_cols;
+    b->on_site = on_site;
+    b->user = user;
+    b->col_off.push_back(0);
+    *out = b;
+    return 0;
+}
+
+static inline unsigned char qbyte(int q) { return q < 0 ? 255 : (q > 254 ? (q == 255 ? 255 : 254) : (unsigned char)q); }
+
+extern "C" int lfb200_builder_add_column(lfb200_builder *b, long long tag, char ref_base, int coverage_plp, int num_bases,
+                                         const int *const base_quals[4], const int *const map_quals[4],
+                                         const int *const baq_quals[4], const int *const source_quals[4], const int n[4])
+{
+    if (!b) return fail("no builder");
+    size_t total = 0;
+    for (int g = 0; g < 4; ++g) {
+        if (n[g] < 0 || (n[g] > 0 && !base_quals[g])) return fail("column %lld: bad base-quality group %d", tag, g);
+        total += (size_t)n[g];
+    }
+    const size_t at = b->bq.size();
+    const size_t pitch = (total + 15) & ~(size_t)15;          // 16-byte aligned columns: full-width loads on the device
+    b->bq.resize(at + pitch, 0);
+    b->mq.resize(at + pitch, 255);
+    b->baq.resize(at + pitch, 255);
+    b->sq.resize(at + pitch, 255);
+    size_t w = at;
+    for (int g = 0; g < 4; ++g) {
+        const int *mqv = map_quals ? map_quals[g] : nullptr;
+        const int *baqv = baq_quals ? baq_quals[g] : nullptr;
+        const int *sqv = source_quals ? source_quals[g] : nullptr;
+        for (int j = 0; j < n[g]; ++j, ++w) {
+            const int q = base_quals[g][j];
+            b->bq[w] = q < 0 ? 0 : (q > 255 ? 255 : (unsigned char)q);
+            // mq 255 is the SAM "unknown" which the reference maps to -1 itself (snpcaller.c:451-453)
+            if (mqv) { b->mq[w] = qbyte(mqv[j]); b->any_mq = true; }
+            if (baqv) { b->baq[w] = qbyte(baqv[j]); b->any_baq = true; }
+            if (sqv) { b->sq[w] = qbyte(sqv[j]); b->any_sq = true; }
+        }
+        b->nt_cnt.push_back(n[g]);
+    }
+    b->col_off.push_back((long long)(at + pitch));
+    b->ref.push_back(ref_base);
+    b->coverage.push_back(coverage_plp);
+    b->num_bases.push_back(num_bases);
+    b->tags.push_back(tag);
+    if ((long long)b->ref.size() >= b->batch_cols) return lfb200_builder_flush(b);
+    return 0;
+}
+
+extern "C" int lfb200_builder_flush(lfb200_builder *b)
+{
+    if (!b) return fail("no builder");
+    const long long n = (long long)b->ref.size();
+    if (n == 0) return 0;
+    lfb200_batch_t hb;
+    hb.n_cols = n;
+    hb.col_off = b->col_off.data();
+    hb.nt_cnt = b->nt_cnt.data();
+    hb.ref_base = b->ref.data();
+    hb.coverage = b->coverage.data();
+    hb.num_bases = b->num_bases.data();
+    // tail padding so that the device may read whole 16-byte chunks
+    for (auto *v : {&b->bq, &b->mq, &b->baq, &b->sq}) v->resize(v->size() + 32, 0);
+    hb.bq = b->bq.data();
+    hb.mq = b->any_mq ? b->mq.data() : nullptr;
+    hb.baq = b->any_baq ? b->baq.data() : nullptr;
+    hb.sq = b->any_sq ? b->sq.data() : nullptr;
+    b->sites.resize((size_t)n);
+    lfb200_summary_t sm;
+    const int rc = lfb200_call_columns(b->ctx, b->conf, &hb, nullptr, b->sites.data(), n, &sm);
+    if (rc == 0)
+        for (long long i = 0; i < sm.n_sites; ++i) {
+            const lfb200_site_t &s = b->sites[(size_t)i];
+            b->on_site(&s, b->tags[(size_t)s.col], b->ref[(size_t)s.col], b->coverage[(size_t)s.col], b->user);
+        }
+    b->col_off.assign(1, 0);
+    b->tags.clear();
+    b->nt_cnt.clear();
+    b->coverage.clear();
+    b->num_bases.clear();
+    b->ref.clear();
+    b->bq.clear();
+    b->mq.clear();
+    b->baq.clear();
+    b->sq.clear();
+    b->any_mq = b->any_baq = b->any_sq = false;
+    return rc;
+}
+
+extern "C" void lfb200_builder_destroy(lfb200_builder *b) { delete b; }
 
 // ------------------------------------------------------------------------------------------------
 // link-compatible single problems

@@ -33,6 +33,7 @@ struct DevBatch {
     const char *ref_base;
     const int *coverage;
     const unsigned char *bq, *mq, *baq, *sq;
+    const int *num_bases;
 };
 
 // pow(10,-q/10) tables built on the host with glibc pow() so that the device

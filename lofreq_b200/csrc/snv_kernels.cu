@@ -418,7 +418,7 @@ __device__ __forceinline__ void screen_small(const DevConf &cf, const DevBatch &
 struct RawGeom {        // the per-column metadata as loaded, one column ahead of its use
     long long off;
     int4 cnt;
-    int cov;
+    int cov, nb;
     char ref;
 };
 
@@ -428,6 +428,7 @@ __device__ __forceinline__ void load_raw(const DevBatch &b, long long c, RawGeom
     r.off = __ldg(b.col_off + c);
     r.ref = __ldg(b.ref_base + c);
     r.cov = b.coverage ? __ldg(b.coverage + c) : -1;
+    r.nb = b.num_bases ? __ldg(b.num_bases + c) : -1;
 }
 
 // Work distribution: a warp takes 32 consecutive columns at a time.  Metadata, gates and the "does this
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevCo
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
 
     RawGeom nxt;
-    nxt.off = 0; nxt.cnt = make_int4(0, 0, 0, 0); nxt.cov = -1; nxt.ref = 'N';
+    nxt.off = 0; nxt.cnt = make_int4(0, 0, 0, 0); nxt.cov = -1; nxt.nb = -1; nxt.ref = 'N';
     if (warp0 * 32 + lane < b.n_cols) load_raw(b, warp0 * 32 + lane, nxt);
     for (long long base = warp0 * 32; base < b.n_cols; base += nwarps * 32) {
         const long long c_mine = base + lane;
@@ -457,7 +458,8 @@ __global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevCo
         const int m_b1 = cur.cnt.x, m_b2 = m_b1 + cur.cnt.y, m_b3 = m_b2 + cur.cnt.z, m_n = m_b3 + cur.cnt.w;
         const int m_ref = ref_index(cur.ref);
         const int m_cov = cur.cov < 0 ? m_n : cur.cov;
-        const bool m_gate = c_mine < b.n_cols && m_ref >= 0 && !(m_n * 2 < m_cov) && !(m_n < cf.min_cov);   // lofreq_call.c:892,931,747,754
+        const int m_nb = cur.nb < 0 ? m_n : cur.nb;           // plp_col_t.num_bases
+        const bool m_gate = c_mine < b.n_cols && m_ref >= 0 && !(m_nb * 2 < m_cov) && !(m_nb < cf.min_cov);   // lofreq_call.c:892,931,747,754
         const int m_refcnt = m_ref == 0 ? cur.cnt.x : m_ref == 1 ? cur.cnt.y : m_ref == 2 ? cur.cnt.z : cur.cnt.w;
         const bool m_need = m_gate && (m_n - m_refcnt) > 0;
         if (c_mine < b.n_cols && !m_need) {

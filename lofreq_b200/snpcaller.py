@@ -98,7 +98,7 @@ class Caller:
         hb = capi.Batch(n, arr(batch["col_off"], np.int64), arr(batch["nt_cnt"], np.int32),
                         arr(batch["ref_base"], np.uint8), arr(batch.get("coverage"), np.int32),
                         arr(batch["bq"], np.uint8), arr(batch.get("mq"), np.uint8),
-                        arr(batch.get("baq"), np.uint8), arr(batch.get("sq"), np.uint8))
+                        arr(batch.get("baq"), np.uint8), arr(batch.get("sq"), np.uint8), arr(batch.get("num_bases"), np.int32))
         max_sites = n if max_sites is None else max_sites
         sites = (capi.Site * max(max_sites, 1))()
         sm = capi.Summary()
@@ -130,7 +130,7 @@ class Caller:
         def p(x):
             return None if x is None else C.c_void_p(x.data_ptr())
         return capi.Batch(int(t["ref_base"].numel()), p(t["col_off"]), p(t["nt_cnt"]), p(t["ref_base"]),
-                          p(t.get("coverage")), p(t["bq"]), p(t.get("mq")), p(t.get("baq")), p(t.get("sq")))
+                          p(t.get("coverage")), p(t["bq"]), p(t.get("mq")), p(t.get("baq")), p(t.get("sq")), p(t.get("num_bases")))
 
     def screen(self, dev_batch, conf, stream=None):
         capi.check(self.lib.lfb200_screen_device(self._ctx, C.byref(conf), C.byref(dev_batch), stream))
@@ -148,3 +148,53 @@ class Caller:
         sm = capi.Summary()
         capi.check(self.lib.lfb200_sites_device(self._ctx, C.byref(conf), stream, sites, max_sites, C.byref(sm)))
         return capi.sites_to_numpy(sites, sm.n_sites), sm
+
+
+class ColumnBuilder:
+    """Mirror of the per-column callback surface (plp.h:159-163): feed one pileup column at a time the way
+    mpileup() feeds call_vars(); sites come back through on_site(site_dict) in input order."""
+
+    def __init__(self, caller, conf, batch_cols, on_site):
+        self.caller = caller
+        self.conf = conf_from(conf)
+        self.lib = caller.lib
+        self._on_site = on_site
+
+        def tramp(site_p, tag, ref_base, coverage, user):
+            s = site_p.contents
+            on_site(dict(tag=tag, ref_base=ref_base.decode(), coverage=coverage, col=s.col, bonf=s.bonf,
+                         lnp=list(s.lnp), pvalue=np.array(list(s.pvalue), np.longdouble), alt_count=list(s.alt_count),
+                         alt_raw_count=list(s.alt_raw_count), qual=list(s.qual), status=list(s.status),
+                         called=list(s.called)))
+        self._tramp = capi.SITE_FN(tramp)
+        self._b = C.c_void_p()
+        capi.check(self.lib.lfb200_builder_create(C.byref(self._b), caller._ctx, C.byref(self.conf), int(batch_cols),
+                                                   self._tramp, None))
+
+    def add_column(self, tag, ref_base, coverage_plp, num_bases, base_quals, map_quals=None, baq_quals=None,
+                   source_quals=None):
+        """*_quals: four int arrays (A, C, G, T) like plp_col_t.base_quals[i].data"""
+        keep = []
+
+        def four(groups):
+            if groups is None:
+                return None
+            arr = (C.c_void_p * 4)()
+            for i, g in enumerate(groups):
+                a = np.ascontiguousarray(g, np.int32)
+                keep.append(a)
+                arr[i] = a.ctypes.data if len(a) else None
+            keep.append(arr)
+            return C.cast(arr, C.c_void_p)
+        n = np.array([len(g) for g in base_quals], np.int32)
+        capi.check(self.lib.lfb200_builder_add_column(self._b, int(tag), ref_base.encode(), int(coverage_plp), int(num_bases),
+                                                       four(base_quals), four(map_quals), four(baq_quals),
+                                                       four(source_quals), n.ctypes.data_as(C.c_void_p)))
+
+    def flush(self):
+        capi.check(self.lib.lfb200_builder_flush(self._b))
+
+    def close(self):
+        if self._b:
+            self.lib.lfb200_builder_destroy(self._b)
+            self._b = C.c_void_p()

@@ -42,6 +42,8 @@ typedef struct {
     const char *ref_base;           /* n_cols, uppercase */
     const int *coverage;            /* n_cols or NULL (= sum of nt_cnt) : plp_col_t.coverage_plp */
     const unsigned char *bq, *mq, *baq, *sq;   /* planes; mq/baq/sq may be NULL */
+    const int *num_bases;           /* n_cols or NULL (= sum of nt_cnt): plp_col_t.num_bases, which also counts
+                                     * reads showing N (plp.c:1019-1022) */
 } oracle_batch_t;
 
 typedef struct {

@@ -47,7 +47,8 @@ class _Conf(C.Structure):
 class _Batch(C.Structure):
     _fields_ = [("n_cols", C.c_longlong), ("col_off", C.c_void_p), ("nt_cnt", C.c_void_p),
                 ("ref_base", C.c_void_p), ("coverage", C.c_void_p),
-                ("bq", C.c_void_p), ("mq", C.c_void_p), ("baq", C.c_void_p), ("sq", C.c_void_p)]
+                ("bq", C.c_void_p), ("mq", C.c_void_p), ("baq", C.c_void_p), ("sq", C.c_void_p),
+                ("num_bases", C.c_void_p)]
 
 
 class _Out(C.Structure):
@@ -165,7 +166,7 @@ class Oracle:
         n = len(b["ref_base"])
         s = _Batch(n, arr(b["col_off"], np.int64), arr(b["nt_cnt"], np.int32), arr(b["ref_base"], np.uint8),
                    arr(b.get("coverage"), np.int32), arr(b["bq"], np.uint8), arr(b.get("mq"), np.uint8),
-                   arr(b.get("baq"), np.uint8), arr(b.get("sq"), np.uint8))
+                   arr(b.get("baq"), np.uint8), arr(b.get("sq"), np.uint8), arr(b.get("num_bases"), np.int32))
         return s, keep, n
 
     def call_columns(self, batch, conf=None):

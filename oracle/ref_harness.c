@@ -97,7 +97,7 @@ int lfref_call_columns(oracle_conf_t *oc, const oracle_batch_t *b, oracle_out_t 
                 nreads++;
             }
         }
-        col.num_bases = nreads;
+        col.num_bases = b->num_bases ? b->num_bases[c] : nreads;
         col.coverage_plp = b->coverage ? b->coverage[c] : nreads;
         col.cons_base[0] = col.ref_base; col.cons_base[1] = '\0';
 

@@ -283,6 +283,7 @@ int lfo_call_columns(oracle_conf_t *cf, const oracle_batch_t *b, oracle_out_t *o
         o->tested[c] = 0; o->bonf_used[c] = 0;
         for (i = 0; i < 4; i++) nreads += b->nt_cnt[4 * c + i];
         cov = b->coverage ? b->coverage[c] : nreads;
+        if (b->num_bases) nreads = b->num_bases[c];      /* only the gates below look at it from here on */
 
         if (ref != 'A' && ref != 'C' && ref != 'G' && ref != 'T') continue;  /* 'N' :892; others are 'N' at HEAD */
         if (nreads * 2 < cov) continue;                                     /* :931 */

@@ -1,0 +1,50 @@
+"""CPU check of the arithmetic the kernels use (tests/algomodel.py: linear-space recurrence, odds form,
+power-of-two rescaling, saddlepoint tilt, the clamp rule) against the golden vectors of the reference."""
+import os
+
+import numpy as np
+
+import algomodel as M
+from test_oracle import GOLD
+
+
+def test_model_reproduces_the_reference_grid():
+    z = np.load(os.path.join(GOLD, "snpcaller_grid.npz"))
+    offs = z["offsets"]
+    worst = 0.0
+    for i, name in enumerate(z["names"].tolist()):
+        if z["counts"][i].max() * (offs[i + 1] - offs[i]) > 400_000:
+            continue                      # keep the pure-Python model quick
+        ep = z["err_probs"][offs[i]:offs[i + 1]]
+        pv, st, _ = M.model_snpcaller(ep, z["counts"][i], int(z["bonf"][i]), float(z["sig"][i]))
+        assert np.array_equal(st, z["status"][i]), name
+        for j in range(3):
+            if st[j] == 0:
+                a, b = float(np.log(pv[j])), float(z["lnp"][i][j])
+                worst = max(worst, abs(a - b) / max(abs(b), 1.0))
+    assert worst < 1e-10
+
+
+def test_model_random_triallelic_against_port(port_oracle):
+    rng = np.random.default_rng(5)
+    sig = float(np.float32(0.01))
+    for _ in range(60):
+        n = int(rng.integers(20, 1200))
+        q = rng.integers(6, 60, n) if rng.random() < 0.5 else np.where(rng.random(n) < 0.3, 3, rng.integers(20, 41, n))
+        ep = np.sort(10.0 ** (-q / 10.0))
+        k1 = int(rng.integers(1, n + 1))
+        k2 = int(rng.integers(0, min(k1, n - k1) + 1))
+        k3 = int(rng.integers(0, min(5, n - k1 - k2) + 1))
+        counts = [k1, k2, k3]
+        rng.shuffle(counts)
+        bonf = int(rng.integers(1, 10 ** 7))
+        want = port_oracle.snpcaller(ep, counts, bonf, sig)
+        wst = np.zeros(3, np.uint8)
+        wst[want == M.LDBL_MAX] = 1
+        wst[want == M.LDBL_MIN] = 2
+        pv, st, _ = M.model_snpcaller(ep, counts, bonf, sig)
+        assert np.array_equal(st, wst), (n, counts, bonf)
+        for j in range(3):
+            if st[j] == 0:
+                a, b = float(np.log(pv[j])), float(np.log(want[j]))
+                assert abs(a - b) <= 1e-10 * max(abs(b), 1.0)

@@ -158,7 +158,8 @@ def _custom_batch(cols, pad=1, with_baq=True):
         ref.append(ord(c["ref"]))
         cov.append(c.get("coverage", n))
     tail = 64
-    return dict(col_off=np.array(col_off, np.int64), nt_cnt=np.array(nt, np.int32).reshape(-1, 4),
+    nb = [c.get("num_bases", sum(len(c["groups"][g][0]) for g in range(4))) for c in cols]
+    return dict(num_bases=np.array(nb, np.int32), col_off=np.array(col_off, np.int64), nt_cnt=np.array(nt, np.int32).reshape(-1, 4),
                 ref_base=np.array(ref, np.uint8), coverage=np.array(cov, np.int32),
                 bq=np.array(bq + [0] * tail, np.uint8), mq=np.array(mq + [0] * tail, np.uint8),
                 baq=np.array(baq + [0] * tail, np.uint8) if with_baq else None, sq=None)
@@ -177,6 +178,8 @@ def test_edge_columns(caller, port_oracle):
         dict(ref="C", groups=[grp(2), grp(40), grp(1), grp(5)], gap=7),       # ragged, unaligned next column
         dict(ref="G", groups=[grp(9), e, grp(100), e], coverage=500),         # num_bases*2 < coverage: skipped
         dict(ref="T", groups=[grp(13), grp(1), grp(1), grp(333)], gap=3),
+        dict(ref="G", groups=[grp(9), e, grp(100), e], coverage=300, num_bases=160),   # reads showing N count as bases
+        dict(ref="G", groups=[grp(9), e, grp(100), e], coverage=300, num_bases=140),
         dict(ref="A", groups=[e, grp(50), e, e]),                             # no ref reads at all, K == N
         dict(ref="A", groups=[grp(60, mqv=255), grp(8, mqv=255), e, e]),      # mq unknown
         dict(ref="A", groups=[grp(60, mqv=0), grp(8, mqv=0), e, e]),          # mq 0 -> 0.5
@@ -286,3 +289,75 @@ def test_full_size_c2_properties(caller, port_oracle):
     assert np.array_equal(s["qual"], s2["qual"])
     # 1 % of the columns are variant sites, nearly all of them significant
     assert 0.005 * n < sm.n_sites < 0.02 * n
+
+
+def test_two_shards_equal_one(caller):
+    """region shards with the tested-count exchange (lofreq_b200/shard.py) == one batch; both shards on
+    this GPU, one context each, driven exactly like bench.py drives one rank per GPU"""
+    import lofreq_b200
+    from lofreq_b200 import shard, synth
+    n, world = 200_000, 2
+    whole = synth.generate_device("C2", 0, n)
+    cf = lofreq_b200.varcall_conf()
+    caller.screen(caller.device_batch(whole), cf)
+    caller.test(cf)
+    want, want_sm = caller.sites(cf, n)
+    ctxs = [lofreq_b200.Caller(0) for _ in range(world)]
+    parts, counts = [], []
+    for r in range(world):
+        lo, hi = shard.shard_range(n, r, world)
+        t = synth.generate_device("C2", lo, hi - lo)
+        parts.append((lo, hi, t))
+        ctxs[r].screen(ctxs[r].device_batch(t), lofreq_b200.varcall_conf())
+        counts.append(ctxs[r].ntested())
+    got = []
+    for r in range(world):
+        cfr = lofreq_b200.varcall_conf(bonf_subst=shard.bonf_start_for_rank(counts, r))
+        ctxs[r].test(cfr)
+        s, sm = ctxs[r].sites(cfr, n)
+        s = s.copy()
+        s["col"] += parts[r][0]
+        got.append(s)
+    got = np.concatenate(got)
+    assert shard.final_counters(counts) == (want_sm.bonf_subst_final, want_sm.num_snv_tests)
+    assert len(got) == len(want)
+    for k in ("col", "bonf", "alt_count", "alt_raw_count", "qual", "status", "called"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(got["lnp"], want["lnp"])
+    for c in ctxs:
+        c.close()
+
+
+def test_column_builder_callback_surface(caller, port_oracle):
+    """one column at a time through lfb200_builder_add_column (the call_vars() replacement), several
+    flushes, sites reported in input order; equals the oracle's per-column loop"""
+    import lofreq_b200
+    from lofreq_b200.snpcaller import ColumnBuilder
+    b = synth_np.generate("C4", 4242, 1300, with_baq=True)
+    want = port_oracle.call_columns(b, default_conf())
+    got = []
+    cf = lofreq_b200.varcall_conf()
+    bld = ColumnBuilder(caller, cf, 256, got.append)
+    for c in range(1300):
+        lo = int(b["col_off"][c])
+        groups_bq, groups_mq, groups_baq = [], [], []
+        for g in range(4):
+            k = int(b["nt_cnt"][c, g])
+            groups_bq.append(b["bq"][lo:lo + k].astype(np.int32))
+            groups_mq.append(b["mq"][lo:lo + k].astype(np.int32))
+            groups_baq.append(b["baq"][lo:lo + k].astype(np.int32))
+            lo += k
+        bld.add_column(1000 + c, chr(b["ref_base"][c]), int(b["nt_cnt"][c].sum()), int(b["nt_cnt"][c].sum()), groups_bq,
+                       groups_mq, groups_baq)
+    bld.flush()
+    assert bld.conf.bonf_subst == want["bonf_subst"] and bld.conf.num_snv_tests == want["num_snv_tests"]
+    tags = [s["tag"] for s in got]
+    assert tags == sorted(tags)
+    called_cols = np.nonzero(want["called"].any(axis=1))[0]
+    got_called = [s for s in got if any(s["called"])]
+    assert [s["tag"] - 1000 for s in got_called] == called_cols.tolist()
+    for s in got_called:
+        c = s["tag"] - 1000
+        assert s["qual"] == want["qual"][c].tolist() and s["called"] == want["called"][c].tolist()
+        assert s["bonf"] == want["bonf_used"][c] and s["alt_count"] == want["alt_counts"][c].tolist()
+    bld.close()
