@@ -226,6 +226,9 @@ def run_ours(args):
     sms = [capi.Summary(), capi.Summary()]
     sm = sms[0]
     confs = [None, None]
+    exchanges = [shard.DeviceCountExchange(dev), shard.DeviceCountExchange(dev)] if world > 1 else None
+    site_mine = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(2)]
+    site_all = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
 
     def launch(i):
         """screen -> (exchange tested counts) -> test for context i, asynchronous"""
@@ -233,11 +236,15 @@ def run_ours(args):
         ctx = callers[i]._ctx
         capi.check(lib.lfb200_screen_device(ctx, C.byref(cf), C.byref(db), sts[i]))
         if world > 1:
-            nt = C.c_longlong()
-            capi.check(lib.lfb200_ntested_device(ctx, sts[i], C.byref(nt)))
-            counts = shard.gather_counts(nt.value, device=dev)       # 1 x int64 per rank over NCCL
-            cf.bonf_subst = shard.bonf_start_for_rank(counts, rank)  # running factor of the shards before this one
-        capi.check(lib.lfb200_test_device(ctx, C.byref(cf), sts[i]))
+            # tested-column counts: 1 x int64 per rank over NCCL on this stream, no host round trip; the test
+            # phase reads the running factor of the shards before this one from device memory
+            ex = exchanges[i]
+            capi.check(lib.lfb200_ntested_copy_device(ctx, sts[i], C.c_void_p(ex.mine.data_ptr())))
+            with torch.cuda.stream(streams[i]):
+                start = ex.exchange(sts[i])
+            capi.check(lib.lfb200_test_device_from(ctx, C.byref(cf), sts[i], C.c_void_p(start.data_ptr())))
+        else:
+            capi.check(lib.lfb200_test_device(ctx, C.byref(cf), sts[i]))
         confs[i] = cf
 
     def finish(i):
@@ -245,7 +252,10 @@ def run_ours(args):
         capi.check(lib.lfb200_sites_device(callers[i]._ctx, C.byref(confs[i]), sts[i], sites_bufs[i], max_sites,
                                            C.byref(sms[i])))
         if world > 1:
-            shard.gather_counts(sms[i].n_sites, device=dev)   # the final per-region variant-count gather (north_star)
+            # the final per-region variant-count gather (north_star): asynchronous, read once after the timed region
+            with torch.cuda.stream(streams[i]):
+                site_mine[i].fill_(int(sms[i].n_sites))
+                dist.all_gather_into_tensor(site_all[i], site_mine[i])
         return sms[i]
 
     def run_steps(k_steps, prof=None):
@@ -360,7 +370,9 @@ def run_ours(args):
                 "config": {"workload": workload_desc(wl, n) + " per GPU (region shard = rank*cols)",
                            "cols_per_gpu": n, "depth": DEPTH.get(wl), "l2": "inputs larger than L2 (%.2f GB per step)" % (2 * total / 1e9),
                            "value_region": "screen + prefix sum + significance test + O(depth*K) kernels + D2H of sites + long double finishing, inputs resident in HBM; two contexts so that the host finishing of one batch overlaps the kernels of the next",
-                           "tested_columns": int(n_tested), "sites": int(n_sites), "heavy_columns": int(n_heavy)},
+                           "tested_columns": int(n_tested), "sites": int(n_sites), "heavy_columns": int(n_heavy),
+                           "sites_all_ranks": [int(x) for x in site_all[(args.steps - 1) % 2].tolist()] if world > 1 else [int(n_sites)],
+                           "bonf_subst_final_this_rank": int(sm.bonf_subst_final)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
                 "gpu_launches": 12 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

@@ -145,6 +145,15 @@ int lfb200_call_columns(lfb200_ctx *ctx, lfb200_conf_t *conf, const lfb200_batch
 int lfb200_screen_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, const lfb200_batch_t *dev_batch, void *stream);
 int lfb200_ntested_device(lfb200_ctx *ctx, void *stream, long long *n_tested);
 int lfb200_test_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *stream);
+/* the same exchange without a host round trip: copy the tested count into caller-owned device memory
+ * (e.g. the send buffer of an NCCL all_gather on the same stream), and start the test from a running factor
+ * that a kernel of the caller left in device memory */
+int lfb200_ntested_copy_device(lfb200_ctx *ctx, void *stream, long long *dst_dev);
+int lfb200_test_device_from(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *stream, const long long *bonf_start_dev);
+/* start_dev[0] = the running factor shard `rank` starts from, given the all-gathered tested counts of every
+ * shard in device memory (lofreq_call.c:794-800 continued across shards) */
+int lfb200_bonf_start_device(void *stream, const long long *tested_counts_dev, int rank, long long bonf_subst,
+                             long long *start_dev);
 int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites,
                         long long max_sites, lfb200_summary_t *summary);
 /* optional per-phase device timing with CUDA events on the launching stream (benchmark / roofline):

@@ -67,7 +67,7 @@ SITE_FN = C.CFUNCTYPE(None, C.POINTER(Site), C.c_longlong, C.c_char, C.c_int, C.
 
 # every symbol include/lofreq_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_conf", "lfb200_call_columns",
-           "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_sites_device",
+           "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_ntested_copy_device", "lfb200_test_device_from", "lfb200_bonf_start_device", "lfb200_sites_device",
            "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
            "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_synth_depths",
            "lfb200_synth_columns"]
@@ -106,6 +106,12 @@ def load():
     lib.lfb200_ntested_device.argtypes = [vp, vp, C.POINTER(ll)]
     lib.lfb200_test_device.restype = C.c_int
     lib.lfb200_test_device.argtypes = [vp, C.POINTER(Conf), vp]
+    lib.lfb200_ntested_copy_device.restype = C.c_int
+    lib.lfb200_ntested_copy_device.argtypes = [vp, vp, vp]
+    lib.lfb200_test_device_from.restype = C.c_int
+    lib.lfb200_test_device_from.argtypes = [vp, C.POINTER(Conf), vp, vp]
+    lib.lfb200_bonf_start_device.restype = C.c_int
+    lib.lfb200_bonf_start_device.argtypes = [vp, vp, C.c_int, ll, vp]
     lib.lfb200_sites_device.restype = C.c_int
     lib.lfb200_sites_device.argtypes = [vp, C.POINTER(Conf), vp, C.POINTER(Site), ll, C.POINTER(Summary)]
     lib.lfb200_device_results.restype = C.c_int

@@ -435,7 +435,7 @@ extern "C" int lfb200_ntested_device(lfb200_ctx *ctx, void *stream, long long *n
     return 0;
 }
 
-extern "C" int lfb200_test_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *stream)
+static int test_device_impl(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *stream, const long long *bonf_start_dev)
 {
     if (!ctx || !ctx->have_batch) return fail("no screened batch");
     lfb200_batch_t hb;
@@ -444,16 +444,43 @@ extern "C" int lfb200_test_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, vo
     DevConf dc;
     if (make_devconf(conf, &hb, dc)) return 1;
     if (ctx->profiling) cudaEventRecord(ctx->ev[3], (cudaStream_t)stream);
-    launch_test(dc, ctx->cur, ctx->d_lut, ctx->ws, (cudaStream_t)stream, ctx->profiling ? ctx->ev[4] : nullptr);
+    launch_test(dc, ctx->cur, ctx->d_lut, ctx->ws, (cudaStream_t)stream, ctx->profiling ? ctx->ev[4] : nullptr, bonf_start_dev);
     if (ctx->profiling) cudaEventRecord(ctx->ev[5], (cudaStream_t)stream);
     CU(cudaGetLastError());
     return 0;
 }
 
-static long long final_bonf(const lfb200_conf_t *conf, long long n_tested)
+extern "C" int lfb200_test_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *stream)
 {
-    if (!conf->bonf_dynamic || n_tested == 0) return conf->bonf_subst;
-    return (conf->bonf_subst == 1 ? 0 : conf->bonf_subst) + 3 * n_tested;     // lofreq_call.c:794-800
+    return test_device_impl(ctx, conf, stream, nullptr);
+}
+
+extern "C" int lfb200_test_device_from(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *stream, const long long *bonf_start_dev)
+{
+    if (!bonf_start_dev) return fail("bonf_start_dev is NULL");
+    return test_device_impl(ctx, conf, stream, bonf_start_dev);
+}
+
+extern "C" int lfb200_bonf_start_device(void *stream, const long long *tested_counts_dev, int rank, long long bonf_subst,
+                                        long long *start_dev)
+{
+    if (!tested_counts_dev || !start_dev || rank < 0) return fail("bad arguments");
+    launch_bonf_start(tested_counts_dev, rank, bonf_subst, start_dev, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lfb200_ntested_copy_device(lfb200_ctx *ctx, void *stream, long long *dst_dev)
+{
+    if (!ctx || !ctx->have_batch) return fail("no screened batch");
+    CU(cudaMemcpyAsync(dst_dev, &ctx->ws.counters->n_tested, sizeof(long long), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+static long long final_bonf(const lfb200_conf_t *conf, long long start, long long n_tested)
+{
+    if (!conf->bonf_dynamic || n_tested == 0) return start;
+    return (start == 1 ? 0 : start) + 3 * n_tested;     // lofreq_call.c:794-800
 }
 
 extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites,
@@ -528,7 +555,7 @@ extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *s
         fprintf(stderr, "[lfb200] sites: wait+counters %.0f us, cand D2H %.0f us, sort %.0f us, finish %.0f us (%lld sites)\n",
                 t1 - t0, t2 - t1, t3 - t2, now() - t3, n_cand);
     sm.n_sites = n_cand;
-    sm.bonf_subst_final = final_bonf(conf, sm.n_tested);
+    sm.bonf_subst_final = final_bonf(conf, ctx->cur.n_cols > 0 ? ctx->h_counters->bonf_start_used : conf->bonf_subst, sm.n_tested);
     conf->bonf_subst = sm.bonf_subst_final;
     conf->num_snv_tests += 3 * sm.n_tested;       // lofreq_call.c:801
     sm.num_snv_tests = conf->num_snv_tests;

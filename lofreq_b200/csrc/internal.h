@@ -63,6 +63,7 @@ struct Counters {
     unsigned int n_jobs[NCLASS];
     unsigned int next_job[NCLASS];
     unsigned int err_flags;
+    long long bonf_start_used;     // running factor the last test started from (host or device supplied)
 };
 
 struct Workspace {
@@ -91,7 +92,8 @@ struct ProbBatch {
 void launch_screen(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
 void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st);
 void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
-                 cudaEvent_t after_finalize);
+                 cudaEvent_t after_finalize, const long long *bonf_start_dev);
+void launch_bonf_start(const long long *counts, int rank, long long bonf_subst, long long *start, cudaStream_t st);
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st);
 // synth.cu
 void launch_synth_depths(int workload, long long c0, long long n, int *depth, cudaStream_t st);

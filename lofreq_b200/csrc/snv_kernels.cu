@@ -608,9 +608,14 @@ __device__ __forceinline__ int class_of(int K)
     return cls;
 }
 
-__global__ void __launch_bounds__(1024) k_finalize(const DevConf cf, const long long n, const Workspace ws)
+__global__ void __launch_bounds__(1024) k_finalize(const DevConf cf, const long long n, const Workspace ws,
+                                                   const long long *bonf_start_dev)
 {
     __shared__ int s_warp[32];
+    // the running factor this batch continues from: the caller's conf, or a value another shard's count
+    // exchange left in device memory (no host round trip)
+    const long long bonf_start = bonf_start_dev ? *bonf_start_dev : cf.bonf_start;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters->bonf_start_used = bonf_start;
     const long long c = (long long)blockIdx.x * 1024 + threadIdx.x;
     const int lane = lane_id(), w = threadIdx.x >> 5;
     const int t = (c < n) ? ws.tested[c] : 0;
@@ -633,7 +638,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const DevConf cf, const long 
         // 1-based rank of this column among the tested columns of the batch
         const long long rank = ws.blocksum[blockIdx.x] + (w ? s_warp[w - 1] : 0) + __popc(bal & ((2u << lane) - 1u));
         // lofreq_call.c:794-800: first tested column sets 3 when bonf_subst was 1, else += 3
-        bonf = cf.bonf_dynamic ? ((cf.bonf_start == 1 ? 0 : cf.bonf_start) + 3 * rank) : cf.bonf_start;
+        bonf = cf.bonf_dynamic ? ((bonf_start == 1 ? 0 : bonf_start) + 3 * rank) : bonf_start;
     }
     ws.bonf_used[c] = bonf;
     if (!t) return;
@@ -1120,13 +1125,13 @@ void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st)
 }
 
 void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
-                 cudaEvent_t after_finalize)
+                 cudaEvent_t after_finalize, const long long *bonf_start_dev)
 {
     if (b.n_cols <= 0) return;
     const int nb = (int)((b.n_cols + 1023) / 1024);
     // n_tested (first 8 bytes) belongs to the scan; everything after it is per-test state
     cudaMemsetAsync(reinterpret_cast<char *>(ws.counters) + 8, 0, sizeof(Counters) - 8, st);
-    k_finalize<<<nb, 1024, 0, st>>>(cf, b.n_cols, ws);
+    k_finalize<<<nb, 1024, 0, st>>>(cf, b.n_cols, ws, bonf_start_dev);
     if (after_finalize) cudaEventRecord(after_finalize, st);
     // The register-tile classes are independent: run them side by side so that their warps share the SMs
     // (each class alone has too few columns to hide its own latencies).
@@ -1154,6 +1159,19 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
         cudaEventRecord(ev_join[i], side[i]);
         cudaStreamWaitEvent(st, ev_join[i], 0);
     }
+}
+
+__global__ void k_bonf_start(const long long *counts, int rank, long long bonf_subst, long long *start)
+{
+    long long before = 0;
+    for (int r = 0; r < rank; ++r) before += counts[r];
+    // lofreq_call.c:794-800: after j tested columns the factor is 3j when it started at 1, else start + 3j
+    *start = before > 0 ? (bonf_subst == 1 ? 0 : bonf_subst) + 3 * before : bonf_subst;
+}
+
+void launch_bonf_start(const long long *counts, int rank, long long bonf_subst, long long *start, cudaStream_t st)
+{
+    k_bonf_start<<<1, 1, 0, st>>>(counts, rank, bonf_subst, start);
 }
 
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st)

@@ -50,3 +50,29 @@ def final_counters(tested_counts, bonf_subst=1, bonf_dynamic=1, num_snv_tests=0)
     if bonf_dynamic and total:
         bonf = (0 if bonf_subst == 1 else bonf_subst) + 3 * total
     return bonf, num_snv_tests + 3 * total
+
+
+class DeviceCountExchange:
+    """The same exchange kept on the device (NCCL on the kernels' stream, no host synchronisation):
+    every rank contributes its tested-column count, `start` ends up holding the running Bonferroni factor
+    this rank's test phase must start from (1 when nothing was tested before it)."""
+
+    def __init__(self, device, bonf_subst=1):
+        import torch
+        import torch.distributed as dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.mine = torch.zeros(1, dtype=torch.int64, device=device)
+        self.all = torch.zeros(self.world, dtype=torch.int64, device=device)
+        self.start = torch.full((1,), bonf_subst, dtype=torch.int64, device=device)
+        self.base = 0 if bonf_subst == 1 else bonf_subst
+        self.bonf_subst = bonf_subst
+
+    def exchange(self, stream_ptr=None):
+        """call with the torch current stream = the stream the count was copied on (stream_ptr = its handle)"""
+        import ctypes as C
+        import torch.distributed as dist
+        from . import capi
+        dist.all_gather_into_tensor(self.all, self.mine)
+        capi.check(capi.load().lfb200_bonf_start_device(stream_ptr, C.c_void_p(self.all.data_ptr()), self.rank,
+                                                         self.bonf_subst, C.c_void_p(self.start.data_ptr())))
+        return self.start

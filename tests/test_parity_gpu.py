@@ -311,10 +311,24 @@ def test_two_shards_equal_one(caller):
         ctxs[r].screen(ctxs[r].device_batch(t), lofreq_b200.varcall_conf())
         counts.append(ctxs[r].ntested())
     got = []
+    import ctypes as C
+    import torch
+    from lofreq_b200 import capi
     for r in range(world):
-        cfr = lofreq_b200.varcall_conf(bonf_subst=shard.bonf_start_for_rank(counts, r))
-        ctxs[r].test(cfr)
+        start = shard.bonf_start_for_rank(counts, r)
+        if r == 0:
+            cfr = lofreq_b200.varcall_conf(bonf_subst=start)
+            ctxs[r].test(cfr)
+        else:
+            # the running factor handed over in device memory (what the NCCL exchange of bench.py produces)
+            cfr = lofreq_b200.varcall_conf()
+            dst = torch.zeros(1, dtype=torch.int64, device="cuda:0")
+            capi.check(ctxs[0].lib.lfb200_ntested_copy_device(ctxs[0]._ctx, None, C.c_void_p(dst.data_ptr())))
+            assert int(dst.item()) == counts[0]
+            start_dev = torch.tensor([start], dtype=torch.int64, device="cuda:0")
+            capi.check(ctxs[r].lib.lfb200_test_device_from(ctxs[r]._ctx, C.byref(cfr), None, C.c_void_p(start_dev.data_ptr())))
         s, sm = ctxs[r].sites(cfr, n)
+        assert cfr.bonf_subst == shard.final_counters(counts[: r + 1])[0]
         s = s.copy()
         s["col"] += parts[r][0]
         got.append(s)
