@@ -72,7 +72,7 @@ struct Workspace {
     unsigned char *tested;         // [n]
     double *tails;                 // [n][4]: linear P(X>=c_i) for the three alleles, min(P[K-1], P(>=K))
     long long *bonf_used;          // [n]
-    long long *blocksum;           // [ceil(n/1024)]
+    long long *blocksum;           // [ceil(n/256)]
     int *jobs;                     // [NCLASS][n]
     Cand *cand;                    // [n]
     Counters *counters;

@@ -368,12 +368,13 @@ __device__ __forceinline__ void mask_chunk(uint4 &v, int pos0, int n)
     v = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Second sweep of a tested column with K <= KS: every lane folds the reads of its 16-byte chunks into a
-// distribution truncated at KV >= K, then the 32 distributions are merged.  The first chunk of every lane
-// was loaded before the alt counts were known (one memory round trip per column instead of two).
+// Full evaluation of a column with K <= KS: every lane folds the reads of its 16-byte chunks into a
+// distribution truncated at KV >= K, then the 32 distributions are merged.  Only columns that survive the
+// 32-read prune of k_finalize get here (true low-frequency variants, and the first few columns of a run
+// whose Bonferroni factor is still small).
 template <int KV>
-__device__ __forceinline__ void screen_small(const DevConf &cf, const DevBatch &b, unsigned lut_sa, const Geom &g,
-                                             const int (&cnt)[3], int K, const Chunk16 &first, double (&tails)[4])
+__device__ __noinline__ void screen_small(const DevConf &cf, const DevBatch &b, unsigned lut_sa, const Geom &g,
+                                          const int (&cnt)[3], int K, double (&tails)[4])
 {
     const int lane = lane_id();
     double P[KV], T = 0.0;
@@ -399,10 +400,10 @@ __device__ __forceinline__ void screen_small(const DevConf &cf, const DevBatch &
     rr.alt_jp = cf.def_alt_jq_prob;
     const bool uniform = cf.min_bq >= 1 && cf.min_alt_bq <= cf.min_bq && !rr.alt_bq && !rr.alt_jq && !cf.jq_filters &&
                          !rr.general_merge;
-    Chunk16 ch = first;
 #pragma unroll 1
     for (int i = lane; i < nchunks; i += 32) {
-        if (i != lane) load_chunk(cf, b, abase + 16ll * i, ch);
+        Chunk16 ch;
+        load_chunk(cf, b, abase + 16ll * i, ch);
         const int pos0 = 16 * i - lead;
         if (uniform) {
             mask_chunk(ch.bq, pos0, g.n);
@@ -431,21 +432,48 @@ __device__ __forceinline__ void load_raw(const DevBatch &b, long long c, RawGeom
     r.nb = b.num_bases ? __ldg(b.num_bases + c) : -1;
 }
 
-// Work distribution: a warp takes 32 consecutive columns at a time.  Metadata, gates and the "does this
-// column show any non-reference base at all" test run lane-per-column (most columns stop here and cost a
-// fraction of an instruction per lane); the columns that do are then processed one by one by the whole warp.
+// k_screen: gates and alt counts.  Only reads that show a non-reference base decide whether a column is
+// tested and what K is (snpcaller.c:418-420,489), so only those bytes are touched.  A warp takes 32
+// consecutive columns: metadata, gates and columns with at most 8 non-reference reads run lane-per-column;
+// the rare columns with more (variant sites) are then counted by the whole warp.
+__device__ __forceinline__ void count_alt_read(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &g,
+                                               int ref_lo, int ref_hi, int i, int (&cnt)[3], int (&raw)[3])
+{
+    const int pos = i < ref_lo ? i : i - ref_lo + ref_hi;
+    const long long a = g.off + pos;
+    const int bq = b.bq[a];
+    int mq = 0, baq = 0, sq = 0;
+    if (cf.jq_filters) {
+        if (cf.use_mq) mq = b.mq[a];
+        if (cf.use_baq) baq = b.baq[a];
+        if (cf.use_sq) sq = b.sq[a];
+    }
+    bool is_alt;
+    int slot;
+    double jp;
+    const bool ok = eval_read<false>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp);
+    raw[0] += slot == 0;              // raw counts precede every filter (snpcaller.c:418-420)
+    raw[1] += slot == 1;
+    raw[2] += slot == 2;
+    if (ok) {
+        cnt[0] += slot == 0;
+        cnt[1] += slot == 1;
+        cnt[2] += slot == 2;
+    }
+}
+
 __global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
                                                    const Lut *lut, const Workspace ws)
 {
     __shared__ double s_lut[768];
     __shared__ int s_hist[8][256];
     load_lut(s_lut, lut);
-    unsigned lut_sa = (unsigned)__cvta_generic_to_shared(s_lut);
-    asm volatile("" : "+r"(lut_sa));          // keep the shared-window address in a register
     const int lane = lane_id();
     const int wib = threadIdx.x >> 5;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    // the median override (def_alt_bq == -1) needs a warp-wide histogram: no lane-per-column path then
+    const int serial_max = cf.alt_bq_mode == 2 ? 0 : 8;
 
     RawGeom nxt;
     nxt.off = 0; nxt.cnt = make_int4(0, 0, 0, 0); nxt.cov = -1; nxt.nb = -1; nxt.ref = 'N';
@@ -455,96 +483,56 @@ __global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevCo
         const RawGeom cur = nxt;
         if (c_mine + nwarps * 32 < b.n_cols) load_raw(b, c_mine + nwarps * 32, nxt);   // next group's metadata in flight
         // ---- lane per column ----
-        const int m_b1 = cur.cnt.x, m_b2 = m_b1 + cur.cnt.y, m_b3 = m_b2 + cur.cnt.z, m_n = m_b3 + cur.cnt.w;
-        const int m_ref = ref_index(cur.ref);
-        const int m_cov = cur.cov < 0 ? m_n : cur.cov;
-        const int m_nb = cur.nb < 0 ? m_n : cur.nb;           // plp_col_t.num_bases
-        const bool m_gate = c_mine < b.n_cols && m_ref >= 0 && !(m_nb * 2 < m_cov) && !(m_nb < cf.min_cov);   // lofreq_call.c:892,931,747,754
-        const int m_refcnt = m_ref == 0 ? cur.cnt.x : m_ref == 1 ? cur.cnt.y : m_ref == 2 ? cur.cnt.z : cur.cnt.w;
-        const bool m_need = m_gate && (m_n - m_refcnt) > 0;
-        if (c_mine < b.n_cols && !m_need) {
-            // no non-reference base (or gated out): not a test (lofreq_call.c:768-780), all counts zero
-            int2 *o = reinterpret_cast<int2 *>(ws.cnt6 + 6 * c_mine);
-            o[0] = make_int2(0, 0);
-            o[1] = make_int2(0, 0);
-            o[2] = make_int2(0, 0);
-            ws.tested[c_mine] = 0;
-        }
-        // ---- whole warp per remaining column ----
-        unsigned todo = __ballot_sync(FULL, m_need);
+        Geom mg;
+        mg.off = cur.off;
+        mg.b1 = cur.cnt.x;
+        mg.b2 = mg.b1 + cur.cnt.y;
+        mg.b3 = mg.b2 + cur.cnt.z;
+        mg.n = mg.b3 + cur.cnt.w;
+        mg.ref_idx = ref_index(cur.ref);
+        mg.alt_bp = cf.alt_bq_prob;
+        const int m_cov = cur.cov < 0 ? mg.n : cur.cov;
+        const int m_nb = cur.nb < 0 ? mg.n : cur.nb;           // plp_col_t.num_bases
+        const bool m_gate = c_mine < b.n_cols && mg.ref_idx >= 0 && !(m_nb * 2 < m_cov) && !(m_nb < cf.min_cov);   // lofreq_call.c:892,931,747,754
+        int m_lo, m_hi;
+        ref_range(mg, m_lo, m_hi);
+        const int m_alt = m_gate ? mg.n - (m_hi - m_lo) : 0;
+        int cnt[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
+        if (m_alt > 0 && m_alt <= serial_max)
+            for (int i = 0; i < m_alt; ++i) count_alt_read(cf, b, s_lut, mg, m_lo, m_hi, i, cnt, raw);
+        // ---- whole warp per column with many non-reference reads ----
+        unsigned todo = __ballot_sync(FULL, m_alt > serial_max);
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
-            const long long c = base + src;
             Geom g;
-            g.off = __shfl_sync(FULL, cur.off, src);
-            g.b1 = __shfl_sync(FULL, m_b1, src);
-            g.b2 = __shfl_sync(FULL, m_b2, src);
-            g.b3 = __shfl_sync(FULL, m_b3, src);
-            g.n = __shfl_sync(FULL, m_n, src);
-            g.ref_idx = __shfl_sync(FULL, m_ref, src);
+            g.off = __shfl_sync(FULL, mg.off, src);
+            g.b1 = __shfl_sync(FULL, mg.b1, src);
+            g.b2 = __shfl_sync(FULL, mg.b2, src);
+            g.b3 = __shfl_sync(FULL, mg.b3, src);
+            g.n = __shfl_sync(FULL, mg.n, src);
+            g.ref_idx = __shfl_sync(FULL, mg.ref_idx, src);
             g.alt_bp = 0.0;
             int ref_lo, ref_hi;
             ref_range(g, ref_lo, ref_hi);
             const int n_alt = g.n - (ref_hi - ref_lo);
-            // issue this lane's share of the first 512-read stripe now; it is consumed after the alt counts
-            Chunk16 first;
-            first.bq = first.mq = first.baq = first.sq = make_uint4(0, 0, 0, 0);
-            const long long abase = g.off & ~15ll;
-            if (16 * lane < (int)(g.off - abase) + g.n) load_chunk(cf, b, abase + 16ll * lane, first);
-            // First sweep: only reads that show a non-reference base decide whether the column is tested
-            // and what K is, so only those are looked at (alt counts, snpcaller.c:418-420,489).
             setup_alt_bq(cf, b, s_lut, g, s_hist[wib]);
-            int cnt[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
-            for (int i = lane; i < n_alt; i += 32) {
-                const int pos = i < ref_lo ? i : i - ref_lo + ref_hi;
-                const long long a = g.off + pos;
-                const int bq = b.bq[a];
-                int mq = 0, baq = 0, sq = 0;
-                if (cf.jq_filters) {
-                    if (cf.use_mq) mq = b.mq[a];
-                    if (cf.use_baq) baq = b.baq[a];
-                    if (cf.use_sq) sq = b.sq[a];
-                }
-                bool is_alt;
-                int slot;
-                double jp;
-                const bool ok = eval_read<false>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp);
-                raw[0] += slot == 0;              // raw counts precede every filter (snpcaller.c:418-420)
-                raw[1] += slot == 1;
-                raw[2] += slot == 2;
-                if (ok) {
-                    cnt[0] += slot == 0;
-                    cnt[1] += slot == 1;
-                    cnt[2] += slot == 2;
-                }
-            }
+            int wc[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
+            for (int i = lane; i < n_alt; i += 32) count_alt_read(cf, b, s_lut, g, ref_lo, ref_hi, i, wc, wr);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                cnt[i] = __reduce_add_sync(FULL, cnt[i]);
-                raw[i] = __reduce_add_sync(FULL, raw[i]);
+                wc[i] = __reduce_add_sync(FULL, wc[i]);
+                wr[i] = __reduce_add_sync(FULL, wr[i]);
+                if (lane == src) { cnt[i] = wc[i]; raw[i] = wr[i]; }
             }
-            const int K = max(cnt[0], max(cnt[1], cnt[2]));
-            const bool tested = K > 0;     // lofreq_call.c:768-780: no alt left after filtering -> not a test
-            if (lane == 0) {
-                int2 *o = reinterpret_cast<int2 *>(ws.cnt6 + 6 * c);
-                o[0] = make_int2(cnt[0], cnt[1]);
-                o[1] = make_int2(cnt[2], raw[0]);
-                o[2] = make_int2(raw[1], raw[2]);
-                ws.tested[c] = tested ? 1 : 0;
-            }
-            if (tested && K <= KS) {
-                double tails[4];
-                if (K == 1) screen_small<1>(cf, b, lut_sa, g, cnt, K, first, tails);
-                else if (K == 2) screen_small<2>(cf, b, lut_sa, g, cnt, K, first, tails);
-                else if (K <= 4) screen_small<4>(cf, b, lut_sa, g, cnt, K, first, tails);
-                else screen_small<8>(cf, b, lut_sa, g, cnt, K, first, tails);
-                if (lane == 0) {
-                    double2 *o = reinterpret_cast<double2 *>(ws.tails + 4 * c);
-                    o[0] = make_double2(tails[0], tails[1]);
-                    o[1] = make_double2(tails[2], tails[3]);
-                }
-            }
+        }
+        if (c_mine < b.n_cols) {
+            int2 *o = reinterpret_cast<int2 *>(ws.cnt6 + 6 * c_mine);
+            o[0] = make_int2(cnt[0], cnt[1]);
+            o[1] = make_int2(cnt[2], raw[0]);
+            o[2] = make_int2(raw[1], raw[2]);
+            // no alt read left after filtering -> not a test (lofreq_call.c:768-780)
+            ws.tested[c_mine] = (cnt[0] | cnt[1] | cnt[2]) ? 1 : 0;
         }
     }
 }
@@ -552,9 +540,11 @@ __global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevCo
 // ------------------------------------------------------------------------------------------------
 // running Bonferroni: prefix sum over tested flags, then the significance screen
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_block_counts(const unsigned char *tested, long long n, long long *blocksum)
+constexpr int FIN_BLOCK = 256;      // columns per CTA of k_block_counts / k_finalize
+
+__global__ void __launch_bounds__(FIN_BLOCK) k_block_counts(const unsigned char *tested, long long n, long long *blocksum)
 {
-    const long long c = (long long)blockIdx.x * 1024 + threadIdx.x;
+    const long long c = (long long)blockIdx.x * FIN_BLOCK + threadIdx.x;
     const int t = (c < n) ? tested[c] : 0;
     const int total = __syncthreads_count(t);
     if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
@@ -608,22 +598,27 @@ __device__ __forceinline__ int class_of(int K)
     return cls;
 }
 
-__global__ void __launch_bounds__(1024) k_finalize(const DevConf cf, const long long n, const Workspace ws,
-                                                   const long long *bonf_start_dev)
+__global__ void __launch_bounds__(FIN_BLOCK) k_finalize(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
+                                                        const Lut *lut, const Workspace ws, const long long *bonf_start_dev)
 {
     __shared__ int s_warp[32];
+    __shared__ double s_lut[768];
+    __shared__ int s_hist[FIN_BLOCK / 32][256];
+    load_lut(s_lut, lut);
+    unsigned lut_sa = (unsigned)__cvta_generic_to_shared(s_lut);
+    const long long n = b.n_cols;
     // the running factor this batch continues from: the caller's conf, or a value another shard's count
     // exchange left in device memory (no host round trip)
     const long long bonf_start = bonf_start_dev ? *bonf_start_dev : cf.bonf_start;
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters->bonf_start_used = bonf_start;
-    const long long c = (long long)blockIdx.x * 1024 + threadIdx.x;
+    const long long c = (long long)blockIdx.x * FIN_BLOCK + threadIdx.x;
     const int lane = lane_id(), w = threadIdx.x >> 5;
     const int t = (c < n) ? ws.tested[c] : 0;
     const unsigned bal = __ballot_sync(FULL, t);
     if (lane == 0) s_warp[w] = __popc(bal);
     __syncthreads();
     if (w == 0) {
-        int z = s_warp[lane];
+        int z = lane < FIN_BLOCK / 32 ? s_warp[lane] : 0;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int y = __shfl_up_sync(FULL, z, d);
@@ -632,7 +627,6 @@ __global__ void __launch_bounds__(1024) k_finalize(const DevConf cf, const long 
         s_warp[lane] = z;
     }
     __syncthreads();
-    if (c >= n) return;
     long long bonf = 0;
     if (t) {
         // 1-based rank of this column among the tested columns of the batch
@@ -640,41 +634,106 @@ __global__ void __launch_bounds__(1024) k_finalize(const DevConf cf, const long 
         // lofreq_call.c:794-800: first tested column sets 3 when bonf_subst was 1, else += 3
         bonf = cf.bonf_dynamic ? ((bonf_start == 1 ? 0 : bonf_start) + 3 * rank) : bonf_start;
     }
-    ws.bonf_used[c] = bonf;
-    if (!t) return;
-    int cnt[3], raw[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        cnt[i] = ws.cnt6[6 * c + i];
-        raw[i] = ws.cnt6[6 * c + 3 + i];
+    if (c < n) ws.bonf_used[c] = bonf;
+    int cnt[3] = {0, 0, 0};
+    if (t) {
+        const int2 *in = reinterpret_cast<const int2 *>(ws.cnt6 + 6 * c);
+        const int2 a0 = in[0], a1 = in[1];
+        cnt[0] = a0.x; cnt[1] = a0.y; cnt[2] = a1.x;
     }
     const int K = max(cnt[0], max(cnt[1], cnt[2]));
-    if (K > KS) {
+    if (t && K > KS) {
         const int cls = class_of(K);
         const unsigned slot = atomicAdd(&ws.counters->n_jobs[cls], 1u);
         ws.jobs[(long long)cls * ws.cap_cols + slot] = (int)c;
-        return;
     }
-    const double4 tl = reinterpret_cast<const double4 *>(ws.tails)[c];
-    const double tails[3] = {tl.x, tl.y, tl.z};
-    const double tK = cnt[0] == K ? tails[0] : cnt[1] == K ? tails[1] : tails[2];
-    // clearly insignificant -> snpcaller() leaves LDBL_MAX everywhere (snpcaller.c:1155); the margin keeps
-    // borderline columns for the host, which repeats the comparison in long double
-    if (tK * (double)bonf > cf.sig * (1.0 + 1e-9)) return;
-    const unsigned slot = atomicAdd(&ws.counters->n_cand, 1u);
-    Cand cd;
-    cd.col = c;
-    cd.bonf = bonf;
+    // ---- columns with K <= KS ----
+    // (1) prune, lane per column: the reference's early exit (snpcaller.c:916-958) — walk the reads until
+    //     P(X >= K among the reads seen) * bonf > sig.  With the Bonferroni factors of a real run this takes
+    //     a handful of reads (K = 1: one; K = 3: ~6; K = 4: ~27 at depth-500 Q30), so almost every column
+    //     ends here without a warp ever being dedicated to it.  Cells are kept top-aligned (register 7 = cell
+    //     K-1, padding below cell 0 stays 0), so one code path serves every K.
+    bool small = t && K <= KS;
+    const double limit = small ? cf.sig * (1.0 + 1e-9) / (double)bonf : 0.0;   // margin: borderline columns go to the host
+    Geom mg;
+    mg.off = 0; mg.b1 = mg.b2 = mg.b3 = mg.n = 0; mg.ref_idx = -1; mg.alt_bp = cf.alt_bq_prob;
+    if (small) {
+        int cov;
+        load_geom(b, c, mg, cov);
+        mg.alt_bp = cf.alt_bq_prob;
+    }
+    if (cf.alt_bq_mode != 2) {          // the median override needs a warp-wide histogram: no lane-serial prune
+        double R[KS], T = 0.0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        cd.lnp[i] = cnt[i] > 0 ? log(tails[i]) : 0.0;
-        cd.cnt[i] = cnt[i];
-        cd.raw[i] = raw[i];
+        for (int j = 0; j < KS; ++j) R[j] = (j == KS - K) ? 1.0 : 0.0;
+        const int cap = min(mg.n, 128);
+        bool live = small;
+#pragma unroll 1
+        for (int i = 0; __any_sync(FULL, live && i < cap); ++i) {
+            if (!(live && i < cap)) continue;
+            const long long a = mg.off + i;
+            bool is_alt;
+            int slot;
+            double jp;
+            if (!eval_read<true>(cf, s_lut, mg, i, b.bq[a], cf.use_mq ? b.mq[a] : 0, cf.use_baq ? b.baq[a] : 0,
+                                 cf.use_sq ? b.sq[a] : 0, is_alt, slot, jp))
+                continue;
+            double p, q;
+            guard_pq(jp, p, q);
+            T = fma(R[KS - 1], p, T);
+#pragma unroll
+            for (int j = KS - 1; j >= 1; --j) R[j] = fma(R[j - 1], p, R[j] * q);
+            R[0] = R[0] * q;
+            if (T > limit) live = false;      // clearly insignificant: snpcaller() leaves LDBL_MAX everywhere (snpcaller.c:1155)
+        }
+        small = live;                          // survivors: not pruned within the cap
     }
-    cd.ln_floor = log(tl.w);
-    cd.flags = 0;
-    cd.pad = 0;
-    ws.cand[slot] = cd;
+    // (2) the survivors (true low-frequency variants, the first columns of a run): whole warp, full evaluation
+    unsigned todo = __ballot_sync(FULL, small);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const long long cc = __shfl_sync(FULL, c, src);
+        const long long cbonf = __shfl_sync(FULL, bonf, src);
+        const double climit = __shfl_sync(FULL, limit, src);
+        int ccnt[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ccnt[i] = __shfl_sync(FULL, cnt[i], src);
+        const int cK = max(ccnt[0], max(ccnt[1], ccnt[2]));
+        Geom g;
+        g.off = __shfl_sync(FULL, mg.off, src);
+        g.b1 = __shfl_sync(FULL, mg.b1, src);
+        g.b2 = __shfl_sync(FULL, mg.b2, src);
+        g.b3 = __shfl_sync(FULL, mg.b3, src);
+        g.n = __shfl_sync(FULL, mg.n, src);
+        g.ref_idx = __shfl_sync(FULL, mg.ref_idx, src);
+        g.alt_bp = 0.0;
+        setup_alt_bq(cf, b, s_lut, g, s_hist[w]);
+        double tails[4];
+        if (cK == 1) screen_small<1>(cf, b, lut_sa, g, ccnt, cK, tails);
+        else if (cK == 2) screen_small<2>(cf, b, lut_sa, g, ccnt, cK, tails);
+        else if (cK <= 4) screen_small<4>(cf, b, lut_sa, g, ccnt, cK, tails);
+        else screen_small<8>(cf, b, lut_sa, g, ccnt, cK, tails);
+        double tK = ccnt[0] == cK ? tails[0] : ccnt[1] == cK ? tails[1] : tails[2];
+        tK = __shfl_sync(FULL, tK, 0);
+        if (tK > climit) continue;
+        if (lane == 0) {
+            const unsigned slot = atomicAdd(&ws.counters->n_cand, 1u);
+            Cand cd;
+            cd.col = cc;
+            cd.bonf = cbonf;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                cd.lnp[i] = ccnt[i] > 0 ? log(tails[i]) : 0.0;
+                cd.cnt[i] = ccnt[i];
+                cd.raw[i] = ws.cnt6[6 * cc + 3 + i];
+            }
+            cd.ln_floor = log(tails[3]);
+            cd.flags = 0;
+            cd.pad = 0;
+            ws.cand[slot] = cd;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1119,8 +1178,8 @@ void launch_screen(const DevConf &cf, const DevBatch &b, const Lut *lut, const W
 void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st)
 {
     if (b.n_cols <= 0) return;
-    const int nb = (int)((b.n_cols + 1023) / 1024);
-    k_block_counts<<<nb, 1024, 0, st>>>(ws.tested, b.n_cols, ws.blocksum);
+    const int nb = (int)((b.n_cols + FIN_BLOCK - 1) / FIN_BLOCK);
+    k_block_counts<<<nb, FIN_BLOCK, 0, st>>>(ws.tested, b.n_cols, ws.blocksum);
     k_scan_blocks<<<1, 1024, 0, st>>>(ws.blocksum, nb, ws.counters);
 }
 
@@ -1128,10 +1187,10 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
                  cudaEvent_t after_finalize, const long long *bonf_start_dev)
 {
     if (b.n_cols <= 0) return;
-    const int nb = (int)((b.n_cols + 1023) / 1024);
+    const int nb = (int)((b.n_cols + FIN_BLOCK - 1) / FIN_BLOCK);
     // n_tested (first 8 bytes) belongs to the scan; everything after it is per-test state
     cudaMemsetAsync(reinterpret_cast<char *>(ws.counters) + 8, 0, sizeof(Counters) - 8, st);
-    k_finalize<<<nb, 1024, 0, st>>>(cf, b.n_cols, ws, bonf_start_dev);
+    k_finalize<<<nb, FIN_BLOCK, 0, st>>>(cf, b, lut, ws, bonf_start_dev);
     if (after_finalize) cudaEventRecord(after_finalize, st);
     // The register-tile classes are independent: run them side by side so that their warps share the SMs
     // (each class alone has too few columns to hide its own latencies).

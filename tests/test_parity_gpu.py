@@ -375,3 +375,31 @@ def test_column_builder_callback_surface(caller, port_oracle):
         assert s["qual"] == want["qual"][c].tolist() and s["called"] == want["called"][c].tolist()
         assert s["bonf"] == want["bonf_used"][c] and s["alt_count"] == want["alt_counts"][c].tolist()
     bld.close()
+
+
+def test_strict_fenv_mode_gives_the_same_sentinels():
+    """host finishing with the literal feclearexcept/fetestexcept sequence of the reference
+    (LFB200_STRICT_FENV=1) == the default result-based underflow test, on the golden grid"""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import lofreq_b200\n"
+        "z = np.load(%r)\n"
+        "offs = z['offsets']; sig = float(np.float32(0.01))\n"
+        "sel = np.nonzero((z['sig'] == sig) & (z['counts'].max(axis=1) <= 2048))[0]\n"
+        "c = lofreq_b200.Caller(0)\n"
+        "pv, lnp, st = c.snpcaller_batch([z['err_probs'][offs[i]:offs[i+1]] for i in sel], z['counts'][sel], z['bonf'][sel], sig)\n"
+        "assert np.array_equal(st, z['status'][sel])\n"
+        "sys.stdout.write(pv.tobytes().hex())\n" % (os.path.dirname(GOLD + '/..').rsplit('/tests', 1)[0], os.path.join(GOLD, 'snpcaller_grid.npz')))
+    outs = []
+    for strict in ("", "1"):
+        env = dict(os.environ)
+        env.pop("LFB200_STRICT_FENV", None)
+        if strict:
+            env["LFB200_STRICT_FENV"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] and len(outs[0]) > 1000
