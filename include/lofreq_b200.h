@@ -160,6 +160,10 @@ int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb2
  * ms4 = { k_screen, prefix-sum kernels, k_finalize, k_heavy<*> } of the last screen + test */
 int lfb200_set_profiling(lfb200_ctx *ctx, int on);
 int lfb200_get_profile(lfb200_ctx *ctx, float *ms4);
+/* copy alt_counts | alt_raw_counts ([n_cols][6] ints) of the last screen into caller-owned device memory */
+int lfb200_copy_counts_device(lfb200_ctx *ctx, void *stream, int *dst_dev);
+/* measured DFMA/s of this GPU (8 independent chains per thread, ~20 ms): the fp64-pipe roofline denominator */
+double lfb200_dfma_peak(lfb200_ctx *ctx, void *stream);
 /* device pointers of the per-column results of the last screen/test (valid
  * until the next screen on this ctx): alt_counts and alt_raw_counts are interleaved, stride 6 ints per
  * column (alt_raw_counts = alt_counts + 3); tested u8[n]; bonf_used i64[n] */

@@ -68,7 +68,7 @@ SITE_FN = C.CFUNCTYPE(None, C.POINTER(Site), C.c_longlong, C.c_char, C.c_int, C.
 # every symbol include/lofreq_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_conf", "lfb200_call_columns",
            "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_ntested_copy_device", "lfb200_test_device_from", "lfb200_bonf_start_device", "lfb200_sites_device",
-           "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
+           "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_dfma_peak", "lfb200_copy_counts_device", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
            "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_synth_depths",
            "lfb200_synth_columns"]
 
@@ -128,6 +128,10 @@ def load():
     lib.lfb200_builder_flush.argtypes = [vp]
     lib.lfb200_builder_destroy.restype = None
     lib.lfb200_builder_destroy.argtypes = [vp]
+    lib.lfb200_copy_counts_device.restype = C.c_int
+    lib.lfb200_copy_counts_device.argtypes = [vp, vp, vp]
+    lib.lfb200_dfma_peak.restype = C.c_double
+    lib.lfb200_dfma_peak.argtypes = [vp, vp]
     lib.lfb200_snpcaller.restype = C.c_int
     lib.lfb200_snpcaller.argtypes = [vp, vp, C.c_int, vp, ll, C.c_double, C.c_int]
     lib.lfb200_snpcaller_batch.restype = C.c_int

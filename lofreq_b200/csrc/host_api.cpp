@@ -598,6 +598,21 @@ extern "C" int lfb200_get_profile(lfb200_ctx *ctx, float *ms4)
     return 0;
 }
 
+extern "C" int lfb200_copy_counts_device(lfb200_ctx *ctx, void *stream, int *dst_dev)
+{
+    if (!ctx || !ctx->have_batch) return fail("no screened batch");
+    if (ctx->cur.n_cols)
+        CU(cudaMemcpyAsync(dst_dev, ctx->ws.cnt6, (size_t)ctx->cur.n_cols * 6 * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" double lfb200_dfma_peak(lfb200_ctx *ctx, void *stream)
+{
+    if (!ctx) return 0.0;
+    cudaSetDevice(ctx->device);
+    return measure_dfma_per_second((cudaStream_t)stream);
+}
+
 extern "C" int lfb200_device_results(lfb200_ctx *ctx, const int **alt_counts, const int **alt_raw_counts,
                                      const unsigned char **tested, const long long **bonf_used)
 {

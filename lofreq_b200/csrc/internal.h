@@ -94,6 +94,7 @@ void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st);
 void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
                  cudaEvent_t after_finalize, const long long *bonf_start_dev);
 void launch_bonf_start(const long long *counts, int rank, long long bonf_subst, long long *start, cudaStream_t st);
+double measure_dfma_per_second(cudaStream_t st);
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st);
 // synth.cu
 void launch_synth_depths(int workload, long long c0, long long n, int *depth, cudaStream_t st);

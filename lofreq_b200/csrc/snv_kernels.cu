@@ -598,7 +598,7 @@ __device__ __forceinline__ int class_of(int K)
     return cls;
 }
 
-__global__ void __launch_bounds__(FIN_BLOCK) k_finalize(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
+__global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
                                                         const Lut *lut, const Workspace ws, const long long *bonf_start_dev)
 {
     __shared__ int s_warp[32];
@@ -1231,6 +1231,48 @@ __global__ void k_bonf_start(const long long *counts, int rank, long long bonf_s
 void launch_bonf_start(const long long *counts, int rank, long long bonf_subst, long long *start, cudaStream_t st)
 {
     k_bonf_start<<<1, 1, 0, st>>>(counts, rank, bonf_subst, start);
+}
+
+static int sm_count();
+// DFMA throughput probe (the fp64-pipe roofline denominator; MEASURED_PEAKS.json has none for fp64)
+__global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters, double a, double b)
+{
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = 1.0 + threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 123.456) out[0] = s;
+}
+
+double measure_dfma_per_second(cudaStream_t st)
+{
+    double *out = nullptr;
+    if (cudaMalloc(&out, 8) != cudaSuccess) return 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int grid = sm_count() * 8, iters = 20000;
+    k_dfma_probe<<<grid, 256, 0, st>>>(out, 1000, 0.999999, 1e-7);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, st);
+        k_dfma_probe<<<grid, 256, 0, st>>>(out, iters, 0.999999, 1e-7);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return (double)grid * 256 * 8 * iters / (best * 1e-3);
 }
 
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st)
