@@ -514,7 +514,7 @@ extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *s
         CU(cudaStreamSynchronize(st));
         const Counters &c = *ctx->h_counters;
         if (c.err_flags & CF_UNSUPPORTED)
-            return fail("a column has an alt count above %d: not supported by this build", MAXK_WARP);
+            return fail("a column has an alt count above %d: not supported by this build", 16384);
         sm.n_tested = (long long)c.n_tested;
         n_cand = c.n_cand;
         for (int i = 0; i < NCLASS; ++i) sm.n_heavy += c.n_jobs[i];
@@ -864,7 +864,7 @@ extern "C" int lfb200_snpcaller_batch(lfb200_ctx *ctx, long long n, const double
     CU(cudaStreamSynchronize(st));
     for (long long i = 0; i < n; ++i) {
         const Cand &cd = ctx->h_cand[(size_t)i];
-        if (cd.flags & CF_UNSUPPORTED) return fail("problem %lld: alt count above %d or above the number of reads", i, MAXK_WARP);
+        if (cd.flags & CF_UNSUPPORTED) return fail("problem %lld: alt count above %d or above the number of reads", i, 16384);
         if (cd.flags & CF_RANGE) return fail("problem %lld: tail outside the representable range", i);
         lfb200_site_t s;
         finish_site(cd, sig_level, s);

@@ -1109,10 +1109,347 @@ __global__ void __launch_bounds__(128) k_heavy(const __grid_constant__ DevConf c
     }
 }
 
-// columns with K > 2048 are not implemented yet: report loudly instead of computing something else
-__global__ void k_heavy_xl(const Workspace ws, int cls)
+// ------------------------------------------------------------------------------------------------
+// k_heavy_xl: one CTA per column for 2048 < K <= 16384 (deep amplicons: depth >= ~4100 at AF 50 %).
+// The same odds-form recurrence as dp_run, K cells over 256 threads x 64 registers; the cell that crosses
+// a warp boundary goes through shared memory (double-buffered, one barrier per read).
+// ------------------------------------------------------------------------------------------------
+constexpr int XL_T = 256, XL_R = 64, XL_W = XL_T / 32;
+
+struct XlShared {
+    double2 par[XL_T];          // (o, 1/q) of the reads of the current stripe, compacted per warp
+    int par_n[XL_W];
+    double edge[2][XL_W];       // top cell of every warp after the previous read
+    double red[XL_W];
+    int redi[XL_W];
+};
+
+__device__ __forceinline__ double block_sum(double v, XlShared &sh)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0 && ws.counters->n_jobs[cls] > 0) atomicOr(&ws.counters->err_flags, (unsigned)CF_UNSUPPORTED);
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane_id() == 0) sh.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < XL_W; ++w) t += sh.red[w];
+    return t;
+}
+
+__device__ __forceinline__ int block_max_int(int v, XlShared &sh)
+{
+    v = __reduce_max_sync(FULL, v);
+    __syncthreads();
+    if (lane_id() == 0) sh.redi[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = sh.redi[0];
+#pragma unroll
+    for (int w = 1; w < XL_W; ++w) t = max(t, sh.redi[w]);
+    return t;
+}
+
+struct XlRow {
+    double E[XL_R];
+    double T;          // valid on the last thread
+    int e2;
+    double sum_lq, ln_s;
+};
+
+__device__ void xl_rescale(XlRow &row, XlShared &sh, bool force)
+{
+    int hi = 0;
+#pragma unroll
+    for (int r = 0; r < XL_R; ++r) hi = max(hi, __double2hiint(row.E[r]));
+    if (threadIdx.x == XL_T - 1) hi = max(hi, __double2hiint(row.T));
+    hi = block_max_int(hi, sh);
+    const int ex = (hi >> 20) - 1023;
+    if (force ? (ex != 0) : (ex > 200 || ex < -200)) {
+        const double f = __hiloint2double((1023 - ex) << 20, 0);
+#pragma unroll
+        for (int r = 0; r < XL_R; ++r) row.E[r] *= f;
+        row.T *= f;
+        row.e2 += ex;
+    }
+}
+
+template <class Src>
+__device__ void xl_dp_run(const Src &src, int K, double ln_s, XlShared &sh, XlRow &row)
+{
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const double s = (ln_s == 0.0) ? 1.0 : exp(ln_s);
+    const int k0 = K - XL_T * XL_R + tid * XL_R;
+#pragma unroll
+    for (int r = 0; r < XL_R; ++r) row.E[r] = (k0 + r == 0) ? 1.0 : 0.0;
+    row.T = 0.0;
+    row.e2 = 0;
+    row.ln_s = ln_s;
+    double lq_acc = 0.0, q_prod = 1.0;
+    if (lane == 31) sh.edge[0][w] = 0.0;     // before the first read every boundary cell is 0 (k0 + 63 == 0 cannot be a warp top unless K is tiny)
+    if (lane == 31 && k0 + XL_R - 1 == 0) sh.edge[0][w] = 1.0;
+    int parity = 0;
+    const int n = src.size();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int n0 = 0; n0 < n; n0 += XL_T) {
+        const int pos = n0 + tid;
+        double jp = 0.0, o = 0.0, rq = 1.0;
+        const bool ok = pos < n && src.get(pos, jp);
+        if (ok) {
+            double p, q;
+            guard_pq(jp, p, q);
+            rq = 1.0 / q;
+            o = p * s * rq;
+            q_prod *= q;
+            if (q_prod < 1e-200) {
+                lq_acc += log(q_prod);
+                q_prod = 1.0;
+            }
+        }
+        const unsigned m = __ballot_sync(FULL, ok);
+        const bool slow = __syncthreads_or(ok && (o > 1048576.0 || rq > 1048576.0));
+        if (ok) sh.par[w * 32 + __popc(m & lt_mask)] = make_double2(o, rq);
+        if (lane == 0) sh.par_n[w] = __popc(m);
+        __syncthreads();
+        for (int ws = 0; ws < XL_W; ++ws) {
+            const int cnt = sh.par_n[ws];
+            for (int j = 0; j < cnt; ++j) {
+                const double2 c = sh.par[ws * 32 + j];
+                const double top = row.E[XL_R - 1];
+                double in = __shfl_up_sync(FULL, top, 1);
+                if (lane == 0) in = w ? sh.edge[parity][w - 1] : 0.0;
+                row.T = fma(top, c.x, row.T * c.y);
+#pragma unroll
+                for (int r = XL_R - 1; r >= 1; --r) row.E[r] = fma(row.E[r - 1], c.x, row.E[r]);
+                row.E[0] = fma(in, c.x, row.E[0]);
+                parity ^= 1;
+                if (slow) xl_rescale(row, sh, true);          // before the boundary copy: it must carry the new scale
+                if (lane == 31) sh.edge[parity][w] = row.E[XL_R - 1];
+                __syncthreads();
+            }
+            if (!slow) {
+                // every 32 reads, like the warp kernel: (1 + 2^20)^32 stays inside fp64
+                xl_rescale(row, sh, false);
+                if (lane == 31) sh.edge[parity][w] = row.E[XL_R - 1];   // same cell, possibly rescaled
+                __syncthreads();
+            }
+        }
+    }
+    lq_acc += log(q_prod);
+    row.sum_lq = block_sum(lq_acc, sh);
+}
+
+template <class Src>
+__device__ double xl_newton(const Src &src, int K, int N, double lam, XlShared &sh)
+{
+    const double kt = fmin((double)K, (double)N - 0.5);
+    const double s0 = kt * fmax((double)N - lam, 1e-300) / (fmax(lam, 1e-300) * ((double)N - kt));
+    double lo = 0.0, hi = 60.0;
+    double ls = fmin(log(fmax(s0, 1.0)), hi);
+    const int n = src.size();
+    for (int it = 0; it < 40; ++it) {
+        const double s = exp(ls);
+        double g = 0.0, d = 0.0;
+        for (int pos = threadIdx.x; pos < n; pos += XL_T) {
+            double jp;
+            if (!src.get(pos, jp)) continue;
+            double p, q;
+            guard_pq(jp, p, q);
+            const double ps = p * s;
+            const double wv = ps / (q + ps);
+            g += wv;
+            d += wv * (1.0 - wv);
+        }
+        g = block_sum(g, sh) - kt;
+        d = block_sum(d, sh);
+        if (g > 0.0) hi = fmin(hi, ls); else lo = fmax(lo, ls);
+        double nl = d > 0.0 ? ls - g / d : 0.5 * (lo + hi);
+        if (!(nl > lo && nl < hi)) nl = 0.5 * (lo + hi);
+        const bool done = fabs(nl - ls) * sqrt(fmax(d, 1.0)) < 0.5;
+        ls = nl;
+        if (done) break;
+    }
+    return ls;
+}
+
+// ln P(X >= K) and ln P(X = K-1) for one column, whole CTA
+template <class Src>
+__device__ TailOut xl_tail(const Src &src, int K, int N, double lam, XlShared &sh, XlRow &row)
+{
+    TailOut out;
+    out.flags = 0;
+    const double cher = ((double)K > lam) ? ((double)K * log((double)K / lam) - (double)K + lam) : 0.0;
+    double ln_s = 0.0;
+    if (cher > 300.0) ln_s = xl_newton(src, K, N, lam, sh);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        xl_dp_run(src, K, ln_s, sh, row);
+        int hi = 0;
+#pragma unroll
+        for (int r = 0; r < XL_R; ++r) hi = max(hi, __double2hiint(row.E[r]));
+        hi = block_max_int(hi, sh);
+        const int hiT = block_max_int(threadIdx.x == XL_T - 1 ? __double2hiint(row.T) : 0, sh);
+        const int gap = ((max(hi, hiT)) >> 20) - (hiT >> 20);
+        if (gap > 580 && ln_s == 0.0 && attempt == 0) {
+            ln_s = xl_newton(src, K, N, lam, sh);
+            continue;
+        }
+        if (gap > 900) out.flags |= CF_RANGE;
+        break;
+    }
+    // T and the cell K-1 live on the last thread
+    __syncthreads();
+    if (threadIdx.x == XL_T - 1) {
+        sh.red[0] = row.T;
+        sh.red[1] = row.E[XL_R - 1];
+    }
+    __syncthreads();
+    const double T = sh.red[0], top = sh.red[1];
+    __syncthreads();
+    const double base = (double)row.e2 * LN2 + row.sum_lq;
+    out.lnT = log(T) + base - (double)K * row.ln_s;
+    out.lnKm1 = log(top) + base - (double)(K - 1) * row.ln_s;
+    return out;
+}
+
+// the snpcaller() arithmetic for one column / problem, whole CTA; false = clearly insignificant
+template <class Src>
+__device__ bool xl_problem(const Src &src, const int (&cnt)[3], long long bonf, double sig, XlShared &sh, double *s_small, Cand &cd)
+{
+    const int K = max(cnt[0], max(cnt[1], cnt[2]));
+    int Nl = 0;
+    double laml = 0.0;
+    for (int pos = threadIdx.x; pos < src.size(); pos += XL_T) {
+        double jp;
+        if (!src.get(pos, jp)) continue;
+        double p, q;
+        guard_pq(jp, p, q);
+        laml += p;
+        ++Nl;
+    }
+    const int N = (int)(block_sum((double)Nl, sh) + 0.5);
+    const double lam = block_sum(laml, sh);
+    XlRow row;
+    const TailOut main_t = xl_tail(src, K, N, lam, sh, row);
+    cd.flags = main_t.flags;
+    cd.lnp[0] = cd.lnp[1] = cd.lnp[2] = 0.0;
+    cd.ln_floor = 0.0;
+    if (main_t.lnT > -700.0 && exp(main_t.lnT) * (double)bonf > sig * (1.0 + 1e-9)) return false;
+    cd.ln_floor = fmin(main_t.lnT, main_t.lnKm1);
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {
+        const int cc = cnt[i];
+        if (cc == 0) continue;
+        if (cc == K) { cd.lnp[i] = main_t.lnT; continue; }
+        if (i == 2 && cc == cnt[1]) { cd.lnp[i] = cd.lnp[1]; continue; }
+        if (i >= 1 && cc == cnt[0]) { cd.lnp[i] = cd.lnp[0]; continue; }
+        if (cc <= KS) {
+            if (threadIdx.x < 32) {
+                double P[KS], T;
+                src_small_dispatch(src, cc, P, T);
+                if (threadIdx.x == 0) s_small[0] = log(T);
+            }
+            __syncthreads();
+            cd.lnp[i] = s_small[0];
+            __syncthreads();
+        } else {
+            const TailOut t2 = xl_tail(src, cc, N, lam, sh, row);
+            cd.flags |= t2.flags;
+            cd.lnp[i] = t2.lnT;
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(XL_T, 1) k_heavy_xl(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
+                                                      const Lut *lut, const Workspace ws, int cls)
+{
+    __shared__ double s_lut[768];
+    __shared__ XlShared sh;
+    __shared__ int s_hist[256];
+    __shared__ unsigned s_job;
+    __shared__ double s_small[KS + 1];
+    load_lut(s_lut, lut);
+    const unsigned njobs = ws.counters->n_jobs[cls];
+    const int *jobs = ws.jobs + (long long)cls * ws.cap_cols;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_job = atomicAdd(&ws.counters->next_job[cls], 1u);
+        __syncthreads();
+        const unsigned j = s_job;
+        if (j >= njobs) break;
+        const long long c = jobs[j];
+        ByteSrc src;
+        src.cf = &cf;
+        src.b = &b;
+        src.lut = s_lut;
+        int cov;
+        load_geom(b, c, src.g, cov);
+        if (cf.alt_bq_mode) {
+            // every warp computes the same override (the median needs a histogram: warp 0 does it, others read it)
+            if (threadIdx.x < 32) setup_alt_bq(cf, b, s_lut, src.g, s_hist);
+            if (threadIdx.x == 0) sh.red[0] = src.g.alt_bp;
+            __syncthreads();
+            src.g.alt_bp = sh.red[0];
+            __syncthreads();
+        }
+        int cnt[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
+        const int K = max(cnt[0], max(cnt[1], cnt[2]));
+        const long long bonf = ws.bonf_used[c];
+        if (K > XL_T * XL_R) {
+            if (threadIdx.x == 0) atomicOr(&ws.counters->err_flags, (unsigned)CF_UNSUPPORTED);
+            continue;
+        }
+        Cand cd;
+        if (!xl_problem(src, cnt, bonf, cf.sig, sh, s_small, cd)) continue;
+        if (threadIdx.x == 0) {
+            cd.col = c;
+            cd.bonf = bonf;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                cd.cnt[i] = cnt[i];
+                cd.raw[i] = ws.cnt6[6 * c + 3 + i];
+            }
+            cd.pad = 0;
+            const unsigned slot = atomicAdd(&ws.counters->n_cand, 1u);
+            ws.cand[slot] = cd;
+        }
+    }
+}
+
+// stand-alone problems with 2048 < K <= 16384, one CTA each
+__global__ void __launch_bounds__(XL_T, 1) k_prob_jobs_xl(const ProbBatch pb, Cand *out)
+{
+    __shared__ XlShared sh;
+    __shared__ double s_small[KS + 1];
+    for (long long i = blockIdx.x; i < pb.n; i += gridDim.x) {
+        int cnt[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) cnt[a] = pb.counts[3 * i + a];
+        const int K = max(cnt[0], max(cnt[1], cnt[2]));
+        if (K <= MAXK_WARP) continue;
+        ProbSrc src;
+        src.ep = pb.err_probs + pb.ep_off[i];
+        src.n = (int)(pb.ep_off[i + 1] - pb.ep_off[i]);
+        Cand cd;
+        cd.flags = 0;
+        cd.ln_floor = 0.0;
+        cd.lnp[0] = cd.lnp[1] = cd.lnp[2] = 0.0;
+        bool site = false;
+        const bool ok = K <= XL_T * XL_R && K <= src.n;
+        __syncthreads();
+        if (ok) site = xl_problem(src, cnt, pb.bonf[i], pb.sig, sh, s_small, cd);
+        if (threadIdx.x == 0) {
+            if (!site) cd.flags |= CF_INSIG;
+            if (!ok) cd.flags |= CF_UNSUPPORTED;
+            cd.col = i;
+            cd.bonf = pb.bonf[i];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { cd.cnt[a] = cnt[a]; cd.raw[a] = cnt[a]; }
+            cd.pad = 0;
+            out[i] = cd;
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1206,7 +1543,7 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
     const int g = sm_count() * 4;
     cudaEventRecord(ev_fork, st);
     for (int i = 0; i < NCLASS; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
-    k_heavy_xl<<<1, 32, 0, side[7]>>>(ws, 7);
+    k_heavy_xl<<<sm_count(), XL_T, 0, side[7]>>>(cf, b, lut, ws, 7);
     k_heavy<64><<<g, 128, 0, side[6]>>>(cf, b, lut, ws, 6);
     k_heavy<32><<<g, 128, 0, side[5]>>>(cf, b, lut, ws, 5);
     k_heavy<16><<<g, 128, 0, side[4]>>>(cf, b, lut, ws, 4);
@@ -1287,7 +1624,7 @@ void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st)
     k_prob_jobs<16><<<g, 128, 0, st>>>(pb, out, 4);
     k_prob_jobs<32><<<g, 128, 0, st>>>(pb, out, 5);
     k_prob_jobs<64><<<g, 128, 0, st>>>(pb, out, 6);
-    k_prob_jobs<64><<<g, 128, 0, st>>>(pb, out, 7);   // XL: only marks CF_UNSUPPORTED
+    k_prob_jobs_xl<<<(int)(pb.n < sm_count() ? pb.n : sm_count()), XL_T, 0, st>>>(pb, out);
 }
 
 }  // namespace lfb

@@ -21,7 +21,7 @@ from oracle.pyoracle import default_conf
 from test_oracle import GOLD, ld_from_bytes, load_conf
 
 LNP_RTOL = 1e-10
-MAXK = 2048          # largest alt count the warp-per-column kernel holds in registers
+MAXK = 16384         # largest alt count supported (CTA-per-column kernel: 256 threads x 64 cells)
 
 
 def status_of(pv):
@@ -207,7 +207,7 @@ def test_random_snpcaller_problems(caller, port_oracle):
     sig = float(np.float32(0.01))
     eps, cnts, bonfs = [], [], []
     for it in range(300):
-        n = int(rng.integers(1, MAXK))
+        n = int(rng.integers(1, 2600))
         mode = rng.integers(0, 4)
         if mode == 0:
             q = rng.integers(20, 41, n)
@@ -403,3 +403,31 @@ def test_strict_fenv_mode_gives_the_same_sentinels():
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout)
     assert outs[0] == outs[1] and len(outs[0]) > 1000
+
+
+def test_deep_columns_cta_per_column_kernel(caller, port_oracle):
+    """alt counts above 2048 (deep amplicon columns) run in the CTA-per-column kernel k_heavy_xl"""
+    rng = np.random.default_rng(9)
+
+    def grp(n, qlo=20, qhi=41):
+        return (rng.integers(qlo, qhi, n), np.full(n, 60), rng.integers(30, 61, n))
+    e = (np.zeros(0, int),) * 3
+    cols = [
+        dict(ref="A", groups=[grp(5000), grp(4000), grp(7), e]),                  # K = 4000
+        dict(ref="C", groups=[grp(2500), grp(3000), grp(2100), grp(12)]),         # tri-allelic, two counts above 2048
+        dict(ref="G", groups=[grp(3), grp(2), grp(30), grp(6000)]),               # nearly all reads alt
+        dict(ref="T", groups=[grp(40), grp(3000, 6, 12), e, grp(9000, 6, 12)]),   # low qualities: large lambda, no tilt
+        dict(ref="A", groups=[grp(600), grp(350), e, e]),                         # an ordinary heavy column in between
+    ]
+    b = _custom_batch(cols, pad=16)
+    for conf in (default_conf(), default_conf(flag=0)):
+        want = port_oracle.call_columns(b, dict(conf))
+        got = caller.call_columns(b, dict(conf))
+        compare_batch(got, want, "deep %s" % conf)
+    # and through the snpcaller() mirror
+    ep = np.sort(10.0 ** (-rng.integers(20, 41, 7000) / 10.0))
+    for counts in ((3000, 0, 0), (2500, 2200, 4)):
+        want = port_oracle.snpcaller(ep, counts, 30000, float(np.float32(0.01)))
+        got = caller.snpcaller(ep, counts, 30000, float(np.float32(0.01)))
+        assert np.array_equal(status_of(got), status_of(want))
+        assert_lnp_close(got, want, status_of(want), "deep snpcaller")
