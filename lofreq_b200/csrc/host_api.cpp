@@ -517,7 +517,7 @@ extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *s
             return fail("a column has an alt count above %d: not supported by this build", 16384);
         sm.n_tested = (long long)c.n_tested;
         n_cand = c.n_cand;
-        for (int i = 0; i < NCLASS; ++i) sm.n_heavy += c.n_jobs[i];
+        for (int i = 0; i < NCLASS; ++i) if (i != CLS_FALLBACK) sm.n_heavy += c.n_jobs[i];
     }
     if (dbg) t1 = now();
     if (n_cand > max_sites) return fail("%lld sites but room for %lld", n_cand, max_sites);

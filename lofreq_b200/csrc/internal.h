@@ -7,7 +7,9 @@
 namespace lfb {
 
 constexpr int KS = 8;              // columns whose largest alt count is <= KS are finished by the screen kernel
-constexpr int NCLASS = 8;          // register-tile classes of the O(depth*K) kernel: R = 1,2,4,..,64 cells per lane, then XL
+constexpr int NCLASS = 9;          // job lists: 0 = K <= 32 (k_mid), 1..6 = register tiles R = 2..64 (k_heavy<R>), 7 = XL (CTA per
+                                   // column), 8 = K <= 32 columns k_mid hands back to k_heavy<1> (tail outside the untilted range)
+constexpr int CLS_XL = 7, CLS_FALLBACK = 8;
 constexpr int MAXK_WARP = 2048;    // 32 lanes * 64 cells
 
 // what the kernels need from varcall_conf_t, pre-digested on the host

@@ -213,6 +213,40 @@ __device__ __forceinline__ void tree_merge(double (&P)[K], double &T)
     }
 }
 
+// Same merge for wide distributions (K up to 32): the partner's cells are fetched one at a time inside the
+// convolution instead of being held in registers.
+template <int K>
+__device__ __forceinline__ void tree_merge_stream(double (&P)[K], double &T)
+{
+#pragma unroll 1
+    for (int m = 1; m < 32; m <<= 1) {
+        double c[K];
+        const double tb = __shfl_xor_sync(FULL, T, m);
+        double sum_a = 0.0, sum_b = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            c[k] = 0.0;
+            sum_a += P[k];
+        }
+        double t = 0.0, asuf = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const double bj = __shfl_xor_sync(FULL, P[j], m);
+            sum_b += bj;
+#pragma unroll
+            for (int k = j; k < K; ++k) c[k] = fma(P[k - j], bj, c[k]);
+            if (j >= 1) {
+                asuf += P[K - j];
+                t = fma(bj, asuf, t);
+            }
+        }
+        t += T * (sum_b + tb) + tb * sum_a;
+#pragma unroll
+        for (int k = 0; k < K; ++k) P[k] = c[k];
+        T = t;
+    }
+}
+
 // The distribution was truncated at KV >= K = max count.  tails[i] = P(X >= cnt[i]) (0 when cnt[i] == 0),
 // tails[3] = min(P(X = K-1), P(X >= K)).
 template <int KV>
@@ -412,7 +446,7 @@ __device__ __noinline__ void screen_small(const DevConf &cf, const DevBatch &b, 
             fold_chunk<KV, false>(rr, lut_sa, g.n, ref_lo, ref_hi, pos0, ch, P, T);
         }
     }
-    tree_merge<KV>(P, T);
+    if (KV > 8) tree_merge_stream<KV>(P, T); else tree_merge<KV>(P, T);
     small_tails<KV>(P, T, cnt, K, tails);
 }
 
@@ -592,7 +626,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(long long *blocksum, int n
 __device__ __forceinline__ int class_of(int K)
 {
     const int need = (K + 31) >> 5;          // cells per lane
-    if (need > 64) return NCLASS - 1;        // XL
+    if (need > 64) return CLS_XL;
     int cls = 0;
     while ((1 << cls) < need) ++cls;
     return cls;
@@ -869,18 +903,42 @@ __device__ __forceinline__ void dp_run(const Src &src, int K, double ln_s, doubl
         __syncwarp();
         if (ok) sm[__popc(m & lt_mask)] = make_double2(o, rq);
         __syncwarp();
-        for (int j = 0; j < cnt; ++j) {
-            const double2 c = sm[j];
-            const double top = row.E[R - 1];
-            double in = __shfl_up_sync(FULL, top, 1);
-            if (lane == 0) in = 0.0;
-            row.T = fma(top, c.x, row.T * c.y);
+        if (!slow) {
+            // software-pipelined: the parameters of read j+1 and the boundary cell for read j+1 (the top cell
+            // right after its own update) are requested before the remaining R-1 cells of read j are updated
+            double2 c_next = sm[0];
+            double in_next = __shfl_up_sync(FULL, row.E[R - 1], 1);
+            for (int j = 0; j < cnt; ++j) {
+                const double2 c = c_next;
+                const double in = lane == 0 ? 0.0 : in_next;
+                c_next = sm[(j + 1) & 31];
+                const double top = row.E[R - 1];
+                row.T = fma(top, c.x, row.T * c.y);
+                if (R > 1) {
+                    row.E[R - 1] = fma(row.E[R > 1 ? R - 2 : 0], c.x, top);
+                    in_next = __shfl_up_sync(FULL, row.E[R - 1], 1);
 #pragma unroll
-            for (int r = R - 1; r >= 1; --r) row.E[r] = fma(row.E[r - 1], c.x, row.E[r]);
-            row.E[0] = fma(in, c.x, row.E[0]);
-            if (slow) rescale<R>(row, true);
+                    for (int r = R - 2; r >= 1; --r) row.E[r] = fma(row.E[r - 1], c.x, row.E[r]);
+                    row.E[0] = fma(in, c.x, row.E[0]);
+                } else {
+                    row.E[0] = fma(in, c.x, top);
+                    in_next = __shfl_up_sync(FULL, row.E[0], 1);
+                }
+            }
+            rescale<R>(row, false);
+        } else {
+            for (int j = 0; j < cnt; ++j) {
+                const double2 c = sm[j];
+                const double top = row.E[R - 1];
+                double in = __shfl_up_sync(FULL, top, 1);
+                if (lane == 0) in = 0.0;
+                row.T = fma(top, c.x, row.T * c.y);
+#pragma unroll
+                for (int r = R - 1; r >= 1; --r) row.E[r] = fma(row.E[r - 1], c.x, row.E[r]);
+                row.E[0] = fma(in, c.x, row.E[0]);
+                rescale<R>(row, true);
+            }
         }
-        if (!slow) rescale<R>(row, false);
     }
     lq_acc += log(q_prod);
     row.sum_lq = warp_sum(lq_acc);
@@ -1059,6 +1117,67 @@ __device__ bool run_problem(const Src &src, const int (&cnt)[3], long long bonf,
         }
     }
     return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_mid: columns with 8 < K <= 32.  At this size the recurrence over reads (depth serial steps of a
+// 32-cell row) is slower than folding the reads in parallel — every lane its 16-byte chunks into a
+// distribution truncated at 16 or 32 — and merging the 32 distributions by truncated convolution.
+// Untilted: if the tail leaves the fp64 range the column is handed to k_heavy<1>.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_mid(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, const Lut *lut,
+                                             const Workspace ws)
+{
+    __shared__ double s_lut[768];
+    __shared__ int s_hist[4][256];
+    load_lut(s_lut, lut);
+    unsigned lut_sa = (unsigned)__cvta_generic_to_shared(s_lut);
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    const unsigned njobs = ws.counters->n_jobs[0];
+    const int *jobs = ws.jobs;
+    for (;;) {
+        unsigned j = 0;
+        if (lane == 0) j = atomicAdd(&ws.counters->next_job[0], 1u);
+        j = __shfl_sync(FULL, j, 0);
+        if (j >= njobs) break;
+        const long long c = jobs[j];
+        Geom g;
+        int cov;
+        load_geom(b, c, g, cov);
+        setup_alt_bq(cf, b, s_lut, g, s_hist[wib]);
+        int cnt[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
+        const int K = max(cnt[0], max(cnt[1], cnt[2]));
+        const long long bonf = ws.bonf_used[c];
+        double tails[4];
+        if (K <= 16) screen_small<16>(cf, b, lut_sa, g, cnt, K, tails);
+        else screen_small<32>(cf, b, lut_sa, g, cnt, K, tails);
+        double tK = cnt[0] == K ? tails[0] : cnt[1] == K ? tails[1] : tails[2];
+        tK = __shfl_sync(FULL, tK, 0);
+        const double fl = __shfl_sync(FULL, tails[3], 0);
+        if (!(fl > 1e-280)) {
+            // too far out for the untilted form: k_heavy<1> has the tilt
+            if (lane == 0) ws.jobs[(long long)CLS_FALLBACK * ws.cap_cols + atomicAdd(&ws.counters->n_jobs[CLS_FALLBACK], 1u)] = (int)c;
+            continue;
+        }
+        if (tK * (double)bonf > cf.sig * (1.0 + 1e-9)) continue;
+        if (lane == 0) {
+            Cand cd;
+            cd.col = c;
+            cd.bonf = bonf;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                cd.lnp[i] = cnt[i] > 0 ? log(tails[i]) : 0.0;
+                cd.cnt[i] = cnt[i];
+                cd.raw[i] = ws.cnt6[6 * c + 3 + i];
+            }
+            cd.ln_floor = log(tails[3]);
+            cd.flags = 0;
+            cd.pad = 0;
+            ws.cand[atomicAdd(&ws.counters->n_cand, 1u)] = cd;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1473,7 +1592,7 @@ __global__ void __launch_bounds__(128) k_prob_jobs(const ProbBatch pb, Cand *out
         src.n = (int)(pb.ep_off[i + 1] - pb.ep_off[i]);
         Cand cd;
         bool site = false;
-        if (K > 0 && K <= src.n && cls < NCLASS - 1) site = run_problem<R>(src, cnt, pb.bonf[i], pb.sig, s_par[wib], cd);
+        if (K > 0 && K <= src.n && cls < CLS_XL) site = run_problem<R>(src, cnt, pb.bonf[i], pb.sig, s_par[wib], cd);
         else { cd.flags = 0; cd.ln_floor = 0.0; cd.lnp[0] = cd.lnp[1] = cd.lnp[2] = 0.0; }
         if (lane == 0) {
             if (!site) cd.flags |= CF_INSIG;
@@ -1531,27 +1650,29 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
     if (after_finalize) cudaEventRecord(after_finalize, st);
     // The register-tile classes are independent: run them side by side so that their warps share the SMs
     // (each class alone has too few columns to hide its own latencies).
-    static cudaStream_t side[NCLASS] = {nullptr};
-    static cudaEvent_t ev_fork = nullptr, ev_join[NCLASS] = {nullptr};
+    constexpr int NSIDE = 8;
+    static cudaStream_t side[NSIDE] = {nullptr};
+    static cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr};
     if (!ev_fork) {
         cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-        for (int i = 0; i < NCLASS; ++i) {
+        for (int i = 0; i < NSIDE; ++i) {
             cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
             cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
         }
     }
     const int g = sm_count() * 4;
     cudaEventRecord(ev_fork, st);
-    for (int i = 0; i < NCLASS; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
-    k_heavy_xl<<<sm_count(), XL_T, 0, side[7]>>>(cf, b, lut, ws, 7);
+    for (int i = 0; i < NSIDE; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
+    k_heavy_xl<<<sm_count(), XL_T, 0, side[7]>>>(cf, b, lut, ws, CLS_XL);
     k_heavy<64><<<g, 128, 0, side[6]>>>(cf, b, lut, ws, 6);
     k_heavy<32><<<g, 128, 0, side[5]>>>(cf, b, lut, ws, 5);
     k_heavy<16><<<g, 128, 0, side[4]>>>(cf, b, lut, ws, 4);
     k_heavy<8><<<g, 128, 0, side[3]>>>(cf, b, lut, ws, 3);
     k_heavy<4><<<g, 128, 0, side[2]>>>(cf, b, lut, ws, 2);
     k_heavy<2><<<g, 128, 0, side[1]>>>(cf, b, lut, ws, 1);
-    k_heavy<1><<<g, 128, 0, side[0]>>>(cf, b, lut, ws, 0);
-    for (int i = 0; i < NCLASS; ++i) {
+    k_mid<<<g, 128, 0, side[0]>>>(cf, b, lut, ws);
+    k_heavy<1><<<g, 128, 0, side[0]>>>(cf, b, lut, ws, CLS_FALLBACK);     // what k_mid handed back (rare)
+    for (int i = 0; i < NSIDE; ++i) {
         cudaEventRecord(ev_join[i], side[i]);
         cudaStreamWaitEvent(st, ev_join[i], 0);
     }
