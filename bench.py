@@ -146,12 +146,11 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes_per_column(wl, with_baq=False):
-    """DESIGN.md §Roofline: planes the configuration merges (bq, mq[, baq]) over the column's reads +
+def algorithmic_bytes(sum_depth, n_cols, planes=2):
+    """DESIGN.md §4: planes the configuration merges (bq, mq[, baq]) over the column's reads +
     per-column metadata in (col_off 8, nt_cnt 16, ref_base 1) + per-column results out (alt counts and
     raw counts 24, tested 1, bonf 8)."""
-    d = DEPTH[wl]
-    return d * (3 if with_baq else 2) + 25 + 33
+    return sum_depth * planes + (25 + 33) * n_cols
 
 
 # ------------------------------------------------------------------------------------------------
@@ -355,7 +354,7 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     ph = prof.mean(axis=0) * 1e-3
     t_stream = float(ph[0] + ph[1] + ph[2])
-    bytes_algo = algorithmic_bytes_per_column(wl) * n
+    bytes_algo = algorithmic_bytes(int(t["depths"].sum().item()), n)
     hbm = {"bound": "hbm", "kernel": "k_screen + k_block_counts + k_scan_blocks + k_finalize", "achieved": bytes_algo / t_stream / 1e9,
            "peak": peak, "unit": "GB/s", "frac": bytes_algo / t_stream / 1e9 / peak, "traffic": None, "peak_source": peak_src,
            "algorithmic_bytes_per_launch": bytes_algo, "kernel_ms": t_stream * 1e3}
@@ -416,7 +415,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4"])
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--cols", type=int, default=1_000_000, help="columns per GPU")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="columns of the single-thread cpu_baseline sample")
     ap.add_argument("--ref-cols-per-proc", type=int, default=30_000)
