@@ -226,51 +226,63 @@ def run_ours(args):
     sm = sms[0]
     confs = [None, None]
     exchanges = [shard.DeviceCountExchange(dev), shard.DeviceCountExchange(dev)] if world > 1 else None
-    site_mine = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(2)]
-    site_all = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
 
-    def launch(i):
-        """screen -> (exchange tested counts) -> test for context i, asynchronous"""
+    def screen(i):
+        """gates + alt counts of the next batch on context i, and (N > 1) the exchange of the tested-column counts:
+        1 x int64 per rank over NCCL on this stream, no host round trip.  Issued one batch ahead so that the
+        collective has a whole batch of kernels to hide behind."""
         cf = lofreq_b200.varcall_conf()
         ctx = callers[i]._ctx
         capi.check(lib.lfb200_screen_device(ctx, C.byref(cf), C.byref(db), sts[i]))
         if world > 1:
-            # tested-column counts: 1 x int64 per rank over NCCL on this stream, no host round trip; the test
-            # phase reads the running factor of the shards before this one from device memory
             ex = exchanges[i]
-            capi.check(lib.lfb200_ntested_copy_device(ctx, sts[i], C.c_void_p(ex.mine.data_ptr())))
+            capi.check(lib.lfb200_ntested_copy_device(ctx, sts[i], C.c_void_p(ex.mine.data_ptr())))   # mine[0]
             with torch.cuda.stream(streams[i]):
-                start = ex.exchange(sts[i])
-            capi.check(lib.lfb200_test_device_from(ctx, C.byref(cf), sts[i], C.c_void_p(start.data_ptr())))
-        else:
-            capi.check(lib.lfb200_test_device(ctx, C.byref(cf), sts[i]))
+                ex.exchange(sts[i])
         confs[i] = cf
 
-    def finish(i):
-        """D2H of the sites of context i + host finishing (synchronises stream i)"""
-        capi.check(lib.lfb200_sites_device(callers[i]._ctx, C.byref(confs[i]), sts[i], sites_bufs[i], max_sites,
-                                           C.byref(sms[i])))
+    def test(i):
+        """running Bonferroni (continued from the shards before this one), early-exit prune, O(depth*K) kernels"""
+        ctx = callers[i]._ctx
         if world > 1:
-            # the final per-region variant-count gather (north_star): asynchronous, read once after the timed region
+            capi.check(lib.lfb200_test_device_from(ctx, C.byref(confs[i]), sts[i], C.c_void_p(exchanges[i].start.data_ptr())))
+        else:
+            capi.check(lib.lfb200_test_device(ctx, C.byref(confs[i]), sts[i]))
+
+    def launch(i):
+        screen(i)
+        test(i)
+
+    def finish_begin(i):
+        """D2H of the sites of context i + host finishing, on the context's own finisher thread"""
+        capi.check(lib.lfb200_sites_begin(callers[i]._ctx, C.byref(confs[i]), sts[i], sites_bufs[i], max_sites))
+
+    def finish_end(i):
+        capi.check(lib.lfb200_sites_end(callers[i]._ctx, C.byref(sms[i])))
+        if world > 1:
+            # the per-region variant-count gather (north_star) rides in this context's next count exchange
             with torch.cuda.stream(streams[i]):
-                site_mine[i].fill_(int(sms[i].n_sites))
-                dist.all_gather_into_tensor(site_all[i], site_mine[i])
+                exchanges[i].mine[1:].fill_(int(sms[i].n_sites))
         return sms[i]
 
-    def run_steps(k_steps, prof=None):
-        launch(0)
-        for k in range(1, k_steps):
-            launch(k % 2)
-            finish((k - 1) % 2)
-            if prof is not None:
-                row = (C.c_float * 4)()
-                capi.check(lib.lfb200_get_profile(callers[(k - 1) % 2]._ctx, row))
-                prof[k - 1] = list(row)
-        finish((k_steps - 1) % 2)
-        if prof is not None:
-            row = (C.c_float * 4)()
-            capi.check(lib.lfb200_get_profile(callers[(k_steps - 1) % 2]._ctx, row))
-            prof[k_steps - 1] = list(row)
+    def finish(i):
+        finish_begin(i)
+        return finish_end(i)
+
+    def run_steps(k_steps):
+        """batch k on context k % 2: screen(k+1) is issued while test(k) runs, and the sites of batch k are finished
+        on a host thread while the launching thread goes on"""
+        screen(0)
+        for k in range(k_steps):
+            test(k % 2)
+            finish_begin(k % 2)
+            if k + 1 < k_steps:
+                if k >= 1:
+                    finish_end((k - 1) % 2)        # context (k+1) % 2 must be done with batch k-1
+                screen((k + 1) % 2)
+        if k_steps >= 2:
+            finish_end((k_steps - 2) % 2)
+        finish_end((k_steps - 1) % 2)
 
     def barrier():
         torch.cuda.synchronize()
@@ -294,6 +306,10 @@ def run_ours(args):
     clocks = sampler.stop()
     sm = sms[(args.steps - 1) % 2]
     n_sites, n_tested, n_heavy = sm.n_sites, sm.n_tested, sm.n_heavy
+    final_sites = [int(n_sites)]
+    if world > 1:
+        # the last batch's site counts: one more (tiny) gather outside the timed region
+        final_sites = shard.gather_counts(int(n_sites), device=dev)
     # CUDA events on the launching stream bracket the K steps (the closing event is recorded after the last
     # batch's host finishing has returned, so that host work is inside the region too); max over ranks
     el = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -396,7 +412,7 @@ def run_ours(args):
                            "cols_per_gpu": n, "depth": DEPTH.get(wl), "l2": "inputs larger than L2 (%.2f GB per step)" % (2 * total / 1e9),
                            "value_region": "screen + prefix sum + significance test + O(depth*K) kernels + D2H of sites + long double finishing, inputs resident in HBM; two contexts so that the host finishing of one batch overlaps the kernels of the next",
                            "tested_columns": int(n_tested), "sites": int(n_sites), "heavy_columns": int(n_heavy),
-                           "sites_all_ranks": [int(x) for x in site_all[(args.steps - 1) % 2].tolist()] if world > 1 else [int(n_sites)],
+                           "sites_all_ranks": final_sites,
                            "bonf_subst_final_this_rank": int(sm.bonf_subst_final)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},

@@ -156,6 +156,11 @@ int lfb200_bonf_start_device(void *stream, const long long *tested_counts_dev, i
                              long long *start_dev);
 int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites,
                         long long max_sites, lfb200_summary_t *summary);
+/* lfb200_sites_device split in two: begin hands the work (wait for the stream, D2H of the sites, long double
+ * finishing) to a thread owned by the context and returns at once; end waits for it.  conf, sites must stay valid
+ * in between; one request per context at a time.  Lets the caller launch the next batch meanwhile. */
+int lfb200_sites_begin(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites, long long max_sites);
+int lfb200_sites_end(lfb200_ctx *ctx, lfb200_summary_t *summary);
 /* optional per-phase device timing with CUDA events on the launching stream (benchmark / roofline):
  * ms4 = { k_screen, prefix-sum kernels, k_finalize, k_heavy<*> } of the last screen + test */
 int lfb200_set_profiling(lfb200_ctx *ctx, int on);

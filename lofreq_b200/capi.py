@@ -67,7 +67,7 @@ SITE_FN = C.CFUNCTYPE(None, C.POINTER(Site), C.c_longlong, C.c_char, C.c_int, C.
 
 # every symbol include/lofreq_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_conf", "lfb200_call_columns",
-           "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_ntested_copy_device", "lfb200_test_device_from", "lfb200_bonf_start_device", "lfb200_sites_device",
+           "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_ntested_copy_device", "lfb200_test_device_from", "lfb200_bonf_start_device", "lfb200_sites_device", "lfb200_sites_begin", "lfb200_sites_end",
            "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_dfma_peak", "lfb200_copy_counts_device", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
            "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_synth_depths",
            "lfb200_synth_columns"]
@@ -114,6 +114,10 @@ def load():
     lib.lfb200_bonf_start_device.argtypes = [vp, vp, C.c_int, ll, vp]
     lib.lfb200_sites_device.restype = C.c_int
     lib.lfb200_sites_device.argtypes = [vp, C.POINTER(Conf), vp, C.POINTER(Site), ll, C.POINTER(Summary)]
+    lib.lfb200_sites_begin.restype = C.c_int
+    lib.lfb200_sites_begin.argtypes = [vp, C.POINTER(Conf), vp, C.POINTER(Site), ll]
+    lib.lfb200_sites_end.restype = C.c_int
+    lib.lfb200_sites_end.argtypes = [vp, C.POINTER(Summary)]
     lib.lfb200_device_results.restype = C.c_int
     lib.lfb200_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.lfb200_set_profiling.restype = C.c_int

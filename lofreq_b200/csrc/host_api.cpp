@@ -169,6 +169,20 @@ struct lfb200_ctx {
     // optional per-phase timing (lfb200_set_profiling): events on the launching stream
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // finisher thread (lfb200_sites_begin / lfb200_sites_end)
+    std::thread fin_thread;
+    std::mutex fin_m;
+    std::condition_variable fin_cv, fin_done;
+    int fin_state = 0;                   // 0 idle, 1 requested, 2 done
+    bool fin_stop = false;
+    lfb200_conf_t *fin_conf = nullptr;
+    void *fin_stream = nullptr;
+    lfb200_site_t *fin_sites = nullptr;
+    long long fin_max = 0;
+    lfb200_summary_t fin_summary{};
+    int fin_rc = 0;
+    char fin_err[512] = "";
+    void finisher_loop();
     // state of the last screen
     DevBatch cur{};
     bool have_batch = false;
@@ -289,6 +303,14 @@ extern "C" int lfb200_create(lfb200_ctx **out, int device)
 extern "C" void lfb200_destroy(lfb200_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->fin_thread.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->fin_m);
+            ctx->fin_stop = true;
+        }
+        ctx->fin_cv.notify_all();
+        ctx->fin_thread.join();
+    }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_tails, &ctx->w_bonf, &ctx->w_blocksum, &ctx->w_jobs,
@@ -496,10 +518,11 @@ static long long final_bonf(const lfb200_conf_t *conf, long long start, long lon
     return (start == 1 ? 0 : start) + 3 * n_tested;     // lofreq_call.c:794-800
 }
 
-extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites,
-                                   long long max_sites, lfb200_summary_t *summary)
+static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites, long long max_sites,
+                      lfb200_summary_t *summary)
 {
     if (!ctx || !ctx->have_batch) return fail("no screened batch");
+    CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     lfb200_summary_t sm;
     memset(&sm, 0, sizeof(sm));
@@ -575,6 +598,60 @@ extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *s
     conf->num_snv_tests += 3 * sm.n_tested;       // lofreq_call.c:801
     sm.num_snv_tests = conf->num_snv_tests;
     if (summary) *summary = sm;
+    return 0;
+}
+
+extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites,
+                                   long long max_sites, lfb200_summary_t *summary)
+{
+    return sites_sync(ctx, conf, stream, sites, max_sites, summary);
+}
+
+// The same work on a per-context finisher thread, so that the caller's thread can go on launching the next batch.
+void lfb200_ctx::finisher_loop()
+{
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(fin_m);
+            fin_cv.wait(lk, [this] { return fin_state == 1 || fin_stop; });
+            if (fin_stop) return;
+        }
+        const int rc = sites_sync(this, fin_conf, fin_stream, fin_sites, fin_max, &fin_summary);
+        {
+            std::lock_guard<std::mutex> lk(fin_m);
+            fin_rc = rc;
+            if (rc) snprintf(fin_err, sizeof(fin_err), "%s", g_err);
+            fin_state = 2;
+        }
+        fin_done.notify_all();
+    }
+}
+
+extern "C" int lfb200_sites_begin(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites, long long max_sites)
+{
+    if (!ctx || !ctx->have_batch) return fail("no screened batch");
+    std::unique_lock<std::mutex> lk(ctx->fin_m);
+    if (ctx->fin_state != 0) return fail("a sites request is already pending on this context");
+    if (!ctx->fin_thread.joinable()) ctx->fin_thread = std::thread([ctx] { ctx->finisher_loop(); });
+    ctx->fin_conf = conf;
+    ctx->fin_stream = stream;
+    ctx->fin_sites = sites;
+    ctx->fin_max = max_sites;
+    ctx->fin_state = 1;
+    lk.unlock();
+    ctx->fin_cv.notify_all();
+    return 0;
+}
+
+extern "C" int lfb200_sites_end(lfb200_ctx *ctx, lfb200_summary_t *summary)
+{
+    if (!ctx) return fail("no context");
+    std::unique_lock<std::mutex> lk(ctx->fin_m);
+    if (ctx->fin_state == 0) return fail("no sites request pending on this context");
+    ctx->fin_done.wait(lk, [ctx] { return ctx->fin_state == 2; });
+    ctx->fin_state = 0;
+    if (summary) *summary = ctx->fin_summary;
+    if (ctx->fin_rc) return fail("%s", ctx->fin_err);
     return 0;
 }
 

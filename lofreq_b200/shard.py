@@ -55,16 +55,18 @@ def final_counters(tested_counts, bonf_subst=1, bonf_dynamic=1, num_snv_tests=0)
 class DeviceCountExchange:
     """The same exchange kept on the device (NCCL on the kernels' stream, no host synchronisation):
     every rank contributes its tested-column count, `start` ends up holding the running Bonferroni factor
-    this rank's test phase must start from (1 when nothing was tested before it)."""
+    this rank's test phase must start from (1 when nothing was tested before it).  A second int64 rides along
+    in the same all_gather: the site count of the batch this context finished before (the "final per-region
+    variant-count gather"), so one collective per batch carries both."""
 
     def __init__(self, device, bonf_subst=1):
         import torch
         import torch.distributed as dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.mine = torch.zeros(1, dtype=torch.int64, device=device)
-        self.all = torch.zeros(self.world, dtype=torch.int64, device=device)
+        self.mine = torch.zeros(2, dtype=torch.int64, device=device)        # [tested (this batch), sites (previous batch)]
+        self.all = torch.zeros((self.world, 2), dtype=torch.int64, device=device)
+        self.tested_all = torch.zeros(self.world, dtype=torch.int64, device=device)
         self.start = torch.full((1,), bonf_subst, dtype=torch.int64, device=device)
-        self.base = 0 if bonf_subst == 1 else bonf_subst
         self.bonf_subst = bonf_subst
 
     def exchange(self, stream_ptr=None):
@@ -72,7 +74,12 @@ class DeviceCountExchange:
         import ctypes as C
         import torch.distributed as dist
         from . import capi
-        dist.all_gather_into_tensor(self.all, self.mine)
-        capi.check(capi.load().lfb200_bonf_start_device(stream_ptr, C.c_void_p(self.all.data_ptr()), self.rank,
+        dist.all_gather_into_tensor(self.all.view(-1), self.mine)
+        self.tested_all.copy_(self.all[:, 0])
+        capi.check(capi.load().lfb200_bonf_start_device(stream_ptr, C.c_void_p(self.tested_all.data_ptr()), self.rank,
                                                          self.bonf_subst, C.c_void_p(self.start.data_ptr())))
         return self.start
+
+    def site_counts(self):
+        """site counts of the previous batch of every rank, as gathered by the last exchange (synchronises)"""
+        return [int(x) for x in self.all[:, 1].tolist()]
