@@ -225,7 +225,8 @@ def run_ours(args):
     sms = [capi.Summary(), capi.Summary()]
     sm = sms[0]
     confs = [None, None]
-    exchanges = [shard.DeviceCountExchange(dev), shard.DeviceCountExchange(dev)] if world > 1 else None
+    exchanges = [shard.ShardComm(callers[0], dev), shard.ShardComm(callers[1], dev)] if world > 1 else None
+    prev_sites = [0, 0]
 
     def screen(i):
         """gates + alt counts of the next batch on context i, and (N > 1) the exchange of the tested-column counts:
@@ -235,17 +236,14 @@ def run_ours(args):
         ctx = callers[i]._ctx
         capi.check(lib.lfb200_screen_device(ctx, C.byref(cf), C.byref(db), sts[i]))
         if world > 1:
-            ex = exchanges[i]
-            capi.check(lib.lfb200_ntested_copy_device(ctx, sts[i], C.c_void_p(ex.mine.data_ptr())))   # mine[0]
-            with torch.cuda.stream(streams[i]):
-                ex.exchange(sts[i])
+            exchanges[i].exchange(sts[i], sites_prev_batch=prev_sites[i])     # ncclAllGather on this stream
         confs[i] = cf
 
     def test(i):
         """running Bonferroni (continued from the shards before this one), early-exit prune, O(depth*K) kernels"""
         ctx = callers[i]._ctx
         if world > 1:
-            capi.check(lib.lfb200_test_device_from(ctx, C.byref(confs[i]), sts[i], C.c_void_p(exchanges[i].start.data_ptr())))
+            capi.check(lib.lfb200_test_device_from(ctx, C.byref(confs[i]), sts[i], exchanges[i].start_ptr))
         else:
             capi.check(lib.lfb200_test_device(ctx, C.byref(confs[i]), sts[i]))
 
@@ -259,10 +257,7 @@ def run_ours(args):
 
     def finish_end(i):
         capi.check(lib.lfb200_sites_end(callers[i]._ctx, C.byref(sms[i])))
-        if world > 1:
-            # the per-region variant-count gather (north_star) rides in this context's next count exchange
-            with torch.cuda.stream(streams[i]):
-                exchanges[i].mine[1:].fill_(int(sms[i].n_sites))
+        prev_sites[i] = int(sms[i].n_sites)   # the per-region variant-count gather rides in this context's next exchange
         return sms[i]
 
     def finish(i):

@@ -154,6 +154,17 @@ int lfb200_test_device_from(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *st
  * shard in device memory (lofreq_call.c:794-800 continued across shards) */
 int lfb200_bonf_start_device(void *stream, const long long *tested_counts_dev, int rank, long long bonf_subst,
                              long long *start_dev);
+/* The exchange done by the library itself over NCCL (dlopen'ed), directly on the kernels' stream:
+ *   comm_unique_id : rank 0 creates the 128-byte id, the caller broadcasts it to all ranks by any means
+ *   comm_init      : one communicator per context (collective: every rank calls it)
+ *   comm_exchange  : after screen — all_gather of {tested columns of this batch, sites_prev_batch} and the
+ *                    starting factor of this shard left in device memory (*bonf_start_dev, for test_device_from)
+ *   comm_gathered  : host copy of what the last exchange gathered (synchronises the stream) */
+int lfb200_comm_unique_id(unsigned char id[128]);
+int lfb200_comm_init(lfb200_ctx *ctx, int world, int rank, const unsigned char id[128]);
+int lfb200_comm_exchange(lfb200_ctx *ctx, void *stream, long long bonf_subst, long long sites_prev_batch,
+                         const long long **bonf_start_dev);
+int lfb200_comm_gathered(lfb200_ctx *ctx, void *stream, long long *tested_all, long long *sites_prev_all);
 int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites,
                         long long max_sites, lfb200_summary_t *summary);
 /* lfb200_sites_device split in two: begin hands the work (wait for the stream, D2H of the sites, long double

@@ -28,6 +28,8 @@
 
 using namespace lfb;
 
+void lfb_comm_release(lfb200_ctx *ctx);      // shard_comm.cpp
+
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
@@ -183,6 +185,7 @@ struct lfb200_ctx {
     int fin_rc = 0;
     char fin_err[512] = "";
     void finisher_loop();
+    void *comm_state = nullptr;          // owned by shard_comm.cpp
     // state of the last screen
     DevBatch cur{};
     bool have_batch = false;
@@ -303,6 +306,7 @@ extern "C" int lfb200_create(lfb200_ctx **out, int device)
 extern "C" void lfb200_destroy(lfb200_ctx *ctx)
 {
     if (!ctx) return;
+    lfb_comm_release(ctx);
     if (ctx->fin_thread.joinable()) {
         {
             std::lock_guard<std::mutex> lk(ctx->fin_m);
@@ -504,6 +508,12 @@ extern "C" int lfb200_bonf_start_device(void *stream, const long long *tested_co
     CU(cudaGetLastError());
     return 0;
 }
+
+// accessors for shard_comm.cpp (the context layout is private to this file)
+const unsigned long long *lfb_ctx_ntested_dev(lfb200_ctx *ctx) { return (ctx && ctx->have_batch) ? &ctx->ws.counters->n_tested : nullptr; }
+int lfb_ctx_device(lfb200_ctx *ctx) { return ctx ? ctx->device : -1; }
+void **lfb_ctx_comm_slot(lfb200_ctx *ctx) { return ctx ? &ctx->comm_state : nullptr; }
+int lfb_fail(const char *msg) { return fail("%s", msg); }
 
 extern "C" int lfb200_ntested_copy_device(lfb200_ctx *ctx, void *stream, long long *dst_dev)
 {

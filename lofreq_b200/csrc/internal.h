@@ -96,6 +96,9 @@ void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st);
 void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
                  cudaEvent_t after_finalize, const long long *bonf_start_dev);
 void launch_bonf_start(const long long *counts, int rank, long long bonf_subst, long long *start, cudaStream_t st);
+void launch_bonf_start_strided(const long long *counts, int stride, int rank, long long bonf_subst, long long *start,
+                               cudaStream_t st);
+void launch_set_i64(long long *dst, long long v, cudaStream_t st);
 double measure_dfma_per_second(cudaStream_t st);
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st);
 // synth.cu

@@ -1691,6 +1691,22 @@ void launch_bonf_start(const long long *counts, int rank, long long bonf_subst, 
     k_bonf_start<<<1, 1, 0, st>>>(counts, rank, bonf_subst, start);
 }
 
+__global__ void k_bonf_start_strided(const long long *counts, int stride, int rank, long long bonf_subst, long long *start)
+{
+    long long before = 0;
+    for (int r = 0; r < rank; ++r) before += counts[(long long)r * stride];
+    *start = before > 0 ? (bonf_subst == 1 ? 0 : bonf_subst) + 3 * before : bonf_subst;
+}
+
+void launch_bonf_start_strided(const long long *counts, int stride, int rank, long long bonf_subst, long long *start, cudaStream_t st)
+{
+    k_bonf_start_strided<<<1, 1, 0, st>>>(counts, stride, rank, bonf_subst, start);
+}
+
+__global__ void k_set_i64(long long *dst, long long v) { *dst = v; }
+
+void launch_set_i64(long long *dst, long long v, cudaStream_t st) { k_set_i64<<<1, 1, 0, st>>>(dst, v); }
+
 static int sm_count();
 // DFMA throughput probe (the fp64-pipe roofline denominator; MEASURED_PEAKS.json has none for fp64)
 __global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters, double a, double b)

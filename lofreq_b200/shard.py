@@ -52,34 +52,43 @@ def final_counters(tested_counts, bonf_subst=1, bonf_dynamic=1, num_snv_tests=0)
     return bonf, num_snv_tests + 3 * total
 
 
-class DeviceCountExchange:
-    """The same exchange kept on the device (NCCL on the kernels' stream, no host synchronisation):
-    every rank contributes its tested-column count, `start` ends up holding the running Bonferroni factor
-    this rank's test phase must start from (1 when nothing was tested before it).  A second int64 rides along
-    in the same all_gather: the site count of the batch this context finished before (the "final per-region
-    variant-count gather"), so one collective per batch carries both."""
+class ShardComm:
+    """The library's own NCCL exchange (include/lofreq_b200.h: lfb200_comm_*), one communicator per context.
+    torch.distributed is used once, to hand rank 0's NCCL unique id to the other ranks."""
 
-    def __init__(self, device, bonf_subst=1):
+    def __init__(self, caller, device):
+        import ctypes as C
         import torch
         import torch.distributed as dist
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.mine = torch.zeros(2, dtype=torch.int64, device=device)        # [tested (this batch), sites (previous batch)]
-        self.all = torch.zeros((self.world, 2), dtype=torch.int64, device=device)
-        self.tested_all = torch.zeros(self.world, dtype=torch.int64, device=device)
-        self.start = torch.full((1,), bonf_subst, dtype=torch.int64, device=device)
-        self.bonf_subst = bonf_subst
-
-    def exchange(self, stream_ptr=None):
-        """call with the torch current stream = the stream the count was copied on (stream_ptr = its handle)"""
-        import ctypes as C
-        import torch.distributed as dist
         from . import capi
-        dist.all_gather_into_tensor(self.all.view(-1), self.mine)
-        self.tested_all.copy_(self.all[:, 0])
-        capi.check(capi.load().lfb200_bonf_start_device(stream_ptr, C.c_void_p(self.tested_all.data_ptr()), self.rank,
-                                                         self.bonf_subst, C.c_void_p(self.start.data_ptr())))
-        return self.start
+        self.lib, self.caller = capi.load(), caller
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            capi.check(self.lib.lfb200_comm_unique_id(buf))
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.to(device)
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().tolist())
+        self._uid = (C.c_ubyte * 128).from_buffer_copy(raw)
+        capi.check(self.lib.lfb200_comm_init(caller._ctx, self.world, self.rank, self._uid))
+        self.start_ptr = C.c_void_p()
 
-    def site_counts(self):
-        """site counts of the previous batch of every rank, as gathered by the last exchange (synchronises)"""
-        return [int(x) for x in self.all[:, 1].tolist()]
+    def exchange(self, stream_ptr, sites_prev_batch=0, bonf_subst=1):
+        """after screen: gathers {tested, sites_prev_batch} of every shard; returns the device pointer of this
+        shard's starting Bonferroni factor (for lfb200_test_device_from).  Asynchronous."""
+        import ctypes as C
+        from . import capi
+        capi.check(self.lib.lfb200_comm_exchange(self.caller._ctx, stream_ptr, int(bonf_subst), int(sites_prev_batch),
+                                                  C.byref(self.start_ptr)))
+        return self.start_ptr
+
+    def gathered(self, stream_ptr):
+        """(tested counts, sites of the previous batch) of every shard from the last exchange; synchronises"""
+        import ctypes as C
+        from . import capi
+        a = (C.c_longlong * self.world)()
+        b = (C.c_longlong * self.world)()
+        capi.check(self.lib.lfb200_comm_gathered(self.caller._ctx, stream_ptr, a, b))
+        return list(a), list(b)
