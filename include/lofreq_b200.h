@@ -230,6 +230,21 @@ int lfb200_snpcaller_batch(lfb200_ctx *ctx, long long n, const double *err_probs
                            const int *noncons_counts, const long long *bonf, double sig_level,
                            long double *snp_pvalues, double *lnp, unsigned char *status);
 
+/* binom() of binom.c:52-93 (caller: lofreq_uniq.c:381; note binom.h:32 names the
+ * last two arguments the other way round): *p = P(X <= num_success), *q = 1 - *p
+ * for X ~ Binomial(num_trials, prob_success); either pointer may be NULL.
+ * Returns cdfbin's status (dcdflib.c:1860-1960): 0 ok, -5 num_trials <= 0,
+ * -4 num_success outside [0, num_trials], -6 prob_success outside [0, 1]; on a
+ * non-zero status *p and *q are left untouched, like the reference.  The
+ * reference reaches the value through cdflib's incomplete beta function
+ * (cumbin -> cumbet -> bratio); the device sums the mass function on the short
+ * side of the mode (csrc/binom.cu).  Same default context as lfb200_snpcaller. */
+int lfb200_binom(double *p, double *q, int num_trials, int num_success, double prob_success);
+/* many binom() calls in one launch; status[i] as above (required), p / q nullable.
+ * Returns non-zero only for CUDA / memory failures (lfb200_last_error). */
+int lfb200_binom_batch(lfb200_ctx *ctx, long long n, const int *num_trials, const int *num_success,
+                       const double *prob_success, double *p, double *q, int *status);
+
 /* ---- synthetic pileup columns on the device (benchmark input,
  *      bit-identical to oracle/synth_np.py) --------------- */
 /* workload: 2..5 = C2..C5.  Writes columns [c0, c0+n_cols) with the given

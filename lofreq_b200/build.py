@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "liblofreq_b200.so")
-SOURCES = ["snv_kernels.cu", "synth.cu", "host_api.cpp", "shard_comm.cpp"]
+SOURCES = ["snv_kernels.cu", "binom.cu", "synth.cu", "host_api.cpp", "shard_comm.cpp"]
 DEPS = SOURCES + ["internal.h", "synth_tables.h", os.path.join("..", "..", "include", "lofreq_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]

@@ -70,7 +70,7 @@ SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_
            "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_ntested_copy_device", "lfb200_test_device_from", "lfb200_bonf_start_device", "lfb200_comm_unique_id", "lfb200_comm_init", "lfb200_comm_exchange", "lfb200_comm_gathered",
            "lfb200_sites_device", "lfb200_sites_begin", "lfb200_sites_end",
            "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_dfma_peak", "lfb200_copy_counts_device", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
-           "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_synth_depths",
+           "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_binom", "lfb200_binom_batch", "lfb200_synth_depths",
            "lfb200_synth_columns"]
 
 _lib = None
@@ -123,6 +123,10 @@ def load():
     lib.lfb200_comm_exchange.argtypes = [vp, vp, ll, ll, C.POINTER(vp)]
     lib.lfb200_comm_gathered.restype = C.c_int
     lib.lfb200_comm_gathered.argtypes = [vp, vp, vp, vp]
+    lib.lfb200_binom.restype = C.c_int
+    lib.lfb200_binom.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
+    lib.lfb200_binom_batch.restype = C.c_int
+    lib.lfb200_binom_batch.argtypes = [vp, ll, vp, vp, vp, vp, vp, vp]
     lib.lfb200_sites_begin.restype = C.c_int
     lib.lfb200_sites_begin.argtypes = [vp, C.POINTER(Conf), vp, C.POINTER(Site), ll]
     lib.lfb200_sites_end.restype = C.c_int

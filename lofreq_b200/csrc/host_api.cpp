@@ -989,6 +989,55 @@ extern "C" int lfb200_snpcaller(long double *snp_pvalues, const double *err_prob
 }
 
 // ------------------------------------------------------------------------------------------------
+// binom() (binom.c:52-93): binomial CDF / survival function, batched on the device
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfb200_binom_batch(lfb200_ctx *ctx, long long n, const int *num_trials, const int *num_success,
+                                  const double *prob_success, double *p, double *q, int *status)
+{
+    if (!ctx) return fail("no context");
+    if (n <= 0) return 0;
+    if (!num_trials || !num_success || !prob_success || !status) return fail("null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_n, *d_s, *d_pr;
+    if (upload(ctx->p_cnt, num_trials, (size_t)n * 4, 0, st, &d_n)) return 1;
+    if (upload(ctx->p_off, num_success, (size_t)n * 4, 0, st, &d_s)) return 1;
+    if (upload(ctx->p_ep, prob_success, (size_t)n * 8, 0, st, &d_pr)) return 1;
+    // outputs: cum | ccum | status in one buffer
+    if (ctx->p_out.ensure((size_t)n * 20)) return fail("out of device memory");
+    double *d_cum = (double *)ctx->p_out.p, *d_ccum = d_cum + n;
+    int *d_status = (int *)(d_ccum + n);
+    if (launch_binom(n, (const int *)d_n, (const int *)d_s, (const double *)d_pr, d_cum, d_ccum, d_status, st))
+        return fail("could not upload the Stirling table");
+    CU(cudaGetLastError());
+    std::vector<double> h((size_t)n * 2);
+    CU(cudaMemcpyAsync(h.data(), d_cum, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (long long i = 0; i < n; ++i) {
+        if (status[i]) continue;         // the reference leaves *p / *q untouched when cdfbin refuses the arguments
+        if (p) p[i] = h[(size_t)i];
+        if (q) q[i] = h[(size_t)(n + i)];
+    }
+    return 0;
+}
+
+// same signature and return value as the reference's binom(): cdfbin's status, 0 = ok
+extern "C" int lfb200_binom(double *p, double *q, int num_trials, int num_success, double prob_success)
+{
+    if (!g_default_ctx && lfb200_create(&g_default_ctx, 0)) {
+        fprintf(stderr, "FATAL(lofreq_b200): %s\n", g_err);
+        return 1;
+    }
+    int status = 1;                      // "error by default" (binom.c:56)
+    if (lfb200_binom_batch(g_default_ctx, 1, &num_trials, &num_success, &prob_success, p, q, &status)) {
+        fprintf(stderr, "FATAL(lofreq_b200): %s\n", g_err);
+        return 1;
+    }
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------------
 // synthetic columns
 // ------------------------------------------------------------------------------------------------
 extern "C" int lfb200_synth_depths(int workload, long long c0, long long n_cols, int *depth_dev, void *stream)

@@ -101,6 +101,9 @@ void launch_bonf_start_strided(const long long *counts, int stride, int rank, lo
 void launch_set_i64(long long *dst, long long v, cudaStream_t st);
 double measure_dfma_per_second(cudaStream_t st);
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st);
+// binom.cu
+int launch_binom(long long n_prob, const int *num_trials, const int *num_success, const double *prob, double *cum, double *ccum,
+                 int *status, cudaStream_t st);
 // synth.cu
 void launch_synth_depths(int workload, long long c0, long long n, int *depth, cudaStream_t st);
 void launch_synth_columns(int workload, long long c0, long long n, const long long *col_off, int *nt_cnt, char *ref,

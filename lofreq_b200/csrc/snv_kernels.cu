@@ -575,6 +575,7 @@ __global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevCo
 // running Bonferroni: prefix sum over tested flags, then the significance screen
 // ------------------------------------------------------------------------------------------------
 constexpr int FIN_BLOCK = 256;      // columns per CTA of k_block_counts / k_finalize
+constexpr int PRUNE_CAP = 32;       // reads the lane-per-column prune of k_finalize looks at before it hands the column on
 
 __global__ void __launch_bounds__(FIN_BLOCK) k_block_counts(const unsigned char *tested, long long n, long long *blocksum)
 {
@@ -637,9 +638,7 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant
 {
     __shared__ int s_warp[32];
     __shared__ double s_lut[768];
-    __shared__ int s_hist[FIN_BLOCK / 32][256];
     load_lut(s_lut, lut);
-    unsigned lut_sa = (unsigned)__cvta_generic_to_shared(s_lut);
     const long long n = b.n_cols;
     // the running factor this batch continues from: the caller's conf, or a value another shard's count
     // exchange left in device memory (no host round trip)
@@ -700,17 +699,24 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant
         double R[KS], T = 0.0;
 #pragma unroll
         for (int j = 0; j < KS; ++j) R[j] = (j == KS - K) ? 1.0 : 0.0;
-        const int cap = min(mg.n, 128);
+        const int cap = min(mg.n, PRUNE_CAP);
         bool live = small;
+        // the reads come in aligned 16-byte chunks per plane: one load per plane covers what most columns need
+        const long long ca = mg.off & ~15ll;
+        const int lead = (int)(mg.off - ca);
+        Chunk16 ch;
+        ch.bq = ch.mq = ch.baq = ch.sq = make_uint4(0, 0, 0, 0);
+        if (live && cap > 0) load_chunk(cf, b, ca, ch);
 #pragma unroll 1
         for (int i = 0; __any_sync(FULL, live && i < cap); ++i) {
             if (!(live && i < cap)) continue;
-            const long long a = mg.off + i;
+            const int idx = lead + i, j = idx & 15;
+            if (j == 0 && i > 0) load_chunk(cf, b, ca + idx, ch);
             bool is_alt;
             int slot;
             double jp;
-            if (!eval_read<true>(cf, s_lut, mg, i, b.bq[a], cf.use_mq ? b.mq[a] : 0, cf.use_baq ? b.baq[a] : 0,
-                                 cf.use_sq ? b.sq[a] : 0, is_alt, slot, jp))
+            if (!eval_read<true>(cf, s_lut, mg, i, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j), byte_of(ch.sq, j),
+                                 is_alt, slot, jp))
                 continue;
             double p, q;
             guard_pq(jp, p, q);
@@ -722,63 +728,33 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant
         }
         small = live;                          // survivors: not pruned within the cap
     }
-    // (2) the survivors (true low-frequency variants, the first columns of a run): whole warp, full evaluation
-    unsigned todo = __ballot_sync(FULL, small);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const long long cc = __shfl_sync(FULL, c, src);
-        const long long cbonf = __shfl_sync(FULL, bonf, src);
-        const double climit = __shfl_sync(FULL, limit, src);
-        int ccnt[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) ccnt[i] = __shfl_sync(FULL, cnt[i], src);
-        const int cK = max(ccnt[0], max(ccnt[1], ccnt[2]));
-        Geom g;
-        g.off = __shfl_sync(FULL, mg.off, src);
-        g.b1 = __shfl_sync(FULL, mg.b1, src);
-        g.b2 = __shfl_sync(FULL, mg.b2, src);
-        g.b3 = __shfl_sync(FULL, mg.b3, src);
-        g.n = __shfl_sync(FULL, mg.n, src);
-        g.ref_idx = __shfl_sync(FULL, mg.ref_idx, src);
-        g.alt_bp = 0.0;
-        setup_alt_bq(cf, b, s_lut, g, s_hist[w]);
-        double tails[4];
-        if (cK == 1) screen_small<1>(cf, b, lut_sa, g, ccnt, cK, tails);
-        else if (cK == 2) screen_small<2>(cf, b, lut_sa, g, ccnt, cK, tails);
-        else if (cK <= 4) screen_small<4>(cf, b, lut_sa, g, ccnt, cK, tails);
-        else screen_small<8>(cf, b, lut_sa, g, ccnt, cK, tails);
-        double tK = ccnt[0] == cK ? tails[0] : ccnt[1] == cK ? tails[1] : tails[2];
-        tK = __shfl_sync(FULL, tK, 0);
-        if (tK > climit) continue;
-        if (lane == 0) {
-            const unsigned slot = atomicAdd(&ws.counters->n_cand, 1u);
-            Cand cd;
-            cd.col = cc;
-            cd.bonf = cbonf;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                cd.lnp[i] = ccnt[i] > 0 ? log(tails[i]) : 0.0;
-                cd.cnt[i] = ccnt[i];
-                cd.raw[i] = ws.cnt6[6 * cc + 3 + i];
-            }
-            cd.ln_floor = log(tails[3]);
-            cd.flags = 0;
-            cd.pad = 0;
-            ws.cand[slot] = cd;
-        }
+    // (2) the survivors (true low-frequency variants, the first columns of a run, every small column when the median
+    //     override is on) join the columns with 8 < K <= 32 in k_mid's job list: full evaluation, whole warp
+    if (small) {
+        const unsigned slot = atomicAdd(&ws.counters->n_jobs[0], 1u);
+        ws.jobs[slot] = (int)c;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // read sources for the O(depth*K) routines
 // ------------------------------------------------------------------------------------------------
+// Every pass over a source walks it tile by tile: `stage(t0)` makes reads [t0, t0 + TILE) available to get().
+// The raw sources read global memory on every get() (TILE = everything, stage is a no-op); Staged<> keeps one
+// tile of merged probabilities in shared memory, so the repeated passes of the O(depth*K) routines (lambda,
+// Newton iterations, one or more runs of the recurrence, secondary alleles) pay the global-memory latency once
+// per tile instead of once per 32 reads and pass.
+constexpr int NO_TILE = 0x40000000;
+
 struct ByteSrc {
+    static constexpr int TILE = NO_TILE;
+    static constexpr bool FILTERS = true;
     const DevConf *cf;
     const DevBatch *b;
     const double *lut;
     Geom g;
     __device__ __forceinline__ int size() const { return g.n; }
+    __device__ __forceinline__ void stage(int) const {}
     __device__ __forceinline__ bool get(int pos, double &jp) const
     {
         const long long a = g.off + pos;
@@ -787,16 +763,86 @@ struct ByteSrc {
         return eval_read<true>(*cf, lut, g, pos, b->bq[a], cf->use_mq ? b->mq[a] : 0, cf->use_baq ? b->baq[a] : 0,
                                cf->use_sq ? b->sq[a] : 0, is_alt, slot, jp);
     }
+    // merged probabilities of reads [t0, t0 + m) into buf (swizzled, see Staged), -1 = filtered out.
+    // 128-bit loads: lane i takes the i-th aligned 16-byte chunk of every plane.
+    __device__ __forceinline__ void fill(int t0, int m, double *buf) const
+    {
+        const long long a0 = g.off + t0;
+        const long long abase = a0 & ~15ll;
+        const int lead = (int)(a0 - abase);
+        const int nch = (lead + m + 15) >> 4;
+        for (int i = lane_id(); i < nch; i += 32) {
+            Chunk16 ch;
+            load_chunk(*cf, *b, abase + 16ll * i, ch);
+#pragma unroll 1
+            for (int w = 0; w < 4; ++w) {
+                const unsigned wbq = w == 0 ? ch.bq.x : w == 1 ? ch.bq.y : w == 2 ? ch.bq.z : ch.bq.w;
+                const unsigned wmq = w == 0 ? ch.mq.x : w == 1 ? ch.mq.y : w == 2 ? ch.mq.z : ch.mq.w;
+                const unsigned wbaq = w == 0 ? ch.baq.x : w == 1 ? ch.baq.y : w == 2 ? ch.baq.z : ch.baq.w;
+                const unsigned wsq = w == 0 ? ch.sq.x : w == 1 ? ch.sq.y : w == 2 ? ch.sq.z : ch.sq.w;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = 16 * i + 4 * w + j;          // chunk-relative slot
+                    const int tp = idx - lead;                    // tile-relative read
+                    if (tp < 0 || tp >= m) continue;
+                    bool is_alt;
+                    int slot;
+                    double jp;
+                    const bool ok = eval_read<true>(*cf, lut, g, t0 + tp, (wbq >> (8 * j)) & 0xff, (wmq >> (8 * j)) & 0xff,
+                                                    (wbaq >> (8 * j)) & 0xff, (wsq >> (8 * j)) & 0xff, is_alt, slot, jp);
+                    buf[idx + (idx >> 4)] = ok ? jp : -1.0;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ int lead_of(int t0) const { return (int)((g.off + t0) & 15ll); }
 };
 
 struct ProbSrc {
+    static constexpr int TILE = NO_TILE;
+    static constexpr bool FILTERS = false;
     const double *ep;
     int n;
     __device__ __forceinline__ int size() const { return n; }
+    __device__ __forceinline__ void stage(int) const {}
     __device__ __forceinline__ bool get(int pos, double &jp) const
     {
         jp = ep[pos];
         return true;
+    }
+    __device__ __forceinline__ void fill(int t0, int m, double *buf) const
+    {
+        for (int i = lane_id(); i < m; i += 32) buf[i + (i >> 4)] = ep[t0 + i];
+    }
+    __device__ __forceinline__ int lead_of(int) const { return 0; }
+};
+
+constexpr int STAGE_TILE = 1024;                                   // reads per tile
+constexpr int STAGE_SLOTS = STAGE_TILE + 16;                       // + the lead bytes of an unaligned column
+constexpr int STAGE_DOUBLES = STAGE_SLOTS + (STAGE_SLOTS >> 4) + 1;   // one pad per 16 slots: the 16-byte-chunk fill is bank-conflict free
+
+template <class Raw>
+struct Staged {
+    static constexpr int TILE = STAGE_TILE;
+    Raw raw;
+    double *buf;        // STAGE_DOUBLES of shared memory owned by this warp
+    mutable int tile0, lead;
+    __device__ __forceinline__ void init(double *smem) { buf = smem; tile0 = -1; lead = 0; }
+    __device__ __forceinline__ int size() const { return raw.size(); }
+    __device__ __forceinline__ void stage(int t0) const
+    {
+        if (t0 == tile0) return;
+        __syncwarp();
+        raw.fill(t0, min(STAGE_TILE, raw.size() - t0), buf);
+        tile0 = t0;
+        lead = raw.lead_of(t0);
+        __syncwarp();
+    }
+    __device__ __forceinline__ bool get(int pos, double &jp) const
+    {
+        const int idx = pos - tile0 + lead;
+        jp = buf[idx + (idx >> 4)];
+        return !Raw::FILTERS || jp >= 0.0;
     }
 };
 
@@ -810,12 +856,16 @@ __device__ __noinline__ void src_small(const Src &src, double (&P8)[KS], double 
 #pragma unroll
     for (int k = 0; k < K; ++k) P[k] = (k == 0) ? 1.0 : 0.0;
     const int n = src.size();
-    for (int pos = lane_id(); pos < n; pos += 32) {
-        double jp;
-        if (!src.get(pos, jp)) continue;
-        double p, q;
-        guard_pq(jp, p, q);
-        lane_update<K>(P, T, p, q);
+    for (int t0 = 0; t0 < n; t0 += Src::TILE) {
+        src.stage(t0);
+        const int t1 = min(n - t0, Src::TILE) + t0;
+        for (int pos = t0 + lane_id(); pos < t1; pos += 32) {
+            double jp;
+            if (!src.get(pos, jp)) continue;
+            double p, q;
+            guard_pq(jp, p, q);
+            lane_update<K>(P, T, p, q);
+        }
     }
     tree_merge<K>(P, T);
 #pragma unroll
@@ -883,6 +933,7 @@ __device__ __forceinline__ void dp_run(const Src &src, int K, double ln_s, doubl
     const int n = src.size();
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int n0 = 0; n0 < n; n0 += 32) {
+        if (n0 % Src::TILE == 0) src.stage(n0);
         const int pos = n0 + lane;
         double jp = 0.0, o = 0.0, rq = 1.0;
         const bool ok = pos < n && src.get(pos, jp);
@@ -958,15 +1009,19 @@ __device__ double newton_tilt(const Src &src, int K, int N, double lam)
     for (int it = 0; it < 40; ++it) {
         const double s = exp(ls);
         double g = 0.0, d = 0.0;
-        for (int pos = lane; pos < n; pos += 32) {
-            double jp;
-            if (!src.get(pos, jp)) continue;
-            double p, q;
-            guard_pq(jp, p, q);
-            const double ps = p * s;
-            const double w = ps / (q + ps);        // o/(1+o)
-            g += w;
-            d += w * (1.0 - w);                    // derivative with respect to ln s = variance of the tilted sum
+        for (int t0 = 0; t0 < n; t0 += Src::TILE) {
+            src.stage(t0);
+            const int t1 = min(n - t0, Src::TILE) + t0;
+            for (int pos = t0 + lane; pos < t1; pos += 32) {
+                double jp;
+                if (!src.get(pos, jp)) continue;
+                double p, q;
+                guard_pq(jp, p, q);
+                const double ps = p * s;
+                const double w = ps / (q + ps);        // o/(1+o)
+                g += w;
+                d += w * (1.0 - w);                    // derivative with respect to ln s = variance of the tilted sum
+            }
         }
         g = warp_sum(g) - kt;
         d = warp_sum(d);
@@ -1074,13 +1129,17 @@ __device__ bool run_problem(const Src &src, const int (&cnt)[3], long long bonf,
     // N = reads that survive the filters, lam = sum of their error probabilities
     int N = 0;
     double lam = 0.0;
-    for (int pos = lane; pos < src.size(); pos += 32) {
-        double jp;
-        if (!src.get(pos, jp)) continue;
-        double p, q;
-        guard_pq(jp, p, q);
-        lam += p;
-        ++N;
+    for (int t0 = 0; t0 < src.size(); t0 += Src::TILE) {
+        src.stage(t0);
+        const int t1 = min(src.size() - t0, Src::TILE) + t0;
+        for (int pos = t0 + lane; pos < t1; pos += 32) {
+            double jp;
+            if (!src.get(pos, jp)) continue;
+            double p, q;
+            guard_pq(jp, p, q);
+            lam += p;
+            ++N;
+        }
     }
     N = __reduce_add_sync(FULL, N);
     lam = __shfl_sync(FULL, warp_sum(lam), 0);
@@ -1120,9 +1179,10 @@ __device__ bool run_problem(const Src &src, const int (&cnt)[3], long long bonf,
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_mid: columns with 8 < K <= 32.  At this size the recurrence over reads (depth serial steps of a
+// k_mid: columns with 8 < K <= 32, and the columns with K <= 8 that k_finalize's lane-per-column prune could
+// not rule out within PRUNE_CAP reads.  At this size the recurrence over reads (depth serial steps of a
 // 32-cell row) is slower than folding the reads in parallel — every lane its 16-byte chunks into a
-// distribution truncated at 16 or 32 — and merging the 32 distributions by truncated convolution.
+// distribution truncated at 2, 4, 8, 16 or 32 — and merging the 32 distributions by truncated convolution.
 // Untilted: if the tail leaves the fp64 range the column is handed to k_heavy<1>.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_mid(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, const Lut *lut,
@@ -1151,7 +1211,10 @@ __global__ void __launch_bounds__(128) k_mid(const __grid_constant__ DevConf cf,
         const int K = max(cnt[0], max(cnt[1], cnt[2]));
         const long long bonf = ws.bonf_used[c];
         double tails[4];
-        if (K <= 16) screen_small<16>(cf, b, lut_sa, g, cnt, K, tails);
+        if (K <= 2) screen_small<2>(cf, b, lut_sa, g, cnt, K, tails);
+        else if (K <= 4) screen_small<4>(cf, b, lut_sa, g, cnt, K, tails);
+        else if (K <= 8) screen_small<8>(cf, b, lut_sa, g, cnt, K, tails);
+        else if (K <= 16) screen_small<16>(cf, b, lut_sa, g, cnt, K, tails);
         else screen_small<32>(cf, b, lut_sa, g, cnt, K, tails);
         double tK = cnt[0] == K ? tails[0] : cnt[1] == K ? tails[1] : tails[2];
         tK = __shfl_sync(FULL, tK, 0);
@@ -1190,6 +1253,7 @@ __global__ void __launch_bounds__(128) k_heavy(const __grid_constant__ DevConf c
     __shared__ double s_lut[768];
     __shared__ double2 s_par[4][32];
     __shared__ int s_hist[4][256];
+    extern __shared__ double s_stage[];          // [4][STAGE_DOUBLES]
     load_lut(s_lut, lut);
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     const unsigned njobs = ws.counters->n_jobs[cls];
@@ -1200,13 +1264,14 @@ __global__ void __launch_bounds__(128) k_heavy(const __grid_constant__ DevConf c
         j = __shfl_sync(FULL, j, 0);
         if (j >= njobs) break;
         const long long c = jobs[j];
-        ByteSrc src;
-        src.cf = &cf;
-        src.b = &b;
-        src.lut = s_lut;
+        Staged<ByteSrc> src;
+        src.init(s_stage + wib * STAGE_DOUBLES);
+        src.raw.cf = &cf;
+        src.raw.b = &b;
+        src.raw.lut = s_lut;
         int cov;
-        load_geom(b, c, src.g, cov);
-        setup_alt_bq(cf, b, s_lut, src.g, s_hist[wib]);
+        load_geom(b, c, src.raw.g, cov);
+        setup_alt_bq(cf, b, s_lut, src.raw.g, s_hist[wib]);
         int cnt[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
@@ -1578,6 +1643,7 @@ template <int R>
 __global__ void __launch_bounds__(128) k_prob_jobs(const ProbBatch pb, Cand *out, int cls)
 {
     __shared__ double2 s_par[4][32];
+    extern __shared__ double s_stage[];          // [4][STAGE_DOUBLES]
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     const long long warp0 = (long long)blockIdx.x * 4 + wib, nwarps = (long long)gridDim.x * 4;
     for (long long i = warp0; i < pb.n; i += nwarps) {
@@ -1587,16 +1653,17 @@ __global__ void __launch_bounds__(128) k_prob_jobs(const ProbBatch pb, Cand *out
         const int K = max(cnt[0], max(cnt[1], cnt[2]));
         const int my_cls = K <= KS ? 0 : class_of(K);
         if (my_cls != cls) continue;
-        ProbSrc src;
-        src.ep = pb.err_probs + pb.ep_off[i];
-        src.n = (int)(pb.ep_off[i + 1] - pb.ep_off[i]);
+        Staged<ProbSrc> src;
+        src.init(s_stage + wib * STAGE_DOUBLES);
+        src.raw.ep = pb.err_probs + pb.ep_off[i];
+        src.raw.n = (int)(pb.ep_off[i + 1] - pb.ep_off[i]);
         Cand cd;
         bool site = false;
-        if (K > 0 && K <= src.n && cls < CLS_XL) site = run_problem<R>(src, cnt, pb.bonf[i], pb.sig, s_par[wib], cd);
+        if (K > 0 && K <= src.raw.n && cls < CLS_XL) site = run_problem<R>(src, cnt, pb.bonf[i], pb.sig, s_par[wib], cd);
         else { cd.flags = 0; cd.ln_floor = 0.0; cd.lnp[0] = cd.lnp[1] = cd.lnp[2] = 0.0; }
         if (lane == 0) {
             if (!site) cd.flags |= CF_INSIG;
-            if (K > MAXK_WARP || K > src.n) cd.flags |= CF_UNSUPPORTED;
+            if (K > MAXK_WARP || K > src.raw.n) cd.flags |= CF_UNSUPPORTED;
             cd.col = i;
             cd.bonf = pb.bonf[i];
 #pragma unroll
@@ -1620,6 +1687,26 @@ static int sm_count()
         if (n <= 0) n = 148;
     }
     return n;
+}
+
+// dynamic shared memory of the kernels that stage a tile of merged probabilities per warp (4 warps per CTA);
+// together with their static arrays they pass the 48 KB default limit, hence the opt-in
+constexpr int STAGE_BYTES = 4 * STAGE_DOUBLES * (int)sizeof(double);
+
+template <int R>
+static void stage_optin_one()
+{
+    cudaFuncSetAttribute(k_heavy<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES);
+    cudaFuncSetAttribute(k_prob_jobs<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES);
+}
+
+static void stage_smem_optin()
+{
+    static bool done = false;
+    if (done) return;
+    stage_optin_one<1>(); stage_optin_one<2>(); stage_optin_one<4>(); stage_optin_one<8>();
+    stage_optin_one<16>(); stage_optin_one<32>(); stage_optin_one<64>();
+    done = true;
 }
 
 void launch_screen(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st)
@@ -1664,14 +1751,15 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
     cudaEventRecord(ev_fork, st);
     for (int i = 0; i < NSIDE; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
     k_heavy_xl<<<sm_count(), XL_T, 0, side[7]>>>(cf, b, lut, ws, CLS_XL);
-    k_heavy<64><<<g, 128, 0, side[6]>>>(cf, b, lut, ws, 6);
-    k_heavy<32><<<g, 128, 0, side[5]>>>(cf, b, lut, ws, 5);
-    k_heavy<16><<<g, 128, 0, side[4]>>>(cf, b, lut, ws, 4);
-    k_heavy<8><<<g, 128, 0, side[3]>>>(cf, b, lut, ws, 3);
-    k_heavy<4><<<g, 128, 0, side[2]>>>(cf, b, lut, ws, 2);
-    k_heavy<2><<<g, 128, 0, side[1]>>>(cf, b, lut, ws, 1);
+    stage_smem_optin();
+    k_heavy<64><<<g, 128, STAGE_BYTES, side[6]>>>(cf, b, lut, ws, 6);
+    k_heavy<32><<<g, 128, STAGE_BYTES, side[5]>>>(cf, b, lut, ws, 5);
+    k_heavy<16><<<g, 128, STAGE_BYTES, side[4]>>>(cf, b, lut, ws, 4);
+    k_heavy<8><<<g, 128, STAGE_BYTES, side[3]>>>(cf, b, lut, ws, 3);
+    k_heavy<4><<<g, 128, STAGE_BYTES, side[2]>>>(cf, b, lut, ws, 2);
+    k_heavy<2><<<g, 128, STAGE_BYTES, side[1]>>>(cf, b, lut, ws, 1);
     k_mid<<<g, 128, 0, side[0]>>>(cf, b, lut, ws);
-    k_heavy<1><<<g, 128, 0, side[0]>>>(cf, b, lut, ws, CLS_FALLBACK);     // what k_mid handed back (rare)
+    k_heavy<1><<<g, 128, STAGE_BYTES, side[0]>>>(cf, b, lut, ws, CLS_FALLBACK);     // what k_mid handed back (rare)
     for (int i = 0; i < NSIDE; ++i) {
         cudaEventRecord(ev_join[i], side[i]);
         cudaStreamWaitEvent(st, ev_join[i], 0);
@@ -1752,15 +1840,16 @@ double measure_dfma_per_second(cudaStream_t st)
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st)
 {
     if (pb.n <= 0) return;
+    stage_smem_optin();
     const long long want = (pb.n + 3) / 4;
     const int g = (int)(want < (long long)sm_count() * 4 ? want : (long long)sm_count() * 4);
-    k_prob_jobs<1><<<g, 128, 0, st>>>(pb, out, 0);
-    k_prob_jobs<2><<<g, 128, 0, st>>>(pb, out, 1);
-    k_prob_jobs<4><<<g, 128, 0, st>>>(pb, out, 2);
-    k_prob_jobs<8><<<g, 128, 0, st>>>(pb, out, 3);
-    k_prob_jobs<16><<<g, 128, 0, st>>>(pb, out, 4);
-    k_prob_jobs<32><<<g, 128, 0, st>>>(pb, out, 5);
-    k_prob_jobs<64><<<g, 128, 0, st>>>(pb, out, 6);
+    k_prob_jobs<1><<<g, 128, STAGE_BYTES, st>>>(pb, out, 0);
+    k_prob_jobs<2><<<g, 128, STAGE_BYTES, st>>>(pb, out, 1);
+    k_prob_jobs<4><<<g, 128, STAGE_BYTES, st>>>(pb, out, 2);
+    k_prob_jobs<8><<<g, 128, STAGE_BYTES, st>>>(pb, out, 3);
+    k_prob_jobs<16><<<g, 128, STAGE_BYTES, st>>>(pb, out, 4);
+    k_prob_jobs<32><<<g, 128, STAGE_BYTES, st>>>(pb, out, 5);
+    k_prob_jobs<64><<<g, 128, STAGE_BYTES, st>>>(pb, out, 6);
     k_prob_jobs_xl<<<(int)(pb.n < sm_count() ? pb.n : sm_count()), XL_T, 0, st>>>(pb, out);
 }
 

@@ -80,6 +80,23 @@ class Caller:
                                                     float(sig_level), _ptr(pv), _ptr(lnp), _ptr(st)))
         return pv, lnp, st
 
+    # ---- binom(): binomial CDF / survival function (binom.c:52-93) ------------------------------
+    def binom_batch(self, num_trials, num_success, prob_success):
+        """(status, p, q) arrays; p = P(X <= num_success), q = 1 - p, NaN where status != 0"""
+        nt = np.ascontiguousarray(num_trials, np.int32).reshape(-1)
+        ns = np.ascontiguousarray(num_success, np.int32).reshape(-1)
+        pr = np.ascontiguousarray(prob_success, np.float64).reshape(-1)
+        n = len(nt)
+        p = np.full(n, np.nan)
+        q = np.full(n, np.nan)
+        st = np.zeros(n, np.int32)
+        capi.check(self.lib.lfb200_binom_batch(self._ctx, n, _ptr(nt), _ptr(ns), _ptr(pr), _ptr(p), _ptr(q), _ptr(st)))
+        return st, p, q
+
+    def binom(self, num_trials, num_success, prob_success):
+        st, p, q = self.binom_batch([num_trials], [num_success], [prob_success])
+        return int(st[0]), float(p[0]), float(q[0])
+
     # ---- host batch -----------------------------------------------------------------------
     def call_columns(self, batch, conf=None, dense=True, max_sites=None):
         """batch: dict of numpy arrays (col_off, nt_cnt, ref_base, bq, mq, baq, sq, coverage), the packed

@@ -217,3 +217,117 @@ def model_snpcaller(ep, counts, bonf, sig):
     d, lnp, fl = device_column(ep, counts, bonf, sig)
     pv, st = host_finish(counts, bonf, sig, d, lnp, fl)
     return pv, st, lnp
+
+
+# ------------------------------------------------------------------------------------------------
+# binom(): the arithmetic of lofreq_b200/csrc/binom.cu (k_binom), restated in Python.
+# cdflib's cdfbin(which=1) (dcdflib.c:1727) reduces the binomial to the incomplete beta function (TOMS 708); the
+# device instead sums the probability mass function on the short side of the mode: one accurately computed term
+# (Loader's saddle-point form: Stirling-series error term + the deviance bd0) and the exact term ratio
+# pmf(k-1)/pmf(k) = k/(n-k+1) * q/p from there on, all terms positive.
+# ------------------------------------------------------------------------------------------------
+LN_2PI = 1.8378770664093454835606594728112
+
+
+def stirlerr_table():
+    """stirlerr(n) = ln n! - ln(sqrt(2 pi n) (n/e)^n) for n = 0..15, in long double like the host does"""
+    ld = np.longdouble
+    out = [0.0]
+    for n in range(1, 16):
+        fact = ld(1)
+        for i in range(2, n + 1):
+            fact *= ld(i)
+        v = np.log(fact) - (ld(n) + ld(0.5)) * np.log(ld(n)) + ld(n) - ld(0.5) * np.log(ld(2) * ld(np.pi))
+        out.append(float(v))
+    return out
+
+
+_STIRL = None
+
+
+def stirlerr(n):
+    global _STIRL
+    if _STIRL is None:
+        _STIRL = stirlerr_table()
+    if n <= 15:
+        return _STIRL[n]
+    S0, S1, S2, S3, S4 = 1.0 / 12, 1.0 / 360, 1.0 / 1260, 1.0 / 1680, 1.0 / 1188
+    x = float(n)
+    nn = x * x
+    if n > 500:
+        return (S0 - S1 / nn) / x
+    if n > 80:
+        return (S0 - (S1 - S2 / nn) / nn) / x
+    if n > 35:
+        return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / x
+    return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / x
+
+
+def bd0(x, np_):
+    """x ln(x/np) + np - x, without cancellation when x is close to np"""
+    if abs(x - np_) < 0.1 * (x + np_):
+        v = (x - np_) / (x + np_)
+        s = (x - np_) * v
+        ej = 2.0 * x * v
+        v = v * v
+        for j in range(1, 1000):
+            ej *= v
+            s1 = s + ej / (2 * j + 1)
+            if s1 == s:
+                return s1
+            s = s1
+    return x * math.log(x / np_) + np_ - x
+
+
+def ln_binom_pmf(x, n, p, q):
+    """ln of the binomial mass at x, 0 < p < 1"""
+    if x == 0:
+        return (-bd0(n, n * q) - n * p) if p < 0.1 else n * math.log(q)
+    if x == n:
+        return (-bd0(n, n * p) - n * q) if q < 0.1 else n * math.log(p)
+    lc = stirlerr(n) - stirlerr(x) - stirlerr(n - x) - bd0(x, n * p) - bd0(n - x, n * q)
+    lf = LN_2PI + math.log(x) + math.log1p(-x / n)
+    return lc - 0.5 * lf
+
+
+def model_binom(num_trials, num_success, pr):
+    """(status, cdf, sf) like binom() (binom.c:52-93): P(X <= s), P(X > s) for X ~ Binomial(n, pr)"""
+    n, s = int(num_trials), int(num_success)
+    if not n > 0:
+        return -5, None, None              # dcdflib.c:1879
+    if s < 0 or s > n:
+        return -4, None, None              # :1889
+    if pr < 0.0 or pr > 1.0:
+        return -6, None, None              # :1904
+    if not s < n:
+        return 0, 1.0, 0.0                 # cumbin, dcdflib.c:5017-5026
+    q = 1.0 - pr
+    if pr == 0.0:
+        return 0, 1.0, 0.0
+    if q == 0.0:
+        return 0, 0.0, 1.0
+    mode = math.floor((n + 1) * pr)
+    if s < mode:
+        # left tail: terms k = s, s-1, ... 0 shrink
+        lt = ln_binom_pmf(s, n, pr, q)
+        ratio = q / pr
+        t, tot, k = 1.0, 1.0, s
+        while k > 0:
+            t *= (k / (n - k + 1.0)) * ratio
+            tot += t
+            k -= 1
+            if t < 1e-18 * tot:
+                break
+        cum = math.exp(lt + math.log(tot))
+        return 0, cum, 1.0 - cum
+    lt = ln_binom_pmf(s + 1, n, pr, q)
+    ratio = pr / q
+    t, tot, k = 1.0, 1.0, s + 1
+    while k < n:
+        t *= ((n - k) / (k + 1.0)) * ratio
+        tot += t
+        k += 1
+        if t < 1e-18 * tot:
+            break
+    ccum = math.exp(lt + math.log(tot))
+    return 0, 1.0 - ccum, ccum

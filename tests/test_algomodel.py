@@ -48,3 +48,22 @@ def test_model_random_triallelic_against_port(port_oracle):
             if st[j] == 0:
                 a, b = float(np.log(pv[j])), float(np.log(want[j]))
                 assert abs(a - b) <= 1e-10 * max(abs(b), 1.0)
+
+
+def binom_close(got, want, rtol=1e-10):
+    """relative agreement on a probability; below 1e-290 both must simply be that small"""
+    if want < 1e-290:
+        return got < 1e-280
+    return abs(got - want) <= rtol * want
+
+
+def test_binom_model_reproduces_the_reference():
+    """the arithmetic of csrc/binom.cu (mass function summed on the short side of the mode) against the outputs of
+    the reference's binom() over cdflib's incomplete beta function"""
+    z = np.load(os.path.join(GOLD, "binom_grid.npz"))
+    for i in range(len(z["status"])):
+        st, cum, ccum = M.model_binom(int(z["num_trials"][i]), int(z["num_success"][i]), float(z["prob_success"][i]))
+        assert st == int(z["status"][i]), i
+        if st == 0:
+            assert binom_close(cum, float(z["cdf"][i])) and binom_close(ccum, float(z["sf"][i])), \
+                (i, int(z["num_trials"][i]), int(z["num_success"][i]), float(z["prob_success"][i]))

@@ -99,3 +99,19 @@ def test_binom_reference_vs_scipy():
         cdf, sf = br.cdf_sf(n, k, p)
         assert abs(cdf - sb.cdf(k, n, p)) <= 1e-12 * max(cdf, 1e-300) + 1e-15
         assert abs(sf - sb.sf(k, n, p)) <= 1e-12 * max(sf, 1e-300) + 1e-15
+
+
+def test_binom_golden_is_the_reference():
+    """tests/golden/binom_grid.npz are outputs of the compiled reference binom()"""
+    from oracle.pyoracle import BinomRef, BINOM_SO
+    if not os.path.exists(BINOM_SO):
+        pytest.skip("oracle/_ref/libbinomref.so not built")
+    import ctypes as C
+    br = BinomRef()
+    z = np.load(os.path.join(GOLD, "binom_grid.npz"))
+    for i in range(0, len(z["status"]), 3):
+        a, b = C.c_double(float("nan")), C.c_double(float("nan"))
+        rc = br.lib.binom(C.byref(a), C.byref(b), int(z["num_trials"][i]), int(z["num_success"][i]), float(z["prob_success"][i]))
+        assert rc == int(z["status"][i])
+        if rc == 0:
+            assert a.value == z["cdf"][i] and b.value == z["sf"][i]

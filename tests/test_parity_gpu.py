@@ -431,3 +431,30 @@ def test_deep_columns_cta_per_column_kernel(caller, port_oracle):
         got = caller.snpcaller(ep, counts, 30000, float(np.float32(0.01)))
         assert np.array_equal(status_of(got), status_of(want))
         assert_lnp_close(got, want, status_of(want), "deep snpcaller")
+
+
+def test_binom_golden(caller):
+    """binom() (binom.c:52-93 -> cdflib cdfbin): status codes exact, cdf and sf within 1e-10 relative of the compiled
+    reference — through the batched entry point and through the link-compatible single call"""
+    import ctypes as C
+    z = np.load(os.path.join(GOLD, "binom_grid.npz"))
+    st, p, q = caller.binom_batch(z["num_trials"], z["num_success"], z["prob_success"])
+    assert np.array_equal(st, z["status"])
+    ok = st == 0
+    assert np.all(np.isnan(p[~ok])) and np.all(np.isnan(q[~ok]))       # untouched where cdfbin refuses
+    for got, want in ((p[ok], z["cdf"][ok]), (q[ok], z["sf"][ok])):
+        big = want >= 1e-290
+        assert np.all(np.abs(got[big] - want[big]) <= 1e-10 * want[big])
+        assert np.all(got[~big] < 1e-280)
+    assert caller.binom_batch([], [], [])[0].shape == (0,)
+    lib = caller.lib
+    for i in (0, 1, 2, 8, 9, 10, 11, 12, 14, 40, 100, 900):
+        a, b = C.c_double(-7.0), C.c_double(-7.0)
+        rc = lib.lfb200_binom(C.byref(a), C.byref(b), int(z["num_trials"][i]), int(z["num_success"][i]), float(z["prob_success"][i]))
+        assert rc == int(z["status"][i])
+        if rc == 0:
+            assert a.value == p[i] and b.value == q[i]
+        else:
+            assert a.value == -7.0 and b.value == -7.0
+    a = C.c_double(-7.0)
+    assert lib.lfb200_binom(C.byref(a), None, 500, 3, 0.05) == 0 and abs(a.value - 2.46755e-08) < 1e-12   # SURVEY §8c probe value
