@@ -130,6 +130,11 @@ void lfb200_init_conf(lfb200_conf_t *conf);
 int lfb200_call_columns(lfb200_ctx *ctx, lfb200_conf_t *conf, const lfb200_batch_t *host_batch,
                         const lfb200_dense_out_t *dense, lfb200_site_t *sites, long long max_sites,
                         lfb200_summary_t *summary);
+/* How lfb200_call_columns (and the column builder) hands the quality planes to the device: 0 = bulk copy
+ * (default); 1 = planes that lie in pinned host memory (cudaHostAlloc / cudaHostRegister) are read in place
+ * over PCIe — the kernels only touch the reads that decide a column, so far fewer bytes cross the bus; planes
+ * in pageable memory are still copied.  Results are identical. */
+int lfb200_set_host_planes(lfb200_ctx *ctx, int mode);
 
 /* Device-resident batch, two phases so that region shards on several GPUs can
  * exchange their tested-column counts in between (the running Bonferroni of a

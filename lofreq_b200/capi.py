@@ -66,7 +66,7 @@ class Summary(C.Structure):
 SITE_FN = C.CFUNCTYPE(None, C.POINTER(Site), C.c_longlong, C.c_char, C.c_int, C.c_void_p)
 
 # every symbol include/lofreq_b200.h declares (tests/test_abi.py checks the header against this list)
-SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_conf", "lfb200_call_columns",
+SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_conf", "lfb200_call_columns", "lfb200_set_host_planes",
            "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_ntested_copy_device", "lfb200_test_device_from", "lfb200_bonf_start_device", "lfb200_comm_unique_id", "lfb200_comm_init", "lfb200_comm_exchange", "lfb200_comm_gathered",
            "lfb200_sites_device", "lfb200_sites_begin", "lfb200_sites_end",
            "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_dfma_peak", "lfb200_copy_counts_device", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
@@ -123,6 +123,8 @@ def load():
     lib.lfb200_comm_exchange.argtypes = [vp, vp, ll, ll, C.POINTER(vp)]
     lib.lfb200_comm_gathered.restype = C.c_int
     lib.lfb200_comm_gathered.argtypes = [vp, vp, vp, vp]
+    lib.lfb200_set_host_planes.restype = C.c_int
+    lib.lfb200_set_host_planes.argtypes = [vp, C.c_int]
     lib.lfb200_binom.restype = C.c_int
     lib.lfb200_binom.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
     lib.lfb200_binom_batch.restype = C.c_int

@@ -186,6 +186,7 @@ struct lfb200_ctx {
     char fin_err[512] = "";
     void finisher_loop();
     void *comm_state = nullptr;          // owned by shard_comm.cpp
+    int host_planes = 0;                 // lfb200_set_host_planes
     // state of the last screen
     DevBatch cur{};
     bool have_batch = false;
@@ -724,6 +725,14 @@ static int upload(DevBuf &buf, const void *src, size_t bytes, size_t pad, cudaSt
     return 0;
 }
 
+extern "C" int lfb200_set_host_planes(lfb200_ctx *ctx, int mode)
+{
+    if (!ctx) return fail("no context");
+    if (mode != 0 && mode != 1) return fail("host plane mode must be 0 (copy) or 1 (read pinned planes in place)");
+    ctx->host_planes = mode;
+    return 0;
+}
+
 extern "C" int lfb200_call_columns(lfb200_ctx *ctx, lfb200_conf_t *conf, const lfb200_batch_t *hb,
                                    const lfb200_dense_out_t *dense, lfb200_site_t *sites, long long max_sites,
                                    lfb200_summary_t *summary)
@@ -746,15 +755,33 @@ extern "C" int lfb200_call_columns(lfb200_ctx *ctx, lfb200_conf_t *conf, const l
     db.coverage = (const int *)d;
     if (upload(ctx->in_nb, hb->num_bases, (size_t)n * 4, 0, st, &d)) return 1;
     db.num_bases = (const int *)d;
-    if (upload(ctx->in_bq, hb->bq, plane_bytes, 32, st, &d)) return 1;
-    db.bq = (const unsigned char *)d;
+    // Quality planes: copied to the device, or — host_planes mode 1 and the plane lies in pinned (page-locked) host
+    // memory — read in place over PCIe.  The kernels touch only the reads that decide (non-reference reads in
+    // k_screen, the first few reads of a tested column in k_finalize, whole columns only for candidate sites), a
+    // fraction of the bytes a bulk copy moves.  Pinned memory is mapped page-wise, so the aligned 16-byte loads
+    // that straddle the end of a plane stay inside the mapping.
+    auto place = [&](DevBuf &buf, const unsigned char *h, const unsigned char **out) -> int {
+        *out = nullptr;
+        if (!h) return 0;
+        if (ctx->host_planes == 1) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
+                ((uintptr_t)at.devicePointer & 15) == 0) {
+                *out = (const unsigned char *)at.devicePointer;
+                return 0;
+            }
+            cudaGetLastError();
+        }
+        const void *dp;
+        if (upload(buf, h, plane_bytes, 32, st, &dp)) return 1;
+        *out = (const unsigned char *)dp;
+        return 0;
+    };
+    if (place(ctx->in_bq, hb->bq, &db.bq)) return 1;
     // planes the flags switch off are not needed on the device
-    if (upload(ctx->in_mq, (conf->flag & LFB200_USE_MQ) ? hb->mq : nullptr, plane_bytes, 32, st, &d)) return 1;
-    db.mq = (const unsigned char *)d;
-    if (upload(ctx->in_baq, (conf->flag & LFB200_USE_BAQ) ? hb->baq : nullptr, plane_bytes, 32, st, &d)) return 1;
-    db.baq = (const unsigned char *)d;
-    if (upload(ctx->in_sq, (conf->flag & LFB200_USE_SQ) ? hb->sq : nullptr, plane_bytes, 32, st, &d)) return 1;
-    db.sq = (const unsigned char *)d;
+    if (place(ctx->in_mq, (conf->flag & LFB200_USE_MQ) ? hb->mq : nullptr, &db.mq)) return 1;
+    if (place(ctx->in_baq, (conf->flag & LFB200_USE_BAQ) ? hb->baq : nullptr, &db.baq)) return 1;
+    if (place(ctx->in_sq, (conf->flag & LFB200_USE_SQ) ? hb->sq : nullptr, &db.sq)) return 1;
 
     if (lfb200_screen_device(ctx, conf, &db, st)) return 1;
     if (lfb200_test_device(ctx, conf, st)) return 1;

@@ -458,3 +458,29 @@ def test_binom_golden(caller):
             assert a.value == -7.0 and b.value == -7.0
     a = C.c_double(-7.0)
     assert lib.lfb200_binom(C.byref(a), None, 500, 3, 0.05) == 0 and abs(a.value - 2.46755e-08) < 1e-12   # SURVEY §8c probe value
+
+
+def test_pinned_planes_read_in_place(caller, port_oracle):
+    """host plane mode 1 (lfb200_set_host_planes): the kernels read pinned quality planes in place over PCIe.
+    Same results as the oracle, with unaligned/ragged columns, with and without baq, and for pageable planes
+    (which fall back to the copy)."""
+    import torch
+    from lofreq_b200 import capi
+    for wl, c0, n, baq in (("C2", 777, 3000, False), ("C5", 99, 150, True)):
+        b = synth_np.generate(wl, c0, n, with_baq=baq)
+        want = port_oracle.call_columns(b, default_conf())
+        pinned = dict(b)
+        hold = []
+        for k in ("bq", "mq", "baq"):
+            if b.get(k) is not None:
+                t = torch.from_numpy(np.ascontiguousarray(b[k], np.uint8)).pin_memory()
+                hold.append(t)
+                pinned[k] = t.numpy()
+        capi.check(caller.lib.lfb200_set_host_planes(caller._ctx, 1))
+        try:
+            got = caller.call_columns(pinned, default_conf())
+            got_pageable = caller.call_columns(b, default_conf())
+        finally:
+            capi.check(caller.lib.lfb200_set_host_planes(caller._ctx, 0))
+        compare_batch(got, want, wl + " pinned in place")
+        compare_batch(got_pageable, want, wl + " pageable, mode 1")
