@@ -144,7 +144,7 @@ struct lfb200_ctx {
     cudaStream_t stream = nullptr;       // used by the host entry points
     Lut *d_lut = nullptr;
     // workspace of the current batch
-    DevBuf w_cnt6, w_tested, w_tails, w_bonf, w_blocksum, w_jobs, w_cand, w_counters;
+    DevBuf w_cnt6, w_tested, w_tails, w_bonf, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_pinfo, w_pkscr;
     Workspace ws{};
     // device copies of host batches (host entry point)
     DevBuf in_off, in_cnt, in_ref, in_cov, in_nb, in_bq, in_mq, in_baq, in_sq;
@@ -319,7 +319,7 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_tails, &ctx->w_bonf, &ctx->w_blocksum, &ctx->w_jobs,
-                      &ctx->w_cand, &ctx->w_counters, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
+                      &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_pinfo, &ctx->w_pkscr, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
                       &ctx->in_bq, &ctx->in_mq, &ctx->in_baq, &ctx->in_sq, &ctx->p_ep, &ctx->p_off, &ctx->p_cnt,
                       &ctx->p_bonf, &ctx->p_out};
     for (DevBuf *b : bufs) b->release();
@@ -342,6 +342,14 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     bad |= ctx->w_blocksum.ensure(((nn + 255) / 256 + 1) * sizeof(long long));
     bad |= ctx->w_jobs.ensure(nn * NCLASS * sizeof(int));
     bad |= ctx->w_cand.ensure(nn * sizeof(Cand));
+    // packed job lists hold a quarter of the batch each (a fuller list spills into the per-column lists); the pool
+    // of scratch rows (step parameters of the packed columns, 16 B per read) holds 16 reads per column of the
+    // batch, at most 256 MB — when it runs out the remaining columns take the per-column kernels
+    const size_t pcap = std::max<size_t>(nn / 4, 4096);
+    const size_t scr_cap = std::min<size_t>(std::max<size_t>(nn * 16, (size_t)1 << 20), (size_t)16 << 20);
+    bad |= ctx->w_pjobs.ensure(pcap * PK_NL * sizeof(int));
+    bad |= ctx->w_pinfo.ensure(pcap * PK_NL * sizeof(PkInfo));
+    bad |= ctx->w_pkscr.ensure(scr_cap * sizeof(double2));
     if (bad) return fail("out of device memory for a batch of %lld columns", n);
     Workspace &w = ctx->ws;
     w.cap_cols = n;
@@ -353,6 +361,12 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     w.jobs = (int *)ctx->w_jobs.p;
     w.cand = (Cand *)ctx->w_cand.p;
     w.counters = (Counters *)ctx->w_counters.p;
+    static const bool no_packed = getenv("LFB200_NO_PACKED") != nullptr;      // A/B timing of k_packed against k_mid / k_heavy<R>
+    w.pjobs = no_packed ? nullptr : (int *)ctx->w_pjobs.p;
+    w.pcap = (long long)pcap;
+    w.pinfo = (PkInfo *)ctx->w_pinfo.p;
+    w.pk_scratch = no_packed ? nullptr : (double2 *)ctx->w_pkscr.p;
+    w.pk_scr_cap = (long long)scr_cap;
     return 0;
 }
 
@@ -552,6 +566,8 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
         sm.n_tested = (long long)c.n_tested;
         n_cand = c.n_cand;
         for (int i = 0; i < NCLASS; ++i) if (i != CLS_FALLBACK) sm.n_heavy += c.n_jobs[i];
+        for (int i = 0; i < PK_NL; ++i) sm.n_heavy += std::min<long long>(c.n_pjobs[i], ctx->ws.pcap);
+        sm.n_heavy -= c.n_pk_fallback;             // those are in the k_heavy<R> lists as well
     }
     if (dbg) t1 = now();
     if (n_cand > max_sites) return fail("%lld sites but room for %lld", n_cand, max_sites);

@@ -12,6 +12,17 @@ constexpr int NCLASS = 9;          // job lists: 0 = K <= 32 (k_mid), 1..6 = reg
 constexpr int CLS_XL = 7, CLS_FALLBACK = 8;
 constexpr int MAXK_WARP = 2048;    // 32 lanes * 64 cells
 
+// k_packed (packed.cu): columns with 8 < K <= 256 share a warp — G = 4, 8, 16 or 32 lanes per column, PK_R cells per
+// lane, all columns of a warp advancing read by read in lock step.  Job lists per (G, depth bin) so that the columns
+// of a warp have similar depths; a list that overflows, or a column the packed form cannot hold, uses the k_mid /
+// k_heavy<R> lists instead.
+constexpr int PK_R = 8;            // cells per lane
+constexpr int PK_NG = 4;           // G = 4 << gi
+constexpr int PK_NB = 8;           // depth bins: <= 64, 128, ..., 8192 reads
+constexpr int PK_NL = PK_NG * PK_NB;
+constexpr int PK_MAXN = 8192;      // deepest column of the packed form
+constexpr int PK_MAXK = 32 * PK_R;
+
 // what the kernels need from varcall_conf_t, pre-digested on the host
 struct DevConf {
     int min_bq, min_alt_bq;
@@ -65,7 +76,19 @@ struct Counters {
     unsigned int n_jobs[NCLASS];
     unsigned int next_job[NCLASS];
     unsigned int err_flags;
+    unsigned int n_pjobs[PK_NL];   // packed job lists (may exceed Workspace::pcap: the excess went to the other lists)
+    unsigned int next_ptask;
+    unsigned int next_pprep;
+    unsigned long long pk_scr_used; // entries of the scratch pool handed out so far
+    unsigned int n_pk_fallback;    // columns k_packed handed to k_heavy<R> (lists 1..6)
     long long bonf_start_used;     // running factor the last test started from (host or device supplied)
+};
+
+// what k_pk_prep leaves for k_packed about one packed column
+struct PkInfo {
+    long long scr_off;             // its row in the scratch pool; -1 = not prepared (pool full: the column went to k_heavy<R>)
+    double ln_s;                   // tilt (0 = none)
+    double sum_lq;                 // sum over the kept reads of ln(1 - p)
 };
 
 struct Workspace {
@@ -78,6 +101,11 @@ struct Workspace {
     int *jobs;                     // [NCLASS][n]
     Cand *cand;                    // [n]
     Counters *counters;
+    int *pjobs;                    // [PK_NL][pcap]
+    long long pcap;
+    PkInfo *pinfo;                 // [PK_NL][pcap], written by k_pk_prep
+    double2 *pk_scratch;           // pool of rows: per read the step parameters (o, 1/q), rows padded to 32 reads
+    long long pk_scr_cap;          // entries
 };
 
 // stand-alone snpcaller problems (link-compatible path)
@@ -100,6 +128,8 @@ void launch_bonf_start_strided(const long long *counts, int stride, int rank, lo
                                cudaStream_t st);
 void launch_set_i64(long long *dst, long long v, cudaStream_t st);
 double measure_dfma_per_second(cudaStream_t st);
+// packed.cu
+void launch_packed(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st);
 // binom.cu
 int launch_binom(long long n_prob, const int *num_trials, const int *num_success, const double *prob, double *cum, double *ccum,

@@ -27,145 +27,9 @@
 #include <math.h>
 #include <float.h>
 #include "internal.h"
+#include "dev_common.cuh"
 
 namespace lfb {
-
-#define FULL 0xffffffffu
-static constexpr double LN2 = 0.69314718055994530942;
-static constexpr double DEPS = 2.220446049250313e-16;   // DBL_EPSILON
-
-// ------------------------------------------------------------------------------------------------
-// small device helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
-    return v;
-}
-
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-
-// merge_srcq_mapq_baq_and_bq (snpcaller.c:334), same association, no contraction
-__device__ __forceinline__ double merge4(double sp, double mp, double bap, double bp)
-{
-    const double om = __dsub_rn(1.0, mp);
-    const double os = __dsub_rn(1.0, sp);
-    const double oa = __dsub_rn(1.0, bap);
-    double acc = __dadd_rn(mp, __dmul_rn(om, sp));
-    const double oms = __dmul_rn(om, os);
-    acc = __dadd_rn(acc, __dmul_rn(oms, bap));
-    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(oms, oa), bp));
-    return acc;
-}
-
-// DBL_EPSILON guards of pruned_calc_prob_dist (snpcaller.c:872-881), in linear space
-__device__ __forceinline__ void guard_pq(double jp, double &p, double &q)
-{
-    p = (fabs(jp) < DEPS) ? DEPS : jp;
-    q = (fabs(jp - 1.0) < DEPS) ? (1.0 - jp + DEPS) : (1.0 - jp);
-}
-
-struct Geom {            // one column of a batch
-    long long off;       // first read in the planes
-    int n;               // reads in the column
-    int b1, b2, b3;      // group boundaries: A [0,b1) C [b1,b2) G [b2,b3) T [b3,n)
-    int ref_idx;         // 0..3, -1 = not A/C/G/T
-    double alt_bp;       // base-quality probability forced on alt reads (alt_bq_mode != 0)
-};
-
-__device__ __forceinline__ int ref_index(char r)
-{
-    return r == 'A' ? 0 : r == 'C' ? 1 : r == 'G' ? 2 : r == 'T' ? 3 : -1;
-}
-
-// plp_to_errprobs for one read (snpcaller.c:399-491).  Returns false when the read is filtered out.
-// lut points at the shared-memory copy of Lut (bq | mq | aq).
-template <bool NEEDP>
-__device__ __forceinline__ bool eval_read(const DevConf &cf, const double *lut, const Geom &g, int pos, int bq, int mq,
-                                          int baq, int sq, bool &is_alt, int &slot, double &jp)
-{
-    const int grp = (pos >= g.b1) + (pos >= g.b2) + (pos >= g.b3);
-    is_alt = grp != g.ref_idx;
-    slot = grp - (grp > g.ref_idx);
-    if (bq < cf.min_bq) return false;
-    if (is_alt && bq < cf.min_alt_bq) return false;
-    if (!NEEDP && !cf.jq_filters) return true;
-    double bp = lut[bq];
-    if (is_alt && cf.alt_bq_mode) bp = g.alt_bp;
-    const double mp = cf.use_mq ? lut[256 + mq] : 0.0;
-    const double bap = cf.use_baq ? lut[512 + baq] : 0.0;
-    const double sp = cf.use_sq ? lut[512 + sq] : 0.0;
-    jp = merge4(sp, mp, bap, bp);
-    if (cf.jq_filters) {
-        if (jp >= cf.skip_jp) return false;
-        if (is_alt && jp >= cf.skip_alt_jp) return false;
-    }
-    if (is_alt && cf.def_alt_jq_on) jp = cf.def_alt_jq_prob;
-    return true;
-}
-
-__device__ __forceinline__ void load_lut(double *s_lut, const Lut *lut)
-{
-    const double *src = reinterpret_cast<const double *>(lut);
-    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = src[i];
-    __syncthreads();
-}
-
-// median of the reference-base qualities (int_median, utils.c:435-458) for def_alt_bq == -1.
-// hist: 256 ints of shared memory owned by this warp.
-__device__ int warp_ref_median(const unsigned char *bqp, long long off, int lo, int hi, int *hist)
-{
-    const int lane = lane_id();
-    for (int i = lane; i < 256; i += 32) hist[i] = 0;
-    __syncwarp();
-    for (int i = lo + lane; i < hi; i += 32) atomicAdd(&hist[bqp[off + i]], 1);
-    __syncwarp();
-    int med = -1;
-    const int n = hi - lo;
-    if (n > 0 && lane == 0) {
-        // order statistics n/2 and n/2-1 of the sorted values
-        const int r_hi = n / 2, r_lo = n / 2 - 1;
-        int acc = 0, v_hi = -1, v_lo = -1;
-        for (int v = 0; v < 256; ++v) {
-            const int nxt = acc + hist[v];
-            if (v_lo < 0 && r_lo >= 0 && r_lo < nxt) v_lo = v;
-            if (v_hi < 0 && r_hi < nxt) v_hi = v;
-            acc = nxt;
-        }
-        med = (n & 1) ? v_hi : (int)((v_hi + v_lo) / 2.0);
-    }
-    med = __shfl_sync(FULL, med, 0);
-    __syncwarp();
-    return med;
-}
-
-__device__ __forceinline__ bool load_geom(const DevBatch &b, long long c, Geom &g, int &cov)
-{
-    const int4 cnt = reinterpret_cast<const int4 *>(b.nt_cnt)[c];
-    g.off = b.col_off[c];
-    g.b1 = cnt.x;
-    g.b2 = g.b1 + cnt.y;
-    g.b3 = g.b2 + cnt.z;
-    g.n = g.b3 + cnt.w;
-    g.ref_idx = ref_index(b.ref_base[c]);
-    g.alt_bp = 0.0;
-    cov = b.coverage ? b.coverage[c] : g.n;
-    return true;
-}
-
-__device__ __forceinline__ void setup_alt_bq(const DevConf &cf, const DevBatch &b, const double *s_lut, Geom &g, int *hist)
-{
-    if (cf.alt_bq_mode == 1) {
-        g.alt_bp = cf.alt_bq_prob;
-    } else if (cf.alt_bq_mode == 2) {
-        const int lo = g.ref_idx == 0 ? 0 : g.ref_idx == 1 ? g.b1 : g.ref_idx == 2 ? g.b2 : g.b3;
-        const int hi = g.ref_idx == 0 ? g.b1 : g.ref_idx == 1 ? g.b2 : g.ref_idx == 2 ? g.b3 : g.n;
-        const int med = warp_ref_median(b.bq, g.off, lo, hi, hist);
-        g.alt_bp = med < 0 ? 0.0 : s_lut[med];      // empty ref group: bq = -1 -> probability 0 (snpcaller.c:435, 331)
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // distribution truncated at K (K <= KS): P[k] = P(k errors), k < K; T = P(>= K errors)
 // ------------------------------------------------------------------------------------------------
@@ -270,17 +134,6 @@ __device__ __forceinline__ void small_tails(const double (&P)[KV], double T, con
 // ------------------------------------------------------------------------------------------------
 // k_screen
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int byte_of(const uint4 &v, int j)
-{
-    const unsigned w = j < 4 ? v.x : j < 8 ? v.y : j < 12 ? v.z : v.w;
-    return (w >> (8 * (j & 3))) & 0xff;
-}
-
-__device__ __forceinline__ uint4 ldg16(const unsigned char *p)
-{
-    return __ldg(reinterpret_cast<const uint4 *>(p));
-}
-
 // [lo, hi) of the reads showing the reference base
 __device__ __forceinline__ void ref_range(const Geom &g, int &lo, int &hi)
 {
@@ -298,19 +151,6 @@ __device__ __forceinline__ double ref_read_prob(const DevConf &cf, const double 
     if (!cf.use_mq) return bp;
     const double mp = lut[256 + mq];
     return __dadd_rn(mp, __dmul_rn(__dsub_rn(1.0, mp), bp));
-}
-
-struct Chunk16 {        // 16 consecutive bytes of each plane, one lane's share of a 512-read stripe
-    uint4 bq, mq, baq, sq;
-};
-
-__device__ __forceinline__ void load_chunk(const DevConf &cf, const DevBatch &b, long long a, Chunk16 &ch)
-{
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-    ch.bq = ldg16(b.bq + a);
-    ch.mq = cf.use_mq ? ldg16(b.mq + a) : zero;
-    ch.baq = cf.use_baq ? ldg16(b.baq + a) : zero;
-    ch.sq = cf.use_sq ? ldg16(b.sq + a) : zero;
 }
 
 __device__ __forceinline__ double lds_f64(unsigned saddr)
@@ -624,15 +464,6 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(long long *blocksum, int n
     if (threadIdx.x == 0) ctr->n_tested = (unsigned long long)s_carry;
 }
 
-__device__ __forceinline__ int class_of(int K)
-{
-    const int need = (K + 31) >> 5;          // cells per lane
-    if (need > 64) return CLS_XL;
-    int cls = 0;
-    while ((1 << cls) < need) ++cls;
-    return cls;
-}
-
 __global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
                                                         const Lut *lut, const Workspace ws, const long long *bonf_start_dev)
 {
@@ -676,9 +507,31 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant
     }
     const int K = max(cnt[0], max(cnt[1], cnt[2]));
     if (t && K > KS) {
-        const int cls = class_of(K);
-        const unsigned slot = atomicAdd(&ws.counters->n_jobs[cls], 1u);
-        ws.jobs[(long long)cls * ws.cap_cols + slot] = (int)c;
+        // 8 < K <= 256: packed kernel (several columns per warp) unless the column is too deep for its scratch row, the
+        // median override needs a warp-wide histogram, or the list is full; everything else: one warp / CTA per column
+        bool routed = false;
+        if (K <= PK_MAXK && cf.alt_bq_mode != 2 && ws.pjobs) {
+            const int4 nc = reinterpret_cast<const int4 *>(b.nt_cnt)[c];
+            const int pl = packed_list(K, nc.x + nc.y + nc.z + nc.w);
+            if (pl >= 0) {
+                // its row in the scratch pool (padded to 32 reads), then its slot in the list
+                const int npad = (nc.x + nc.y + nc.z + nc.w + 31) & ~31;
+                const long long off = (long long)atomicAdd(&ws.counters->pk_scr_used, (unsigned long long)npad);
+                if (off + npad <= ws.pk_scr_cap) {
+                    const unsigned slot = atomicAdd(&ws.counters->n_pjobs[pl], 1u);
+                    if (slot < (unsigned)ws.pcap) {
+                        ws.pjobs[(long long)pl * ws.pcap + slot] = (int)c;
+                        ws.pinfo[(long long)pl * ws.pcap + slot].scr_off = off;
+                        routed = true;
+                    }
+                }
+            }
+        }
+        if (!routed) {
+            const int cls = class_of(K);
+            const unsigned slot = atomicAdd(&ws.counters->n_jobs[cls], 1u);
+            ws.jobs[(long long)cls * ws.cap_cols + slot] = (int)c;
+        }
     }
     // ---- columns with K <= KS ----
     // (1) prune, lane per column: the reference's early exit (snpcaller.c:916-958) — walk the reads until
@@ -1748,18 +1601,25 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
         }
     }
     const int g = sm_count() * 4;
+    stage_smem_optin();
+    // k_mid (K <= 8 survivors, unpackable K <= 32) runs beside k_packed; both may hand columns to the k_heavy<R> lists,
+    // which therefore run after them, side by side (each class alone has too few columns to hide its own latencies)
+    cudaEventRecord(ev_fork, st);
+    cudaStreamWaitEvent(side[0], ev_fork, 0);
+    k_mid<<<g, 128, 0, side[0]>>>(cf, b, lut, ws);
+    cudaEventRecord(ev_join[0], side[0]);
+    launch_packed(cf, b, lut, ws, st);
+    cudaStreamWaitEvent(st, ev_join[0], 0);
     cudaEventRecord(ev_fork, st);
     for (int i = 0; i < NSIDE; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
     k_heavy_xl<<<sm_count(), XL_T, 0, side[7]>>>(cf, b, lut, ws, CLS_XL);
-    stage_smem_optin();
     k_heavy<64><<<g, 128, STAGE_BYTES, side[6]>>>(cf, b, lut, ws, 6);
     k_heavy<32><<<g, 128, STAGE_BYTES, side[5]>>>(cf, b, lut, ws, 5);
     k_heavy<16><<<g, 128, STAGE_BYTES, side[4]>>>(cf, b, lut, ws, 4);
     k_heavy<8><<<g, 128, STAGE_BYTES, side[3]>>>(cf, b, lut, ws, 3);
     k_heavy<4><<<g, 128, STAGE_BYTES, side[2]>>>(cf, b, lut, ws, 2);
     k_heavy<2><<<g, 128, STAGE_BYTES, side[1]>>>(cf, b, lut, ws, 1);
-    k_mid<<<g, 128, 0, side[0]>>>(cf, b, lut, ws);
-    k_heavy<1><<<g, 128, STAGE_BYTES, side[0]>>>(cf, b, lut, ws, CLS_FALLBACK);     // what k_mid handed back (rare)
+    k_heavy<1><<<g, 128, STAGE_BYTES, side[0]>>>(cf, b, lut, ws, CLS_FALLBACK);     // what k_mid / k_packed handed back (rare)
     for (int i = 0; i < NSIDE; ++i) {
         cudaEventRecord(ev_join[i], side[i]);
         cudaStreamWaitEvent(st, ev_join[i], 0);
