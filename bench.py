@@ -264,6 +264,18 @@ def run_ours(args):
         finish_begin(i)
         return finish_end(i)
 
+    host_t = {"screen": 0.0, "test": 0.0, "finish_begin": 0.0, "finish_end": 0.0}
+    if os.environ.get("LFB200_HOST_TIMING"):       # where the launching thread spends its time (diagnostics only)
+        def timed(name, fn):
+            def wrapped(i):
+                t0 = time.perf_counter()
+                r = fn(i)
+                host_t[name] += time.perf_counter() - t0
+                return r
+            return wrapped
+        screen, test, finish_begin, finish_end = (timed("screen", screen), timed("test", test),
+                                                  timed("finish_begin", finish_begin), timed("finish_end", finish_end))
+
     def run_steps(k_steps):
         """batch k on context k % 2: screen(k+1) is issued while test(k) runs, and the sites of batch k are finished
         on a host thread while the launching thread goes on"""
@@ -292,12 +304,16 @@ def run_ours(args):
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(streams[0])
+    for k_ in host_t:
+        host_t[k_] = 0.0
     t0 = time.perf_counter()
     run_steps(args.steps)
     e1.record(streams[0])          # issued after the last batch's host finishing returned
     barrier()
     wall = time.perf_counter() - t0
     dev_ms = e0.elapsed_time(e1)
+    if os.environ.get("LFB200_HOST_TIMING"):
+        print("host seconds in the launching thread (timed steps):", host_t, "wall of timed steps", wall, file=sys.stderr)
     clocks = sampler.stop()
     sm = sms[(args.steps - 1) % 2]
     n_sites, n_tested, n_heavy = sm.n_sites, sm.n_tested, sm.n_heavy

@@ -567,7 +567,6 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
         n_cand = c.n_cand;
         for (int i = 0; i < NCLASS; ++i) if (i != CLS_FALLBACK) sm.n_heavy += c.n_jobs[i];
         for (int i = 0; i < PK_NL; ++i) sm.n_heavy += std::min<long long>(c.n_pjobs[i], ctx->ws.pcap);
-        sm.n_heavy -= c.n_pk_fallback;             // those are in the k_heavy<R> lists as well
     }
     if (dbg) t1 = now();
     if (n_cand > max_sites) return fail("%lld sites but room for %lld", n_cand, max_sites);

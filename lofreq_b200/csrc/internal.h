@@ -78,9 +78,7 @@ struct Counters {
     unsigned int err_flags;
     unsigned int n_pjobs[PK_NL];   // packed job lists (may exceed Workspace::pcap: the excess went to the other lists)
     unsigned int next_ptask;
-    unsigned int next_pprep;
     unsigned long long pk_scr_used; // entries of the scratch pool handed out so far
-    unsigned int n_pk_fallback;    // columns k_packed handed to k_heavy<R> (lists 1..6)
     long long bonf_start_used;     // running factor the last test started from (host or device supplied)
 };
 

@@ -21,7 +21,7 @@
 //   4. ln P(X >= K), and the tails of the other alleles from the same (possibly tilted) row:
 //      P(X >= c) = sum_{k >= c} E[k] s^-k — all terms positive.
 // Columns the packed form cannot finish (parameters above 2^20, tail outside the untilted range after the fact,
-// a low cell of a strongly tilted row lost to underflow) are appended to the k_heavy<R> job lists, which run next.
+// a low cell of a strongly tilted row lost to underflow) are appended to the fallback list, which k_heavy<8> takes next.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -121,7 +121,8 @@ __device__ double warp_newton(const double2 *row, int n, int K, int N, double la
 // running sums of k_pk_prep's first sweep
 struct PrepAcc {
     int N;
-    double lam, lq, qp, max_o, max_rq;
+    int hi_o, hi_rq;       // largest o and 1/q seen, as the high words of the doubles (positive: ordered like the values)
+    double lam, lq, qp;
 };
 
 __device__ __forceinline__ void prep_take(PrepAcc &a, double jp, bool ok, bool may_be_one, double2 &out)
@@ -132,7 +133,7 @@ __device__ __forceinline__ void prep_take(PrepAcc &a, double jp, bool ok, bool m
     if (may_be_one) {
         guard_pq(jp, p, q);
     } else {                                           // jp <= 0.96: only the p-guard of snpcaller.c:872-881 can fire
-        p = fmax(jp, DEPS);
+        p = jp < DEPS ? DEPS : jp;
         q = 1.0 - jp;
     }
     const double rq = 1.0 / q;
@@ -141,8 +142,8 @@ __device__ __forceinline__ void prep_take(PrepAcc &a, double jp, bool ok, bool m
     a.lam += p;
     ++a.N;
     a.qp *= q;
-    a.max_o = fmax(a.max_o, o);
-    a.max_rq = fmax(a.max_rq, rq);
+    a.hi_o = max(a.hi_o, __double2hiint(o));
+    a.hi_rq = max(a.hi_rq, __double2hiint(rq));
 }
 
 constexpr int PREP_WARPS = 8;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 4) k_pk_prep(const __grid_con
         if (!fb) {
             double2 *row = ws.pk_scratch + off;
             PrepAcc a;
-            a.N = 0; a.lam = 0.0; a.lq = 0.0; a.qp = 1.0; a.max_o = 0.0; a.max_rq = 0.0;
+            a.N = 0; a.lam = 0.0; a.lq = 0.0; a.qp = 1.0; a.hi_o = 0; a.hi_rq = 0;
             const long long abase = g.off & ~15ll;
             const int lead = (int)(g.off - abase);
             const int nch = (lead + g.n + 15) >> 4;
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 4) k_pk_prep(const __grid_con
                 load_chunk(cf, b, abase + 16ll * i, ch);
                 const int pos0 = 16 * i - lead;
                 const bool inside = pos0 >= 0 && pos0 + 16 <= g.n;
-#pragma unroll 1
+#pragma unroll
                 for (int w = 0; w < 4; ++w) {
                     const unsigned wbq = w == 0 ? ch.bq.x : w == 1 ? ch.bq.y : w == 2 ? ch.bq.z : ch.bq.w;
                     const unsigned wmq = w == 0 ? ch.mq.x : w == 1 ? ch.mq.y : w == 2 ? ch.mq.z : ch.mq.w;
@@ -235,12 +236,9 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 4) k_pk_prep(const __grid_con
             const int N = __reduce_add_sync(FULL, a.N);
             const double lam = __shfl_sync(FULL, warp_sum(a.lam), 0);
             sum_lq = __shfl_sync(FULL, warp_sum(a.lq), 0);
-            double max_o = a.max_o, max_rq = a.max_rq;
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) {
-                max_o = fmax(max_o, __shfl_xor_sync(FULL, max_o, m));
-                max_rq = fmax(max_rq, __shfl_xor_sync(FULL, max_rq, m));
-            }
+            // upper bounds of the largest o and 1/q of the column
+            const double max_o = __hiloint2double(__reduce_max_sync(FULL, a.hi_o), (int)0xffffffff);
+            const double max_rq = __hiloint2double(__reduce_max_sync(FULL, a.hi_rq), (int)0xffffffff);
             __syncwarp();                              // the row is read by other lanes from here on
             // Chernoff exponent of the tail: beyond ~300 nats the untilted cells of interest drift out of fp64 range
             const double cher = ((double)K > lam) ? ((double)K * log((double)K / lam) - (double)K + lam) : 0.0;
@@ -261,10 +259,8 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 4) k_pk_prep(const __grid_con
         if (lane == 0) {
             if (fb) {
                 info->scr_off = -1;
-                const int cls = K <= 32 ? CLS_FALLBACK : class_of(K);      // k_mid is already running: not its list
-                const unsigned sl = atomicAdd(&ws.counters->n_jobs[cls], 1u);
-                ws.jobs[(long long)cls * ws.cap_cols + sl] = (int)c;
-                if (cls != CLS_FALLBACK) atomicAdd(&ws.counters->n_pk_fallback, 1u);
+                const unsigned sl = atomicAdd(&ws.counters->n_jobs[CLS_FALLBACK], 1u);
+                ws.jobs[(long long)CLS_FALLBACK * ws.cap_cols + sl] = (int)c;
             } else {
                 info->ln_s = ln_s;
                 info->sum_lq = sum_lq;
@@ -430,10 +426,8 @@ __device__ void packed_task(const DevConf &cf, const DevBatch &b, const Workspac
     if (fb) site = false;
     if (have && gl == 0) {
         if (fb) {
-            const int cls = K <= 32 ? CLS_FALLBACK : class_of(K);
-            const unsigned slot = atomicAdd(&ws.counters->n_jobs[cls], 1u);
-            ws.jobs[(long long)cls * ws.cap_cols + slot] = (int)c;
-            if (cls != CLS_FALLBACK) atomicAdd(&ws.counters->n_pk_fallback, 1u);
+            const unsigned slot = atomicAdd(&ws.counters->n_jobs[CLS_FALLBACK], 1u);
+            ws.jobs[(long long)CLS_FALLBACK * ws.cap_cols + slot] = (int)c;
         } else if (site) {
             Cand cd;
             cd.col = c;

@@ -1043,6 +1043,7 @@ __global__ void __launch_bounds__(128) k_mid(const __grid_constant__ DevConf cf,
 {
     __shared__ double s_lut[768];
     __shared__ int s_hist[4][256];
+    if (ws.counters->n_jobs[0] == 0) return;                 // nothing listed: leave before the table is even loaded
     load_lut(s_lut, lut);
     unsigned lut_sa = (unsigned)__cvta_generic_to_shared(s_lut);
     const int lane = lane_id(), wib = threadIdx.x >> 5;
@@ -1107,6 +1108,7 @@ __global__ void __launch_bounds__(128) k_heavy(const __grid_constant__ DevConf c
     __shared__ double2 s_par[4][32];
     __shared__ int s_hist[4][256];
     extern __shared__ double s_stage[];          // [4][STAGE_DOUBLES]
+    if (ws.counters->n_jobs[cls] == 0) return;                 // nothing listed: leave before the table is even loaded
     load_lut(s_lut, lut);
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     const unsigned njobs = ws.counters->n_jobs[cls];
@@ -1403,6 +1405,7 @@ __global__ void __launch_bounds__(XL_T, 1) k_heavy_xl(const __grid_constant__ De
     __shared__ int s_hist[256];
     __shared__ unsigned s_job;
     __shared__ double s_small[KS + 1];
+    if (ws.counters->n_jobs[cls] == 0) return;                 // nothing listed: leave before the table is even loaded
     load_lut(s_lut, lut);
     const unsigned njobs = ws.counters->n_jobs[cls];
     const int *jobs = ws.jobs + (long long)cls * ws.cap_cols;
@@ -1602,8 +1605,10 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
     }
     const int g = sm_count() * 4;
     stage_smem_optin();
-    // k_mid (K <= 8 survivors, unpackable K <= 32) runs beside k_packed; both may hand columns to the k_heavy<R> lists,
-    // which therefore run after them, side by side (each class alone has too few columns to hide its own latencies)
+    // k_mid (K <= 8 survivors, unpackable K <= 32) runs beside k_pk_prep -> k_packed.  Both hand the few columns they
+    // cannot finish to one fallback list, which k_heavy<8> (any K <= 256) takes afterwards, side by side with the
+    // per-column kernels for what k_finalize listed for them (K > 256, very deep columns, median override) — each
+    // class alone has too few columns to hide its own latencies; an empty list costs an early exit.
     cudaEventRecord(ev_fork, st);
     cudaStreamWaitEvent(side[0], ev_fork, 0);
     k_mid<<<g, 128, 0, side[0]>>>(cf, b, lut, ws);
@@ -1619,7 +1624,7 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
     k_heavy<8><<<g, 128, STAGE_BYTES, side[3]>>>(cf, b, lut, ws, 3);
     k_heavy<4><<<g, 128, STAGE_BYTES, side[2]>>>(cf, b, lut, ws, 2);
     k_heavy<2><<<g, 128, STAGE_BYTES, side[1]>>>(cf, b, lut, ws, 1);
-    k_heavy<1><<<g, 128, STAGE_BYTES, side[0]>>>(cf, b, lut, ws, CLS_FALLBACK);     // what k_mid / k_packed handed back (rare)
+    k_heavy<8><<<g, 128, STAGE_BYTES, side[0]>>>(cf, b, lut, ws, CLS_FALLBACK);
     for (int i = 0; i < NSIDE; ++i) {
         cudaEventRecord(ev_join[i], side[i]);
         cudaStreamWaitEvent(st, ev_join[i], 0);

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -15 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 20 --no-cpu > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"
+timeout 600 python bench.py --steps 100 --no-cpu > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_quick.json'))
