@@ -69,7 +69,7 @@ SITE_FN = C.CFUNCTYPE(None, C.POINTER(Site), C.c_longlong, C.c_char, C.c_int, C.
 SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_conf", "lfb200_call_columns", "lfb200_set_host_planes",
            "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_ntested_copy_device", "lfb200_test_device_from", "lfb200_bonf_start_device", "lfb200_comm_unique_id", "lfb200_comm_init", "lfb200_comm_exchange", "lfb200_comm_gathered",
            "lfb200_sites_device", "lfb200_sites_begin", "lfb200_sites_end",
-           "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_dfma_peak", "lfb200_copy_counts_device", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
+           "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_dfma_peak", "lfb200_last_job_counts", "lfb200_copy_counts_device", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
            "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_binom", "lfb200_binom_batch", "lfb200_synth_depths",
            "lfb200_synth_columns"]
 
@@ -149,6 +149,8 @@ def load():
     lib.lfb200_builder_destroy.argtypes = [vp]
     lib.lfb200_copy_counts_device.restype = C.c_int
     lib.lfb200_copy_counts_device.argtypes = [vp, vp, vp]
+    lib.lfb200_last_job_counts.restype = C.c_int
+    lib.lfb200_last_job_counts.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.lfb200_dfma_peak.restype = C.c_double
     lib.lfb200_dfma_peak.argtypes = [vp, vp]
     lib.lfb200_snpcaller.restype = C.c_int

@@ -709,6 +709,18 @@ extern "C" int lfb200_copy_counts_device(lfb200_ctx *ctx, void *stream, int *dst
     return 0;
 }
 
+extern "C" int lfb200_last_job_counts(lfb200_ctx *ctx, long long out[4])
+{
+    if (!ctx || !out) return fail("null argument");
+    const Counters &c = *ctx->h_counters;          // copied back by the last sites_sync
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (int i = 0; i < PK_NL; ++i) out[0] += std::min<long long>(c.n_pjobs[i], ctx->ws.pcap);
+    out[1] = c.n_jobs[CLS_FALLBACK];               // includes the few k_mid hands back
+    for (int i = 1; i < NCLASS; ++i) if (i != CLS_FALLBACK) out[2] += c.n_jobs[i];
+    out[3] = c.n_jobs[0];
+    return 0;
+}
+
 extern "C" double lfb200_dfma_peak(lfb200_ctx *ctx, void *stream)
 {
     if (!ctx) return 0.0;

@@ -136,6 +136,9 @@ class Caller:
         out["n_sites"] = sm.n_sites
         out["n_tested"] = sm.n_tested
         out["n_heavy"] = sm.n_heavy
+        jc = (C.c_longlong * 4)()
+        capi.check(self.lib.lfb200_last_job_counts(self._ctx, jc))
+        out["job_counts"] = dict(packed=jc[0], fallback=jc[1], per_column=jc[2], mid=jc[3])
         out["bonf_subst"] = cf.bonf_subst
         out["num_snv_tests"] = cf.num_snv_tests
         return out

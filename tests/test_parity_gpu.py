@@ -433,6 +433,72 @@ def test_deep_columns_cta_per_column_kernel(caller, port_oracle):
         assert_lnp_close(got, want, status_of(want), "deep snpcaller")
 
 
+def test_packed_kernel_classes(caller, port_oracle):
+    """8 < K <= 256: k_pk_prep + k_packed, 4/8/16/32 lanes per column, columns of one warp in lock step.
+    Every group width, tilted and untilted rows, secondary alleles read off a tilted row, ragged depths inside
+    one warp, neutral steps for filtered reads, and the hand-over to the fallback list."""
+    rng = np.random.default_rng(77)
+
+    def grp(n, qlo=20, qhi=41, mqv=60, baqv=None):
+        return (rng.integers(qlo, qhi, n), np.full(n, mqv), rng.integers(30, 61, n) if baqv is None else np.full(n, baqv))
+    e = (np.zeros(0, int),) * 3
+    cols = []
+    # every group width at several depths (each depth bin has its own job list), ragged inside a bin
+    for K in (9, 17, 32, 33, 50, 64, 65, 100, 128, 129, 200, 256):
+        for depth in (K + 1, 2 * K + 37, 600, 1100, 3000):
+            if depth <= K:
+                continue
+            cols.append(dict(ref="A", groups=[grp(depth - K), grp(K), e, e]))
+    # high qualities: far tails -> tilted rows; second and third allele read off the same row
+    for K, c2, c3 in ((40, 3, 0), (90, 12, 1), (130, 60, 9), (250, 120, 119), (256, 1, 1), (70, 70, 2)):
+        cols.append(dict(ref="C", groups=[grp(c2, 35, 41), grp(700, 35, 41), grp(K, 35, 41), grp(c3, 35, 41)]))
+    # nearly all reads alt (a low cell of the tilted row underflows -> fallback list), K == N
+    cols.append(dict(ref="G", groups=[grp(250, 38, 41), e, grp(3, 38, 41), grp(2, 38, 41)]))
+    cols.append(dict(ref="G", groups=[grp(200, 38, 41), e, e, e]))
+    cols.append(dict(ref="T", groups=[grp(120, 30, 41), grp(2, 30, 41), grp(1, 30, 41), e]))
+    # filtered reads in between (bq < min_bq): neutral steps; mq 0 -> p >= 0.5, odds >= 1
+    cols.append(dict(ref="A", groups=[grp(400, 0, 41), grp(60, 0, 41), grp(5, 0, 12), e]))
+    cols.append(dict(ref="A", groups=[grp(300, 20, 41, mqv=0), grp(40, 20, 41, mqv=0), e, e]))
+    # baq 0 -> merged probability exactly 1: 1/q = 2^52 -> parameters above 2^20 -> fallback list
+    cols.append(dict(ref="C", groups=[grp(20, baqv=0), grp(300), grp(30), e]))
+    # deeper than the packed form holds (n > 8192): per-column kernel
+    cols.append(dict(ref="T", groups=[grp(100), e, e, grp(9000)]))
+    order = rng.permutation(len(cols))
+    cols = [cols[i] for i in order]
+    for pad in (1, 16):
+        b = _custom_batch(cols, pad=pad)
+        for conf in (default_conf(), default_conf(flag=0), default_conf(bonf_dynamic=0, bonf_subst=3000000),
+                     default_conf(min_bq=3, min_alt_bq=20, min_jq=15, min_alt_jq=25, def_alt_jq=35), default_conf(def_alt_bq=25)):
+            want = port_oracle.call_columns(b, dict(conf))
+            got = caller.call_columns(b, dict(conf))
+            compare_batch(got, want, "packed pad=%d %s" % (pad, conf))
+            jc = got["job_counts"]
+            assert jc["packed"] >= 60, jc                      # the packed kernel really took them
+            assert jc["fallback"] < jc["packed"] // 4, jc
+    # median override needs a warp-wide histogram per column: none of these may take the packed form
+    got = caller.call_columns(b, default_conf(def_alt_bq=-1))
+    compare_batch(got, port_oracle.call_columns(b, default_conf(def_alt_bq=-1)), "packed median")
+    assert got["job_counts"]["packed"] == 0
+
+
+def test_packed_scratch_pool_overflow(caller, port_oracle):
+    """more heavy reads than the scratch pool holds (16 reads per column of the batch, at least 1 Mi): the columns
+    that do not get a row take the per-column kernels, with the same results"""
+    rng = np.random.default_rng(3)
+    e = (np.zeros(0, int),) * 3
+    cols = []
+    for i in range(450):
+        n, K = 2600 + int(rng.integers(0, 200)), int(rng.integers(20, 250))
+        cols.append(dict(ref="A", groups=[(rng.integers(25, 41, n - K), np.full(n - K, 60), np.full(n - K, 40)),
+                                          (rng.integers(25, 41, K), np.full(K, 60), np.full(K, 40)), e, e]))
+    b = _custom_batch(cols, pad=16)
+    want = port_oracle.call_columns(b, default_conf())
+    got = caller.call_columns(b, default_conf())
+    compare_batch(got, want, "pool overflow")
+    jc = got["job_counts"]
+    assert 0 < jc["packed"] < 450 and jc["per_column"] + jc["mid"] > 0, jc
+
+
 def test_binom_golden(caller):
     """binom() (binom.c:52-93 -> cdflib cdfbin): status codes exact, cdf and sf within 1e-10 relative of the compiled
     reference — through the batched entry point and through the link-compatible single call"""
