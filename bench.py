@@ -146,6 +146,29 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+STREAM_KERNELS = ("k_screen", "k_block_counts", "k_scan_blocks", "k_finalize")
+HEAVY_KERNELS = ("k_mid", "k_pk_prep", "k_packed", "k_heavy")      # k_heavy<R>, k_heavy_xl
+
+
+def ncu_traffic(names):
+    """dram__bytes_read.sum + dram__bytes_write.sum per step of the named kernels, from the committed `ncu --set full`
+    capture of one step of this workload (profiles/r1_step_kernels.json, written by tools/ncu_extract.py); None when
+    the capture is not there."""
+    p = os.path.join(ROOT, "profiles", "r1_step_kernels.json")
+    try:
+        with open(p) as f:
+            ks = json.load(f)
+    except Exception:
+        return None
+    tot, hit = 0.0, False
+    for k in ks:
+        nm = k.get("kernel", "")
+        if any(nm.startswith(n) or ("lfb::" + n) in nm or (" " + n) in nm for n in names):
+            tot += k.get("dram__bytes_read.sum [bytes]", 0.0) + k.get("dram__bytes_write.sum [bytes]", 0.0)
+            hit = True
+    return tot if hit else None
+
+
 def algorithmic_bytes(sum_depth, n_cols, planes=2):
     """planes the configuration merges (bq, mq[, baq]) over the column's reads +
     per-column metadata in (col_off 8, nt_cnt 16, ref_base 1) + per-column results out (alt counts and
@@ -381,7 +404,7 @@ def run_ours(args):
         e2e_s, sites_map, tests_map = time_e2e(1)
         capi.check(lib.lfb200_set_host_planes(caller._ctx, 0))
         assert (sites_copy, tests_copy) == (sites_map, tests_map), "in-place and copied planes disagree"
-    e2e_value = world * n / e2e_s
+    e2e_value = world * n / e2e_copy_s            # headline: every input byte is copied host -> device inside the timed region
     d2h = 128 + int(sm.n_sites) * 80
     h2d_meta = 8 * (n + 1) + 16 * n + n
 
@@ -397,7 +420,9 @@ def run_ours(args):
     t_stream = float(ph[0] + ph[1] + ph[2])
     bytes_algo = algorithmic_bytes(int(t["depths"].sum().item()), n)
     hbm = {"bound": "hbm", "kernel": "k_screen + k_block_counts + k_scan_blocks + k_finalize", "achieved": bytes_algo / t_stream / 1e9,
-           "peak": peak, "unit": "GB/s", "frac": bytes_algo / t_stream / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+           "peak": peak, "unit": "GB/s", "frac": bytes_algo / t_stream / 1e9 / peak, "traffic": ncu_traffic(STREAM_KERNELS), "peak_source": peak_src,
+           "note": "algorithmic bytes = every quality byte the configuration merges (SURVEY.md 8d); the early-exit prune reads far fewer "
+                   "(see traffic), so a fraction above 1 means bytes skipped, not bandwidth above peak",
            "algorithmic_bytes_per_launch": bytes_algo, "kernel_ms": t_stream * 1e3}
     # heavy columns of the last batch: K and depth from the device-resident results
     cnt6 = torch.empty((n, 6), dtype=torch.int32, device=dev)
@@ -413,9 +438,9 @@ def run_ours(args):
     dfma = lib.lfb200_dfma_peak(callers[0]._ctx, sts[0])
     fp64_peak = 2.0 * dfma / 1e12
     t_heavy = float(ph[3])
-    fp64 = {"bound": "fp64", "kernel": "k_heavy<1..64> (7 register-tile classes, concurrent)", "achieved": flops_algo / t_heavy / 1e12,
+    fp64 = {"bound": "fp64", "kernel": "k_pk_prep + k_packed (8 < K <= 256, several columns per warp) beside k_mid; k_heavy<R> for the rest", "achieved": flops_algo / t_heavy / 1e12,
             "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops_algo / t_heavy / 1e12 / fp64_peak if fp64_peak else None,
-            "traffic": None, "peak_source": "DFMA microbenchmark run in this process (lfb200_dfma_peak); MEASURED_PEAKS.json has no fp64 entry",
+            "traffic": ncu_traffic(HEAVY_KERNELS), "peak_source": "DFMA microbenchmark run in this process (lfb200_dfma_peak); MEASURED_PEAKS.json has no fp64 entry",
             "algorithmic_flops_per_launch": flops_algo, "kernel_ms": t_heavy * 1e3, "columns": int(heavy.sum().item())}
     roofline = dict(fp64 if t_heavy >= t_stream else hbm)
     roofline["phase_ms"] = {"k_screen": float(ph[0] * 1e3), "prefix_sum": float(ph[1] * 1e3), "k_finalize": float(ph[2] * 1e3),
@@ -440,14 +465,14 @@ def run_ours(args):
                            "sites_all_ranks": final_sites,
                            "bonf_subst_final_this_rank": int(sm.bonf_subst_final)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                        "h2d_mode": "lfb200_call_columns on pinned host buffers, host plane mode 1: the kernels read the "
-                                    "quality planes in place over PCIe (only the reads that decide a column cross the bus); "
-                                    "the per-column metadata (%d bytes) is copied; h2d_bytes_per_step counts all host "
-                                    "input tensors of the step" % h2d_meta,
-                        "bulk_copy": {"value": world * n / e2e_copy_s, "ms_per_step": e2e_copy_s * 1e3,
-                                      "h2d_mode": "host plane mode 0: every plane copied to the device first"}},
-                "gpu_launches": 12 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                        "ms_per_step": e2e_copy_s * 1e3, "steps": e2e_steps,
+                        "h2d_mode": "lfb200_call_columns on pinned host buffers (its default, host plane mode 0): every plane and the "
+                                    "per-column metadata are copied to the device, then screen/test/sites; PCIe-bound",
+                        "in_place": {"value": world * n / e2e_s, "ms_per_step": e2e_s * 1e3, "h2d_bytes_copied_per_step": h2d_meta,
+                                     "h2d_mode": "optional host plane mode 1 (lfb200_set_host_planes): the kernels read the pinned quality "
+                                                 "planes in place over PCIe, so only the reads that decide a column cross the bus; "
+                                                 "only the per-column metadata is copied"}},
+                "gpu_launches": 15 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "wall_ms_per_step": wall * 1e3 / args.steps}
         print(json.dumps(line))
     if world > 1:

@@ -240,6 +240,45 @@ int lfb200_snpcaller_batch(lfb200_ctx *ctx, long long n, const double *err_probs
                            const int *noncons_counts, const long long *bonf, double sig_level,
                            long double *snp_pvalues, double *lnp, unsigned char *status);
 
+/* poissbin() of snpcaller.h:93-96 (snpcaller.c:1019-1062; called by snpcaller() and by source_qual, plp.c:554):
+ * same arguments; returns a malloc()ed row of num_failures+1 natural-log probabilities the caller free()s —
+ * row[k < K] = ln P(k errors), row[K] = ln P(>= K errors) among the reads seen when pruned_calc_prob_dist
+ * (snpcaller.c:830-971) stopped, i.e. a partial row when its Bonferroni-aware early exit fired — and
+ * *pvalue = expl(row[K]) with the reference's LDBL_MIN / LDBL_MAX clamp.  NULL on error (the reference: on
+ * failed malloc).  The reads are walked in the caller's order with the reference's log-space recurrence, one CTA
+ * per problem.  num_failures must be >= 1; for num_failures > num_err_probs the reference leaves row[K]
+ * uninitialised, here it is -1e100 (LOGZERO). */
+double *lfb200_poissbin(long double *pvalue, const double *err_probs, const int num_err_probs, const int num_failures,
+                        const long long int bonf, const double sig);
+/* n problems at once: problem i has err_probs[ep_off[i] .. ep_off[i+1]), num_failures[i], bonf[i]; its row goes to
+ * rows[row_off[i] .. row_off[i] + num_failures[i]], row_off[n] = total.  n_end (optional): the read at which the
+ * recurrence stopped (= the number of reads when it was not pruned). */
+int lfb200_poissbin_batch(lfb200_ctx *ctx, long long n, const double *err_probs, const long long *ep_off,
+                          const int *num_failures, const long long *bonf, double sig, const long long *row_off,
+                          double *rows, long double *pvalues, int *n_end);
+
+/* plp_to_errprobs() of snpcaller.h:72-75 (snpcaller.c:345-498) for every column of a host batch: the merged error
+ * probabilities of the reads that pass the filters, in pileup order (A, C, G, T groups, the order the reference
+ * walks them), column c at err_probs[col_off[c] ..] (so err_probs needs col_off[n_cols] doubles), their number in
+ * num_err_probs[c], and alt_bases / alt_counts / alt_raw_counts[3c .. 3c+2] as the reference fills them.
+ * Columns whose ref_base is not A/C/G/T get num_err_probs 0 and zero counts (call_snvs never gets that far:
+ * lofreq_call.c:754,892). */
+int lfb200_batch_errprobs(lfb200_ctx *ctx, const lfb200_conf_t *conf, const lfb200_batch_t *host_batch, double *err_probs,
+                          int *num_err_probs, int *alt_bases, int *alt_counts, int *alt_raw_counts);
+/* The part of plp_col_t (plp.h:73-145) plp_to_errprobs reads: per nt4 index A,C,G,T the int_varray_t data pointers and
+ * lengths of base_quals / map_quals / baq_quals / source_quals (pointer NULL = that varray is empty). */
+typedef struct {
+    char ref_base;
+    int coverage_plp;
+    int n[4];
+    const int *base_quals[4], *map_quals[4], *baq_quals[4], *source_quals[4];
+} lfb200_plp_col_t;
+/* Same contract as the reference function: *err_probs is malloc()ed with room for coverage_plp doubles and the caller
+ * free()s it (lofreq_call.c:778,878); the three int arrays have 3 slots; on failure a FATAL line goes to stderr and
+ * *err_probs is NULL (snpcaller.c:354-359).  A batch of one on the default ctx. */
+void lfb200_plp_to_errprobs(double **err_probs, int *num_err_probs, int *alt_bases, int *alt_counts, int *alt_raw_counts,
+                            const lfb200_plp_col_t *p, const lfb200_conf_t *conf);
+
 /* binom() of binom.c:52-93 (caller: lofreq_uniq.c:381; note binom.h:32 names the
  * last two arguments the other way round): *p = P(X <= num_success), *q = 1 - *p
  * for X ~ Binomial(num_trials, prob_success); either pointer may be NULL.

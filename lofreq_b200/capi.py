@@ -63,6 +63,13 @@ class Summary(C.Structure):
                 ("n_heavy", C.c_longlong), ("bonf_subst_final", C.c_longlong), ("num_snv_tests", C.c_longlong)]
 
 
+class PlpCol(C.Structure):
+    """lfb200_plp_col_t: what plp_to_errprobs reads of a plp_col_t (plp.h:73-145)"""
+    _fields_ = [("ref_base", C.c_char), ("coverage_plp", C.c_int), ("n", C.c_int * 4),
+                ("base_quals", C.c_void_p * 4), ("map_quals", C.c_void_p * 4), ("baq_quals", C.c_void_p * 4),
+                ("source_quals", C.c_void_p * 4)]
+
+
 SITE_FN = C.CFUNCTYPE(None, C.POINTER(Site), C.c_longlong, C.c_char, C.c_int, C.c_void_p)
 
 # every symbol include/lofreq_b200.h declares (tests/test_abi.py checks the header against this list)
@@ -70,7 +77,7 @@ SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_
            "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_ntested_copy_device", "lfb200_test_device_from", "lfb200_bonf_start_device", "lfb200_comm_unique_id", "lfb200_comm_init", "lfb200_comm_exchange", "lfb200_comm_gathered",
            "lfb200_sites_device", "lfb200_sites_begin", "lfb200_sites_end",
            "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_dfma_peak", "lfb200_last_job_counts", "lfb200_copy_counts_device", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
-           "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_binom", "lfb200_binom_batch", "lfb200_synth_depths",
+           "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_poissbin", "lfb200_poissbin_batch", "lfb200_batch_errprobs", "lfb200_plp_to_errprobs", "lfb200_binom", "lfb200_binom_batch", "lfb200_synth_depths",
            "lfb200_synth_columns"]
 
 _lib = None
@@ -157,6 +164,14 @@ def load():
     lib.lfb200_snpcaller.argtypes = [vp, vp, C.c_int, vp, ll, C.c_double, C.c_int]
     lib.lfb200_snpcaller_batch.restype = C.c_int
     lib.lfb200_snpcaller_batch.argtypes = [vp, ll, vp, vp, vp, vp, C.c_double, vp, vp, vp]
+    lib.lfb200_poissbin.restype = vp
+    lib.lfb200_poissbin.argtypes = [vp, vp, C.c_int, C.c_int, ll, C.c_double]
+    lib.lfb200_poissbin_batch.restype = C.c_int
+    lib.lfb200_poissbin_batch.argtypes = [vp, ll, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
+    lib.lfb200_batch_errprobs.restype = C.c_int
+    lib.lfb200_batch_errprobs.argtypes = [vp, C.POINTER(Conf), C.POINTER(Batch), vp, vp, vp, vp, vp]
+    lib.lfb200_plp_to_errprobs.restype = None
+    lib.lfb200_plp_to_errprobs.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), vp, vp, vp, C.POINTER(PlpCol), C.POINTER(Conf)]
     lib.lfb200_synth_depths.restype = C.c_int
     lib.lfb200_synth_depths.argtypes = [C.c_int, ll, ll, vp, vp]
     lib.lfb200_synth_columns.restype = C.c_int

@@ -1043,6 +1043,195 @@ extern "C" int lfb200_snpcaller(long double *snp_pvalues, const double *err_prob
 }
 
 // ------------------------------------------------------------------------------------------------
+// poissbin() rows and plp_to_errprobs() (snpcaller.h:72-75, 93-96)
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfb200_poissbin_batch(lfb200_ctx *ctx, long long n, const double *err_probs, const long long *ep_off,
+                                     const int *num_failures, const long long *bonf, double sig, const long long *row_off,
+                                     double *rows, long double *pvalues, int *n_end)
+{
+    if (!ctx) return fail("no context");
+    if (n <= 0) return 0;
+    if (!err_probs || !ep_off || !num_failures || !bonf || !row_off || !rows) return fail("null argument");
+    for (long long i = 0; i < n; ++i) {
+        if (num_failures[i] < 1) return fail("problem %lld: num_failures must be at least 1", i);
+        if (row_off[i + 1] - row_off[i] < num_failures[i] + 1) return fail("problem %lld: row_off leaves no room for the row", i);
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n_ep = (size_t)ep_off[n], n_rows = (size_t)row_off[n];
+    const void *d;
+    ProbBatch pb;
+    pb.n = n;
+    pb.sig = sig;
+    pb.counts = nullptr;
+    if (upload(ctx->p_ep, err_probs, n_ep * 8, 8, st, &d)) return 1;
+    pb.err_probs = (const double *)d;
+    if (upload(ctx->p_off, ep_off, (size_t)(n + 1) * 8, 0, st, &d)) return 1;
+    pb.ep_off = (const long long *)d;
+    if (upload(ctx->p_bonf, bonf, (size_t)n * 8, 0, st, &d)) return 1;
+    pb.bonf = (const long long *)d;
+    // num_failures | row_off in one buffer; rows | double buffers | n_end in another
+    std::vector<long long> meta((size_t)n + 1 + ((size_t)n + 1) / 2 + 1);
+    memcpy(meta.data(), row_off, (size_t)(n + 1) * 8);
+    memcpy(meta.data() + n + 1, num_failures, (size_t)n * 4);
+    if (upload(ctx->p_cnt, meta.data(), meta.size() * 8, 0, st, &d)) return 1;
+    const long long *d_row_off = (const long long *)d;
+    const int *d_k = (const int *)(d_row_off + n + 1);
+    if (ctx->p_out.ensure(n_rows * 8 * 3 + (size_t)n * 4 + 64)) return fail("out of device memory");
+    double *d_rows = (double *)ctx->p_out.p, *d_buf = d_rows + n_rows;
+    int *d_nend = (int *)(d_buf + 2 * n_rows);
+    launch_poissbin_rows(pb, d_k, d_row_off, d_buf, d_rows, d_nend, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rows, d_rows, n_rows * 8, cudaMemcpyDeviceToHost, st));
+    std::vector<int> h_end((size_t)n);
+    CU(cudaMemcpyAsync(h_end.data(), d_nend, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (long long i = 0; i < n; ++i) {
+        if (pvalues) pvalues[i] = expl_clamped(rows[row_off[i] + num_failures[i]], false);      // snpcaller.c:1047-1059
+        if (n_end) n_end[i] = h_end[(size_t)i];
+    }
+    return 0;
+}
+
+
+extern "C" double *lfb200_poissbin(long double *pvalue, const double *err_probs, const int num_err_probs, const int num_failures,
+                                   const long long int bonf, const double sig)
+{
+    if (pvalue) *pvalue = LDBL_MAX;                    // snpcaller.c:1030
+    if (!g_default_ctx && lfb200_create(&g_default_ctx, 0)) {
+        fprintf(stderr, "FATAL(lofreq_b200): %s\n", g_err);
+        return nullptr;
+    }
+    if (num_failures < 1 || num_err_probs < 0) {
+        fprintf(stderr, "FATAL(lofreq_b200): poissbin needs num_failures >= 1\n");
+        return nullptr;
+    }
+    double *row = (double *)malloc(((size_t)num_failures + 1) * sizeof(double));
+    if (!row) {
+        fprintf(stderr, "FATAL: couldn't allocate memory at %s:%s():%d\n", __FILE__, __FUNCTION__, __LINE__);
+        return nullptr;
+    }
+    const long long off[2] = {0, num_err_probs}, roff[2] = {0, (long long)num_failures + 1}, b[1] = {bonf};
+    long double pv = LDBL_MAX;
+    if (lfb200_poissbin_batch(g_default_ctx, 1, err_probs, off, &num_failures, b, sig, roff, row, &pv, nullptr)) {
+        fprintf(stderr, "FATAL(lofreq_b200): %s\n", g_err);
+        free(row);
+        return nullptr;
+    }
+    if (pvalue) *pvalue = pv;
+    return row;
+}
+
+extern "C" int lfb200_batch_errprobs(lfb200_ctx *ctx, const lfb200_conf_t *conf, const lfb200_batch_t *hb, double *err_probs,
+                                     int *num_err_probs, int *alt_bases, int *alt_counts, int *alt_raw_counts)
+{
+    if (!ctx) return fail("no context");
+    if (!hb || !conf || !err_probs || !num_err_probs) return fail("null argument");
+    const long long n = hb->n_cols;
+    if (n <= 0) return 0;
+    if (!hb->bq) return fail("the bq plane is required");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevConf dc;
+    if (make_devconf(conf, hb, dc)) return 1;
+    const size_t total = (size_t)hb->col_off[n];
+    lfb200_batch_t db = *hb;
+    const void *d;
+    if (upload(ctx->in_off, hb->col_off, (size_t)(n + 1) * 8, 0, st, &d)) return 1;
+    db.col_off = (const long long *)d;
+    if (upload(ctx->in_cnt, hb->nt_cnt, (size_t)n * 16, 0, st, &d)) return 1;
+    db.nt_cnt = (const int *)d;
+    if (upload(ctx->in_ref, hb->ref_base, (size_t)n, 0, st, &d)) return 1;
+    db.ref_base = (const char *)d;
+    db.coverage = nullptr;
+    db.num_bases = nullptr;
+    if (upload(ctx->in_bq, hb->bq, total, 32, st, &d)) return 1;
+    db.bq = (const unsigned char *)d;
+    if (upload(ctx->in_mq, hb->mq, total, 32, st, &d)) return 1;
+    db.mq = (const unsigned char *)d;
+    if (upload(ctx->in_baq, hb->baq, total, 32, st, &d)) return 1;
+    db.baq = (const unsigned char *)d;
+    if (upload(ctx->in_sq, hb->sq, total, 32, st, &d)) return 1;
+    db.sq = (const unsigned char *)d;
+    DevBatch dbatch;
+    to_devbatch(&db, dbatch);
+    if (ctx->p_ep.ensure(total * 8 + 64)) return fail("out of device memory");
+    if (ctx->p_out.ensure((size_t)n * 40 + 64)) return fail("out of device memory");
+    double *d_ep = (double *)ctx->p_ep.p;
+    int *d_n = (int *)ctx->p_out.p, *d_c9 = d_n + n;
+    CU(cudaMemsetAsync(d_n, 0, (size_t)n * 40, st));
+    launch_errprobs(dc, dbatch, ctx->d_lut, d_ep, d_n, d_c9, st);
+    CU(cudaGetLastError());
+    std::vector<int> h((size_t)n * 10);
+    CU(cudaMemcpyAsync(err_probs, d_ep, total * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h.data(), d_n, (size_t)n * 40, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (long long c = 0; c < n; ++c) {
+        const char r = hb->ref_base[c];
+        const bool acgt = r == 'A' || r == 'C' || r == 'G' || r == 'T';
+        num_err_probs[c] = acgt ? h[(size_t)c] : 0;
+        const int *o = h.data() + n + 9 * c;
+        for (int k = 0; k < 3; ++k) {
+            if (alt_bases) alt_bases[3 * c + k] = acgt ? o[k] : 0;
+            if (alt_counts) alt_counts[3 * c + k] = acgt ? o[3 + k] : 0;
+            if (alt_raw_counts) alt_raw_counts[3 * c + k] = acgt ? o[6 + k] : 0;
+        }
+    }
+    return 0;
+}
+
+extern "C" void lfb200_plp_to_errprobs(double **err_probs, int *num_err_probs, int *alt_bases, int *alt_counts, int *alt_raw_counts,
+                                       const lfb200_plp_col_t *p, const lfb200_conf_t *conf)
+{
+    *err_probs = nullptr;
+    *num_err_probs = 0;
+    if (!g_default_ctx && lfb200_create(&g_default_ctx, 0)) {
+        fprintf(stderr, "FATAL(lofreq_b200): %s\n", g_err);
+        return;
+    }
+    size_t total = 0;
+    for (int g = 0; g < 4; ++g) total += (size_t)std::max(p->n[g], 0);
+    const size_t room = std::max<size_t>(std::max<size_t>(total, (size_t)std::max(p->coverage_plp, 0)), 1);
+    double *ep = (double *)malloc(room * sizeof(double));                // the reference: coverage_plp doubles (snpcaller.c:352)
+    if (!ep) {
+        fprintf(stderr, "FATAL: couldn't allocate memory at %s:%s():%d\n", __FILE__, __FUNCTION__, __LINE__);
+        return;
+    }
+    std::vector<unsigned char> bq(total + 32, 0), mq(total + 32, 255), baq(total + 32, 255), sq(total + 32, 255);
+    bool any_mq = false, any_baq = false, any_sq = false;
+    size_t w = 0;
+    int nt_cnt[4];
+    for (int g = 0; g < 4; ++g) {
+        nt_cnt[g] = std::max(p->n[g], 0);
+        for (int j = 0; j < nt_cnt[g]; ++j, ++w) {
+            const int q = p->base_quals[g][j];
+            bq[w] = q < 0 ? 0 : (q > 255 ? 255 : (unsigned char)q);
+            if (p->map_quals[g]) { mq[w] = qbyte(p->map_quals[g][j]); any_mq = true; }
+            if (p->baq_quals[g]) { baq[w] = qbyte(p->baq_quals[g][j]); any_baq = true; }
+            if (p->source_quals[g]) { sq[w] = qbyte(p->source_quals[g][j]); any_sq = true; }
+        }
+    }
+    const long long col_off[2] = {0, (long long)total};
+    lfb200_batch_t hb;
+    memset(&hb, 0, sizeof(hb));
+    hb.n_cols = 1;
+    hb.col_off = col_off;
+    hb.nt_cnt = nt_cnt;
+    hb.ref_base = &p->ref_base;
+    hb.bq = bq.data();
+    hb.mq = any_mq ? mq.data() : nullptr;
+    hb.baq = any_baq ? baq.data() : nullptr;
+    hb.sq = any_sq ? sq.data() : nullptr;
+    if (lfb200_batch_errprobs(g_default_ctx, conf, &hb, ep, num_err_probs, alt_bases, alt_counts, alt_raw_counts)) {
+        fprintf(stderr, "FATAL(lofreq_b200): %s\n", g_err);
+        free(ep);
+        *num_err_probs = 0;
+        return;
+    }
+    *err_probs = ep;
+}
+
+// ------------------------------------------------------------------------------------------------
 // binom() (binom.c:52-93): binomial CDF / survival function, batched on the device
 // ------------------------------------------------------------------------------------------------
 extern "C" int lfb200_binom_batch(lfb200_ctx *ctx, long long n, const int *num_trials, const int *num_success,

@@ -129,6 +129,10 @@ double measure_dfma_per_second(cudaStream_t st);
 // packed.cu
 void launch_packed(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st);
+// poissbin.cu
+void launch_poissbin_rows(const ProbBatch &pb, const int *num_failures, const long long *row_off, double *buf, double *rows,
+                          int *n_end, cudaStream_t st);
+void launch_errprobs(const DevConf &cf, const DevBatch &b, const Lut *lut, double *ep_out, int *n_out, int *counts9, cudaStream_t st);
 // binom.cu
 int launch_binom(long long n_prob, const int *num_trials, const int *num_success, const double *prob, double *cum, double *ccum,
                  int *status, cudaStream_t st);

@@ -80,6 +80,84 @@ class Caller:
                                                     float(sig_level), _ptr(pv), _ptr(lnp), _ptr(st)))
         return pv, lnp, st
 
+    # ---- poissbin(): the row of ln probabilities (snpcaller.h:93-96) -------------------------------
+    def poissbin_batch(self, err_probs_list, num_failures, bonf, sig):
+        """[(pvalue longdouble, row float64[K+1], n_end)] — row may be partial after the early exit, like the reference's"""
+        n = len(err_probs_list)
+        off = np.zeros(n + 1, np.int64)
+        off[1:] = np.cumsum([len(e) for e in err_probs_list])
+        ep = np.ascontiguousarray(np.concatenate([np.asarray(e, np.float64) for e in err_probs_list]) if n else np.zeros(0))
+        ks = np.ascontiguousarray(num_failures, np.int32).reshape(n)
+        bf = np.ascontiguousarray(bonf, np.int64).reshape(n)
+        roff = np.zeros(n + 1, np.int64)
+        roff[1:] = np.cumsum(ks.astype(np.int64) + 1)
+        rows = np.zeros(int(roff[-1]), np.float64)
+        pv = np.zeros(n, np.longdouble)
+        nend = np.zeros(n, np.int32)
+        capi.check(self.lib.lfb200_poissbin_batch(self._ctx, n, _ptr(ep), _ptr(off), _ptr(ks), _ptr(bf), float(sig), _ptr(roff),
+                                                   _ptr(rows), _ptr(pv), _ptr(nend)))
+        return [(pv[i], rows[roff[i]:roff[i + 1]].copy(), int(nend[i])) for i in range(n)]
+
+    def poissbin(self, err_probs, num_failures, bonf, sig):
+        """the link-compatible symbol: malloc()ed row handed back, freed here"""
+        ep = np.ascontiguousarray(err_probs, np.float64)
+        pv = np.zeros(1, np.longdouble)
+        p = self.lib.lfb200_poissbin(_ptr(pv), _ptr(ep), len(ep), int(num_failures), int(bonf), float(sig))
+        if not p:
+            raise capi.Lfb200Error("lfb200_poissbin returned NULL")
+        row = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(int(num_failures) + 1,)).copy()
+        C.CDLL(None).free(C.c_void_p(p))
+        return pv[0], row
+
+    # ---- plp_to_errprobs() (snpcaller.h:72-75) ----------------------------------------------------
+    def batch_errprobs(self, batch, conf=None):
+        """per column: (err_probs in pileup order, alt_bases, alt_counts, alt_raw_counts)"""
+        cf = conf_from(conf)
+        keep = []
+
+        def arr(x, dt):
+            if x is None:
+                return None
+            a = np.ascontiguousarray(x, dtype=dt)
+            keep.append(a)
+            return _ptr(a)
+        n = len(batch["ref_base"])
+        col_off = np.ascontiguousarray(batch["col_off"], np.int64)
+        hb = capi.Batch(n, arr(col_off, np.int64), arr(batch["nt_cnt"], np.int32), arr(batch["ref_base"], np.uint8), None,
+                        arr(batch["bq"], np.uint8), arr(batch.get("mq"), np.uint8), arr(batch.get("baq"), np.uint8),
+                        arr(batch.get("sq"), np.uint8), None)
+        ep = np.zeros(max(int(col_off[-1]), 1), np.float64)
+        ne = np.zeros(n, np.int32)
+        ab = np.zeros((n, 3), np.int32); ac = np.zeros((n, 3), np.int32); ar = np.zeros((n, 3), np.int32)
+        capi.check(self.lib.lfb200_batch_errprobs(self._ctx, C.byref(cf), C.byref(hb), _ptr(ep), _ptr(ne), _ptr(ab), _ptr(ac), _ptr(ar)))
+        return [(ep[col_off[c]:col_off[c] + ne[c]].copy(), ab[c], ac[c], ar[c]) for c in range(n)]
+
+    def plp_to_errprobs(self, ref_base, coverage_plp, base_quals, map_quals=None, baq_quals=None, source_quals=None, conf=None):
+        """the link-compatible symbol on one column given as int arrays per A,C,G,T (plp_col_t varrays)"""
+        cf = conf_from(conf)
+        keep = []
+        pc = capi.PlpCol()
+        pc.ref_base = ref_base.encode() if isinstance(ref_base, str) else ref_base
+        pc.coverage_plp = int(coverage_plp)
+        for g in range(4):
+            pc.n[g] = len(base_quals[g])
+            for name, src in (("base_quals", base_quals), ("map_quals", map_quals), ("baq_quals", baq_quals), ("source_quals", source_quals)):
+                if src is None or (name != "base_quals" and len(src[g]) == 0):
+                    getattr(pc, name)[g] = None
+                    continue
+                a = np.ascontiguousarray(src[g], np.int32)
+                keep.append(a)
+                getattr(pc, name)[g] = a.ctypes.data if len(a) else None
+        p = C.c_void_p()
+        ne = C.c_int(0)
+        ab = np.zeros(3, np.int32); ac = np.zeros(3, np.int32); ar = np.zeros(3, np.int32)
+        self.lib.lfb200_plp_to_errprobs(C.byref(p), C.byref(ne), _ptr(ab), _ptr(ac), _ptr(ar), C.byref(pc), C.byref(cf))
+        if not p.value:
+            raise capi.Lfb200Error("lfb200_plp_to_errprobs returned NULL")
+        ep = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(max(ne.value, 1),))[:ne.value].copy()
+        C.CDLL(None).free(p)
+        return ep, ab, ac, ar
+
     # ---- binom(): binomial CDF / survival function (binom.c:52-93) ------------------------------
     def binom_batch(self, num_trials, num_success, prob_success):
         """(status, p, q) arrays; p = P(X <= num_success), q = 1 - p, NaN where status != 0"""

@@ -89,6 +89,17 @@ def test_poissbin_row_matches_reference(port_oracle, ref_oracle):
         assert pa == pr and np.array_equal(ra[:k + 1], rr[:k + 1])
 
 
+def test_poissbin_rows_golden(port_oracle):
+    """the port's poissbin() rows — partial rows after the early exit included — are the reference's, bit for bit"""
+    z = np.load(os.path.join(GOLD, "poissbin_rows.npz"))
+    for i, name in enumerate(z["names"]):
+        ep = z["err_probs"][z["offsets"][i]:z["offsets"][i + 1]]
+        pv, row = port_oracle.poissbin(ep, int(z["k"][i]), int(z["bonf"][i]), float(z["sig"][i]))
+        want = z["rows"][z["row_offsets"][i]:z["row_offsets"][i + 1]]
+        assert np.array_equal(row, want), name
+        assert pv == ld_from_bytes(z["pvalue_ld"][i]), name
+
+
 def test_binom_reference_vs_scipy():
     from oracle.pyoracle import BinomRef, BINOM_SO
     if not os.path.exists(BINOM_SO):

@@ -499,6 +499,60 @@ def test_packed_scratch_pool_overflow(caller, port_oracle):
     assert 0 < jc["packed"] < 450 and jc["per_column"] + jc["mid"] > 0, jc
 
 
+def test_poissbin_rows_golden(caller):
+    """poissbin() (snpcaller.h:93-96): the whole row, the LDBL clamp of *pvalue and — through the row — the read at
+    which the reference's early exit fired, against rows produced by the compiled reference"""
+    z = np.load(os.path.join(GOLD, "poissbin_rows.npz"))
+    n = len(z["names"])
+    eps = [z["err_probs"][z["offsets"][i]:z["offsets"][i + 1]] for i in range(n)]
+    for i, name in enumerate(z["names"]):
+        want = z["rows"][z["row_offsets"][i]:z["row_offsets"][i + 1]]
+        pv, row, n_end = caller.poissbin_batch([eps[i]], [z["k"][i]], [z["bonf"][i]], float(z["sig"][i]))[0]
+        assert row.shape == want.shape, name
+        err = np.abs(row - want) / np.maximum(np.abs(want), 1.0)
+        assert err.max() <= LNP_RTOL, (name, float(err.max()), int(np.argmax(err)), n_end)
+        want_pv = ld_from_bytes(z["pvalue_ld"][i])
+        assert status_of(np.array([pv])) == status_of(np.array([want_pv])), name
+        if status_of(np.array([want_pv]))[0] == 0:
+            assert abs(float(np.log(pv)) - float(np.log(want_pv))) <= LNP_RTOL * max(abs(float(np.log(want_pv))), 1.0), name
+        if i % 6 == 0:                                  # the link-compatible symbol (malloc'ed row)
+            pv1, row1 = caller.poissbin(eps[i], int(z["k"][i]), int(z["bonf"][i]), float(z["sig"][i]))
+            assert np.array_equal(row1, row) and pv1 == pv, name
+    # several problems in one call
+    sel = [i for i in range(n) if float(z["sig"][i]) == float(np.float32(0.01))]
+    many = caller.poissbin_batch([eps[i] for i in sel], z["k"][sel], z["bonf"][sel], float(np.float32(0.01)))
+    for (pv, row, _), i in zip(many, sel):
+        want = z["rows"][z["row_offsets"][i]:z["row_offsets"][i + 1]]
+        assert (np.abs(row - want) / np.maximum(np.abs(want), 1.0)).max() <= LNP_RTOL, z["names"][i]
+
+
+def test_plp_to_errprobs(caller, port_oracle):
+    """plp_to_errprobs() (snpcaller.h:72-75): error probabilities in pileup order bit-exact, alt bases and both counts"""
+    for wl, c0, ncol, baq in (("C2", 77, 300, True), ("C3", 5000, 60, False), ("C5", 900, 80, True)):
+        b = synth_np.generate(wl, c0, ncol, with_baq=baq)
+        for conf in (default_conf(), default_conf(flag=0), default_conf(def_alt_bq=-1), default_conf(def_alt_bq=30),
+                     default_conf(min_bq=3, min_alt_bq=20, min_jq=15, min_alt_jq=25, def_alt_jq=35)):
+            got = caller.batch_errprobs(b, dict(conf))
+            for c in range(ncol):
+                if chr(int(b["ref_base"][c])) not in "ACGT":
+                    continue
+                ep, ab, ac, ar = port_oracle.column_errprobs(b, c, dict(conf))
+                gep, gab, gac, gar = got[c]
+                assert np.array_equal(gep, ep), (wl, c, conf)
+                assert np.array_equal(gab, ab) and np.array_equal(gac, ac) and np.array_equal(gar, ar), (wl, c, conf)
+    # the link-compatible symbol on int arrays per nt4 (plp_col_t varrays), -1 = quality not available
+    rng = np.random.default_rng(11)
+    bqs = [rng.integers(0, 42, n) for n in (40, 3, 0, 7)]
+    mqs = [rng.integers(0, 61, len(x)) for x in bqs]
+    mqs[0][:3] = 255
+    baqs = [rng.integers(-1, 60, len(x)) for x in bqs]
+    cols = [dict(ref="A", groups=[(bqs[g], np.where(mqs[g] == 255, 255, mqs[g]), np.where(baqs[g] < 0, 255, baqs[g])) for g in range(4)])]
+    bb = _custom_batch(cols)
+    want = port_oracle.column_errprobs(bb, 0, default_conf())
+    got = caller.plp_to_errprobs("A", 50, bqs, mqs, baqs, None, default_conf())
+    assert np.array_equal(got[0], want[0]) and all(np.array_equal(g, w) for g, w in zip(got[1:], want[1:]))
+
+
 def test_binom_golden(caller):
     """binom() (binom.c:52-93 -> cdflib cdfbin): status codes exact, cdf and sf within 1e-10 relative of the compiled
     reference — through the batched entry point and through the link-compatible single call"""
