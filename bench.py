@@ -30,6 +30,27 @@ UNIT = "columns/s"
 DEPTH = {"C2": 500, "C3": 2000, "C4": 300}
 
 
+_OUT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version line there) must not add to it:
+    fd 1 is pointed at stderr for the whole run and the line goes out through a duplicate of the original."""
+    global _OUT_FD
+    if _OUT_FD is None:
+        sys.stdout.flush()
+        _OUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _OUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, data)
+
+
 def workload_desc(wl, cols):
     return {"C2": "C2: %d synthetic pileup columns, depth 500, uniform Q30, MQ60, 1%% variant sites" % cols,
             "C3": "C3: %d synthetic columns, depth 2000, Q20-40" % cols,
@@ -205,7 +226,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def kind_desc(kind):
@@ -232,10 +253,13 @@ def run_ours(args):
     wl, n = args.workload, args.cols
     # two contexts = two workspaces: the host finishing (D2H of the sites + long double arithmetic) of
     # batch k overlaps the kernels of batch k+1, the way a caller streaming many batches would run it
-    callers = [lofreq_b200.Caller(local), lofreq_b200.Caller(local)]
+    # N > 1: a third context, so that the count exchange of a batch is issued two batches ahead and has a whole step
+    # to complete behind the kernels of the batches before it
+    NC = args.contexts if args.contexts else (3 if world > 1 else 2)
+    callers = [lofreq_b200.Caller(local) for _ in range(NC)]
     caller = callers[0]
     lib = caller.lib
-    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NC)]
     sts = [C.c_void_p(s_.cuda_stream) for s_ in streams]
 
     # this rank's region shard: columns [rank*n, (rank+1)*n)
@@ -243,13 +267,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     db = caller.device_batch(t)
     max_sites = n
-    sites_bufs = [(capi.Site * max_sites)(), (capi.Site * max_sites)()]
+    sites_bufs = [(capi.Site * max_sites)() for _ in range(NC)]
     sites_buf = sites_bufs[0]
-    sms = [capi.Summary(), capi.Summary()]
+    sms = [capi.Summary() for _ in range(NC)]
     sm = sms[0]
-    confs = [None, None]
-    exchanges = [shard.ShardComm(callers[0], dev), shard.ShardComm(callers[1], dev)] if world > 1 else None
-    prev_sites = [0, 0]
+    confs = [None] * NC
+    exchanges = [shard.ShardComm(callers[i], dev) for i in range(NC)] if world > 1 else None
+    prev_sites = [0] * NC
 
     def screen(i):
         """gates + alt counts of the next batch on context i, and (N > 1) the exchange of the tested-column counts:
@@ -300,19 +324,24 @@ def run_ours(args):
                                                   timed("finish_begin", finish_begin), timed("finish_end", finish_end))
 
     def run_steps(k_steps):
-        """batch k on context k % 2: screen(k+1) is issued while test(k) runs, and the sites of batch k are finished
-        on a host thread while the launching thread goes on"""
-        screen(0)
+        """batch k on context k % NC.  The screen (and, N > 1, the count exchange) of a batch is issued NC - 1 batches
+        ahead of its test, and the sites of batch k are finished on a host thread while the launching thread goes on"""
+        lead = NC - 1
+        for j in range(min(lead, k_steps)):
+            screen(j % NC)
+        done = 0                                   # batches whose finishing has been waited for
         for k in range(k_steps):
-            test(k % 2)
-            finish_begin(k % 2)
-            if k + 1 < k_steps:
-                if k >= 1:
-                    finish_end((k - 1) % 2)        # context (k+1) % 2 must be done with batch k-1
-                screen((k + 1) % 2)
-        if k_steps >= 2:
-            finish_end((k_steps - 2) % 2)
-        finish_end((k_steps - 1) % 2)
+            test(k % NC)
+            finish_begin(k % NC)
+            nxt = k + lead
+            if nxt < k_steps:
+                while done <= nxt - NC:            # context nxt % NC must be done with batch nxt - NC
+                    finish_end(done % NC)
+                    done += 1
+                screen(nxt % NC)
+        while done < k_steps:
+            finish_end(done % NC)
+            done += 1
 
     def barrier():
         torch.cuda.synchronize()
@@ -338,7 +367,7 @@ def run_ours(args):
     if os.environ.get("LFB200_HOST_TIMING"):
         print("host seconds in the launching thread (timed steps):", host_t, "wall of timed steps", wall, file=sys.stderr)
     clocks = sampler.stop()
-    sm = sms[(args.steps - 1) % 2]
+    sm = sms[(args.steps - 1) % NC]
     n_sites, n_tested, n_heavy = sm.n_sites, sm.n_tested, sm.n_heavy
     final_sites = [int(n_sites)]
     if world > 1:
@@ -460,7 +489,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_desc(wl, n) + " per GPU (region shard = rank*cols)",
                            "cols_per_gpu": n, "depth": DEPTH.get(wl), "l2": "inputs larger than L2 (%.2f GB per step)" % (2 * total / 1e9),
-                           "value_region": "screen + prefix sum + significance test + O(depth*K) kernels + D2H of sites + long double finishing, inputs resident in HBM; two contexts so that the host finishing of one batch overlaps the kernels of the next",
+                           "value_region": "screen + prefix sum + significance test + O(depth*K) kernels + D2H of sites + long double finishing, inputs resident in HBM; %d contexts so that the host finishing of one batch overlaps the kernels of the next" % NC + "",
                            "tested_columns": int(n_tested), "sites": int(n_sites), "heavy_columns": int(n_heavy),
                            "sites_all_ranks": final_sites,
                            "bonf_subst_final_this_rank": int(sm.bonf_subst_final)},
@@ -474,7 +503,7 @@ def run_ours(args):
                                                  "only the per-column metadata is copied"}},
                 "gpu_launches": 15 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "wall_ms_per_step": wall * 1e3 / args.steps}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     for c_ in callers:
@@ -491,9 +520,11 @@ def main():
     ap.add_argument("--cols", type=int, default=1_000_000, help="columns per GPU")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="columns of the single-thread cpu_baseline sample")
     ap.add_argument("--ref-cols-per-proc", type=int, default=30_000)
+    ap.add_argument("--contexts", type=int, default=0, help="contexts (batches in flight) per GPU; default 2, 3 when N > 1")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e measurement (profiling runs)")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

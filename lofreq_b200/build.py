@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "liblofreq_b200.so")
-SOURCES = ["snv_kernels.cu", "packed.cu", "poissbin.cu", "binom.cu", "synth.cu", "host_api.cpp", "shard_comm.cpp"]
+SOURCES = ["snv_kernels.cu", "packed.cu", "poissbin.cu", "mailbox.cu", "binom.cu", "synth.cu", "host_api.cpp", "shard_comm.cpp"]
 HEADERS = ["internal.h", "dev_common.cuh", "synth_tables.h", os.path.join("..", "..", "include", "lofreq_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
     todo = [s for s in SOURCES if force or _stale(_obj(s), [os.path.join(CSRC, s)] + hdrs)]
     with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
         list(ex.map(lambda s: _compile(s, verbose), todo))
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [_obj(s) for s in SOURCES] + ["-ldl"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [_obj(s) for s in SOURCES] + ["-ldl", "-lrt"]
     if verbose:
         print(" ".join(cmd))
     out = subprocess.run(cmd, capture_output=True, text=True)

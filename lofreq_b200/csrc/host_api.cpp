@@ -429,7 +429,7 @@ static void finish_site(const Cand &cd, double sig, lfb200_site_t &s)
         // and the next term are more than 708.396 nats apart.  The row is log-concave, so the widest gap is
         // against the last two entries, min(row[K-1], row[K]) = ln_floor.
         const bool pre = (c < K) && (t - cd.ln_floor > LN_EXP_UNDERFLOW);
-        const long double p = expl_clamped(t, pre);
+        const long double p = (c == K) ? pK : expl_clamped(t, pre);      // c == K: the same expl() as poissbin's
         s.pvalue[i] = p;
         s.status[i] = (p == LDBL_MAX) ? LFB200_ST_LDBLMAX : (p == LDBL_MIN) ? LFB200_ST_LDBLMIN : LFB200_ST_VALUE;
         if (p * (double)cd.bonf < sig) {                 // lofreq_call.c:832
@@ -581,11 +581,11 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
         if (cands[i].flags & CF_RANGE) return fail("column %lld: tail outside the representable range", cands[i].col);
     // long double finishing, independent per site; then emit in column order (device order is arbitrary)
     const double sig = (double)conf->sig;
-    // column order: LSD radix sort of (col, index) pairs, 3 passes of 11 bits (n_cols < 2^31)
     ctx->h_order.resize((size_t)n_cand);
     ctx->h_order2.resize((size_t)n_cand);
-    for (long long i = 0; i < n_cand; ++i) ctx->h_order[(size_t)i] = std::make_pair(cands[i].col, (unsigned)i);
-    {
+    // column order: LSD radix sort of (col, index) pairs, 3 passes of 11 bits (n_cols < 2^31)
+    auto sort_by_column = [&] {
+        for (long long i = 0; i < n_cand; ++i) ctx->h_order[(size_t)i] = std::make_pair(cands[i].col, (unsigned)i);
         std::pair<long long, unsigned> *a = ctx->h_order.data(), *b2 = ctx->h_order2.data();
         for (int pass = 0; pass < 3; ++pass) {
             unsigned hist[2049] = {0};
@@ -596,25 +596,48 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
             std::swap(a, b2);
         }
         if (a != ctx->h_order.data()) ctx->h_order.swap(ctx->h_order2);
-    }
-    const std::pair<long long, unsigned> *order = ctx->h_order.data();
-    if (dbg) t3 = now();
-    auto work = [&](unsigned part, unsigned parts) {
-        const long long per = (n_cand + parts - 1) / parts;
-        const long long lo = (long long)part * per, hi = std::min<long long>(n_cand, lo + per);
-        for (long long i = lo; i < hi; ++i) finish_site(cands[order[i].second], sig, sites[i]);
     };
     if (n_cand < 1024) {
-        work(0, 1);
+        sort_by_column();
+        const std::pair<long long, unsigned> *order = ctx->h_order.data();
+        for (long long i = 0; i < n_cand; ++i) finish_site(cands[order[i].second], sig, sites[i]);
+        if (dbg) t3 = now();
     } else {
         if (!ctx->pool) {
+            // share the host cores with the other shards of this node (torchrun exports LOCAL_WORLD_SIZE) and with
+            // the second context of this process
             unsigned hw = std::thread::hardware_concurrency();
-            ctx->pool.reset(new WorkerPool(std::max(1u, std::min(hw, 16u)) - 1));
+            const char *lws = getenv("LOCAL_WORLD_SIZE");
+            const unsigned procs = lws ? (unsigned)std::max(1, atoi(lws)) : 1u;
+            const unsigned want = std::max(3u, std::min(hw / (2 * procs), 16u));
+            ctx->pool.reset(new WorkerPool(want - 1));
         }
-        ctx->pool->run(work);
+        // the workers finish the sites in device order while this thread sorts the keys; then all of them move the
+        // finished sites to their places
+        ctx->h_sites.resize((size_t)n_cand);
+        lfb200_site_t *tmp = ctx->h_sites.data();
+        auto finish_part = [&](unsigned part, unsigned parts) {
+            if (part == parts - 1) {                   // the calling thread
+                sort_by_column();
+                return;
+            }
+            const unsigned workers = parts - 1;
+            const long long per = (n_cand + workers - 1) / workers;
+            const long long lo = (long long)part * per, hi = std::min<long long>(n_cand, lo + per);
+            for (long long i = lo; i < hi; ++i) finish_site(cands[i], sig, tmp[i]);
+        };
+        ctx->pool->run(finish_part);
+        if (dbg) t3 = now();
+        const std::pair<long long, unsigned> *order = ctx->h_order.data();
+        auto place_part = [&](unsigned part, unsigned parts) {
+            const long long per = (n_cand + parts - 1) / parts;
+            const long long lo = (long long)part * per, hi = std::min<long long>(n_cand, lo + per);
+            for (long long i = lo; i < hi; ++i) sites[i] = tmp[order[i].second];
+        };
+        ctx->pool->run(place_part);
     }
     if (dbg)
-        fprintf(stderr, "[lfb200] sites: wait+counters %.0f us, cand D2H %.0f us, sort %.0f us, finish %.0f us (%lld sites)\n",
+        fprintf(stderr, "[lfb200] sites: wait+counters %.0f us, cand D2H %.0f us, sort|finish %.0f us, place %.0f us (%lld sites)\n",
                 t1 - t0, t2 - t1, t3 - t2, now() - t3, n_cand);
     errno = 0;
     feclearexcept(FE_ALL_EXCEPT);

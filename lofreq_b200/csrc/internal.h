@@ -129,6 +129,15 @@ double measure_dfma_per_second(cudaStream_t st);
 // packed.cu
 void launch_packed(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
 void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st);
+// mailbox.cu: the per-batch count exchange between shards through shared host memory
+constexpr int MAIL_DEPTH = 64;
+struct MailSlot {
+    unsigned long long seq;        // written last (release): the exchange this slot holds
+    long long tested, sites, pad;
+};
+void launch_mail_exchange(MailSlot *slots, unsigned long long *ack, int world, int rank, unsigned long long seq,
+                          const unsigned long long *n_tested_dev, long long sites_prev, long long bonf_subst, long long *d_mine,
+                          long long *d_start, int *d_err, cudaStream_t st);
 // poissbin.cu
 void launch_poissbin_rows(const ProbBatch &pb, const int *num_failures, const long long *row_off, double *buf, double *rows,
                           int *n_end, cudaStream_t st);
