@@ -253,9 +253,8 @@ def run_ours(args):
     wl, n = args.workload, args.cols
     # two contexts = two workspaces: the host finishing (D2H of the sites + long double arithmetic) of
     # batch k overlaps the kernels of batch k+1, the way a caller streaming many batches would run it
-    # N > 1: a third context, so that the count exchange of a batch is issued two batches ahead and has a whole step
-    # to complete behind the kernels of the batches before it
-    NC = args.contexts if args.contexts else (3 if world > 1 else 2)
+    # contexts = batches in flight; a third one (screen and count exchange two batches ahead) measured slower at 1 and 2 GPUs
+    NC = args.contexts if args.contexts else 2
     callers = [lofreq_b200.Caller(local) for _ in range(NC)]
     caller = callers[0]
     lib = caller.lib
@@ -520,7 +519,7 @@ def main():
     ap.add_argument("--cols", type=int, default=1_000_000, help="columns per GPU")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="columns of the single-thread cpu_baseline sample")
     ap.add_argument("--ref-cols-per-proc", type=int, default=30_000)
-    ap.add_argument("--contexts", type=int, default=0, help="contexts (batches in flight) per GPU; default 2, 3 when N > 1")
+    ap.add_argument("--contexts", type=int, default=0, help="contexts (batches in flight) per GPU; default 2")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e measurement (profiling runs)")
     args = ap.parse_args()

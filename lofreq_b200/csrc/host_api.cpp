@@ -604,12 +604,11 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
         if (dbg) t3 = now();
     } else {
         if (!ctx->pool) {
-            // share the host cores with the other shards of this node (torchrun exports LOCAL_WORLD_SIZE) and with
-            // the second context of this process
+            // share the host cores with the other shards of this node (torchrun exports LOCAL_WORLD_SIZE)
             unsigned hw = std::thread::hardware_concurrency();
             const char *lws = getenv("LOCAL_WORLD_SIZE");
             const unsigned procs = lws ? (unsigned)std::max(1, atoi(lws)) : 1u;
-            const unsigned want = std::max(3u, std::min(hw / (2 * procs), 16u));
+            const unsigned want = std::max(3u, std::min(hw / procs, 16u));
             ctx->pool.reset(new WorkerPool(want - 1));
         }
         // the workers finish the sites in device order while this thread sorts the keys; then all of them move the
