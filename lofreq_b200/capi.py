@@ -95,7 +95,8 @@ def load():
     if not os.path.exists(_build.LIB):
         raise RuntimeError("liblofreq_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`"
                            " (there is no CPU fallback)")
-    lib = C.CDLL(_build.LIB)
+    # LFB200_LIB: another build of the same library (A/B timing of two builds on one GPU box)
+    lib = C.CDLL(os.environ.get("LFB200_LIB") or _build.LIB)
     vp, ll = C.c_void_p, C.c_longlong
     lib.lfb200_create.restype = C.c_int
     lib.lfb200_create.argtypes = [C.POINTER(vp), C.c_int]

@@ -144,7 +144,7 @@ struct lfb200_ctx {
     cudaStream_t stream = nullptr;       // used by the host entry points
     Lut *d_lut = nullptr;
     // workspace of the current batch
-    DevBuf w_cnt6, w_tested, w_tails, w_bonf, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_pinfo, w_pkscr;
+    DevBuf w_cnt6, w_tested, w_tails, w_bonf, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_pinfo, w_pkscr, w_tilecount;
     Workspace ws{};
     // device copies of host batches (host entry point)
     DevBuf in_off, in_cnt, in_ref, in_cov, in_nb, in_bq, in_mq, in_baq, in_sq;
@@ -319,7 +319,7 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_tails, &ctx->w_bonf, &ctx->w_blocksum, &ctx->w_jobs,
-                      &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_pinfo, &ctx->w_pkscr, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
+                      &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_pinfo, &ctx->w_pkscr, &ctx->w_tilecount, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
                       &ctx->in_bq, &ctx->in_mq, &ctx->in_baq, &ctx->in_sq, &ctx->p_ep, &ctx->p_off, &ctx->p_cnt,
                       &ctx->p_bonf, &ctx->p_out};
     for (DevBuf *b : bufs) b->release();
@@ -340,6 +340,11 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     bad |= ctx->w_tails.ensure(nn * 4 * sizeof(double));
     bad |= ctx->w_bonf.ensure(nn * sizeof(long long));
     bad |= ctx->w_blocksum.ensure(((nn + 255) / 256 + 1) * sizeof(long long));
+    {
+        const void *before = ctx->w_tilecount.p;
+        bad |= ctx->w_tilecount.ensure(((nn + 255) / 256 + 1) * sizeof(unsigned int));
+        if (!bad && ctx->w_tilecount.p != before) cudaMemset(ctx->w_tilecount.p, 0, ctx->w_tilecount.cap);   // k_scan_blocks keeps it zero afterwards
+    }
     bad |= ctx->w_jobs.ensure(nn * NCLASS * sizeof(int));
     bad |= ctx->w_cand.ensure(nn * sizeof(Cand));
     // packed job lists hold a quarter of the batch each (a fuller list spills into the per-column lists); the pool
@@ -358,6 +363,7 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     w.tails = (double *)ctx->w_tails.p;
     w.bonf_used = (long long *)ctx->w_bonf.p;
     w.blocksum = (long long *)ctx->w_blocksum.p;
+    w.tilecount = (unsigned int *)ctx->w_tilecount.p;
     w.jobs = (int *)ctx->w_jobs.p;
     w.cand = (Cand *)ctx->w_cand.p;
     w.counters = (Counters *)ctx->w_counters.p;
@@ -565,7 +571,7 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
             return fail("a column has an alt count above %d: not supported by this build", 16384);
         sm.n_tested = (long long)c.n_tested;
         n_cand = c.n_cand;
-        for (int i = 0; i < NCLASS; ++i) if (i != CLS_FALLBACK) sm.n_heavy += c.n_jobs[i];
+        for (int i = 0; i < NCLASS; ++i) if (i != CLS_FALLBACK && i != CLS_PRUNE2) sm.n_heavy += c.n_jobs[i];
         for (int i = 0; i < PK_NL; ++i) sm.n_heavy += std::min<long long>(c.n_pjobs[i], ctx->ws.pcap);
     }
     if (dbg) t1 = now();
@@ -738,7 +744,7 @@ extern "C" int lfb200_last_job_counts(lfb200_ctx *ctx, long long out[4])
     out[0] = out[1] = out[2] = out[3] = 0;
     for (int i = 0; i < PK_NL; ++i) out[0] += std::min<long long>(c.n_pjobs[i], ctx->ws.pcap);
     out[1] = c.n_jobs[CLS_FALLBACK];               // includes the few k_mid hands back
-    for (int i = 1; i < NCLASS; ++i) if (i != CLS_FALLBACK) out[2] += c.n_jobs[i];
+    for (int i = 1; i < NCLASS; ++i) if (i != CLS_FALLBACK && i != CLS_PRUNE2) out[2] += c.n_jobs[i];
     out[3] = c.n_jobs[0];
     return 0;
 }

@@ -7,9 +7,10 @@
 namespace lfb {
 
 constexpr int KS = 8;              // columns whose largest alt count is <= KS are finished by the screen kernel
-constexpr int NCLASS = 9;          // job lists: 0 = K <= 32 (k_mid), 1..6 = register tiles R = 2..64 (k_heavy<R>), 7 = XL (CTA per
+constexpr int NCLASS = 10;         // job lists: 0 = K <= 32 (k_mid), 1..6 = register tiles R = 2..64 (k_heavy<R>), 7 = XL (CTA per
                                    // column), 8 = K <= 32 columns k_mid hands back to k_heavy<1> (tail outside the untilted range)
 constexpr int CLS_XL = 7, CLS_FALLBACK = 8;
+constexpr int CLS_PRUNE2 = 9;       // K <= 8 columns still alive after the first reads of k_finalize's prune: k_prune2's input
 constexpr int MAXK_WARP = 2048;    // 32 lanes * 64 cells
 
 // k_packed (packed.cu): columns with 8 < K <= 256 share a warp — G = 4, 8, 16 or 32 lanes per column, PK_R cells per
@@ -95,7 +96,8 @@ struct Workspace {
     unsigned char *tested;         // [n]
     double *tails;                 // [n][4]: linear P(X>=c_i) for the three alleles, min(P[K-1], P(>=K))
     long long *bonf_used;          // [n]
-    long long *blocksum;           // [ceil(n/256)]
+    long long *blocksum;           // [ceil(n/256)]: tested columns before each tile of 256 columns
+    unsigned int *tilecount;       // [ceil(n/256)]: tested columns per tile, accumulated by k_screen, zeroed again by the scan
     int *jobs;                     // [NCLASS][n]
     Cand *cand;                    // [n]
     Counters *counters;

@@ -336,6 +336,8 @@ __device__ __forceinline__ void count_alt_read(const DevConf &cf, const DevBatch
     }
 }
 
+constexpr int FIN_BLOCK = 256;      // columns per tile of the prefix sum = per CTA of k_finalize
+
 __global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
                                                    const Lut *lut, const Workspace ws)
 {
@@ -408,25 +410,19 @@ __global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevCo
             // no alt read left after filtering -> not a test (lofreq_call.c:768-780)
             ws.tested[c_mine] = (cnt[0] | cnt[1] | cnt[2]) ? 1 : 0;
         }
+        // tested columns per tile of FIN_BLOCK columns (a warp's 32 columns lie in one tile): input of the prefix sum
+        const unsigned tb = __ballot_sync(FULL, c_mine < b.n_cols && (cnt[0] | cnt[1] | cnt[2]) != 0);
+        if (lane == 0 && tb) atomicAdd(&ws.tilecount[base / FIN_BLOCK], (unsigned)__popc(tb));
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // running Bonferroni: prefix sum over tested flags, then the significance screen
 // ------------------------------------------------------------------------------------------------
-constexpr int FIN_BLOCK = 256;      // columns per CTA of k_block_counts / k_finalize
 constexpr int PRUNE_CAP = 32;       // reads the lane-per-column prune of k_finalize looks at before it hands the column on
 
-__global__ void __launch_bounds__(FIN_BLOCK) k_block_counts(const unsigned char *tested, long long n, long long *blocksum)
-{
-    const long long c = (long long)blockIdx.x * FIN_BLOCK + threadIdx.x;
-    const int t = (c < n) ? tested[c] : 0;
-    const int total = __syncthreads_count(t);
-    if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
-}
-
-// exclusive scan of blocksum in place, one block
-__global__ void __launch_bounds__(1024) k_scan_blocks(long long *blocksum, int nb, Counters *ctr)
+// exclusive scan of the per-tile counts k_screen accumulated, one block; the counts are zeroed for the next batch
+__global__ void __launch_bounds__(1024) k_scan_blocks(unsigned int *tilecount, long long *blocksum, int nb, Counters *ctr)
 {
     __shared__ long long s_warp[32];
     __shared__ long long s_carry;
@@ -435,7 +431,8 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(long long *blocksum, int n
     const int lane = lane_id(), w = threadIdx.x >> 5;
     for (int base = 0; base < nb; base += 1024) {
         const int i = base + threadIdx.x;
-        const long long v = (i < nb) ? blocksum[i] : 0;
+        const long long v = (i < nb) ? (long long)tilecount[i] : 0;
+        if (i < nb) tilecount[i] = 0;
         long long x = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -464,6 +461,47 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(long long *blocksum, int n
     if (threadIdx.x == 0) ctr->n_tested = (unsigned long long)s_carry;
 }
 
+// The reference's early exit (snpcaller.c:916-958), one lane per column: walk the first `cap` reads until
+// P(X >= K among the reads seen) > limit = sig / bonf.  Returns true when the column is still alive after `cap` reads.
+// Cells are kept top-aligned (register 7 = cell K-1, padding below cell 0 stays 0), so one code path serves every
+// K <= KS.  Lanes with live == false only take part in the votes.
+__device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &mg, int K,
+                                           double limit, int cap_reads, bool live)
+{
+    double R[KS], T = 0.0;
+#pragma unroll
+    for (int j = 0; j < KS; ++j) R[j] = (j == KS - K) ? 1.0 : 0.0;
+    const int cap = min(mg.n, cap_reads);
+    // the reads come in aligned 16-byte chunks per plane: one load per plane covers what most columns need
+    const long long ca = mg.off & ~15ll;
+    const int lead = (int)(mg.off - ca);
+    Chunk16 ch;
+    ch.bq = ch.mq = ch.baq = ch.sq = make_uint4(0, 0, 0, 0);
+    if (live && cap > 0) load_chunk(cf, b, ca, ch);
+#pragma unroll 1
+    for (int i = 0; __any_sync(FULL, live && i < cap); ++i) {
+        if (!(live && i < cap)) continue;
+        const int idx = lead + i, j = idx & 15;
+        if (j == 0 && i > 0) load_chunk(cf, b, ca + idx, ch);
+        bool is_alt;
+        int slot;
+        double jp;
+        if (!eval_read<true>(cf, s_lut, mg, i, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j), byte_of(ch.sq, j),
+                             is_alt, slot, jp))
+            continue;
+        double p, q;
+        guard_pq(jp, p, q);
+        T = fma(R[KS - 1], p, T);
+#pragma unroll
+        for (int j2 = KS - 1; j2 >= 1; --j2) R[j2] = fma(R[j2 - 1], p, R[j2] * q);
+        R[0] = R[0] * q;
+        if (T > limit) live = false;          // clearly insignificant: snpcaller() leaves LDBL_MAX everywhere (snpcaller.c:1155)
+    }
+    return live;
+}
+
+constexpr int PRUNE_CAP1 = 8;       // reads k_finalize itself looks at (K <= 3 is decided by then); the rest of the prune is k_prune2's
+
 __global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
                                                         const Lut *lut, const Workspace ws, const long long *bonf_start_dev)
 {
@@ -475,9 +513,25 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant
     // exchange left in device memory (no host round trip)
     const long long bonf_start = bonf_start_dev ? *bonf_start_dev : cf.bonf_start;
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters->bonf_start_used = bonf_start;
-    const long long c = (long long)blockIdx.x * FIN_BLOCK + threadIdx.x;
+    // one CTA per tile of FIN_BLOCK columns (CTAs that pull tiles from a counter, loading the table once, measured slower)
+    const long long tile = blockIdx.x;
+    const long long c = tile * FIN_BLOCK + threadIdx.x;
     const int lane = lane_id(), w = threadIdx.x >> 5;
-    const int t = (c < n) ? ws.tested[c] : 0;
+    // everything the column may need is requested at once, whether or not it turns out to be tested: the kernel is
+    // bound by the chain of dependent loads (flag -> counts -> geometry -> quality bytes), not by bytes
+    int t = 0;
+    int2 a0 = make_int2(0, 0), a1 = make_int2(0, 0);
+    Geom mg;
+    mg.off = 0; mg.b1 = mg.b2 = mg.b3 = mg.n = 0; mg.ref_idx = -1; mg.alt_bp = cf.alt_bq_prob;
+    if (c < n) {
+        t = ws.tested[c];
+        const int2 *in = reinterpret_cast<const int2 *>(ws.cnt6 + 6 * c);
+        a0 = in[0];
+        a1 = in[1];
+        int cov;
+        load_geom(b, c, mg, cov);
+        mg.alt_bp = cf.alt_bq_prob;
+    }
     const unsigned bal = __ballot_sync(FULL, t);
     if (lane == 0) s_warp[w] = __popc(bal);
     __syncthreads();
@@ -494,15 +548,13 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant
     long long bonf = 0;
     if (t) {
         // 1-based rank of this column among the tested columns of the batch
-        const long long rank = ws.blocksum[blockIdx.x] + (w ? s_warp[w - 1] : 0) + __popc(bal & ((2u << lane) - 1u));
+        const long long rank = ws.blocksum[tile] + (w ? s_warp[w - 1] : 0) + __popc(bal & ((2u << lane) - 1u));
         // lofreq_call.c:794-800: first tested column sets 3 when bonf_subst was 1, else += 3
         bonf = cf.bonf_dynamic ? ((bonf_start == 1 ? 0 : bonf_start) + 3 * rank) : bonf_start;
     }
     if (c < n) ws.bonf_used[c] = bonf;
     int cnt[3] = {0, 0, 0};
     if (t) {
-        const int2 *in = reinterpret_cast<const int2 *>(ws.cnt6 + 6 * c);
-        const int2 a0 = in[0], a1 = in[1];
         cnt[0] = a0.x; cnt[1] = a0.y; cnt[2] = a1.x;
     }
     const int K = max(cnt[0], max(cnt[1], cnt[2]));
@@ -511,11 +563,10 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant
         // median override needs a warp-wide histogram, or the list is full; everything else: one warp / CTA per column
         bool routed = false;
         if (K <= PK_MAXK && cf.alt_bq_mode != 2 && ws.pjobs) {
-            const int4 nc = reinterpret_cast<const int4 *>(b.nt_cnt)[c];
-            const int pl = packed_list(K, nc.x + nc.y + nc.z + nc.w);
+            const int pl = packed_list(K, mg.n);
             if (pl >= 0) {
                 // its row in the scratch pool (padded to 32 reads), then its slot in the list
-                const int npad = (nc.x + nc.y + nc.z + nc.w + 31) & ~31;
+                const int npad = (mg.n + 31) & ~31;
                 const long long off = (long long)atomicAdd(&ws.counters->pk_scr_used, (unsigned long long)npad);
                 if (off + npad <= ws.pk_scr_cap) {
                     const unsigned slot = atomicAdd(&ws.counters->n_pjobs[pl], 1u);
@@ -534,58 +585,59 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant
         }
     }
     // ---- columns with K <= KS ----
-    // (1) prune, lane per column: the reference's early exit (snpcaller.c:916-958) — walk the reads until
-    //     P(X >= K among the reads seen) * bonf > sig.  With the Bonferroni factors of a real run this takes
-    //     a handful of reads (K = 1: one; K = 3: ~6; K = 4: ~27 at depth-500 Q30), so almost every column
-    //     ends here without a warp ever being dedicated to it.  Cells are kept top-aligned (register 7 = cell
-    //     K-1, padding below cell 0 stays 0), so one code path serves every K.
+    // (1) prune, lane per column, in two stages.  With the Bonferroni factors of a real run the early exit fires after a
+    //     handful of reads (K = 1: one; K = 3: ~6; K = 4: ~27 at depth-500 Q30), so almost every column ends here
+    //     without a warp ever being dedicated to it.  A warp runs as long as its slowest lane, and the few columns
+    //     with K >= 4 would keep 31 finished lanes waiting: this kernel stops after PRUNE_CAP1 reads and lists what is
+    //     still alive for k_prune2, whose warps are full of such columns.
     bool small = t && K <= KS;
     const double limit = small ? cf.sig * (1.0 + 1e-9) / (double)bonf : 0.0;   // margin: borderline columns go to the host
-    Geom mg;
-    mg.off = 0; mg.b1 = mg.b2 = mg.b3 = mg.n = 0; mg.ref_idx = -1; mg.alt_bp = cf.alt_bq_prob;
-    if (small) {
-        int cov;
-        load_geom(b, c, mg, cov);
-        mg.alt_bp = cf.alt_bq_prob;
-    }
     if (cf.alt_bq_mode != 2) {          // the median override needs a warp-wide histogram: no lane-serial prune
-        double R[KS], T = 0.0;
-#pragma unroll
-        for (int j = 0; j < KS; ++j) R[j] = (j == KS - K) ? 1.0 : 0.0;
-        const int cap = min(mg.n, PRUNE_CAP);
-        bool live = small;
-        // the reads come in aligned 16-byte chunks per plane: one load per plane covers what most columns need
-        const long long ca = mg.off & ~15ll;
-        const int lead = (int)(mg.off - ca);
-        Chunk16 ch;
-        ch.bq = ch.mq = ch.baq = ch.sq = make_uint4(0, 0, 0, 0);
-        if (live && cap > 0) load_chunk(cf, b, ca, ch);
-#pragma unroll 1
-        for (int i = 0; __any_sync(FULL, live && i < cap); ++i) {
-            if (!(live && i < cap)) continue;
-            const int idx = lead + i, j = idx & 15;
-            if (j == 0 && i > 0) load_chunk(cf, b, ca + idx, ch);
-            bool is_alt;
-            int slot;
-            double jp;
-            if (!eval_read<true>(cf, s_lut, mg, i, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j), byte_of(ch.sq, j),
-                                 is_alt, slot, jp))
-                continue;
-            double p, q;
-            guard_pq(jp, p, q);
-            T = fma(R[KS - 1], p, T);
-#pragma unroll
-            for (int j = KS - 1; j >= 1; --j) R[j] = fma(R[j - 1], p, R[j] * q);
-            R[0] = R[0] * q;
-            if (T > limit) live = false;      // clearly insignificant: snpcaller() leaves LDBL_MAX everywhere (snpcaller.c:1155)
+        small = lane_prune(cf, b, s_lut, mg, K, limit, PRUNE_CAP1, small);
+        if (small) {
+            const unsigned slot = atomicAdd(&ws.counters->n_jobs[CLS_PRUNE2], 1u);
+            ws.jobs[(long long)CLS_PRUNE2 * ws.cap_cols + slot] = (int)c;
         }
-        small = live;                          // survivors: not pruned within the cap
-    }
-    // (2) the survivors (true low-frequency variants, the first columns of a run, every small column when the median
-    //     override is on) join the columns with 8 < K <= 32 in k_mid's job list: full evaluation, whole warp
-    if (small) {
+    } else if (small) {
+        // every small column joins the columns with 8 < K <= 32 in k_mid's job list: full evaluation, whole warp
         const unsigned slot = atomicAdd(&ws.counters->n_jobs[0], 1u);
         ws.jobs[slot] = (int)c;
+    }
+}
+
+// (2) second stage of the prune: the columns k_finalize could not rule out within PRUNE_CAP1 reads, one lane each, up to
+//     PRUNE_CAP reads (from the first read again: eight reads are cheaper to redo than to carry).  The survivors (true
+//     low-frequency variants, the first columns of a run) join k_mid's job list.
+__global__ void __launch_bounds__(128) k_prune2(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, const Lut *lut,
+                                                const Workspace ws)
+{
+    __shared__ double s_lut[768];
+    const unsigned njobs = ws.counters->n_jobs[CLS_PRUNE2];
+    if (njobs == 0) return;
+    load_lut(s_lut, lut);
+    const int *jobs = ws.jobs + (long long)CLS_PRUNE2 * ws.cap_cols;
+    for (unsigned j0 = blockIdx.x * blockDim.x; j0 < njobs; j0 += gridDim.x * blockDim.x) {
+        const unsigned j = j0 + threadIdx.x;
+        bool live = j < njobs;
+        const long long c = live ? jobs[j] : 0;
+        Geom mg;
+        mg.off = 0; mg.b1 = mg.b2 = mg.b3 = mg.n = 0; mg.ref_idx = -1; mg.alt_bp = cf.alt_bq_prob;
+        int K = 1;
+        double limit = 0.0;
+        if (live) {
+            int cov;
+            load_geom(b, c, mg, cov);
+            mg.alt_bp = cf.alt_bq_prob;
+            const int2 *in = reinterpret_cast<const int2 *>(ws.cnt6 + 6 * c);
+            const int2 a0 = in[0], a1 = in[1];
+            K = max(a0.x, max(a0.y, a1.x));
+            limit = cf.sig * (1.0 + 1e-9) / (double)ws.bonf_used[c];
+        }
+        live = lane_prune(cf, b, s_lut, mg, K, limit, PRUNE_CAP, live);
+        if (live) {
+            const unsigned slot = atomicAdd(&ws.counters->n_jobs[0], 1u);
+            ws.jobs[slot] = (int)c;
+        }
     }
 }
 
@@ -1578,8 +1630,7 @@ void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st)
 {
     if (b.n_cols <= 0) return;
     const int nb = (int)((b.n_cols + FIN_BLOCK - 1) / FIN_BLOCK);
-    k_block_counts<<<nb, FIN_BLOCK, 0, st>>>(ws.tested, b.n_cols, ws.blocksum);
-    k_scan_blocks<<<1, 1024, 0, st>>>(ws.blocksum, nb, ws.counters);
+    k_scan_blocks<<<1, 1024, 0, st>>>(ws.tilecount, ws.blocksum, nb, ws.counters);
 }
 
 void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
@@ -1590,6 +1641,7 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
     // n_tested (first 8 bytes) belongs to the scan; everything after it is per-test state
     cudaMemsetAsync(reinterpret_cast<char *>(ws.counters) + 8, 0, sizeof(Counters) - 8, st);
     k_finalize<<<nb, FIN_BLOCK, 0, st>>>(cf, b, lut, ws, bonf_start_dev);
+    k_prune2<<<sm_count() * 2, 128, 0, st>>>(cf, b, lut, ws);
     if (after_finalize) cudaEventRecord(after_finalize, st);
     // The register-tile classes are independent: run them side by side so that their warps share the SMs
     // (each class alone has too few columns to hide its own latencies).
