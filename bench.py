@@ -470,6 +470,8 @@ def run_ours(args):
             "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops_algo / t_heavy / 1e12 / fp64_peak if fp64_peak else None,
             "traffic": ncu_traffic(HEAVY_KERNELS), "peak_source": "DFMA microbenchmark run in this process (lfb200_dfma_peak); MEASURED_PEAKS.json has no fp64 entry",
             "algorithmic_flops_per_launch": flops_algo, "kernel_ms": t_heavy * 1e3, "columns": int(heavy.sum().item())}
+    if hbm["traffic"] is not None:
+        hbm["traffic_frac"] = hbm["traffic"] / t_stream / 1e9 / peak      # measured DRAM bytes / time / peak: the real pressure
     roofline = dict(fp64 if t_heavy >= t_stream else hbm)
     roofline["phase_ms"] = {"k_screen": float(ph[0] * 1e3), "prefix_sum": float(ph[1] * 1e3), "k_finalize": float(ph[2] * 1e3),
                             "k_heavy": float(ph[3] * 1e3)}

@@ -348,10 +348,10 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     bad |= ctx->w_jobs.ensure(nn * NCLASS * sizeof(int));
     bad |= ctx->w_cand.ensure(nn * sizeof(Cand));
     // packed job lists hold a quarter of the batch each (a fuller list spills into the per-column lists); the pool
-    // of scratch rows (step parameters of the packed columns, 16 B per read) holds 16 reads per column of the
-    // batch, at most 256 MB — when it runs out the remaining columns take the per-column kernels
+    // of scratch rows (step parameters of the packed columns, 16 B per read) holds 64 reads per column of the
+    // batch, between 16 MB and 1 GB — when it runs out the remaining columns take the per-column kernels
     const size_t pcap = std::max<size_t>(nn / 4, 4096);
-    const size_t scr_cap = std::min<size_t>(std::max<size_t>(nn * 16, (size_t)1 << 20), (size_t)16 << 20);
+    const size_t scr_cap = std::min<size_t>(std::max<size_t>(nn * 64, (size_t)1 << 20), (size_t)64 << 20);
     bad |= ctx->w_pjobs.ensure(pcap * PK_NL * sizeof(int));
     bad |= ctx->w_pinfo.ensure(pcap * PK_NL * sizeof(PkInfo));
     bad |= ctx->w_pkscr.ensure(scr_cap * sizeof(double2));
