@@ -279,6 +279,23 @@ typedef struct {
 void lfb200_plp_to_errprobs(double **err_probs, int *num_err_probs, int *alt_bases, int *alt_counts, int *alt_raw_counts,
                             const lfb200_plp_col_t *p, const lfb200_conf_t *conf);
 
+/* ---- indel tests: call_indels -> plp_to_ins_errprobs / plp_to_del_errprobs -> snpcaller ------
+ * One test per indel event of a column (lofreq_call.c:618-726).  Its error probabilities are, for every read of the
+ * column, merge_srcq_mapq_baq_and_bq(sq, mq, aq, iq) (snpcaller.c:501-623): iq = the read's insertion / deletion
+ * quality, mq its mapping quality, aq its indel alignment quality — only for the reads of the event under test
+ * (snpcaller.c:541,597) — and sq its source quality (event reads only); the count handed to snpcaller() is
+ * (event count, 0, 0) with bonf_indel (lofreq_call.c:305-320, 360-385).
+ * Test t owns reads [read_off[t], read_off[t+1]) of the planes, the reads of its event LAST: event_count[t] of them.
+ * Byte 255 = quality not available (aq of every read that is not of the event; sq of non-indel reads; mq 255).
+ * mq / aq / sq may be NULL; conf->flag selects MQ / IDAQ / SQ as in the reference; conf->sig is the level.
+ * Outputs per test (any may be NULL except pvalues): pvalues = snp_pvalues[0], lnp, status (LFB200_ST_*),
+ * called = pvalue * bonf < sig (lofreq_call.c:326,392), qual = PROB_TO_PHREDQUAL(pvalue) where called, else -1.
+ * Everything between the quality bytes and ln p stays on the device (k_errprobs -> k_prob_jobs). */
+int lfb200_indel_tests(lfb200_ctx *ctx, const lfb200_conf_t *conf, long long n_tests, const long long *read_off,
+                       const unsigned char *iq, const unsigned char *mq, const unsigned char *aq, const unsigned char *sq,
+                       const int *event_count, const long long *bonf_indel, long double *pvalues, double *lnp,
+                       unsigned char *status, unsigned char *called, int *qual);
+
 /* binom() of binom.c:52-93 (caller: lofreq_uniq.c:381; note binom.h:32 names the
  * last two arguments the other way round): *p = P(X <= num_success), *q = 1 - *p
  * for X ~ Binomial(num_trials, prob_success); either pointer may be NULL.

@@ -77,7 +77,7 @@ SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_
            "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_ntested_copy_device", "lfb200_test_device_from", "lfb200_bonf_start_device", "lfb200_comm_unique_id", "lfb200_comm_init", "lfb200_comm_exchange", "lfb200_comm_gathered",
            "lfb200_sites_device", "lfb200_sites_begin", "lfb200_sites_end",
            "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_dfma_peak", "lfb200_last_job_counts", "lfb200_copy_counts_device", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
-           "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_poissbin", "lfb200_poissbin_batch", "lfb200_batch_errprobs", "lfb200_plp_to_errprobs", "lfb200_binom", "lfb200_binom_batch", "lfb200_synth_depths",
+           "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_poissbin", "lfb200_poissbin_batch", "lfb200_batch_errprobs", "lfb200_plp_to_errprobs", "lfb200_indel_tests", "lfb200_binom", "lfb200_binom_batch", "lfb200_synth_depths",
            "lfb200_synth_columns"]
 
 _lib = None
@@ -173,6 +173,8 @@ def load():
     lib.lfb200_batch_errprobs.argtypes = [vp, C.POINTER(Conf), C.POINTER(Batch), vp, vp, vp, vp, vp]
     lib.lfb200_plp_to_errprobs.restype = None
     lib.lfb200_plp_to_errprobs.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), vp, vp, vp, C.POINTER(PlpCol), C.POINTER(Conf)]
+    lib.lfb200_indel_tests.restype = C.c_int
+    lib.lfb200_indel_tests.argtypes = [vp, C.POINTER(Conf), ll, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.lfb200_synth_depths.restype = C.c_int
     lib.lfb200_synth_depths.argtypes = [C.c_int, ll, ll, vp, vp]
     lib.lfb200_synth_columns.restype = C.c_int

@@ -1260,6 +1260,91 @@ extern "C" void lfb200_plp_to_errprobs(double **err_probs, int *num_err_probs, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// indel tests: plp_to_ins_errprobs / plp_to_del_errprobs (snpcaller.c:501-623) + snpcaller with (count, 0, 0)
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfb200_indel_tests(lfb200_ctx *ctx, const lfb200_conf_t *conf, long long n, const long long *read_off,
+                                  const unsigned char *iq, const unsigned char *mq, const unsigned char *aq, const unsigned char *sq,
+                                  const int *event_count, const long long *bonf_indel, long double *pvalues, double *lnp,
+                                  unsigned char *status, unsigned char *called, int *qual)
+{
+    if (!ctx) return fail("no context");
+    if (n <= 0) return 0;
+    if (!conf || !read_off || !iq || !event_count || !bonf_indel || !pvalues) return fail("null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t total = (size_t)read_off[n];
+    // a test is a pseudo-column: "reference" group = the other reads, first alt group = the reads of the event
+    std::vector<int> nt((size_t)n * 4, 0), cnt3((size_t)n * 3, 0);
+    std::vector<char> ref((size_t)n, 'A');
+    for (long long t = 0; t < n; ++t) {
+        const long long reads = read_off[t + 1] - read_off[t];
+        if (reads < 0 || event_count[t] < 0 || event_count[t] > reads) return fail("test %lld: bad read range / event count", t);
+        nt[(size_t)4 * t] = (int)(reads - event_count[t]);
+        nt[(size_t)4 * t + 1] = event_count[t];
+        cnt3[(size_t)3 * t] = event_count[t];
+    }
+    DevConf dc;
+    memset(&dc, 0, sizeof(dc));                        // no bq / jq filters, no overrides: every read counts (snpcaller.c:516-560)
+    dc.use_mq = (conf->flag & LFB200_USE_MQ) && mq;
+    dc.use_baq = (conf->flag & LFB200_USE_IDAQ) && aq;
+    dc.use_sq = (conf->flag & LFB200_USE_SQ) && sq;
+    dc.skip_jp = dc.skip_alt_jp = INFINITY;
+    dc.sig = (double)conf->sig;
+    dc.bonf_start = 1;
+    DevBatch db;
+    memset(&db, 0, sizeof(db));
+    db.n_cols = n;
+    const void *d;
+    if (upload(ctx->in_off, read_off, (size_t)(n + 1) * 8, 0, st, &d)) return 1;
+    db.col_off = (const long long *)d;
+    if (upload(ctx->in_cnt, nt.data(), (size_t)n * 16, 0, st, &d)) return 1;
+    db.nt_cnt = (const int *)d;
+    if (upload(ctx->in_ref, ref.data(), (size_t)n, 0, st, &d)) return 1;
+    db.ref_base = (const char *)d;
+    if (upload(ctx->in_bq, iq, total, 32, st, &d)) return 1;
+    db.bq = (const unsigned char *)d;
+    if (upload(ctx->in_mq, dc.use_mq ? mq : nullptr, total, 32, st, &d)) return 1;
+    db.mq = (const unsigned char *)d;
+    if (upload(ctx->in_baq, dc.use_baq ? aq : nullptr, total, 32, st, &d)) return 1;
+    db.baq = (const unsigned char *)d;
+    if (upload(ctx->in_sq, dc.use_sq ? sq : nullptr, total, 32, st, &d)) return 1;
+    db.sq = (const unsigned char *)d;
+    if (ctx->p_ep.ensure(total * 8 + 64)) return fail("out of device memory");
+    if (ctx->p_off.ensure((size_t)n * 40 + 64)) return fail("out of device memory");
+    double *d_ep = (double *)ctx->p_ep.p;
+    int *d_n = (int *)ctx->p_off.p, *d_c9 = d_n + n;
+    launch_errprobs(dc, db, ctx->d_lut, d_ep, d_n, d_c9, st);      // nothing is filtered: column t fills [read_off[t], read_off[t+1])
+    ProbBatch pb;
+    pb.n = n;
+    pb.sig = dc.sig;
+    pb.err_probs = d_ep;
+    pb.ep_off = db.col_off;
+    if (upload(ctx->p_cnt, cnt3.data(), (size_t)n * 12, 0, st, &d)) return 1;
+    pb.counts = (const int *)d;
+    if (upload(ctx->p_bonf, bonf_indel, (size_t)n * 8, 0, st, &d)) return 1;
+    pb.bonf = (const long long *)d;
+    if (ctx->p_out.ensure((size_t)n * sizeof(Cand))) return fail("out of device memory");
+    launch_prob_jobs(pb, (Cand *)ctx->p_out.p, st);
+    CU(cudaGetLastError());
+    if (ctx->ensure_cand((size_t)n)) return fail("out of pinned host memory");
+    CU(cudaMemcpyAsync(ctx->h_cand, ctx->p_out.p, (size_t)n * sizeof(Cand), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (long long t = 0; t < n; ++t) {
+        const Cand &cd = ctx->h_cand[(size_t)t];
+        if (cd.flags & CF_UNSUPPORTED) return fail("test %lld: event count above %d", t, 16384);
+        if (cd.flags & CF_RANGE) return fail("test %lld: tail outside the representable range", t);
+        lfb200_site_t s;
+        finish_site(cd, dc.sig, s);
+        pvalues[t] = s.pvalue[0];
+        if (lnp) lnp[t] = s.lnp[0];
+        if (status) status[t] = s.status[0];
+        if (called) called[t] = s.called[0];
+        if (qual) qual[t] = s.qual[0];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // binom() (binom.c:52-93): binomial CDF / survival function, batched on the device
 // ------------------------------------------------------------------------------------------------
 extern "C" int lfb200_binom_batch(lfb200_ctx *ctx, long long n, const int *num_trials, const int *num_success,

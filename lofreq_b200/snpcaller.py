@@ -158,6 +158,31 @@ class Caller:
         C.CDLL(None).free(p)
         return ep, ab, ac, ar
 
+    # ---- indel tests (call_indels, lofreq_call.c:618-726) -------------------------------------------
+    def indel_tests(self, read_off, iq, mq, aq, sq, event_count, bonf_indel, conf=None):
+        """one test per indel event; reads of the event last in its range; 255 = quality not available.
+        Returns dict(pvalues longdouble[n], lnp, status, called, qual)"""
+        cf = conf_from(conf)
+        n = len(event_count)
+        ro = np.ascontiguousarray(read_off, np.int64)
+        total = int(ro[-1]) if n else 0
+
+        def plane(x):
+            if x is None:
+                return None, None
+            a = np.zeros(total + 32, np.uint8)
+            a[:total] = np.asarray(x, np.uint8)[:total]
+            return a, _ptr(a)
+        k_iq, p_iq = plane(iq); k_mq, p_mq = plane(mq); k_aq, p_aq = plane(aq); k_sq, p_sq = plane(sq)
+        ec = np.ascontiguousarray(event_count, np.int32)
+        bf = np.ascontiguousarray(bonf_indel, np.int64)
+        out = dict(pvalues=np.zeros(n, np.longdouble), lnp=np.zeros(n), status=np.zeros(n, np.uint8),
+                   called=np.zeros(n, np.uint8), qual=np.zeros(n, np.int32))
+        capi.check(self.lib.lfb200_indel_tests(self._ctx, C.byref(cf), n, _ptr(ro), p_iq, p_mq, p_aq, p_sq, _ptr(ec), _ptr(bf),
+                                                _ptr(out["pvalues"]), _ptr(out["lnp"]), _ptr(out["status"]), _ptr(out["called"]),
+                                                _ptr(out["qual"])))
+        return out
+
     # ---- binom(): binomial CDF / survival function (binom.c:52-93) ------------------------------
     def binom_batch(self, num_trials, num_success, prob_success):
         """(status, p, q) arrays; p = P(X <= num_success), q = 1 - p, NaN where status != 0"""

@@ -148,6 +148,24 @@ class Oracle:
         self.libc.free(p)
         return pv[0], row
 
+    def indel_test(self, is_del, flag, sig, bonf, other_q, other_mq, events, test_event):
+        """reference only: events = list of (q, aq, mq, sq) int arrays (-1 = not available) -> (pvalue, count, n_err_probs)"""
+        if self.kind != "reference":
+            raise RuntimeError("the indel harness drives the compiled reference (oracle/_ref/libsnpref.so)")
+        f = self.lib.lfref_indel_test
+        f.restype = C.c_int
+        f.argtypes = [C.c_int, C.c_int, C.c_double, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        oq = np.ascontiguousarray(other_q, np.int32); om = np.ascontiguousarray(other_mq, np.int32)
+        off = np.zeros(len(events) + 1, np.int32)
+        off[1:] = np.cumsum([len(e[0]) for e in events])
+        cat = [np.ascontiguousarray(np.concatenate([np.asarray(e[k], np.int32) for e in events]), np.int32) for k in range(4)]
+        pv = np.zeros(1, np.longdouble)
+        cnt = C.c_int(0)
+        n = f(int(is_del), int(flag), float(sig), int(bonf), len(oq), _ptr(oq), _ptr(om), len(events), _ptr(off),
+              _ptr(cat[0]), _ptr(cat[1]), _ptr(cat[2]), _ptr(cat[3]), int(test_event), _ptr(pv), C.byref(cnt))
+        return pv[0], cnt.value, n
+
     def tailsum(self, row, start):
         r = np.ascontiguousarray(row, dtype=np.float64)
         return self._tailsum(_ptr(r), int(start), len(r))

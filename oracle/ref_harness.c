@@ -185,3 +185,61 @@ int lfref_prob_to_phredqual_safe(double p) { return PROB_TO_PHREDQUAL_SAFE(p); }
 double lfref_phredqual_to_prob(int q) { return PHREDQUAL_TO_PROB(q); }
 int lfref_sizeof_plp_col(void) { return (int)sizeof(plp_col_t); }
 int lfref_sizeof_varcall_conf(void) { return (int)sizeof(varcall_conf_t); }
+
+/* One indel test through the reference's own functions: the column is rebuilt with the reference's add_ins_sequence /
+ * add_del_sequence (utils.c:559,619) and int_varray_add_value, then plp_to_ins_errprobs / plp_to_del_errprobs
+ * (snpcaller.c:501-623), qsort(dbl_cmp) and snpcaller() with (event count, 0, 0) — the steps of call_indels /
+ * call_alt_ins / call_alt_del (lofreq_call.c:305-426, 618-726) minus the VCF writing.
+ * Non-indel reads: other_q / other_mq [n_other].  Events: event e owns reads [ev_off[e], ev_off[e+1]) of ev_q / ev_aq /
+ * ev_mq / ev_sq (-1 = not available); the event under test is test_event.  Returns the number of error probabilities. */
+int lfref_indel_test(int is_del, int flag, double sig, long long bonf, int n_other, const int *other_q, const int *other_mq,
+                     int n_events, const int *ev_off, const int *ev_q, const int *ev_aq, const int *ev_mq, const int *ev_sq,
+                     int test_event, long double *pvalue, int *event_count)
+{
+    varcall_conf_t conf;
+    plp_col_t p;
+    double *ep = NULL;
+    int n_ep = 0, i, e, counts[3] = {0, 0, 0};
+    long double pv[3];
+    char key[MAX_INDELSIZE], test_key[MAX_INDELSIZE];
+    init_varcall_conf(&conf);
+    conf.flag = flag;
+    memset(&p, 0, sizeof(p));
+    int_varray_init(&p.ins_quals, 0); int_varray_init(&p.ins_map_quals, 0);
+    int_varray_init(&p.del_quals, 0); int_varray_init(&p.del_map_quals, 0);
+    p.coverage_plp = n_other + ev_off[n_events];
+    for (i = 0; i < n_other; i++) {
+        int_varray_add_value(is_del ? &p.del_quals : &p.ins_quals, other_q[i]);
+        int_varray_add_value(is_del ? &p.del_map_quals : &p.ins_map_quals, other_mq[i]);
+    }
+    test_key[0] = '\0';
+    for (e = 0; e < n_events; e++) {
+        int len = 1 + e % (MAX_INDELSIZE - 2), j;
+        for (j = 0; j < len; j++) key[j] = "ACGT"[(e + j) & 3];
+        key[len] = '\0';
+        if (e >= 4) key[0] = "ACGT"[(e / 4) & 3];
+        if (e == test_event) strcpy(test_key, key);
+        for (i = ev_off[e]; i < ev_off[e + 1]; i++) {
+            if (is_del) add_del_sequence(&p.del_event_counts, key, ev_q[i], ev_aq[i], ev_mq[i], ev_sq[i], i & 1);
+            else add_ins_sequence(&p.ins_event_counts, key, ev_q[i], ev_aq[i], ev_mq[i], ev_sq[i], i & 1);
+        }
+    }
+    if (is_del) {
+        del_event *it = find_del_sequence(&p.del_event_counts, test_key);
+        plp_to_del_errprobs(&ep, &n_ep, &p, &conf, test_key);
+        counts[0] = it ? it->count : 0;
+    } else {
+        ins_event *it = find_ins_sequence(&p.ins_event_counts, test_key);
+        plp_to_ins_errprobs(&ep, &n_ep, &p, &conf, test_key);
+        counts[0] = it ? it->count : 0;
+    }
+    qsort(ep, n_ep, sizeof(double), dbl_cmp);
+    snpcaller(pv, ep, n_ep, counts, bonf, sig, -1);
+    *pvalue = pv[0];
+    *event_count = counts[0];
+    free(ep);
+    if (is_del) destruct_del_event_counts(&p.del_event_counts); else destruct_ins_event_counts(&p.ins_event_counts);
+    int_varray_free(&p.ins_quals); int_varray_free(&p.ins_map_quals);
+    int_varray_free(&p.del_quals); int_varray_free(&p.del_map_quals);
+    return n_ep;
+}

@@ -553,6 +553,35 @@ def test_plp_to_errprobs(caller, port_oracle):
     assert np.array_equal(got[0], want[0]) and all(np.array_equal(g, w) for g, w in zip(got[1:], want[1:]))
 
 
+def test_indel_tests_golden(caller):
+    """the indel path: quality bytes -> merged probabilities -> snpcaller with (event count, 0, 0),
+    against p-values the reference's plp_to_ins_errprobs / plp_to_del_errprobs + snpcaller produced"""
+    z = np.load(os.path.join(GOLD, "indel_tests.npz"))
+    sig = float(z["sig"])
+    for flag in sorted(set(z["flag"].tolist())):
+        sel = np.flatnonzero(z["flag"] == flag)
+        off = np.zeros(len(sel) + 1, np.int64)
+        parts = {k: [] for k in ("iq", "mq", "aq", "sq")}
+        for j, i in enumerate(sel):
+            lo, hi = int(z["read_off"][i]), int(z["read_off"][i + 1])
+            off[j + 1] = off[j] + hi - lo
+            for k in parts:
+                parts[k].append(z[k][lo:hi])
+        planes = {k: np.concatenate(v) for k, v in parts.items()}
+        got = caller.indel_tests(off, planes["iq"], planes["mq"], planes["aq"], planes["sq"], z["event_count"][sel], z["bonf"][sel],
+                                 default_conf(flag=int(flag), sig=sig))
+        want = ld_from_bytes(z["pvalue_ld"][sel])
+        st = status_of(want)
+        assert np.array_equal(got["status"], st), (flag, np.argwhere(got["status"] != st)[:5].tolist())
+        assert_lnp_close(got["pvalues"], want, st, "indel flag=%d" % flag)
+        with np.errstate(all="ignore"):
+            want_called = (want * z["bonf"][sel].astype(np.longdouble) < np.longdouble(sig)).astype(np.uint8)
+        assert np.array_equal(got["called"], want_called), flag
+        with np.errstate(all="ignore"):
+            want_q = np.where(want_called == 1, (-10.0 * np.log10(want)).astype(np.int64), -1)
+        assert np.all(np.abs(got["qual"] - want_q) <= (np.abs(-10.0 * np.log10(want).astype(np.float64) % 1.0) < 1e-6)), flag
+
+
 def test_binom_golden(caller):
     """binom() (binom.c:52-93 -> cdflib cdfbin): status codes exact, cdf and sf within 1e-10 relative of the compiled
     reference — through the batched entry point and through the link-compatible single call"""
