@@ -187,7 +187,7 @@ __device__ __forceinline__ int packed_list(int K, int n)
     if (K <= KS || K > PK_MAXK || n > PK_MAXN) return -1;
     const int gi = K <= 4 * PK_R ? 0 : K <= 8 * PK_R ? 1 : K <= 16 * PK_R ? 2 : 3;
     int bin = 0;
-    while (bin < PK_NB - 1 && n > (64 << bin)) ++bin;
+    while (bin < PK_NB - 1 && n > (128 << bin)) ++bin;
     return bin * PK_NG + gi;
 }
 }  // namespace lfb

@@ -157,6 +157,7 @@ struct lfb200_ctx {
     std::vector<lfb200_site_t> h_sites;  // finished in device order, then emitted sorted by column
     std::vector<std::pair<long long, unsigned>> h_order, h_order2;
     std::unique_ptr<WorkerPool> pool;
+    size_t scr_want = 0;                 // entries of the packed scratch pool the last batch would have needed
     int ensure_cand(size_t n)
     {
         if (n <= h_cand_cap) return 0;
@@ -351,7 +352,9 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     // of scratch rows (step parameters of the packed columns, 16 B per read) holds 64 reads per column of the
     // batch, between 16 MB and 1 GB — when it runs out the remaining columns take the per-column kernels
     const size_t pcap = std::max<size_t>(nn / 4, 4096);
-    const size_t scr_cap = std::min<size_t>(std::max<size_t>(nn * 64, (size_t)1 << 20), (size_t)64 << 20);
+    // and grows to what the last batch asked for (deep, noisy columns: lfb200_ctx::scr_want), up to 4 GB
+    const size_t scr_cap = std::max(std::min<size_t>(std::max<size_t>(nn * 64, (size_t)1 << 20), (size_t)64 << 20),
+                                    std::min<size_t>(ctx->scr_want, (size_t)256 << 20));
     bad |= ctx->w_pjobs.ensure(pcap * PK_NL * sizeof(int));
     bad |= ctx->w_pinfo.ensure(pcap * PK_NL * sizeof(PkInfo));
     bad |= ctx->w_pkscr.ensure(scr_cap * sizeof(double2));
@@ -571,6 +574,7 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
             return fail("a column has an alt count above %d: not supported by this build", 16384);
         sm.n_tested = (long long)c.n_tested;
         n_cand = c.n_cand;
+        if ((long long)c.pk_scr_used > ctx->ws.pk_scr_cap) ctx->scr_want = (size_t)c.pk_scr_used + (size_t)c.pk_scr_used / 4;
         for (int i = 0; i < NCLASS; ++i) if (i != CLS_FALLBACK && i != CLS_PRUNE2) sm.n_heavy += c.n_jobs[i];
         for (int i = 0; i < PK_NL; ++i) sm.n_heavy += std::min<long long>(c.n_pjobs[i], ctx->ws.pcap);
     }

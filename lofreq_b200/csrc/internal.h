@@ -19,9 +19,9 @@ constexpr int MAXK_WARP = 2048;    // 32 lanes * 64 cells
 // k_heavy<R> lists instead.
 constexpr int PK_R = 8;            // cells per lane
 constexpr int PK_NG = 4;           // G = 4 << gi
-constexpr int PK_NB = 8;           // depth bins: <= 64, 128, ..., 8192 reads
+constexpr int PK_NB = 8;           // depth bins: <= 128, 256, ..., 16384 reads
 constexpr int PK_NL = PK_NG * PK_NB;
-constexpr int PK_MAXN = 8192;      // deepest column of the packed form
+constexpr int PK_MAXN = 16384;     // deepest column of the packed form
 constexpr int PK_MAXK = 32 * PK_R;
 
 // what the kernels need from varcall_conf_t, pre-digested on the host

@@ -328,6 +328,12 @@ __device__ void packed_task(const DevConf &cf, const DevBatch &b, const Workspac
             else *dst = make_double2(0.0, 1.0);        // this column has no reads left: neutral steps
         }
     };
+    // Early exit (the reference's, snpcaller.c:916-958, in a form that needs no running sum of ln q): the tail over the
+    // reads seen so far can only grow, and the product of the q of ALL reads is a lower bound of the product over the
+    // reads seen, so  T * 2^e2 * exp(sum_lq) * s^-K  <=  P(X >= K).  Once that bound passes sig / bonf the column is
+    // insignificant whatever follows.  Tested on the exponent of T alone (floor(log2 T) <= log2 T), once per block.
+    const double thr_ln = log(cf.sig * (1.0 + 1e-9) / (double)bonf) - sum_lq + (double)K * ln_s;
+    bool dead = !have;
     stage(0, par);
     int cur = 0;
     for (int n0 = 0; n0 < nmax; n0 += 32, cur ^= 1) {
@@ -366,8 +372,13 @@ __device__ void packed_task(const DevConf &cf, const DevBatch &b, const Workspac
             T *= f;
             e2 += ex;
         }
+        const bool over = lane == last && (double)(((__double2hiint(T) >> 20) - 1023) + e2) * LN2 > thr_ln;
+        const bool over_g = __shfl_sync(FULL, (int)over, last) != 0;     // every lane takes part, dead or not
+        dead = dead || over_g;
         __syncwarp();                                  // this buffer is refilled during the next block
+        if (__all_sync(FULL, dead || n0 + 32 >= npad)) break;      // nothing left to decide in this warp
     }
+    cp_async_wait_all();
     bool fb = false;
 
     // ---- 4. tails
@@ -384,7 +395,7 @@ __device__ void packed_task(const DevConf &cf, const DevBatch &b, const Workspac
     const double base = (double)e2 * LN2 + sum_lq;
     const double lnT = log(Tl) + base - (double)K * ln_s;
     const double lnKm1 = log(topl) + base - (double)(K - 1) * ln_s;
-    bool site = have && !fb;
+    bool site = have && !fb && !dead;
     if (site && lnT > -700.0 && exp(lnT) * (double)bonf > cf.sig * (1.0 + 1e-9)) site = false;   // snpcaller.c:1155
     double lnp[3] = {0.0, 0.0, 0.0};
     const double invs = (ln_s == 0.0) ? 1.0 : exp(-ln_s);
@@ -423,6 +434,7 @@ __device__ void packed_task(const DevConf &cf, const DevBatch &b, const Workspac
             lnp[i] = lnT;
         }
     }
+    if (dead) fb = false;                              // ruled out for good: nothing for the fallback list to decide
     if (fb) site = false;
     if (have && gl == 0) {
         if (fb) {

@@ -461,8 +461,9 @@ def test_packed_kernel_classes(caller, port_oracle):
     cols.append(dict(ref="A", groups=[grp(300, 20, 41, mqv=0), grp(40, 20, 41, mqv=0), e, e]))
     # baq 0 -> merged probability exactly 1: 1/q = 2^52 -> parameters above 2^20 -> fallback list
     cols.append(dict(ref="C", groups=[grp(20, baqv=0), grp(300), grp(30), e]))
-    # deeper than the packed form holds (n > 8192): per-column kernel
-    cols.append(dict(ref="T", groups=[grp(100), e, e, grp(9000)]))
+    # deeper than the packed form holds (n > 16384): per-column kernel; and a deep one it does hold
+    cols.append(dict(ref="T", groups=[grp(100), e, e, grp(17000)]))
+    cols.append(dict(ref="T", groups=[grp(100), e, grp(3), grp(9000)]))
     order = rng.permutation(len(cols))
     cols = [cols[i] for i in order]
     for pad in (1, 16):
