@@ -167,7 +167,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-STREAM_KERNELS = ("k_screen", "k_scan_blocks", "k_finalize")
+STREAM_KERNELS = ("k_screen", "k_scan_blocks", "k_finalize", "k_prune2")
 HEAVY_KERNELS = ("k_mid", "k_pk_prep", "k_packed", "k_heavy")      # k_heavy<R>, k_heavy_xl
 
 
@@ -447,7 +447,7 @@ def run_ours(args):
     ph = prof.mean(axis=0) * 1e-3
     t_stream = float(ph[0] + ph[1] + ph[2])
     bytes_algo = algorithmic_bytes(int(t["depths"].sum().item()), n)
-    hbm = {"bound": "hbm", "kernel": "k_screen + k_scan_blocks + k_finalize", "achieved": bytes_algo / t_stream / 1e9,
+    hbm = {"bound": "hbm", "kernel": "k_screen + k_scan_blocks + k_finalize + k_prune2", "achieved": bytes_algo / t_stream / 1e9,
            "peak": peak, "unit": "GB/s", "frac": bytes_algo / t_stream / 1e9 / peak, "traffic": ncu_traffic(STREAM_KERNELS), "peak_source": peak_src,
            "note": "algorithmic bytes = every quality byte the configuration merges (SURVEY.md 8d); the early-exit prune reads far fewer "
                    "(see traffic), so a fraction above 1 means bytes skipped, not bandwidth above peak",
