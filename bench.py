@@ -502,7 +502,7 @@ def run_ours(args):
                                      "h2d_mode": "optional host plane mode 1 (lfb200_set_host_planes): the kernels read the pinned quality "
                                                  "planes in place over PCIe, so only the reads that decide a column cross the bus; "
                                                  "only the per-column metadata is copied"}},
-                "gpu_launches": 15 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_launches": 17 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "wall_ms_per_step": wall * 1e3 / args.steps}
         emit(line)
     if world > 1:

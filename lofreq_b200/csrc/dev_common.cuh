@@ -180,6 +180,13 @@ __device__ __forceinline__ int class_of(int K)
 }
 
 
+// a candidate was emitted for column c: one mark per column, counted per tile of 256 columns (k_rank_cands)
+__device__ __forceinline__ void mark_cand(const Workspace &ws, long long c)
+{
+    ws.is_cand[c] = 1;
+    atomicAdd(&ws.candtile[c >> 8], 1u);
+}
+
 // packed job list (k_packed) of a column with largest alt count K and n reads; -1 = not packable.
 // list = depth bin * PK_NG + gi, G = 4 << gi lanes per column: the smallest G with G * PK_R >= K.
 __device__ __forceinline__ int packed_list(int K, int n)

@@ -144,7 +144,7 @@ struct lfb200_ctx {
     cudaStream_t stream = nullptr;       // used by the host entry points
     Lut *d_lut = nullptr;
     // workspace of the current batch
-    DevBuf w_cnt6, w_tested, w_tails, w_bonf, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_pinfo, w_pkscr, w_tilecount;
+    DevBuf w_cnt6, w_tested, w_tails, w_bonf, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_pinfo, w_pkscr, w_tilecount, w_iscand, w_candtile, w_candpre, w_perm;
     Workspace ws{};
     // device copies of host batches (host entry point)
     DevBuf in_off, in_cnt, in_ref, in_cov, in_nb, in_bq, in_mq, in_baq, in_sq;
@@ -158,6 +158,19 @@ struct lfb200_ctx {
     std::vector<std::pair<long long, unsigned>> h_order, h_order2;
     std::unique_ptr<WorkerPool> pool;
     size_t scr_want = 0;                 // entries of the packed scratch pool the last batch would have needed
+    int *h_perm = nullptr;               // pinned
+    size_t h_perm_cap = 0;
+    int ensure_perm(size_t n)
+    {
+        if (n <= h_perm_cap) return 0;
+        if (h_perm) cudaFreeHost(h_perm);
+        h_perm = nullptr;
+        h_perm_cap = 0;
+        const size_t want = n + n / 4 + 1024;
+        if (cudaMallocHost(&h_perm, want * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return 1; }
+        h_perm_cap = want;
+        return 0;
+    }
     int ensure_cand(size_t n)
     {
         if (n <= h_cand_cap) return 0;
@@ -320,13 +333,14 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_tails, &ctx->w_bonf, &ctx->w_blocksum, &ctx->w_jobs,
-                      &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_pinfo, &ctx->w_pkscr, &ctx->w_tilecount, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
+                      &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_pinfo, &ctx->w_pkscr, &ctx->w_tilecount, &ctx->w_iscand, &ctx->w_candtile, &ctx->w_candpre, &ctx->w_perm, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
                       &ctx->in_bq, &ctx->in_mq, &ctx->in_baq, &ctx->in_sq, &ctx->p_ep, &ctx->p_off, &ctx->p_cnt,
                       &ctx->p_bonf, &ctx->p_out};
     for (DevBuf *b : bufs) b->release();
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_cand) cudaFreeHost(ctx->h_cand);
+    if (ctx->h_perm) cudaFreeHost(ctx->h_perm);
     ctx->pool.reset();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -348,6 +362,14 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     }
     bad |= ctx->w_jobs.ensure(nn * NCLASS * sizeof(int));
     bad |= ctx->w_cand.ensure(nn * sizeof(Cand));
+    bad |= ctx->w_iscand.ensure(((nn + 255) / 256 + 1) * 256);
+    bad |= ctx->w_candpre.ensure(((nn + 255) / 256 + 1) * sizeof(long long));
+    bad |= ctx->w_perm.ensure(nn * sizeof(int));
+    {
+        const void *before = ctx->w_candtile.p;
+        bad |= ctx->w_candtile.ensure(((nn + 255) / 256 + 1) * sizeof(unsigned int));
+        if (!bad && ctx->w_candtile.p != before) cudaMemset(ctx->w_candtile.p, 0, ctx->w_candtile.cap);   // the scan keeps it zero afterwards
+    }
     // packed job lists hold a quarter of the batch each (a fuller list spills into the per-column lists); the pool
     // of scratch rows (step parameters of the packed columns, 16 B per read) holds 64 reads per column of the
     // batch, between 16 MB and 1 GB — when it runs out the remaining columns take the per-column kernels
@@ -369,6 +391,10 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     w.tilecount = (unsigned int *)ctx->w_tilecount.p;
     w.jobs = (int *)ctx->w_jobs.p;
     w.cand = (Cand *)ctx->w_cand.p;
+    w.is_cand = (unsigned char *)ctx->w_iscand.p;
+    w.candtile = (unsigned int *)ctx->w_candtile.p;
+    w.candpre = (long long *)ctx->w_candpre.p;
+    w.cand_perm = (int *)ctx->w_perm.p;
     w.counters = (Counters *)ctx->w_counters.p;
     static const bool no_packed = getenv("LFB200_NO_PACKED") != nullptr;      // A/B timing of k_packed against k_mid / k_heavy<R>
     w.pjobs = no_packed ? nullptr : (int *)ctx->w_pjobs.p;
@@ -411,6 +437,20 @@ static long double expl_clamped(double t, bool pre_flag)
     return p;
 }
 
+// PROB_TO_PHREDQUAL(p) = (int)(-10 * log10l(p)) (utils.h:45) for p = expl(t).  Only the integer part is used, and
+// -10 t / ln 10 in double is within |q| * 5e-16 of the long double expression (expl and log10l are each good to
+// ~1e-19 relative), so whenever its fractional part is further than 1e-7 from an integer the truncation is decided
+// and log10l — a third of the finishing time — is not needed.  Sentinels and near-integer values take the literal path.
+static int phredqual_of(long double p, double t)
+{
+    if (p != LDBL_MIN && p != LDBL_MAX && t < 0.0 && t > -11000.0) {
+        const double q = t * -4.3429448190325182765;       // -10 / ln 10
+        const double f = q - floor(q);
+        if (f > 1e-7 && f < 1.0 - 1e-7) return (int)q;
+    }
+    return (int)(-10.0 * log10l(p));
+}
+
 static void finish_site(const Cand &cd, double sig, lfb200_site_t &s)
 {
     s.col = cd.col;
@@ -443,7 +483,7 @@ static void finish_site(const Cand &cd, double sig, lfb200_site_t &s)
         s.status[i] = (p == LDBL_MAX) ? LFB200_ST_LDBLMAX : (p == LDBL_MIN) ? LFB200_ST_LDBLMIN : LFB200_ST_VALUE;
         if (p * (double)cd.bonf < sig) {                 // lofreq_call.c:832
             s.called[i] = 1;
-            s.qual[i] = (int)(-10.0 * log10l(p));        // PROB_TO_PHREDQUAL, lofreq_call.c:863
+            s.qual[i] = phredqual_of(p, t);              // PROB_TO_PHREDQUAL, lofreq_call.c:863
         }
     }
 }
@@ -581,37 +621,21 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
     if (dbg) t1 = now();
     if (n_cand > max_sites) return fail("%lld sites but room for %lld", n_cand, max_sites);
     if (ctx->ensure_cand((size_t)n_cand)) return fail("out of pinned host memory");
+    if (ctx->ensure_perm((size_t)n_cand)) return fail("out of pinned host memory");
     if (n_cand) {
         CU(cudaMemcpyAsync(ctx->h_cand, ctx->ws.cand, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_perm, ctx->ws.cand_perm, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     if (dbg) t2 = now();
     const Cand *cands = ctx->h_cand;
+    const int *perm = ctx->h_perm;                 // column order, computed on the device (k_rank_cands)
     for (long long i = 0; i < n_cand; ++i)
         if (cands[i].flags & CF_RANGE) return fail("column %lld: tail outside the representable range", cands[i].col);
-    // long double finishing, independent per site; then emit in column order (device order is arbitrary)
+    // long double finishing, independent per site, straight into its place in column order
     const double sig = (double)conf->sig;
-    ctx->h_order.resize((size_t)n_cand);
-    ctx->h_order2.resize((size_t)n_cand);
-    // column order: LSD radix sort of (col, index) pairs, 3 passes of 11 bits (n_cols < 2^31)
-    auto sort_by_column = [&] {
-        for (long long i = 0; i < n_cand; ++i) ctx->h_order[(size_t)i] = std::make_pair(cands[i].col, (unsigned)i);
-        std::pair<long long, unsigned> *a = ctx->h_order.data(), *b2 = ctx->h_order2.data();
-        for (int pass = 0; pass < 3; ++pass) {
-            unsigned hist[2049] = {0};
-            const int sh = 11 * pass;
-            for (long long i = 0; i < n_cand; ++i) ++hist[((a[i].first >> sh) & 2047) + 1];
-            for (int d = 0; d < 2048; ++d) hist[d + 1] += hist[d];
-            for (long long i = 0; i < n_cand; ++i) b2[hist[(a[i].first >> sh) & 2047]++] = a[i];
-            std::swap(a, b2);
-        }
-        if (a != ctx->h_order.data()) ctx->h_order.swap(ctx->h_order2);
-    };
     if (n_cand < 1024) {
-        sort_by_column();
-        const std::pair<long long, unsigned> *order = ctx->h_order.data();
-        for (long long i = 0; i < n_cand; ++i) finish_site(cands[order[i].second], sig, sites[i]);
-        if (dbg) t3 = now();
+        for (long long i = 0; i < n_cand; ++i) finish_site(cands[perm[i]], sig, sites[i]);
     } else {
         if (!ctx->pool) {
             // share the host cores with the other shards of this node (torchrun exports LOCAL_WORLD_SIZE)
@@ -621,33 +645,17 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
             const unsigned want = std::max(3u, std::min(hw / procs, 16u));
             ctx->pool.reset(new WorkerPool(want - 1));
         }
-        // the workers finish the sites in device order while this thread sorts the keys; then all of them move the
-        // finished sites to their places
-        ctx->h_sites.resize((size_t)n_cand);
-        lfb200_site_t *tmp = ctx->h_sites.data();
         auto finish_part = [&](unsigned part, unsigned parts) {
-            if (part == parts - 1) {                   // the calling thread
-                sort_by_column();
-                return;
-            }
-            const unsigned workers = parts - 1;
-            const long long per = (n_cand + workers - 1) / workers;
-            const long long lo = (long long)part * per, hi = std::min<long long>(n_cand, lo + per);
-            for (long long i = lo; i < hi; ++i) finish_site(cands[i], sig, tmp[i]);
-        };
-        ctx->pool->run(finish_part);
-        if (dbg) t3 = now();
-        const std::pair<long long, unsigned> *order = ctx->h_order.data();
-        auto place_part = [&](unsigned part, unsigned parts) {
             const long long per = (n_cand + parts - 1) / parts;
             const long long lo = (long long)part * per, hi = std::min<long long>(n_cand, lo + per);
-            for (long long i = lo; i < hi; ++i) sites[i] = tmp[order[i].second];
+            for (long long i = lo; i < hi; ++i) finish_site(cands[perm[i]], sig, sites[i]);
         };
-        ctx->pool->run(place_part);
+        ctx->pool->run(finish_part);
     }
+    if (dbg) t3 = now();
     if (dbg)
-        fprintf(stderr, "[lfb200] sites: wait+counters %.0f us, cand D2H %.0f us, sort|finish %.0f us, place %.0f us (%lld sites)\n",
-                t1 - t0, t2 - t1, t3 - t2, now() - t3, n_cand);
+        fprintf(stderr, "[lfb200] sites: wait+counters %.0f us, cand D2H %.0f us, finish %.0f us (%lld sites)\n",
+                t1 - t0, t2 - t1, t3 - t2, n_cand);
     errno = 0;
     feclearexcept(FE_ALL_EXCEPT);
     sm.n_sites = n_cand;

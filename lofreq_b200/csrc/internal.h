@@ -100,6 +100,10 @@ struct Workspace {
     unsigned int *tilecount;       // [ceil(n/256)]: tested columns per tile, accumulated by k_screen, zeroed again by the scan
     int *jobs;                     // [NCLASS][n]
     Cand *cand;                    // [n]
+    unsigned char *is_cand;        // [n rounded up to 256]: column emitted a candidate
+    unsigned int *candtile;        // [ceil(n/256)]: candidates per tile, zeroed again by the scan
+    long long *candpre;            // [ceil(n/256)]: candidates before each tile
+    int *cand_perm;                // [n]: cand_perm[rank in column order] = index into cand
     Counters *counters;
     int *pjobs;                    // [PK_NL][pcap]
     long long pcap;

@@ -454,6 +454,7 @@ __device__ void packed_task(const DevConf &cf, const DevBatch &b, const Workspac
             cd.flags = 0;
             cd.pad = 0;
             ws.cand[atomicAdd(&ws.counters->n_cand, 1u)] = cd;
+            mark_cand(ws, c);
         }
     }
     __syncwarp();

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevCo
 constexpr int PRUNE_CAP = 32;       // reads the lane-per-column prune of k_finalize looks at before it hands the column on
 
 // exclusive scan of the per-tile counts k_screen accumulated, one block; the counts are zeroed for the next batch
-__global__ void __launch_bounds__(1024) k_scan_blocks(unsigned int *tilecount, long long *blocksum, int nb, Counters *ctr)
+__global__ void __launch_bounds__(1024) k_scan_blocks(unsigned int *tilecount, long long *blocksum, int nb, unsigned long long *total)
 {
     __shared__ long long s_warp[32];
     __shared__ long long s_carry;
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(unsigned int *tilecount, l
         if (threadIdx.x == 1023) s_carry = incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) ctr->n_tested = (unsigned long long)s_carry;
+    if (threadIdx.x == 0 && total) *total = (unsigned long long)s_carry;
 }
 
 // The reference's early exit (snpcaller.c:916-958), one lane per column: walk the first `cap` reads until
@@ -1145,6 +1145,7 @@ __global__ void __launch_bounds__(128) k_mid(const __grid_constant__ DevConf cf,
             cd.flags = 0;
             cd.pad = 0;
             ws.cand[atomicAdd(&ws.counters->n_cand, 1u)] = cd;
+            mark_cand(ws, c);
         }
     }
 }
@@ -1196,6 +1197,7 @@ __global__ void __launch_bounds__(128) k_heavy(const __grid_constant__ DevConf c
             cd.pad = 0;
             const unsigned slot = atomicAdd(&ws.counters->n_cand, 1u);
             ws.cand[slot] = cd;
+            mark_cand(ws, c);
         }
     }
 }
@@ -1504,6 +1506,7 @@ __global__ void __launch_bounds__(XL_T, 1) k_heavy_xl(const __grid_constant__ De
             cd.pad = 0;
             const unsigned slot = atomicAdd(&ws.counters->n_cand, 1u);
             ws.cand[slot] = cd;
+            mark_cand(ws, c);
         }
     }
 }
@@ -1630,8 +1633,10 @@ void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st)
 {
     if (b.n_cols <= 0) return;
     const int nb = (int)((b.n_cols + FIN_BLOCK - 1) / FIN_BLOCK);
-    k_scan_blocks<<<1, 1024, 0, st>>>(ws.tilecount, ws.blocksum, nb, ws.counters);
+    k_scan_blocks<<<1, 1024, 0, st>>>(ws.tilecount, ws.blocksum, nb, &ws.counters->n_tested);
 }
+
+__global__ void k_rank_cands(const Workspace ws);
 
 void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
                  cudaEvent_t after_finalize, const long long *bonf_start_dev)
@@ -1640,6 +1645,7 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
     const int nb = (int)((b.n_cols + FIN_BLOCK - 1) / FIN_BLOCK);
     // n_tested (first 8 bytes) belongs to the scan; everything after it is per-test state
     cudaMemsetAsync(reinterpret_cast<char *>(ws.counters) + 8, 0, sizeof(Counters) - 8, st);
+    cudaMemsetAsync(ws.is_cand, 0, (size_t)nb * FIN_BLOCK, st);
     k_finalize<<<nb, FIN_BLOCK, 0, st>>>(cf, b, lut, ws, bonf_start_dev);
     k_prune2<<<sm_count() * 2, 128, 0, st>>>(cf, b, lut, ws);
     if (after_finalize) cudaEventRecord(after_finalize, st);
@@ -1680,6 +1686,38 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
     for (int i = 0; i < NSIDE; ++i) {
         cudaEventRecord(ev_join[i], side[i]);
         cudaStreamWaitEvent(st, ev_join[i], 0);
+    }
+    // the sites in column order (see k_rank_cands)
+    k_scan_blocks<<<1, 1024, 0, st>>>(ws.candtile, ws.candpre, nb, nullptr);
+    k_rank_cands<<<sm_count(), 256, 0, st>>>(ws);
+}
+
+// Column order of the sites on the device: every kernel that emits a candidate marks its column (mark_cand), a prefix
+// sum over the marks per tile of 256 columns gives each candidate its rank, and perm[rank] = index into ws.cand — the
+// host finishes the sites straight into their final places instead of sorting them (a column yields one candidate).
+__global__ void __launch_bounds__(256) k_rank_cands(const Workspace ws)
+{
+    const unsigned n_cand = ws.counters->n_cand;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += gridDim.x * blockDim.x) {
+        const long long c = ws.cand[i].col;
+        const long long t0 = c & ~255ll;
+        int before = 0;
+        for (long long a = t0; a < c; a += 16) {              // marks of the tile before column c, 16 at a time
+            uint4 v = *reinterpret_cast<const uint4 *>(ws.is_cand + a);
+            const int keep = (int)(c - a);                     // bytes of this chunk that lie before c
+            if (keep < 16) {
+                unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int kb = keep - 4 * q;
+                    if (kb <= 0) w[q] = 0;
+                    else if (kb < 4) w[q] &= (1u << (8 * kb)) - 1u;
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            before += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        }
+        ws.cand_perm[ws.candpre[c >> 8] + before] = (int)i;
     }
 }
 
