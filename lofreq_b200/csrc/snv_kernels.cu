@@ -6,18 +6,19 @@
 //   snpcaller -> poissbin -> pruned_calc_prob_dist (snpcaller.c:830-1204)
 //                                           Poisson-binomial DP in log space, tail p-value per allele
 //
-// What runs here:
-//   k_screen    one warp per column, ONE streaming pass over the quality planes with 128-bit loads:
-//               gates, alt counts, and — when the largest alt count K <= 8, i.e. almost every column —
-//               the exact distribution truncated at K, evaluated in linear space on 32 disjoint read
-//               subsets and merged by truncated convolution over warp shuffles.  HBM-bound.
-//   k_block_counts / k_scan_blocks / k_finalize
-//               running Bonferroni factor = prefix sum over the tested flags (lofreq_call.c:794-800),
-//               significance screen, compaction of the surviving columns ("sites"), job lists.
-//   k_heavy<R>  one warp per remaining column (K > 8): the O(depth*K) recurrence in fp64, K cells tiled
-//               over lanes x R registers, one shuffle per read for the lane boundary.  Odds form
+// What runs here (DESIGN.md has the whole picture; packed.cu, poissbin.cu, mailbox.cu, binom.cu hold the rest):
+//   k_screen    gates and alt counts: only the reads showing a non-reference base are looked at; a warp takes 32
+//               columns (lane per column for few alt reads, whole warp otherwise); tested columns per tile of 256.
+//   k_scan_blocks / k_finalize / k_prune2
+//               running Bonferroni factor = prefix sum over the tested flags (lofreq_call.c:794-800); the reference's
+//               early exit, one lane per column, in two stages; job lists for everything that survives.
+//   k_mid       K <= 8 survivors: the exact distribution truncated at K, evaluated in linear space on 32 disjoint read
+//               subsets and merged by truncated convolution over warp shuffles.
+//   k_heavy<R>  one warp per column (K > 256, very deep columns, fallback list): the O(depth*K) recurrence in fp64,
+//               K cells tiled over lanes x R registers, one shuffle per read for the lane boundary.  Odds form
 //               E[k] += E[k-1]*o (one DFMA per cell), exact power-of-two rescaling, exponential tilting
-//               when the tail is further out than fp64 can hold.  fp64-pipe-bound.
+//               when the tail is further out than fp64 can hold.  k_heavy_xl: one CTA per column for K > 2048.
+//   k_rank_cands  the sites in column order (a permutation), so that the host needs no sort.
 //   k_prob_jobs the same routines fed with ready-made double error probabilities (snpcaller() symbol).
 //
 // All sums are over positive terms, so the relative error of a tail is O(depth * 2^-53); the reference's
