@@ -144,7 +144,7 @@ struct lfb200_ctx {
     cudaStream_t stream = nullptr;       // used by the host entry points
     Lut *d_lut = nullptr;
     // workspace of the current batch
-    DevBuf w_cnt6, w_tested, w_tails, w_bonf, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_pinfo, w_pkscr, w_tilecount, w_iscand, w_candtile, w_candpre, w_perm;
+    DevBuf w_cnt6, w_tested, w_bonf, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_pinfo, w_pkscr, w_tilecount, w_iscand, w_candtile, w_candpre, w_perm;
     Workspace ws{};
     // device copies of host batches (host entry point)
     DevBuf in_off, in_cnt, in_ref, in_cov, in_nb, in_bq, in_mq, in_baq, in_sq;
@@ -154,8 +154,6 @@ struct lfb200_ctx {
     Counters *h_counters = nullptr;
     Cand *h_cand = nullptr;              // pinned
     size_t h_cand_cap = 0;
-    std::vector<lfb200_site_t> h_sites;  // finished in device order, then emitted sorted by column
-    std::vector<std::pair<long long, unsigned>> h_order, h_order2;
     std::unique_ptr<WorkerPool> pool;
     size_t scr_want = 0;                 // entries of the packed scratch pool the last batch would have needed
     int *h_perm = nullptr;               // pinned
@@ -332,7 +330,7 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_tails, &ctx->w_bonf, &ctx->w_blocksum, &ctx->w_jobs,
+    DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_bonf, &ctx->w_blocksum, &ctx->w_jobs,
                       &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_pinfo, &ctx->w_pkscr, &ctx->w_tilecount, &ctx->w_iscand, &ctx->w_candtile, &ctx->w_candpre, &ctx->w_perm, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
                       &ctx->in_bq, &ctx->in_mq, &ctx->in_baq, &ctx->in_sq, &ctx->p_ep, &ctx->p_off, &ctx->p_cnt,
                       &ctx->p_bonf, &ctx->p_out};
@@ -352,7 +350,6 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     int bad = 0;
     bad |= ctx->w_cnt6.ensure(nn * 6 * sizeof(int));
     bad |= ctx->w_tested.ensure(nn + 1024);
-    bad |= ctx->w_tails.ensure(nn * 4 * sizeof(double));
     bad |= ctx->w_bonf.ensure(nn * sizeof(long long));
     bad |= ctx->w_blocksum.ensure(((nn + 255) / 256 + 1) * sizeof(long long));
     {
@@ -385,7 +382,6 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     w.cap_cols = n;
     w.cnt6 = (int *)ctx->w_cnt6.p;
     w.tested = (unsigned char *)ctx->w_tested.p;
-    w.tails = (double *)ctx->w_tails.p;
     w.bonf_used = (long long *)ctx->w_bonf.p;
     w.blocksum = (long long *)ctx->w_blocksum.p;
     w.tilecount = (unsigned int *)ctx->w_tilecount.p;

@@ -94,7 +94,6 @@ struct Workspace {
     long long cap_cols;
     int *cnt6;                     // [n][6]: alt_counts[3], alt_raw_counts[3]
     unsigned char *tested;         // [n]
-    double *tails;                 // [n][4]: linear P(X>=c_i) for the three alleles, min(P[K-1], P(>=K))
     long long *bonf_used;          // [n]
     long long *blocksum;           // [ceil(n/256)]: tested columns before each tile of 256 columns
     unsigned int *tilecount;       // [ceil(n/256)]: tested columns per tile, accumulated by k_screen, zeroed again by the scan
