@@ -159,12 +159,19 @@ int lfb200_test_device_from(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *st
  * shard in device memory (lofreq_call.c:794-800 continued across shards) */
 int lfb200_bonf_start_device(void *stream, const long long *tested_counts_dev, int rank, long long bonf_subst,
                              long long *start_dev);
-/* The exchange done by the library itself over NCCL (dlopen'ed), directly on the kernels' stream:
- *   comm_unique_id : rank 0 creates the 128-byte id, the caller broadcasts it to all ranks by any means
- *   comm_init      : one communicator per context (collective: every rank calls it)
- *   comm_exchange  : after screen — all_gather of {tested columns of this batch, sites_prev_batch} and the
- *                    starting factor of this shard left in device memory (*bonf_start_dev, for test_device_from)
- *   comm_gathered  : host copy of what the last exchange gathered (synchronises the stream) */
+/* The exchange between region shards done by the library itself, directly on the kernels' stream (one process per
+ * GPU, all on one node):
+ *   comm_unique_id : rank 0 creates the 128-byte id (an NCCL unique id; libnccl is dlopen'ed), the caller broadcasts
+ *                    it to all ranks by any means
+ *   comm_init      : one communicator per context (collective: every rank calls it); also maps the count mailbox, a
+ *                    POSIX shared-memory segment named after the id and registered with CUDA
+ *   comm_exchange  : after screen — one warp posts {tested columns of this batch, sites_prev_batch} in the mailbox and
+ *                    waits for the shards BEFORE this one (a shard continues their running Bonferroni factor; rank 0
+ *                    never waits); the starting factor of this shard is left in device memory (*bonf_start_dev, for
+ *                    test_device_from).  No collective, no host round trip.  LFB200_EXCHANGE_NCCL=1 in the
+ *                    environment selects one ncclAllGather per batch instead.
+ *   comm_gathered  : the counts of every shard from the last exchange: one ncclAllGather of 2 x int64 per rank (the
+ *                    final gather of the per-region counts) and a host copy; synchronises the stream */
 int lfb200_comm_unique_id(unsigned char id[128]);
 int lfb200_comm_init(lfb200_ctx *ctx, int world, int rank, const unsigned char id[128]);
 int lfb200_comm_exchange(lfb200_ctx *ctx, void *stream, long long bonf_subst, long long sites_prev_batch,

@@ -6,9 +6,10 @@ region restarts its running Bonferroni factor.  Here the shards exchange their t
 between the screen and the test phase, so every shard continues the running factor exactly where
 the previous shard ends and the multi-GPU result equals the single-process `lofreq call`.
 
-The only data-path communication is 1 x int64 per rank (all_gather), twice: tested columns, then
-site counts.  Works with the nccl backend (GPU tensors) and with gloo (CPU tensors, used by the
-CPU tests)."""
+The only data-path communication is 2 x int64 per rank and batch (tested columns, site counts).  On
+the GPUs it is the library's own exchange (ShardComm -> lfb200_comm_*: a shared-memory mailbox polled
+by one warp, NCCL for the final gather); the torch.distributed helpers below (gather_counts) work
+with the nccl backend (GPU tensors) and with gloo (CPU tensors, used by the CPU tests)."""
 
 
 def shard_range(n_cols, rank, world):
@@ -53,8 +54,8 @@ def final_counters(tested_counts, bonf_subst=1, bonf_dynamic=1, num_snv_tests=0)
 
 
 class ShardComm:
-    """The library's own NCCL exchange (include/lofreq_b200.h: lfb200_comm_*), one communicator per context.
-    torch.distributed is used once, to hand rank 0's NCCL unique id to the other ranks."""
+    """The library's own exchange (include/lofreq_b200.h: lfb200_comm_*), one communicator per context.
+    torch.distributed is used once, to hand rank 0's unique id to the other ranks."""
 
     def __init__(self, caller, device):
         import ctypes as C
