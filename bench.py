@@ -222,7 +222,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_desc(args.workload, args.cols), "cpu_path": kind_desc(kind)},
+            "config": {"workload": workload_desc(args.workload, args.cols) + " per GPU (region shard = rank*cols)",
+                       "cols_per_gpu": args.cols, "depth": DEPTH.get(args.workload), "cpu_path": kind_desc(kind)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
