@@ -628,6 +628,12 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
     const int *perm = ctx->h_perm;                 // column order, computed on the device (k_rank_cands)
     for (long long i = 0; i < n_cand; ++i)
         if (cands[i].flags & CF_RANGE) return fail("column %lld: tail outside the representable range", cands[i].col);
+    // the permutation must be one, and in strictly increasing column order (one candidate per column): anything else
+    // is an internal error and must not become an out-of-bounds read
+    for (long long i = 0; i < n_cand; ++i) {
+        if ((unsigned)perm[i] >= (unsigned)n_cand) return fail("internal error: site order (entry %lld)", i);
+        if (i && cands[perm[i]].col <= cands[perm[i - 1]].col) return fail("internal error: site order (column %lld)", cands[perm[i]].col);
+    }
     // long double finishing, independent per site, straight into its place in column order
     const double sig = (double)conf->sig;
     if (n_cand < 1024) {
