@@ -331,3 +331,91 @@ def model_binom(num_trials, num_success, pr):
             break
     ccum = math.exp(lt + math.log(tot))
     return 0, 1.0 - ccum, ccum
+
+
+# ------------------------------------------------------------------------------------------------
+# packed kernels (lofreq_b200/csrc/packed.cu): what k_pk_prep / k_packed add to the arithmetic above
+# ------------------------------------------------------------------------------------------------
+def newton_tilt_fp32(p, q, K):
+    """k_pk_prep's root finder: the sums that steer it are taken in fp32 (the tolerance is |e| sqrt(d) < 0.5),
+    o = p/q per read, ln s capped at 60; one accepted step ends the iteration."""
+    n = int(np.sum(np.ones_like(p)))
+    kt = min(float(K), n - 0.5)
+    lam = float(np.sum(p))
+    s0 = kt * max(n - lam, 1e-300) / (max(lam, 1e-300) * max(n - kt, 0.5))
+    lo, hi = 0.0, 60.0
+    ls = min(math.log(max(s0, 1.0)), hi)
+    o32 = (p / q).astype(np.float32)
+    for _ in range(40):
+        a = o32 * np.float32(math.exp(ls))
+        w = a / (np.float32(1.0) + a)
+        g = float(np.sum(w, dtype=np.float64)) - kt
+        d = float(np.sum(w * (np.float32(1.0) - w), dtype=np.float64))
+        step = g / d if d > 0 else 0.0
+        if d > 0 and abs(step) * math.sqrt(max(d, 1.0)) < 0.5:
+            return min(max(ls - step, 0.0), 60.0)
+        if g > 0:
+            hi = min(hi, ls)
+        else:
+            lo = max(lo, ls)
+        nl = ls - step if d > 0 else 0.5 * (lo + hi)
+        if not (lo < nl < hi):
+            nl = 0.5 * (lo + hi)
+        ls = nl
+    return ls
+
+
+def packed_column(ep, counts, bonf, sig, chunk=32):
+    """One column the way k_pk_prep + k_packed evaluate it (8 < K <= 256).  Returns
+    (dead, lnp[3], ln_floor, blocks_run): dead = the conservative early exit fired, i.e. the column is insignificant."""
+    counts = [int(c) for c in counts]
+    K = max(counts)
+    p, q = guards(ep)
+    n = len(p)
+    lam = float(np.sum(p))
+    sum_lq = float(np.sum(np.log(q)))
+    ln_s = newton_tilt_fp32(p, q, K) if chernoff_exponent(K, lam) > 300.0 else 0.0
+    s = math.exp(ln_s) if ln_s != 0.0 else 1.0
+    rq = 1.0 / q
+    o = p * rq * s
+    E = np.zeros(K); E[0] = 1.0
+    T, e2 = 0.0, 0
+    thr_ln = math.log(sig * (1.0 + 1e-9) / float(bonf)) - sum_lq + K * ln_s
+    dead, blocks = False, 0
+    for c0 in range(0, n, chunk):
+        for j in range(c0, min(c0 + chunk, n)):
+            top = E[K - 1]
+            E[1:] = E[1:] + E[:-1] * o[j]
+            T = T * rq[j] + top * o[j]
+        blocks += 1
+        m = max(E.max(), T)
+        _, ex = math.frexp(m)
+        ex -= 1                                   # the kernel takes the exponent field: m in [2^ex, 2^(ex+1))
+        if ex > 200 or ex < -200:
+            E = np.ldexp(E, -ex); T = math.ldexp(T, -ex); e2 += ex
+        # early exit on the exponent of T alone: floor(log2 T) + e2 is a lower bound of log2 of the scaled tail, and
+        # exp(sum_lq) (ALL reads) a lower bound of the product of q over the reads seen so far
+        if T > 0 and ((math.frexp(T)[1] - 1) + e2) * math.log(2.0) > thr_ln:
+            dead = True
+            break
+    if dead:
+        return True, [0.0] * 3, 0.0, blocks
+    base = e2 * math.log(2.0) + sum_lq
+    lnT = math.log(T) + base - K * ln_s
+    lnKm1 = math.log(E[K - 1]) + base - (K - 1) * ln_s
+    lnp = [0.0] * 3
+    invs = math.exp(-ln_s)
+    for i, c in enumerate(counts):
+        if c == 0:
+            continue
+        if c == K:
+            lnp[i] = lnT
+            continue
+        # the other alleles off the same (possibly tilted) row: P(X >= c) = sum_{k >= c} E[k] s^-(k-c) + T s^-(K-c), times s^-c
+        f, acc = 1.0, 0.0
+        for k in range(c, K):
+            acc += E[k] * f
+            f *= invs
+        acc += T * math.exp(-(K - c) * ln_s)
+        lnp[i] = math.log(acc) + base - c * ln_s
+    return False, lnp, min(lnT, lnKm1), blocks

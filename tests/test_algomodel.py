@@ -67,3 +67,40 @@ def test_binom_model_reproduces_the_reference():
         if st == 0:
             assert binom_close(cum, float(z["cdf"][i])) and binom_close(ccum, float(z["sf"][i])), \
                 (i, int(z["num_trials"][i]), int(z["num_success"][i]), float(z["prob_success"][i]))
+
+
+def test_packed_model_against_port(port_oracle):
+    """the packed kernels' arithmetic (tests/algomodel.py: packed_column): fp32 Newton sums, secondary alleles read off a
+    tilted row, and the conservative early exit — which may only ever fire on columns the reference leaves at LDBL_MAX"""
+    rng = np.random.default_rng(17)
+    sig = float(np.float32(0.01))
+    fired = kept = 0
+    for it in range(70):
+        n = int(rng.integers(40, 900))
+        K = int(rng.integers(9, min(256, n) + 1))
+        hi_q = it % 2 == 0                         # high qualities: far tails, tilted rows
+        qv = rng.integers(33, 41, n) if hi_q else rng.integers(8, 30, n)
+        ep = 10.0 ** (-qv / 10.0)                  # pileup order, not sorted (the device does not sort)
+        c2 = int(rng.integers(0, min(K, n - K) + 1)) if it % 3 else 0
+        c3 = int(rng.integers(0, min(4, n - K - c2) + 1))
+        counts = [K, c2, c3]
+        rng.shuffle(counts)
+        bonf = int(rng.choice([3, 3000, 3_000_000]))
+        want = port_oracle.snpcaller(np.sort(ep), counts, bonf, sig)
+        dead, lnp, fl, blocks = M.packed_column(ep, counts, bonf, sig)
+        if dead:
+            fired += 1
+            assert np.all(want == M.LDBL_MAX), (n, counts, bonf)      # pruned columns are insignificant in the reference
+            assert blocks <= (n + 31) // 32
+            continue
+        kept += 1
+        pv, st = M.host_finish(counts, bonf, sig, False, lnp, fl)
+        wst = np.zeros(3, np.uint8)
+        wst[want == M.LDBL_MAX] = 1
+        wst[want == M.LDBL_MIN] = 2
+        assert np.array_equal(st, wst), (n, counts, bonf, lnp)
+        for j in range(3):
+            if st[j] == 0:
+                a, b = float(np.log(pv[j])), float(np.log(want[j]))
+                assert abs(a - b) <= 1e-10 * max(abs(b), 1.0), (n, counts, j, a, b)
+    assert fired >= 5 and kept >= 20, (fired, kept)
