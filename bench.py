@@ -267,8 +267,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     db = caller.device_batch(t)
     max_sites = n
-    sites_bufs = [(capi.Site * max_sites)() for _ in range(NC)]
-    sites_buf = sites_bufs[0]
+    sites_buf = (capi.Site * max_sites)()          # e2e leg (lfb200_call_columns copies the sites out)
+    # `value` leg: the sites stay in each context's pinned buffer (lfb200_sites_buffer), where k_emit_sites wrote them in
+    # column order with status / called / QUAL decided on the device; the x87 long double images of the p-values are
+    # not requested (lfb200_set_site_pvalues 0) — a caller that writes VCF needs QUAL, not the long double
+    for c_ in callers:
+        capi.check(lib.lfb200_set_site_pvalues(c_._ctx, 0))
     sms = [capi.Summary() for _ in range(NC)]
     sm = sms[0]
     confs = [None] * NC
@@ -300,7 +304,7 @@ def run_ours(args):
 
     def finish_begin(i):
         """D2H of the sites of context i + host finishing, on the context's own finisher thread"""
-        capi.check(lib.lfb200_sites_begin(callers[i]._ctx, C.byref(confs[i]), sts[i], sites_bufs[i], max_sites))
+        capi.check(lib.lfb200_sites_begin(callers[i]._ctx, C.byref(confs[i]), sts[i], None, 0))
 
     def finish_end(i):
         capi.check(lib.lfb200_sites_end(callers[i]._ctx, C.byref(sms[i])))
@@ -373,6 +377,13 @@ def run_ours(args):
     if world > 1:
         # the last batch's site counts: one more (tiny) gather outside the timed region
         final_sites = shard.gather_counts(int(n_sites), device=dev)
+        # every run checks the exchange it just timed: the factor this shard's last batch started from must be the
+        # exclusive prefix of the tested counts of all shards (lofreq_call.c:794-800 continued across shards)
+        li = (args.steps - 1) % NC
+        tested_all, _ = exchanges[li].gathered(sts[li])
+        assert tested_all[rank] == int(n_tested), ("tested count", tested_all, int(n_tested))
+        assert int(sm.bonf_subst_final) == 3 * sum(tested_all[: rank + 1]), ("running Bonferroni across shards", rank,
+                                                                            int(sm.bonf_subst_final), tested_all)
     # CUDA events on the launching stream bracket the K steps (the closing event is recorded after the last
     # batch's host finishing has returned, so that host work is inside the region too); max over ranks
     el = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -393,6 +404,7 @@ def run_ours(args):
         capi.check(lib.lfb200_get_profile(callers[0]._ctx, row))
         prof[k] = list(row)
     capi.check(lib.lfb200_set_profiling(callers[0]._ctx, 0))
+    capi.check(lib.lfb200_set_site_pvalues(caller._ctx, 1))     # the e2e leg runs the host entry point with its defaults
 
     # ---- e2e: host buffers through lfb200_call_columns ----------------------------------------
     total = t["total_bytes"]

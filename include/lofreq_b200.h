@@ -36,6 +36,13 @@ extern "C" {
 #define LFB200_ST_VALUE   0           /* ln p / pvalue hold a computed value              */
 #define LFB200_ST_LDBLMAX 1           /* reference returns LDBL_MAX: not computed / pruned / clamped high */
 #define LFB200_ST_LDBLMIN 2           /* reference returns LDBL_MIN: clamped low (snpcaller.c:1177)      */
+#define LFB200_ST_UNSUPPORTED 3       /* not computed: the allele's column has an alt count above what this build's kernels take;
+                                       * the site is reported so that the caller sees it (summary.n_unsupported counts them) */
+
+/* lfb200_site_t.flags */
+#define LFB200_SITE_HOST_FINISHED 1   /* a comparison of the decision fell inside its guard band on the device: the host
+                                       * repeated the reference's long double sequence for this site */
+#define LFB200_SITE_UNSUPPORTED   2
 
 /* The fields of varcall_conf_t (snpcaller.h:38-63) this path reads, same names
  * and meaning; defaults = init_varcall_conf (snpcaller.c:626-651) via
@@ -77,20 +84,31 @@ typedef struct {
 } lfb200_batch_t;
 
 /* One column the device could not rule out (a candidate variant site), after
- * host finishing.  pvalue[] are what snpcaller() would have written to
- * snp_pvalues[] (snpcaller.h:97-102) including the LDBL_MAX / LDBL_MIN
- * sentinels; called[] is the test of lofreq_call.c:832; qual[] is
- * PROB_TO_PHREDQUAL(pvalue) where called, else -1 (lofreq_call.c:863). */
+ * the decision.  status[] / called[] / qual[] are decided on the device from the
+ * natural-log p-values (the comparisons of snpcaller.c:1047-1059, 1155, 1166-1196,
+ * lofreq_call.c:832 and the truncation of PROB_TO_PHREDQUAL, utils.h:45, are
+ * comparisons of ln p with constants; a site with one of them inside its guard
+ * band is re-decided by the host in long double, flags & LFB200_SITE_HOST_FINISHED).
+ * pvalue[] are what snpcaller() would have written to snp_pvalues[]
+ * (snpcaller.h:97-102) including the LDBL_MAX / LDBL_MIN sentinels — x87 long
+ * double images computed by the host, for callers that ask for them
+ * (lfb200_set_site_pvalues, default on; zero when off); called[] is the test of
+ * lofreq_call.c:832; qual[] is PROB_TO_PHREDQUAL(pvalue) where called, else -1
+ * (lofreq_call.c:863). */
 typedef struct {
     long long col;                     /* index into the batch */
     long long bonf;                    /* Bonferroni factor handed to the test */
     double lnp[LFB200_NUM_NONCONS];    /* natural log of the tail probability from the device */
+    double ln_floor;                   /* min(ln P(X = K-1), ln P(X >= K)), K = largest alt count: input of the
+                                        * FE-underflow clamp rule of probvec_tailsum (snpcaller.c:1169-1188) */
     long double pvalue[LFB200_NUM_NONCONS];
     int alt_count[LFB200_NUM_NONCONS]; /* filtered counts, A,C,G,T-minus-ref order (snpcaller.c:489) */
     int alt_raw_count[LFB200_NUM_NONCONS];
     int qual[LFB200_NUM_NONCONS];
     unsigned char status[LFB200_NUM_NONCONS];
     unsigned char called[LFB200_NUM_NONCONS];
+    unsigned char flags;               /* LFB200_SITE_* */
+    unsigned char reserved;
 } lfb200_site_t;
 
 /* Optional dense per-column outputs of the host entry point; any pointer may
@@ -110,6 +128,7 @@ typedef struct {
 typedef struct {
     long long n_cols, n_tested, n_sites, n_heavy;   /* n_heavy: columns that needed the O(depth*K) kernel */
     long long bonf_subst_final, num_snv_tests;
+    long long n_unsupported;           /* columns reported with LFB200_ST_UNSUPPORTED (alt count above 16384) */
 } lfb200_summary_t;
 
 typedef struct lfb200_ctx lfb200_ctx;
@@ -141,12 +160,19 @@ int lfb200_set_host_planes(lfb200_ctx *ctx, int mode);
  * shard starts where the previous shard's ends; lofreq2_call_pparallel.py
  * instead restarts it per region and sums the counts at the end, :131-161).
  * stream is a cudaStream_t (or NULL).
- *   screen : gates, alt counts, tested flags, exact tails for columns with
- *            max alt count <= 8 — one streaming pass over the quality planes
+ *   screen : gates (lofreq_call.c:747,754,892,931), alt counts and raw counts
+ *            from the reads showing a non-reference base, tested flags and the
+ *            number of tested columns per tile
  *   ntested: number of tested columns found by screen (synchronises)
- *   test   : running Bonferroni from conf->bonf_subst, significance screen,
- *            O(depth*K) kernel for the remaining columns, site compaction
- *   sites  : copy the sites back and finish them on the host (synchronises) */
+ *   test   : running Bonferroni from conf->bonf_subst (or from device memory),
+ *            the reference's early exit lane-per-column, the O(depth*K) kernels for
+ *            the columns it cannot rule out, then the decision (status / called /
+ *            QUAL) per site on the device and the sites in column order into
+ *            pinned host memory.  Nothing of this needs the host.
+ *   sites  : wait for the test, re-decide the few guard-band sites in long
+ *            double, fill the long double p-values when asked for (synchronises)
+ * One batch per context at a time: screen fails while a lfb200_sites_begin
+ * request is pending on the same context. */
 int lfb200_screen_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, const lfb200_batch_t *dev_batch, void *stream);
 int lfb200_ntested_device(lfb200_ctx *ctx, void *stream, long long *n_tested);
 int lfb200_test_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *stream);
@@ -179,11 +205,25 @@ int lfb200_comm_exchange(lfb200_ctx *ctx, void *stream, long long bonf_subst, lo
 int lfb200_comm_gathered(lfb200_ctx *ctx, void *stream, long long *tested_all, long long *sites_prev_all);
 int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites,
                         long long max_sites, lfb200_summary_t *summary);
-/* lfb200_sites_device split in two: begin hands the work (wait for the stream, D2H of the sites, long double
- * finishing) to a thread owned by the context and returns at once; end waits for it.  conf, sites must stay valid
- * in between; one request per context at a time.  Lets the caller launch the next batch meanwhile. */
+/* The same without a copy: *sites points at the context's own pinned buffer (summary->n_sites entries, column
+ * order), valid until the next lfb200_test_device* on this context. */
+int lfb200_sites_view(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, const lfb200_site_t **sites,
+                      lfb200_summary_t *summary);
+/* lfb200_sites_device split in two: begin registers the request and returns at once (with the long double p-values
+ * switched on they are computed by a thread owned by the context meanwhile); end waits for the test and hands the
+ * sites over.  conf, sites must stay valid in between; one request per context at a time, and the NEXT batch must go
+ * to another context until lfb200_sites_end has returned (lfb200_screen_device refuses otherwise: the request reads
+ * this context's workspace). */
 int lfb200_sites_begin(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites, long long max_sites);
 int lfb200_sites_end(lfb200_ctx *ctx, lfb200_summary_t *summary);
+/* sites == NULL in lfb200_sites_device / lfb200_sites_begin: nothing is copied; the sites of the batch are read in
+ * place from the context's pinned buffer (summary->n_sites entries, valid until the next test on this context) */
+int lfb200_sites_buffer(lfb200_ctx *ctx, const lfb200_site_t **sites);
+/* lfb200_site_t.pvalue[] (x87 long double images of the p-values, the only per-site work left on the host):
+ * on = 1 (default) fills them for every site; on = 0 leaves them zero — status / called / qual / lnp are complete
+ * either way, and lfb200_site_fill_pvalues() computes them later for the sites a caller keeps. */
+int lfb200_set_site_pvalues(lfb200_ctx *ctx, int on);
+void lfb200_site_fill_pvalues(lfb200_site_t *sites, long long n);
 /* optional per-phase device timing with CUDA events on the launching stream (benchmark / roofline):
  * ms4 = { k_screen, prefix-sum kernels, k_finalize, k_heavy<*> } of the last screen + test */
 int lfb200_set_profiling(lfb200_ctx *ctx, int on);

@@ -26,9 +26,10 @@ class Batch(C.Structure):
 
 
 class Site(C.Structure):
-    _fields_ = [("col", C.c_longlong), ("bonf", C.c_longlong), ("lnp", C.c_double * 3),
+    _fields_ = [("col", C.c_longlong), ("bonf", C.c_longlong), ("lnp", C.c_double * 3), ("ln_floor", C.c_double),
                 ("pvalue", C.c_longdouble * 3), ("alt_count", C.c_int * 3), ("alt_raw_count", C.c_int * 3),
-                ("qual", C.c_int * 3), ("status", C.c_ubyte * 3), ("called", C.c_ubyte * 3)]
+                ("qual", C.c_int * 3), ("status", C.c_ubyte * 3), ("called", C.c_ubyte * 3),
+                ("flags", C.c_ubyte), ("reserved", C.c_ubyte)]
 
 
 def _site_dtype():
@@ -36,7 +37,7 @@ def _site_dtype():
     names, formats, offsets = [], [], []
     for name, np_fmt in (("col", "<i8"), ("bonf", "<i8"), ("lnp", ("<f8", (3,))), ("pvalue", (np.longdouble, (3,))),
                          ("alt_count", ("<i4", (3,))), ("alt_raw_count", ("<i4", (3,))), ("qual", ("<i4", (3,))),
-                         ("status", ("u1", (3,))), ("called", ("u1", (3,)))):
+                         ("status", ("u1", (3,))), ("called", ("u1", (3,))), ("flags", "u1"), ("ln_floor", "<f8")):
         names.append(name)
         formats.append(np_fmt)
         offsets.append(getattr(Site, name).offset)
@@ -60,7 +61,8 @@ class DenseOut(C.Structure):
 
 class Summary(C.Structure):
     _fields_ = [("n_cols", C.c_longlong), ("n_tested", C.c_longlong), ("n_sites", C.c_longlong),
-                ("n_heavy", C.c_longlong), ("bonf_subst_final", C.c_longlong), ("num_snv_tests", C.c_longlong)]
+                ("n_heavy", C.c_longlong), ("bonf_subst_final", C.c_longlong), ("num_snv_tests", C.c_longlong),
+                ("n_unsupported", C.c_longlong)]
 
 
 class PlpCol(C.Structure):
@@ -75,7 +77,7 @@ SITE_FN = C.CFUNCTYPE(None, C.POINTER(Site), C.c_longlong, C.c_char, C.c_int, C.
 # every symbol include/lofreq_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_conf", "lfb200_call_columns", "lfb200_set_host_planes",
            "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_ntested_copy_device", "lfb200_test_device_from", "lfb200_bonf_start_device", "lfb200_comm_unique_id", "lfb200_comm_init", "lfb200_comm_exchange", "lfb200_comm_gathered",
-           "lfb200_sites_device", "lfb200_sites_begin", "lfb200_sites_end",
+           "lfb200_sites_device", "lfb200_sites_view", "lfb200_sites_buffer", "lfb200_sites_begin", "lfb200_sites_end", "lfb200_set_site_pvalues", "lfb200_site_fill_pvalues",
            "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_dfma_peak", "lfb200_last_job_counts", "lfb200_copy_counts_device", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy",
            "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_poissbin", "lfb200_poissbin_batch", "lfb200_batch_errprobs", "lfb200_plp_to_errprobs", "lfb200_indel_tests", "lfb200_binom", "lfb200_binom_batch", "lfb200_synth_depths",
            "lfb200_synth_columns"]
@@ -123,6 +125,14 @@ def load():
     lib.lfb200_bonf_start_device.argtypes = [vp, vp, C.c_int, ll, vp]
     lib.lfb200_sites_device.restype = C.c_int
     lib.lfb200_sites_device.argtypes = [vp, C.POINTER(Conf), vp, C.POINTER(Site), ll, C.POINTER(Summary)]
+    lib.lfb200_sites_view.restype = C.c_int
+    lib.lfb200_sites_view.argtypes = [vp, C.POINTER(Conf), vp, C.POINTER(C.POINTER(Site)), C.POINTER(Summary)]
+    lib.lfb200_sites_buffer.restype = C.c_int
+    lib.lfb200_sites_buffer.argtypes = [vp, C.POINTER(C.POINTER(Site))]
+    lib.lfb200_set_site_pvalues.restype = C.c_int
+    lib.lfb200_set_site_pvalues.argtypes = [vp, C.c_int]
+    lib.lfb200_site_fill_pvalues.restype = None
+    lib.lfb200_site_fill_pvalues.argtypes = [C.POINTER(Site), ll]
     lib.lfb200_comm_unique_id.restype = C.c_int
     lib.lfb200_comm_unique_id.argtypes = [vp]
     lib.lfb200_comm_init.restype = C.c_int

@@ -10,6 +10,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +30,7 @@
 using namespace lfb;
 
 void lfb_comm_release(lfb200_ctx *ctx);      // shard_comm.cpp
+int lfb_comm_error(lfb200_ctx *ctx);
 
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -156,19 +158,6 @@ struct lfb200_ctx {
     size_t h_cand_cap = 0;
     std::unique_ptr<WorkerPool> pool;
     size_t scr_want = 0;                 // entries of the packed scratch pool the last batch would have needed
-    int *h_perm = nullptr;               // pinned
-    size_t h_perm_cap = 0;
-    int ensure_perm(size_t n)
-    {
-        if (n <= h_perm_cap) return 0;
-        if (h_perm) cudaFreeHost(h_perm);
-        h_perm = nullptr;
-        h_perm_cap = 0;
-        const size_t want = n + n / 4 + 1024;
-        if (cudaMallocHost(&h_perm, want * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return 1; }
-        h_perm_cap = want;
-        return 0;
-    }
     int ensure_cand(size_t n)
     {
         if (n <= h_cand_cap) return 0;
@@ -199,6 +188,28 @@ struct lfb200_ctx {
     void finisher_loop();
     void *comm_state = nullptr;          // owned by shard_comm.cpp
     int host_planes = 0;                 // lfb200_set_host_planes
+    LaunchState ls;                      // side streams / events / SM count of this context's device
+    // sites of the last test, written by k_emit_sites in column order straight into mapped pinned memory
+    lfb200_site_t *h_sites = nullptr;
+    SiteRec *d_sites = nullptr;          // device view of h_sites
+    size_t h_sites_cap = 0;
+    cudaEvent_t ev_done = nullptr;       // recorded after the sites and the counters of a test have been written
+    DevConf last_dc{};                   // configuration of the last test (to emit again after growing h_sites)
+    bool test_enqueued = false;
+    int site_pvalues = 1;                // lfb200_set_site_pvalues
+    int ensure_sites(size_t n)
+    {
+        if (n <= h_sites_cap) return 0;
+        if (h_sites) cudaFreeHost(h_sites);
+        h_sites = nullptr;
+        d_sites = nullptr;
+        h_sites_cap = 0;
+        const size_t want = n + n / 4 + 1024;
+        if (cudaHostAlloc((void **)&h_sites, want * sizeof(lfb200_site_t), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return 1; }
+        if (cudaHostGetDevicePointer((void **)&d_sites, h_sites, 0) != cudaSuccess) { cudaGetLastError(); return 1; }
+        h_sites_cap = want;
+        return 0;
+    }
     // state of the last screen
     DevBatch cur{};
     bool have_batch = false;
@@ -249,6 +260,13 @@ static double jq_cut(int min_q)
     return d;
 }
 
+static_assert(sizeof(lfb200_site_t) == sizeof(SiteRec), "k_emit_sites writes byte images of lfb200_site_t");
+static_assert(offsetof(lfb200_site_t, lnp) == offsetof(SiteRec, lnp) && offsetof(lfb200_site_t, pvalue) == offsetof(SiteRec, pvalue_bits) &&
+              offsetof(lfb200_site_t, alt_count) == offsetof(SiteRec, cnt) && offsetof(lfb200_site_t, alt_raw_count) == offsetof(SiteRec, raw) &&
+              offsetof(lfb200_site_t, qual) == offsetof(SiteRec, qual) && offsetof(lfb200_site_t, status) == offsetof(SiteRec, status) &&
+              offsetof(lfb200_site_t, called) == offsetof(SiteRec, called) && offsetof(lfb200_site_t, flags) == offsetof(SiteRec, flags) &&
+              offsetof(lfb200_site_t, ln_floor) == offsetof(SiteRec, ln_floor), "lfb200_site_t / SiteRec layout");
+
 static int make_devconf(const lfb200_conf_t *c, const lfb200_batch_t *b, DevConf &d)
 {
     memset(&d, 0, sizeof(d));
@@ -270,6 +288,8 @@ static int make_devconf(const lfb200_conf_t *c, const lfb200_batch_t *b, DevConf
     d.def_alt_jq_on = c->def_alt_jq != 0;
     d.def_alt_jq_prob = d.def_alt_jq_on ? pow(10.0, -1.0 * c->def_alt_jq / 10.0) : 0.0;
     d.sig = (double)c->sig;
+    d.ln_sig = log(d.sig);
+    d.qual_ldblmin = (int)(-10.0 * log10l(LDBL_MIN));      // PROB_TO_PHREDQUAL(LDBL_MIN), utils.h:45
     d.bonf_dynamic = c->bonf_dynamic;
     d.bonf_start = c->bonf_subst;
     return 0;
@@ -311,7 +331,11 @@ extern "C" int lfb200_create(lfb200_ctx **out, int device)
     CU(cudaMalloc(&ctx->d_lut, sizeof(Lut)));
     CU(cudaMemcpy(ctx->d_lut, &l, sizeof(Lut), cudaMemcpyHostToDevice));
     CU(cudaMallocHost(&ctx->h_counters, sizeof(Counters)));
+    memset(ctx->h_counters, 0, sizeof(Counters));
     if (ctx->w_counters.ensure(sizeof(Counters))) return fail("out of device memory");
+    // streams, events, SM count and shared-memory opt-ins belong to this context and this device
+    if (launch_state_init(ctx->ls, device)) return fail("could not create the streams / events of the context");
+    CU(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
     *out = ctx;
     return 0;
 }
@@ -338,7 +362,9 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_cand) cudaFreeHost(ctx->h_cand);
-    if (ctx->h_perm) cudaFreeHost(ctx->h_perm);
+    if (ctx->h_sites) cudaFreeHost(ctx->h_sites);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    launch_state_destroy(ctx->ls);
     ctx->pool.reset();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -451,6 +477,9 @@ static void finish_site(const Cand &cd, double sig, lfb200_site_t &s)
 {
     s.col = cd.col;
     s.bonf = cd.bonf;
+    s.flags = 0;
+    s.reserved = 0;
+    s.ln_floor = cd.ln_floor;
     int K = 0, imax = 0;
     for (int i = 0; i < 3; ++i) {
         s.lnp[i] = cd.lnp[i];
@@ -506,16 +535,22 @@ extern "C" int lfb200_screen_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, 
     if (!ctx) return fail("no context");
     if (b->n_cols < 0 || b->n_cols > 2000000000ll) return fail("n_cols %lld out of range", b->n_cols);
     if (!b->bq) return fail("the bq plane is required");
+    {
+        // the finisher of the previous batch reads this context's workspace: the next batch must wait for lfb200_sites_end
+        std::lock_guard<std::mutex> lk(ctx->fin_m);
+        if (ctx->fin_state != 0) return fail("a sites request is pending on this context: call lfb200_sites_end first (or use a second context)");
+    }
     CU(cudaSetDevice(ctx->device));
     DevConf dc;
     if (make_devconf(conf, b, dc)) return 1;
     if (ensure_workspace(ctx, b->n_cols)) return 1;
+    ctx->test_enqueued = false;
     to_devbatch(b, ctx->cur);
     ctx->have_batch = true;
     ctx->n_tested = -1;
     cudaStream_t st = (cudaStream_t)stream;
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
-    launch_screen(dc, ctx->cur, ctx->d_lut, ctx->ws, st);
+    launch_screen(ctx->ls, dc, ctx->cur, ctx->d_lut, ctx->ws, st);
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
     launch_scan(ctx->cur, ctx->ws, st);
     if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
@@ -542,9 +577,22 @@ static int test_device_impl(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *st
     hb.mq = ctx->cur.mq; hb.baq = ctx->cur.baq; hb.sq = ctx->cur.sq;
     DevConf dc;
     if (make_devconf(conf, &hb, dc)) return 1;
-    if (ctx->profiling) cudaEventRecord(ctx->ev[3], (cudaStream_t)stream);
-    launch_test(dc, ctx->cur, ctx->d_lut, ctx->ws, (cudaStream_t)stream, ctx->profiling ? ctx->ev[4] : nullptr, bonf_start_dev);
-    if (ctx->profiling) cudaEventRecord(ctx->ev[5], (cudaStream_t)stream);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->profiling) cudaEventRecord(ctx->ev[3], st);
+    launch_test(ctx->ls, dc, ctx->cur, ctx->d_lut, ctx->ws, st, ctx->profiling ? ctx->ev[4] : nullptr, bonf_start_dev);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[5], st);
+    // the sites, decided on the device, in column order into pinned host memory; then the counters; then the event the
+    // host waits for: nothing of this needs the host before lfb200_sites_*
+    ctx->last_dc = dc;
+    ctx->test_enqueued = false;
+    if (ctx->cur.n_cols > 0) {
+        if (ctx->ensure_sites(std::max<size_t>(65536, (size_t)ctx->cur.n_cols / 16))) return fail("out of pinned host memory");
+        launch_emit_sites(ctx->ls, dc, ctx->ws, ctx->d_sites, (unsigned)std::min<size_t>(ctx->h_sites_cap, 0xffffffffu), st);
+        CU(cudaMemcpyAsync(ctx->h_counters, ctx->ws.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaEventRecord(ctx->ev_done, st));
+    ctx->test_enqueued = true;
     CU(cudaGetLastError());
     return 0;
 }
@@ -588,10 +636,43 @@ static long long final_bonf(const lfb200_conf_t *conf, long long start, long lon
     return (start == 1 ? 0 : start) + 3 * n_tested;     // lofreq_call.c:794-800
 }
 
+// the long double images of the p-values of one site whose status the device has decided (snpcaller.c:1047-1059, 1166-1196)
+static inline void fill_pvalues(lfb200_site_t &s)
+{
+    for (int i = 0; i < 3; ++i) {
+        const unsigned char st = s.status[i];
+        s.pvalue[i] = st == LFB200_ST_VALUE ? expl((long double)s.lnp[i]) : st == LFB200_ST_LDBLMIN ? LDBL_MIN : LDBL_MAX;
+    }
+}
+
+// a site with a comparison inside its guard band: the reference's own long double sequence
+static void refinish_site(lfb200_site_t &s, double sig)
+{
+    Cand cd;
+    cd.col = s.col;
+    cd.bonf = s.bonf;
+    for (int i = 0; i < 3; ++i) {
+        cd.lnp[i] = s.lnp[i];
+        cd.cnt[i] = s.alt_count[i];
+        cd.raw[i] = s.alt_raw_count[i];
+    }
+    cd.ln_floor = s.ln_floor;
+    cd.flags = 0;
+    cd.pad = 0;
+    const unsigned char fl = s.flags;
+    finish_site(cd, sig, s);
+    s.flags = fl;
+    s.ln_floor = cd.ln_floor;
+}
+
+// Waits for the test enqueued by lfb200_test_device*, finishes what is left for the host and advances the counters.
+// view != NULL: *view points at the context's own pinned buffer (valid until the next test on this context) and nothing
+// is copied; otherwise the sites are copied to `sites`.
 static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites, long long max_sites,
-                      lfb200_summary_t *summary)
+                      const lfb200_site_t **view, lfb200_summary_t *summary)
 {
     if (!ctx || !ctx->have_batch) return fail("no screened batch");
+    if (!ctx->test_enqueued) return fail("lfb200_test_device has not been called for this batch");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     lfb200_summary_t sm;
@@ -602,64 +683,78 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
     auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = dbg ? now() : 0.0;
     double t1 = 0, t2 = 0, t3 = 0;
-    if (ctx->cur.n_cols > 0) {
-        CU(cudaMemcpyAsync(ctx->h_counters, ctx->ws.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        const Counters &c = *ctx->h_counters;
-        if (c.err_flags & CF_UNSUPPORTED)
-            return fail("a column has an alt count above %d: not supported by this build", 16384);
-        sm.n_tested = (long long)c.n_tested;
-        n_cand = c.n_cand;
-        if ((long long)c.pk_scr_used > ctx->ws.pk_scr_cap) ctx->scr_want = (size_t)c.pk_scr_used + (size_t)c.pk_scr_used / 4;
-        for (int i = 0; i < NCLASS; ++i) if (i != CLS_FALLBACK && i != CLS_PRUNE2) sm.n_heavy += c.n_jobs[i];
-        for (int i = 0; i < PK_NL; ++i) sm.n_heavy += std::min<long long>(c.n_pjobs[i], ctx->ws.pcap);
-    }
+    CU(cudaEventSynchronize(ctx->ev_done));
+    if (lfb_comm_error(ctx)) return fail("count exchange: a shard did not post its counts within the timeout (this batch started from a poisoned factor)");
     if (dbg) t1 = now();
-    if (n_cand > max_sites) return fail("%lld sites but room for %lld", n_cand, max_sites);
-    if (ctx->ensure_cand((size_t)n_cand)) return fail("out of pinned host memory");
-    if (ctx->ensure_perm((size_t)n_cand)) return fail("out of pinned host memory");
-    if (n_cand) {
-        CU(cudaMemcpyAsync(ctx->h_cand, ctx->ws.cand, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(ctx->h_perm, ctx->ws.cand_perm, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-    }
-    if (dbg) t2 = now();
-    const Cand *cands = ctx->h_cand;
-    const int *perm = ctx->h_perm;                 // column order, computed on the device (k_rank_cands)
-    for (long long i = 0; i < n_cand; ++i)
-        if (cands[i].flags & CF_RANGE) return fail("column %lld: tail outside the representable range", cands[i].col);
-    // the permutation must be one, and in strictly increasing column order (one candidate per column): anything else
-    // is an internal error and must not become an out-of-bounds read
-    for (long long i = 0; i < n_cand; ++i) {
-        if ((unsigned)perm[i] >= (unsigned)n_cand) return fail("internal error: site order (entry %lld)", i);
-        if (i && cands[perm[i]].col <= cands[perm[i - 1]].col) return fail("internal error: site order (column %lld)", cands[perm[i]].col);
-    }
-    // long double finishing, independent per site, straight into its place in column order
     const double sig = (double)conf->sig;
-    if (n_cand < 1024) {
-        for (long long i = 0; i < n_cand; ++i) finish_site(cands[perm[i]], sig, sites[i]);
-    } else {
-        if (!ctx->pool) {
-            // share the host cores with the other shards of this node (torchrun exports LOCAL_WORLD_SIZE)
-            unsigned hw = std::thread::hardware_concurrency();
-            const char *lws = getenv("LOCAL_WORLD_SIZE");
-            const unsigned procs = lws ? (unsigned)std::max(1, atoi(lws)) : 1u;
-            const unsigned want = std::max(3u, std::min(hw / procs, 16u));
-            ctx->pool.reset(new WorkerPool(want - 1));
+    if (ctx->cur.n_cols > 0) {
+        const Counters *c = ctx->h_counters;
+        if (c->emit_overflow) {
+            // more sites than the pinned buffer held: grow it and emit again (the candidates are still on the device)
+            if (ctx->ensure_sites((size_t)c->n_cand)) return fail("out of pinned host memory for %u sites", c->n_cand);
+            CU(cudaMemsetAsync(&ctx->ws.counters->n_fix, 0, sizeof(Counters) - offsetof(Counters, n_fix), st));
+            launch_emit_sites(ctx->ls, ctx->last_dc, ctx->ws, ctx->d_sites, (unsigned)std::min<size_t>(ctx->h_sites_cap, 0xffffffffu), st);
+            CU(cudaMemcpyAsync(ctx->h_counters, ctx->ws.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (c->emit_overflow) return fail("internal error: site buffer");
         }
-        auto finish_part = [&](unsigned part, unsigned parts) {
-            const long long per = (n_cand + parts - 1) / parts;
-            const long long lo = (long long)part * per, hi = std::min<long long>(n_cand, lo + per);
-            for (long long i = lo; i < hi; ++i) finish_site(cands[perm[i]], sig, sites[i]);
-        };
-        ctx->pool->run(finish_part);
+        if (c->err_flags & CF_RANGE) return fail("a column's tail lies outside the representable range");
+        sm.n_tested = (long long)c->n_tested;
+        sm.n_unsupported = c->n_unsupported;
+        n_cand = c->n_cand;
+        if ((long long)c->pk_scr_used > ctx->ws.pk_scr_cap) ctx->scr_want = (size_t)c->pk_scr_used + (size_t)c->pk_scr_used / 4;
+        for (int i = 0; i < NCLASS; ++i) if (i != CLS_FALLBACK && i != CLS_PRUNE2) sm.n_heavy += c->n_jobs[i];
+        for (int i = 0; i < PK_NL; ++i) sm.n_heavy += std::min<long long>(c->n_pjobs[i], ctx->ws.pcap);
+        lfb200_site_t *hs = ctx->h_sites;
+        // the few sites with a comparison inside its guard band
+        if (c->n_fix) {
+            if (c->n_fix <= (unsigned)EMIT_FIX_MAX) {
+                for (unsigned k = 0; k < c->n_fix; ++k) {
+                    if (c->fix[k] >= (unsigned)n_cand) return fail("internal error: site index");
+                    refinish_site(hs[c->fix[k]], sig);
+                }
+            } else {
+                for (long long i = 0; i < n_cand; ++i)
+                    if (hs[i].flags & SITE_NEEDS_HOST) refinish_site(hs[i], sig);
+            }
+        }
+        if (dbg) t2 = now();
+        // long double images of the p-values, for callers that want them (lfb200_set_site_pvalues)
+        if (ctx->site_pvalues && n_cand) {
+            if (n_cand < 1024) {
+                for (long long i = 0; i < n_cand; ++i) fill_pvalues(hs[i]);
+            } else {
+                if (!ctx->pool) {
+                    // share the host cores with the other shards of this node (torchrun exports LOCAL_WORLD_SIZE)
+                    unsigned hw = std::thread::hardware_concurrency();
+                    const char *lws = getenv("LOCAL_WORLD_SIZE");
+                    const unsigned procs = lws ? (unsigned)std::max(1, atoi(lws)) : 1u;
+                    const unsigned want = std::max(2u, std::min(hw / std::max(1u, 2 * procs), 8u));
+                    ctx->pool.reset(new WorkerPool(want - 1));
+                }
+                auto part_fn = [&](unsigned part, unsigned parts) {
+                    const long long per = (n_cand + parts - 1) / parts;
+                    const long long lo = (long long)part * per, hi = std::min<long long>(n_cand, lo + per);
+                    for (long long i = lo; i < hi; ++i) fill_pvalues(hs[i]);
+                };
+                ctx->pool->run(part_fn);
+            }
+            errno = 0;
+            feclearexcept(FE_ALL_EXCEPT);
+        }
+        if (view) {
+            *view = hs;
+        } else if (sites) {
+            if (n_cand > max_sites) return fail("%lld sites but room for %lld", n_cand, max_sites);
+            if (n_cand) memcpy(sites, hs, (size_t)n_cand * sizeof(lfb200_site_t));
+        }
+    } else if (view) {
+        *view = ctx->h_sites;
     }
     if (dbg) t3 = now();
     if (dbg)
-        fprintf(stderr, "[lfb200] sites: wait+counters %.0f us, cand D2H %.0f us, finish %.0f us (%lld sites)\n",
-                t1 - t0, t2 - t1, t3 - t2, n_cand);
-    errno = 0;
-    feclearexcept(FE_ALL_EXCEPT);
+        fprintf(stderr, "[lfb200] sites: wait %.0f us, fix-ups %.0f us (%u), p-values + copy %.0f us (%lld sites)\n",
+                t1 - t0, t2 - t1, ctx->cur.n_cols > 0 ? ctx->h_counters->n_fix : 0u, t3 - t2, n_cand);
     sm.n_sites = n_cand;
     sm.bonf_subst_final = final_bonf(conf, ctx->cur.n_cols > 0 ? ctx->h_counters->bonf_start_used : conf->bonf_subst, sm.n_tested);
     conf->bonf_subst = sm.bonf_subst_final;
@@ -672,10 +767,39 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
 extern "C" int lfb200_sites_device(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200_site_t *sites,
                                    long long max_sites, lfb200_summary_t *summary)
 {
-    return sites_sync(ctx, conf, stream, sites, max_sites, summary);
+    return sites_sync(ctx, conf, stream, sites, max_sites, nullptr, summary);
 }
 
-// The same work on a per-context finisher thread, so that the caller's thread can go on launching the next batch.
+extern "C" int lfb200_sites_view(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, const lfb200_site_t **sites,
+                                 lfb200_summary_t *summary)
+{
+    if (!sites) return fail("null argument");
+    return sites_sync(ctx, conf, stream, nullptr, 0, sites, summary);
+}
+
+extern "C" int lfb200_sites_buffer(lfb200_ctx *ctx, const lfb200_site_t **sites)
+{
+    if (!ctx || !sites) return fail("null argument");
+    *sites = ctx->h_sites;
+    return 0;
+}
+
+extern "C" int lfb200_set_site_pvalues(lfb200_ctx *ctx, int on)
+{
+    if (!ctx) return fail("no context");
+    ctx->site_pvalues = on != 0;
+    return 0;
+}
+
+extern "C" void lfb200_site_fill_pvalues(lfb200_site_t *sites, long long n)
+{
+    for (long long i = 0; i < n; ++i) fill_pvalues(sites[i]);
+    errno = 0;
+    feclearexcept(FE_ALL_EXCEPT);
+}
+
+// The same work on a per-context finisher thread, so that the caller's thread can go on launching the next batch
+// (on another context) while the long double images of this batch's p-values are computed.
 void lfb200_ctx::finisher_loop()
 {
     for (;;) {
@@ -684,7 +808,7 @@ void lfb200_ctx::finisher_loop()
             fin_cv.wait(lk, [this] { return fin_state == 1 || fin_stop; });
             if (fin_stop) return;
         }
-        const int rc = sites_sync(this, fin_conf, fin_stream, fin_sites, fin_max, &fin_summary);
+        const int rc = sites_sync(this, fin_conf, fin_stream, fin_sites, fin_max, nullptr, &fin_summary);
         {
             std::lock_guard<std::mutex> lk(fin_m);
             fin_rc = rc;
@@ -700,11 +824,16 @@ extern "C" int lfb200_sites_begin(lfb200_ctx *ctx, lfb200_conf_t *conf, void *st
     if (!ctx || !ctx->have_batch) return fail("no screened batch");
     std::unique_lock<std::mutex> lk(ctx->fin_m);
     if (ctx->fin_state != 0) return fail("a sites request is already pending on this context");
-    if (!ctx->fin_thread.joinable()) ctx->fin_thread = std::thread([ctx] { ctx->finisher_loop(); });
     ctx->fin_conf = conf;
     ctx->fin_stream = stream;
     ctx->fin_sites = sites;
     ctx->fin_max = max_sites;
+    if (!ctx->site_pvalues) {
+        // nothing is left for the host but a wait and a copy: done by lfb200_sites_end itself, no thread involved
+        ctx->fin_state = 3;
+        return 0;
+    }
+    if (!ctx->fin_thread.joinable()) ctx->fin_thread = std::thread([ctx] { ctx->finisher_loop(); });
     ctx->fin_state = 1;
     lk.unlock();
     ctx->fin_cv.notify_all();
@@ -716,6 +845,11 @@ extern "C" int lfb200_sites_end(lfb200_ctx *ctx, lfb200_summary_t *summary)
     if (!ctx) return fail("no context");
     std::unique_lock<std::mutex> lk(ctx->fin_m);
     if (ctx->fin_state == 0) return fail("no sites request pending on this context");
+    if (ctx->fin_state == 3) {
+        ctx->fin_state = 0;
+        lk.unlock();
+        return sites_sync(ctx, ctx->fin_conf, ctx->fin_stream, ctx->fin_sites, ctx->fin_max, nullptr, summary);
+    }
     ctx->fin_done.wait(lk, [ctx] { return ctx->fin_state == 2; });
     ctx->fin_state = 0;
     if (summary) *summary = ctx->fin_summary;
@@ -767,7 +901,7 @@ extern "C" double lfb200_dfma_peak(lfb200_ctx *ctx, void *stream)
 {
     if (!ctx) return 0.0;
     cudaSetDevice(ctx->device);
-    return measure_dfma_per_second((cudaStream_t)stream);
+    return measure_dfma_per_second(ctx->ls.sms, (cudaStream_t)stream);
 }
 
 extern "C" int lfb200_device_results(lfb200_ctx *ctx, const int **alt_counts, const int **alt_raw_counts,
@@ -1040,7 +1174,7 @@ extern "C" int lfb200_snpcaller_batch(lfb200_ctx *ctx, long long n, const double
     if (upload(ctx->p_bonf, bonf, (size_t)n * 8, 0, st, &d)) return 1;
     pb.bonf = (const long long *)d;
     if (ctx->p_out.ensure((size_t)n * sizeof(Cand))) return fail("out of device memory");
-    launch_prob_jobs(pb, (Cand *)ctx->p_out.p, st);
+    launch_prob_jobs(ctx->ls.sms, pb, (Cand *)ctx->p_out.p, st);
     CU(cudaGetLastError());
     if (ctx->ensure_cand((size_t)n)) return fail("out of pinned host memory");
     CU(cudaMemcpyAsync(ctx->h_cand, ctx->p_out.p, (size_t)n * sizeof(Cand), cudaMemcpyDeviceToHost, st));
@@ -1338,7 +1472,7 @@ extern "C" int lfb200_indel_tests(lfb200_ctx *ctx, const lfb200_conf_t *conf, lo
     if (upload(ctx->p_bonf, bonf_indel, (size_t)n * 8, 0, st, &d)) return 1;
     pb.bonf = (const long long *)d;
     if (ctx->p_out.ensure((size_t)n * sizeof(Cand))) return fail("out of device memory");
-    launch_prob_jobs(pb, (Cand *)ctx->p_out.p, st);
+    launch_prob_jobs(ctx->ls.sms, pb, (Cand *)ctx->p_out.p, st);
     CU(cudaGetLastError());
     if (ctx->ensure_cand((size_t)n)) return fail("out of pinned host memory");
     CU(cudaMemcpyAsync(ctx->h_cand, ctx->p_out.p, (size_t)n * sizeof(Cand), cudaMemcpyDeviceToHost, st));

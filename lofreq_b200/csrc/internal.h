@@ -36,6 +36,8 @@ struct DevConf {
     int def_alt_jq_on;
     double def_alt_jq_prob;
     double sig;                    // (double)conf->sig, as call_snvs passes it (lofreq_call.c:807)
+    double ln_sig;                 // glibc log(sig): k_emit_sites decides `pvalue * bonf < sig` on ln p (lofreq_call.c:832)
+    int qual_ldblmin;              // PROB_TO_PHREDQUAL(LDBL_MIN) as the host evaluates it (utils.h:45)
     int bonf_dynamic;
     long long bonf_start;          // conf->bonf_subst on entry
 };
@@ -71,6 +73,22 @@ struct Cand {
 };
 enum { CF_INSIG = 1, CF_RANGE = 2, CF_UNSUPPORTED = 4 };
 
+// A site as the host sees it: byte image of lfb200_site_t (include/lofreq_b200.h) on x86-64, written by k_emit_sites
+// straight into pinned host memory in column order.  The long double p-values are the host's business (x87).
+struct alignas(16) SiteRec {
+    long long col, bonf;
+    double lnp[3];
+    double ln_floor;
+    unsigned long long pvalue_bits[6];   // long double pvalue[3]: zeroed here, filled by the host on request
+    int cnt[3], raw[3], qual[3];
+    unsigned char status[3], called[3];
+    unsigned char flags;           // SITE_NEEDS_HOST: a comparison fell inside its guard band, the host repeats it in long double
+    unsigned char pad;
+};
+static_assert(sizeof(SiteRec) == 144, "SiteRec must mirror lfb200_site_t");
+enum { SITE_NEEDS_HOST = 1, SITE_UNSUPPORTED = 2 };
+constexpr int EMIT_FIX_MAX = 60;
+
 struct Counters {
     unsigned long long n_tested;   // written by the block-sum scan
     unsigned int n_cand;
@@ -81,6 +99,11 @@ struct Counters {
     unsigned int next_ptask;
     unsigned long long pk_scr_used; // entries of the scratch pool handed out so far
     long long bonf_start_used;     // running factor the last test started from (host or device supplied)
+    // written by k_emit_sites
+    unsigned int n_fix;            // sites whose decision the host must repeat (may exceed EMIT_FIX_MAX: then all are rechecked)
+    unsigned int emit_overflow;    // more sites than the host buffer holds: the host grows it and emits again
+    unsigned int n_unsupported;    // columns with an alt count no kernel of this build takes
+    unsigned int fix[EMIT_FIX_MAX];
 };
 
 // what k_pk_prep leaves for k_packed about one packed column
@@ -121,19 +144,34 @@ struct ProbBatch {
     double sig;
 };
 
+// per-context launch state: side streams and fork/join events of the job classes, SM count of the context's device.
+// Owned by lfb200_ctx (created after cudaSetDevice), so that contexts on different devices or driven by different
+// host threads never share a stream or an event.
+constexpr int NSIDE = 8;
+struct LaunchState {
+    int sms = 148;
+    cudaStream_t side[NSIDE] = {};
+    cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[NSIDE] = {};
+    bool ready = false;
+};
+int launch_state_init(LaunchState &ls, int device);
+void launch_state_destroy(LaunchState &ls);
+
 // launchers (snv_kernels.cu)
-void launch_screen(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
+void launch_screen(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
 void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st);
-void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
+void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
                  cudaEvent_t after_finalize, const long long *bonf_start_dev);
+// sites in column order, decided on the device, into (mapped pinned) host memory
+void launch_emit_sites(const LaunchState &ls, const DevConf &cf, const Workspace &ws, SiteRec *out, unsigned cap, cudaStream_t st);
 void launch_bonf_start(const long long *counts, int rank, long long bonf_subst, long long *start, cudaStream_t st);
 void launch_bonf_start_strided(const long long *counts, int stride, int rank, long long bonf_subst, long long *start,
                                cudaStream_t st);
 void launch_set_i64(long long *dst, long long v, cudaStream_t st);
-double measure_dfma_per_second(cudaStream_t st);
+double measure_dfma_per_second(int sms, cudaStream_t st);
 // packed.cu
-void launch_packed(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
-void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st);
+void launch_packed(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
+void launch_prob_jobs(int sms, const ProbBatch &pb, Cand *out, cudaStream_t st);
 // mailbox.cu: the per-batch count exchange between shards through shared host memory
 constexpr int MAIL_DEPTH = 64;
 struct MailSlot {

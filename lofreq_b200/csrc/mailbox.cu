@@ -69,7 +69,12 @@ __global__ void k_mail_exchange(MailSlot *slots, unsigned long long *ack, int wo
     if (lane == 0) {
         // lofreq_call.c:794-800: after j tested columns the factor is 3j when it started at 1, else start + 3j
         *d_start = before > 0 ? (bonf_subst == 1 ? 0 : bonf_subst) + 3 * before : bonf_subst;
-        if (late) *d_err = 1;
+        if (late) {
+            // a peer did not post in time: the partial sum would be a factor that is too small (false positives), so the
+            // batch gets a factor no tail can pass, and the host turns the flag into an error at lfb200_sites_* / comm_gathered
+            *d_start = 0x3fffffffffffffffll;
+            *d_err = 1;
+        }
         st_release_sys(&ack[rank], seq);
     }
 }

@@ -496,25 +496,13 @@ __global__ void __launch_bounds__(32 * PK_WARPS) k_packed(const __grid_constant_
     }
 }
 
-static int pk_sm_count()
-{
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 constexpr int PK_CTAS_PER_SM = 6;
 
-void launch_packed(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st)
+void launch_packed(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st)
 {
     if (b.n_cols <= 0 || !ws.pk_scratch) return;
-    k_pk_prep<<<pk_sm_count() * 4, 32 * PREP_WARPS, 0, st>>>(cf, b, lut, ws);
-    k_packed<<<pk_sm_count() * PK_CTAS_PER_SM, 32 * PK_WARPS, 0, st>>>(cf, b, ws);
+    k_pk_prep<<<ls.sms * 4, 32 * PREP_WARPS, 0, st>>>(cf, b, lut, ws);
+    k_packed<<<ls.sms * PK_CTAS_PER_SM, 32 * PK_WARPS, 0, st>>>(cf, b, ws);
 }
 
 }  // namespace lfb

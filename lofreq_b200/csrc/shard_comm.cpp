@@ -180,6 +180,15 @@ void lfb_comm_release(lfb200_ctx *ctx)
     *slot = nullptr;
 }
 
+// non-zero when an exchange of this context timed out (checked by lfb200_sites_* after the stream has been waited for)
+int lfb_comm_error(lfb200_ctx *ctx)
+{
+    void **slot = lfb_ctx_comm_slot(ctx);
+    if (!slot || !*slot) return 0;
+    CommState *cs = (CommState *)*slot;
+    return cs->h_err ? *(volatile int *)cs->h_err : 0;
+}
+
 extern "C" int lfb200_comm_exchange(lfb200_ctx *ctx, void *stream, long long bonf_subst, long long sites_prev_batch,
                                     const long long **bonf_start_dev)
 {
@@ -223,6 +232,7 @@ extern "C" int lfb200_comm_gathered(lfb200_ctx *ctx, void *stream, long long *te
     if (cudaMemcpyAsync(cs->h_all, cs->d_all, 16 * (size_t)cs->world, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess)
         return lfb_fail("copy of the gathered counts failed");
+    if (cs->h_err && *(volatile int *)cs->h_err) return lfb_fail("count exchange: a shard did not post its counts within the timeout");
     for (int r = 0; r < cs->world; ++r) {
         if (tested_all) tested_all[r] = cs->h_all[2 * r];
         if (sites_prev_all) sites_prev_all[r] = cs->h_all[2 * r + 1];

@@ -1490,12 +1490,14 @@ __global__ void __launch_bounds__(XL_T, 1) k_heavy_xl(const __grid_constant__ De
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
         const int K = max(cnt[0], max(cnt[1], cnt[2]));
         const long long bonf = ws.bonf_used[c];
-        if (K > XL_T * XL_R) {
-            if (threadIdx.x == 0) atomicOr(&ws.counters->err_flags, (unsigned)CF_UNSUPPORTED);
-            continue;
-        }
         Cand cd;
-        if (!xl_problem(src, cnt, bonf, cf.sig, sh, s_small, cd)) continue;
+        if (K > XL_T * XL_R) {
+            // no kernel of this build takes an alt count this large: the column is reported as a site whose alleles carry
+            // the status "unsupported" (never silently skipped), every other column of the batch is unaffected
+            cd.flags = CF_UNSUPPORTED;
+            cd.lnp[0] = cd.lnp[1] = cd.lnp[2] = 0.0;
+            cd.ln_floor = 0.0;
+        } else if (!xl_problem(src, cnt, bonf, cf.sig, sh, s_small, cd)) continue;
         if (threadIdx.x == 0) {
             cd.col = c;
             cd.bonf = bonf;
@@ -1589,18 +1591,6 @@ __global__ void __launch_bounds__(128) k_prob_jobs(const ProbBatch pb, Cand *out
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-static int sm_count()
-{
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 // dynamic shared memory of the kernels that stage a tile of merged probabilities per warp (4 warps per CTA);
 // together with their static arrays they pass the 48 KB default limit, hence the opt-in
 constexpr int STAGE_BYTES = 4 * STAGE_DOUBLES * (int)sizeof(double);
@@ -1612,21 +1602,44 @@ static void stage_optin_one()
     cudaFuncSetAttribute(k_prob_jobs<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES);
 }
 
-static void stage_smem_optin()
+// Everything a launch needs besides its arguments lives in the context: created once per context, after
+// cudaSetDevice(device) — function attributes are per device, streams and events belong to the device current at
+// creation, and two contexts (two host threads, two GPUs) must never fork and join through the same events.
+int launch_state_init(LaunchState &ls, int device)
 {
-    static bool done = false;
-    if (done) return;
+    if (ls.ready) return 0;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+    ls.sms = n;
     stage_optin_one<1>(); stage_optin_one<2>(); stage_optin_one<4>(); stage_optin_one<8>();
     stage_optin_one<16>(); stage_optin_one<32>(); stage_optin_one<64>();
-    done = true;
+    if (cudaEventCreateWithFlags(&ls.ev_fork, cudaEventDisableTiming) != cudaSuccess) return 1;
+    if (cudaEventCreateWithFlags(&ls.ev_fork2, cudaEventDisableTiming) != cudaSuccess) return 1;
+    for (int i = 0; i < NSIDE; ++i) {
+        if (cudaStreamCreateWithFlags(&ls.side[i], cudaStreamNonBlocking) != cudaSuccess) return 1;
+        if (cudaEventCreateWithFlags(&ls.ev_join[i], cudaEventDisableTiming) != cudaSuccess) return 1;
+    }
+    ls.ready = true;
+    return 0;
 }
 
-void launch_screen(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st)
+void launch_state_destroy(LaunchState &ls)
+{
+    if (ls.ev_fork) cudaEventDestroy(ls.ev_fork);
+    if (ls.ev_fork2) cudaEventDestroy(ls.ev_fork2);
+    for (int i = 0; i < NSIDE; ++i) {
+        if (ls.side[i]) cudaStreamDestroy(ls.side[i]);
+        if (ls.ev_join[i]) cudaEventDestroy(ls.ev_join[i]);
+    }
+    ls = LaunchState();
+}
+
+void launch_screen(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st)
 {
     if (b.n_cols <= 0) return;
     // one resident wave: 4 CTAs of 8 warps per SM, every warp strides over groups of 32 columns
     const long long want = (b.n_cols + 255) / 256;
-    const int grid = (int)(want < (long long)sm_count() * 4 ? want : (long long)sm_count() * 4);
+    const int grid = (int)(want < (long long)ls.sms * 4 ? want : (long long)ls.sms * 4);
     k_screen<<<grid, 256, 0, st>>>(cf, b, lut, ws);
 }
 
@@ -1639,7 +1652,7 @@ void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st)
 
 __global__ void k_rank_cands(const Workspace ws);
 
-void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
+void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
                  cudaEvent_t after_finalize, const long long *bonf_start_dev)
 {
     if (b.n_cols <= 0) return;
@@ -1648,49 +1661,38 @@ void launch_test(const DevConf &cf, const DevBatch &b, const Lut *lut, const Wor
     cudaMemsetAsync(reinterpret_cast<char *>(ws.counters) + 8, 0, sizeof(Counters) - 8, st);
     cudaMemsetAsync(ws.is_cand, 0, (size_t)nb * FIN_BLOCK, st);
     k_finalize<<<nb, FIN_BLOCK, 0, st>>>(cf, b, lut, ws, bonf_start_dev);
-    k_prune2<<<sm_count() * 2, 128, 0, st>>>(cf, b, lut, ws);
+    k_prune2<<<ls.sms * 2, 128, 0, st>>>(cf, b, lut, ws);
     if (after_finalize) cudaEventRecord(after_finalize, st);
     // The register-tile classes are independent: run them side by side so that their warps share the SMs
     // (each class alone has too few columns to hide its own latencies).
-    constexpr int NSIDE = 8;
-    static cudaStream_t side[NSIDE] = {nullptr};
-    static cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr};
-    if (!ev_fork) {
-        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-        for (int i = 0; i < NSIDE; ++i) {
-            cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
-            cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
-        }
-    }
-    const int g = sm_count() * 4;
-    stage_smem_optin();
+    const int g = ls.sms * 4;
     // k_mid (K <= 8 survivors, unpackable K <= 32) runs beside k_pk_prep -> k_packed.  Both hand the few columns they
     // cannot finish to one fallback list, which k_heavy<8> (any K <= 256) takes afterwards, side by side with the
     // per-column kernels for what k_finalize listed for them (K > 256, very deep columns, median override) — each
     // class alone has too few columns to hide its own latencies; an empty list costs an early exit.
-    cudaEventRecord(ev_fork, st);
-    cudaStreamWaitEvent(side[0], ev_fork, 0);
-    k_mid<<<g, 128, 0, side[0]>>>(cf, b, lut, ws);
-    cudaEventRecord(ev_join[0], side[0]);
-    launch_packed(cf, b, lut, ws, st);
-    cudaStreamWaitEvent(st, ev_join[0], 0);
-    cudaEventRecord(ev_fork, st);
-    for (int i = 0; i < NSIDE; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
-    k_heavy_xl<<<sm_count(), XL_T, 0, side[7]>>>(cf, b, lut, ws, CLS_XL);
-    k_heavy<64><<<g, 128, STAGE_BYTES, side[6]>>>(cf, b, lut, ws, 6);
-    k_heavy<32><<<g, 128, STAGE_BYTES, side[5]>>>(cf, b, lut, ws, 5);
-    k_heavy<16><<<g, 128, STAGE_BYTES, side[4]>>>(cf, b, lut, ws, 4);
-    k_heavy<8><<<g, 128, STAGE_BYTES, side[3]>>>(cf, b, lut, ws, 3);
-    k_heavy<4><<<g, 128, STAGE_BYTES, side[2]>>>(cf, b, lut, ws, 2);
-    k_heavy<2><<<g, 128, STAGE_BYTES, side[1]>>>(cf, b, lut, ws, 1);
-    k_heavy<8><<<g, 128, STAGE_BYTES, side[0]>>>(cf, b, lut, ws, CLS_FALLBACK);
+    cudaEventRecord(ls.ev_fork, st);
+    cudaStreamWaitEvent(ls.side[0], ls.ev_fork, 0);
+    k_mid<<<g, 128, 0, ls.side[0]>>>(cf, b, lut, ws);
+    cudaEventRecord(ls.ev_join[0], ls.side[0]);
+    launch_packed(ls, cf, b, lut, ws, st);
+    cudaStreamWaitEvent(st, ls.ev_join[0], 0);
+    cudaEventRecord(ls.ev_fork2, st);
+    for (int i = 0; i < NSIDE; ++i) cudaStreamWaitEvent(ls.side[i], ls.ev_fork2, 0);
+    k_heavy_xl<<<ls.sms, XL_T, 0, ls.side[7]>>>(cf, b, lut, ws, CLS_XL);
+    k_heavy<64><<<g, 128, STAGE_BYTES, ls.side[6]>>>(cf, b, lut, ws, 6);
+    k_heavy<32><<<g, 128, STAGE_BYTES, ls.side[5]>>>(cf, b, lut, ws, 5);
+    k_heavy<16><<<g, 128, STAGE_BYTES, ls.side[4]>>>(cf, b, lut, ws, 4);
+    k_heavy<8><<<g, 128, STAGE_BYTES, ls.side[3]>>>(cf, b, lut, ws, 3);
+    k_heavy<4><<<g, 128, STAGE_BYTES, ls.side[2]>>>(cf, b, lut, ws, 2);
+    k_heavy<2><<<g, 128, STAGE_BYTES, ls.side[1]>>>(cf, b, lut, ws, 1);
+    k_heavy<8><<<g, 128, STAGE_BYTES, ls.side[0]>>>(cf, b, lut, ws, CLS_FALLBACK);
     for (int i = 0; i < NSIDE; ++i) {
-        cudaEventRecord(ev_join[i], side[i]);
-        cudaStreamWaitEvent(st, ev_join[i], 0);
+        cudaEventRecord(ls.ev_join[i], ls.side[i]);
+        cudaStreamWaitEvent(st, ls.ev_join[i], 0);
     }
     // the sites in column order (see k_rank_cands)
     k_scan_blocks<<<1, 1024, 0, st>>>(ws.candtile, ws.candpre, nb, nullptr);
-    k_rank_cands<<<sm_count(), 256, 0, st>>>(ws);
+    k_rank_cands<<<ls.sms, 256, 0, st>>>(ws);
 }
 
 // Column order of the sites on the device: every kernel that emits a candidate marks its column (mark_cand), a prefix
@@ -1722,6 +1724,124 @@ __global__ void __launch_bounds__(256) k_rank_cands(const Workspace ws)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_emit_sites: the decision of lofreq_call.c:832 / snpcaller.c:1144-1196 and PROB_TO_PHREDQUAL (utils.h:45) on ln p.
+// The reference decides on long double p-values, p = expl(ln p):  clamp to LDBL_MIN / LDBL_MAX when an exp()
+// underflowed, `p * bonf > sig` -> nothing called, per allele `p * bonf < sig` -> called with QUAL = (int)(-10 log10l(p)).
+// Every one of these is a comparison of ln p (or of a difference of two ln p) with a constant, so it is made here in
+// double with a guard band: a site with any comparison inside its band is flagged SITE_NEEDS_HOST and the host repeats
+// exactly the reference's long double sequence for it (finish_site, host_api.cpp) — a handful per million columns.
+// Records go out in column order (cand_perm) as byte images of lfb200_site_t, straight into mapped pinned memory.
+// ------------------------------------------------------------------------------------------------
+constexpr double LN_LDBL_MIN = -11355.137111933024;        // expl() underflows (FE_UNDERFLOW) below this
+constexpr double LN_DBL_EPS = -36.04365338911715;          // ln(DBL_EPSILON)
+constexpr double LN_EXP_UNDER = 708.3964185322641;         // glibc exp() raises FE_UNDERFLOW for arguments below -this
+
+__device__ __forceinline__ bool near(double x, double band) { return fabs(x) < band; }
+
+__global__ void __launch_bounds__(128) k_emit_sites(const __grid_constant__ DevConf cf, const Workspace ws, SiteRec *out, unsigned cap)
+{
+    Counters *hdr = ws.counters;
+    const unsigned n_cand = hdr->n_cand;
+    if (blockIdx.x == 0 && threadIdx.x == 0) hdr->emit_overflow = n_cand > cap;
+    const unsigned n = min(n_cand, cap);
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const Cand cd = ws.cand[ws.cand_perm[r]];
+        SiteRec s;
+        s.col = cd.col;
+        s.bonf = cd.bonf;
+        int K = 0, imax = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            s.lnp[i] = cd.lnp[i];
+            s.cnt[i] = cd.cnt[i];
+            s.raw[i] = cd.raw[i];
+            s.qual[i] = -1;
+            s.status[i] = 1;                     // LFB200_ST_LDBLMAX
+            s.called[i] = 0;
+            s.pvalue_bits[2 * i] = s.pvalue_bits[2 * i + 1] = 0ull;
+            if (cd.cnt[i] > K) { K = cd.cnt[i]; imax = i; }
+        }
+        s.flags = 0;
+        s.pad = 0;
+        s.ln_floor = cd.ln_floor;
+        bool host = false;
+        if (cd.flags & CF_UNSUPPORTED) {
+            s.flags |= SITE_UNSUPPORTED;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) if (cd.cnt[i] > 0) s.status[i] = 3;      // LFB200_ST_UNSUPPORTED
+            atomicAdd(&hdr->n_unsupported, 1u);
+        } else if (K > 0 && !(cd.flags & CF_INSIG)) {
+            if (cd.flags & CF_RANGE) atomicOr(&ws.counters->err_flags, (unsigned)CF_RANGE);
+            const double lb = log((double)cd.bonf);
+            const double tK = cd.lnp[imax];
+            // poissbin: pvalue = expl(row[K]), clamped to LDBL_MIN when expl underflows (snpcaller.c:1047-1059)
+            host |= near(tK - LN_LDBL_MIN, 1e-6);
+            const bool underK = tK < LN_LDBL_MIN;
+            bool go = true;
+            if (!underK) {                        // snpcaller.c:1155: pvalue * bonf > sig -> every allele stays LDBL_MAX
+                const double d = tK + lb - cf.ln_sig;
+                host |= near(d, 1e-9);
+                go = !(d > 0.0);
+            }
+            if (go) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int c = cd.cnt[i];
+                    if (c == 0) continue;
+                    const double t = cd.lnp[i];
+                    bool flagged;
+                    if (c == K) {
+                        flagged = underK;         // the same expl() as poissbin's
+                    } else {
+                        // probvec_tailsum's exp() underflows when the running sum and the next term are more than
+                        // 708.396 nats apart; the widest gap of the log-concave row is against ln_floor
+                        const double g = t - cd.ln_floor - LN_EXP_UNDER;
+                        host |= near(g, 1e-6) || near(t - LN_LDBL_MIN, 1e-6);
+                        flagged = g > 0.0 || t < LN_LDBL_MIN;
+                    }
+                    int st = 0;                   // LFB200_ST_VALUE
+                    if (flagged) {                // snpcaller.c:1174-1188: p < DBL_EPSILON ? LDBL_MIN : LDBL_MAX
+                        host |= near(t - LN_DBL_EPS, 1e-9);
+                        st = t < LN_DBL_EPS ? 2 : 1;
+                    }
+                    s.status[i] = (unsigned char)st;
+                    if (st == 2) {                // LDBL_MIN * bonf < sig for every representable bonf
+                        s.called[i] = 1;
+                        s.qual[i] = cf.qual_ldblmin;
+                    } else if (st == 0) {
+                        const double d = t + lb - cf.ln_sig;              // lofreq_call.c:832
+                        host |= near(d, 1e-9);
+                        if (d < 0.0) {
+                            s.called[i] = 1;
+                            // PROB_TO_PHREDQUAL truncates -10 log10l(p): decided unless that lies within 1e-7 of an integer
+                            const double q = t * -4.3429448190325182765;
+                            const double f = q - floor(q);
+                            host |= !(f > 1e-7 && f < 1.0 - 1e-7) || !(t < 0.0 && t > -11000.0);
+                            s.qual[i] = (int)q;
+                        }
+                    }
+                }
+            }
+        }
+        if (host) {
+            s.flags |= SITE_NEEDS_HOST;
+            const unsigned k = atomicAdd(&hdr->n_fix, 1u);
+            if (k < (unsigned)EMIT_FIX_MAX) hdr->fix[k] = r;
+        }
+        // 144 bytes as nine 16-byte stores
+        const uint4 *src = reinterpret_cast<const uint4 *>(&s);
+        uint4 *dst = reinterpret_cast<uint4 *>(out + r);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dst[k] = src[k];
+    }
+}
+
+void launch_emit_sites(const LaunchState &ls, const DevConf &cf, const Workspace &ws, SiteRec *out, unsigned cap, cudaStream_t st)
+{
+    k_emit_sites<<<ls.sms, 128, 0, st>>>(cf, ws, out, cap);
+}
+
 __global__ void k_bonf_start(const long long *counts, int rank, long long bonf_subst, long long *start)
 {
     long long before = 0;
@@ -1751,7 +1871,6 @@ __global__ void k_set_i64(long long *dst, long long v) { *dst = v; }
 
 void launch_set_i64(long long *dst, long long v, cudaStream_t st) { k_set_i64<<<1, 1, 0, st>>>(dst, v); }
 
-static int sm_count();
 // DFMA throughput probe (the fp64-pipe roofline denominator; MEASURED_PEAKS.json has none for fp64)
 __global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters, double a, double b)
 {
@@ -1768,14 +1887,14 @@ __global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters, doub
     if (s == 123.456) out[0] = s;
 }
 
-double measure_dfma_per_second(cudaStream_t st)
+double measure_dfma_per_second(int sms, cudaStream_t st)
 {
     double *out = nullptr;
     if (cudaMalloc(&out, 8) != cudaSuccess) return 0.0;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const int grid = sm_count() * 8, iters = 20000;
+    const int grid = sms * 8, iters = 20000;
     k_dfma_probe<<<grid, 256, 0, st>>>(out, 1000, 0.999999, 1e-7);
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
@@ -1793,12 +1912,11 @@ double measure_dfma_per_second(cudaStream_t st)
     return (double)grid * 256 * 8 * iters / (best * 1e-3);
 }
 
-void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st)
+void launch_prob_jobs(int sms, const ProbBatch &pb, Cand *out, cudaStream_t st)
 {
     if (pb.n <= 0) return;
-    stage_smem_optin();
     const long long want = (pb.n + 3) / 4;
-    const int g = (int)(want < (long long)sm_count() * 4 ? want : (long long)sm_count() * 4);
+    const int g = (int)(want < (long long)sms * 4 ? want : (long long)sms * 4);
     k_prob_jobs<1><<<g, 128, STAGE_BYTES, st>>>(pb, out, 0);
     k_prob_jobs<2><<<g, 128, STAGE_BYTES, st>>>(pb, out, 1);
     k_prob_jobs<4><<<g, 128, STAGE_BYTES, st>>>(pb, out, 2);
@@ -1806,7 +1924,7 @@ void launch_prob_jobs(const ProbBatch &pb, Cand *out, cudaStream_t st)
     k_prob_jobs<16><<<g, 128, STAGE_BYTES, st>>>(pb, out, 4);
     k_prob_jobs<32><<<g, 128, STAGE_BYTES, st>>>(pb, out, 5);
     k_prob_jobs<64><<<g, 128, STAGE_BYTES, st>>>(pb, out, 6);
-    k_prob_jobs_xl<<<(int)(pb.n < sm_count() ? pb.n : sm_count()), XL_T, 0, st>>>(pb, out);
+    k_prob_jobs_xl<<<(int)(pb.n < sms ? pb.n : sms), XL_T, 0, st>>>(pb, out);
 }
 
 }  // namespace lfb
