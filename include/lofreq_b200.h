@@ -270,6 +270,43 @@ int lfb200_builder_add_column(lfb200_builder *bld, long long tag, char ref_base,
                               const int *const baq_quals[4], const int *const source_quals[4], const int n[4]);
 int lfb200_builder_flush(lfb200_builder *bld);
 void lfb200_builder_destroy(lfb200_builder *bld);
+long long lfb200_builder_pending(const lfb200_builder *bld);      /* columns buffered since the last flush */
+
+/* ---- the reporting tail of a called allele: what report_var() (lofreq_call.c:92-137) adds ------
+ * DP4 = strand counts of the reference base and of the alt base (plp_col_t.fw_counts / rv_counts, lofreq_call.c:853-857);
+ * SB  = PROB_TO_PHREDQUAL_SAFE of the two-tailed p of Fisher's exact test on DP4 (kt_fisher_exact, fet.c:62-101),
+ *       INT_MAX when there are no reference reads and the alt reads sit on one strand (lofreq_call.c:112-113);
+ * AF  = alt_raw_count / (float)coverage_plp (lofreq_call.c:835); DP = coverage_plp; HQA = filtered alt count (:860). */
+typedef struct { int ref_fw, ref_rv, alt_fw, alt_rv; } lfb200_dp4_t;          /* dp4_counts_t, vcf.h:60-65 */
+/* n tables at once, one GPU thread per table; the few results within a guard band of an integer boundary of
+ * -10 log10(p) are repeated on the host with glibc (same routine), so SB is the reference's integer */
+int lfb200_sb_qual_batch(lfb200_ctx *ctx, long long n, const lfb200_dp4_t *dp4, int *sb_qual);
+/* the INFO string of a SNV record exactly as vcf_var_sprintf_info writes it (vcf.c:608-629):
+ * "DP=%d;AF=%f;SB=%d;DP4=%d,%d,%d,%d;HQA=%d"; returns its length or -1 when buf is too small */
+int lfb200_format_snv_info(char *buf, unsigned long size, int dp, float af, int sb, const lfb200_dp4_t *dp4, int hqa);
+/* the record line as vcf_write_var writes it (vcf.c:469-495): CHROM POS(1-based) . REF ALT QUAL . INFO \n */
+int lfb200_format_snv_record(char *buf, unsigned long size, const char *chrom, long pos0, char ref, char alt, int qual,
+                             const char *info);
+/* One reported variant = one iteration of the loop of call_snvs that passes `pvalue * bonf < sig`
+ * (lofreq_call.c:818-871), with everything report_var() needs. */
+typedef struct {
+    long long tag;                     /* as given to lfb200_builder_add_column_strands */
+    long long bonf;
+    double lnp;
+    float af;
+    int qual, dp, sb, hqa;
+    lfb200_dp4_t dp4;
+    char ref_base, alt_base;
+} lfb200_variant_t;
+typedef void (*lfb200_variant_fn)(const lfb200_variant_t *v, void *user);
+/* Column with its strand counts: fw_counts / rv_counts = plp_col_t.fw_counts / rv_counts (long int[NUM_NT4], the first
+ * four entries A,C,G,T are read).  With a variant callback set, every flush runs the SB kernel over the called alleles of
+ * the batch and reports them in input order, alleles in A,C,G,T-minus-ref order like call_snvs. */
+int lfb200_builder_add_column_strands(lfb200_builder *bld, long long tag, char ref_base, int coverage_plp, int num_bases,
+                                      const int *const base_quals[4], const int *const map_quals[4],
+                                      const int *const baq_quals[4], const int *const source_quals[4], const int n[4],
+                                      const long *fw_counts, const long *rv_counts);
+int lfb200_builder_on_variant(lfb200_builder *bld, lfb200_variant_fn fn, void *user);
 
 /* ---- link-compatible single-column symbols ----------------------------- */
 /* snpcaller() of snpcaller.h:97-102 (callers: lofreq_call.c:319,384,807,

@@ -1046,13 +1046,18 @@ struct lfb200_builder {
     std::vector<unsigned char> bq, mq, baq, sq;
     bool any_mq = false, any_baq = false, any_sq = false;
     std::vector<lfb200_site_t> sites;
+    // reporting tail: strand counts per column (fw A,C,G,T then rv A,C,G,T), variant callback
+    std::vector<int> strands;
+    bool any_strands = false, defer_flush = false;
+    lfb200_variant_fn on_variant = nullptr;
+    void *variant_user = nullptr;
 };
 
 extern "C" int lfb200_builder_create(lfb200_builder **out, lfb200_ctx *ctx, lfb200_conf_t *conf, long long batch_cols,
                                      lfb200_site_fn on_site, void *user)
 {
     *out = nullptr;
-    if (!ctx || !conf || !on_site) return fail("builder needs a context, a conf and a site callback");
+    if (!ctx || !conf) return fail("builder needs a context and a conf");
     if (batch_cols <= 0) return fail("batch_cols must be positive");
     lfb200_builder *b = new lfb200_builder();
     b->ctx = ctx;
@@ -1103,9 +1108,43 @@ extern "C" int lfb200_builder_add_column(lfb200_builder *b, long long tag, char 
     b->coverage.push_back(coverage_plp);
     b->num_bases.push_back(num_bases);
     b->tags.push_back(tag);
+    b->strands.resize(b->ref.size() * 8, 0);
+    if (b->defer_flush) return 0;
     if ((long long)b->ref.size() >= b->batch_cols) return lfb200_builder_flush(b);
     return 0;
 }
+
+extern "C" int lfb200_builder_add_column_strands(lfb200_builder *b, long long tag, char ref_base, int coverage_plp, int num_bases,
+                                                 const int *const base_quals[4], const int *const map_quals[4],
+                                                 const int *const baq_quals[4], const int *const source_quals[4], const int n[4],
+                                                 const long *fw_counts, const long *rv_counts)
+{
+    if (!b) return fail("no builder");
+    b->defer_flush = true;
+    const int rc = lfb200_builder_add_column(b, tag, ref_base, coverage_plp, num_bases, base_quals, map_quals, baq_quals, source_quals, n);
+    b->defer_flush = false;
+    if (rc) return rc;
+    if (fw_counts && rv_counts) {
+        int *s8 = b->strands.data() + (b->ref.size() - 1) * 8;
+        for (int g = 0; g < 4; ++g) {
+            s8[g] = (int)fw_counts[g];
+            s8[4 + g] = (int)rv_counts[g];
+        }
+        b->any_strands = true;
+    }
+    if ((long long)b->ref.size() >= b->batch_cols) return lfb200_builder_flush(b);
+    return 0;
+}
+
+extern "C" int lfb200_builder_on_variant(lfb200_builder *b, lfb200_variant_fn fn, void *user)
+{
+    if (!b) return fail("no builder");
+    b->on_variant = fn;
+    b->variant_user = user;
+    return 0;
+}
+
+extern "C" long long lfb200_builder_pending(const lfb200_builder *b) { return b ? (long long)b->ref.size() : 0; }
 
 extern "C" int lfb200_builder_flush(lfb200_builder *b)
 {
@@ -1127,12 +1166,52 @@ extern "C" int lfb200_builder_flush(lfb200_builder *b)
     hb.sq = b->any_sq ? b->sq.data() : nullptr;
     b->sites.resize((size_t)n);
     lfb200_summary_t sm;
-    const int rc = lfb200_call_columns(b->ctx, b->conf, &hb, nullptr, b->sites.data(), n, &sm);
-    if (rc == 0)
+    int rc = lfb200_call_columns(b->ctx, b->conf, &hb, nullptr, b->sites.data(), n, &sm);
+    if (rc == 0 && b->on_site)
         for (long long i = 0; i < sm.n_sites; ++i) {
             const lfb200_site_t &s = b->sites[(size_t)i];
             b->on_site(&s, b->tags[(size_t)s.col], b->ref[(size_t)s.col], b->coverage[(size_t)s.col], b->user);
         }
+    if (rc == 0 && b->on_variant) {
+        // the loop of call_snvs over the alt bases of every site (lofreq_call.c:818-871), with report_var()'s additions
+        std::vector<lfb200_variant_t> vars;
+        std::vector<lfb200_dp4_t> tabs;
+        for (long long i = 0; i < sm.n_sites; ++i) {
+            const lfb200_site_t &s = b->sites[(size_t)i];
+            const size_t c = (size_t)s.col;
+            const char ref = b->ref[c];
+            const int ref_i = ref == 'A' ? 0 : ref == 'C' ? 1 : ref == 'G' ? 2 : 3;
+            const int *s8 = b->strands.data() + c * 8;
+            for (int a = 0; a < 3; ++a) {
+                if (!s.called[a]) continue;
+                const int alt_i = a + (a >= ref_i);                     // A,C,G,T minus the reference base (snpcaller.c:391-397)
+                lfb200_variant_t v;
+                v.tag = b->tags[c];
+                v.bonf = s.bonf;
+                v.lnp = s.lnp[a];
+                v.af = s.alt_raw_count[a] / (float)b->coverage[c];      // lofreq_call.c:835
+                v.qual = s.qual[a];
+                v.dp = b->coverage[c];
+                v.sb = 0;
+                v.hqa = s.alt_count[a];                                 // lofreq_call.c:860
+                v.dp4.ref_fw = s8[ref_i]; v.dp4.ref_rv = s8[4 + ref_i];
+                v.dp4.alt_fw = s8[alt_i]; v.dp4.alt_rv = s8[4 + alt_i];
+                v.ref_base = ref;
+                v.alt_base = "ACGT"[alt_i];
+                vars.push_back(v);
+                tabs.push_back(v.dp4);
+            }
+        }
+        std::vector<int> sb(vars.size());
+        rc = lfb200_sb_qual_batch(b->ctx, (long long)vars.size(), tabs.data(), sb.data());
+        if (rc == 0)
+            for (size_t k = 0; k < vars.size(); ++k) {
+                vars[k].sb = sb[k];
+                b->on_variant(&vars[k], b->variant_user);
+            }
+    }
+    b->strands.clear();
+    b->any_strands = false;
     b->col_off.assign(1, 0);
     b->tags.clear();
     b->nt_cnt.clear();
@@ -1539,6 +1618,52 @@ extern "C" int lfb200_binom(double *p, double *q, int num_trials, int num_succes
         return 1;
     }
     return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reporting tail: strand-bias quality on the device, INFO / record text on the host
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfb200_sb_qual_batch(lfb200_ctx *ctx, long long n, const lfb200_dp4_t *dp4, int *sb_qual)
+{
+    if (!ctx) return fail("no context");
+    if (n <= 0) return 0;
+    if (!dp4 || !sb_qual) return fail("null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_tab;
+    if (upload(ctx->p_cnt, dp4, (size_t)n * sizeof(lfb200_dp4_t), 0, st, &d_tab)) return 1;
+    if (ctx->p_out.ensure((size_t)n * 5 + 64)) return fail("out of device memory");
+    int *d_sb = (int *)ctx->p_out.p;
+    unsigned char *d_unsure = (unsigned char *)(d_sb + n);
+    launch_sb_qual(ctx->ls.sms, (const int *)d_tab, n, d_sb, d_unsure, st);
+    CU(cudaGetLastError());
+    std::vector<unsigned char> unsure((size_t)n);
+    CU(cudaMemcpyAsync(sb_qual, d_sb, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(unsure.data(), d_unsure, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (long long i = 0; i < n; ++i)
+        if (unsure[(size_t)i]) sb_qual[i] = sb_qual_host(&dp4[i].ref_fw);      // inside the guard band: glibc, like the reference
+    return 0;
+}
+
+extern "C" int lfb200_format_snv_info(char *buf, unsigned long size, int dp, float af, int sb, const lfb200_dp4_t *dp4, int hqa)
+{
+    if (!buf || !dp4) return -1;
+    const int k = snprintf(buf, size, "DP=%d;AF=%f;SB=%d;DP4=%d,%d,%d,%d;HQA=%d", dp, af, sb, dp4->ref_fw, dp4->ref_rv,
+                           dp4->alt_fw, dp4->alt_rv, hqa);                      // vcf.c:615-624
+    return (k < 0 || (unsigned long)k >= size) ? -1 : k;
+}
+
+extern "C" int lfb200_format_snv_record(char *buf, unsigned long size, const char *chrom, long pos0, char ref, char alt, int qual,
+                                        const char *info)
+{
+    if (!buf) return -1;
+    int k;
+    if (qual > -1)                                                              // vcf.c:472-495
+        k = snprintf(buf, size, "%s\t%ld\t.\t%c\t%c\t%d\t.\t%s\n", chrom ? chrom : ".", pos0 + 1, ref, alt, qual, info ? info : ".");
+    else
+        k = snprintf(buf, size, "%s\t%ld\t.\t%c\t%c\t.\t.\t%s\n", chrom ? chrom : ".", pos0 + 1, ref, alt, info ? info : ".");
+    return (k < 0 || (unsigned long)k >= size) ? -1 : k;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -188,6 +188,9 @@ void launch_errprobs(const DevConf &cf, const DevBatch &b, const Lut *lut, doubl
 // binom.cu
 int launch_binom(long long n_prob, const int *num_trials, const int *num_success, const double *prob, double *cum, double *ccum,
                  int *status, cudaStream_t st);
+// fisher.cu: SB = PROB_TO_PHREDQUAL_SAFE(Fisher two-tailed p) per DP4 table (lofreq_call.c:108-125, fet.c:62-101)
+void launch_sb_qual(int sms, const int *dp4, long long n, int *sb, unsigned char *unsure, cudaStream_t st);
+int sb_qual_host(const int *dp4);
 // synth.cu
 void launch_synth_depths(int workload, long long c0, long long n, int *depth, cudaStream_t st);
 void launch_synth_columns(int workload, long long c0, long long n, const long long *col_off, int *nt_cnt, char *ref,

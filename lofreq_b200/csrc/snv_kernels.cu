@@ -1745,9 +1745,14 @@ __global__ void __launch_bounds__(128) k_emit_sites(const __grid_constant__ DevC
     const unsigned n_cand = hdr->n_cand;
     if (blockIdx.x == 0 && threadIdx.x == 0) hdr->emit_overflow = n_cand > cap;
     const unsigned n = min(n_cand, cap);
-    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    // a CTA takes 128 consecutive records: every thread decides one into shared memory, then the CTA writes the
+    // 128 x 144 bytes out as consecutive 16-byte words (full lines over PCIe instead of nine scattered stores per site)
+    __shared__ SiteRec s_rec[128];
+    for (unsigned r0 = blockIdx.x * 128u; r0 < n; r0 += gridDim.x * 128u) {
+      const unsigned r = r0 + threadIdx.x;
+      if (r < n) {
         const Cand cd = ws.cand[ws.cand_perm[r]];
-        SiteRec s;
+        SiteRec &s = s_rec[threadIdx.x];
         s.col = cd.col;
         s.bonf = cd.bonf;
         int K = 0, imax = 0;
@@ -1829,11 +1834,13 @@ __global__ void __launch_bounds__(128) k_emit_sites(const __grid_constant__ DevC
             const unsigned k = atomicAdd(&hdr->n_fix, 1u);
             if (k < (unsigned)EMIT_FIX_MAX) hdr->fix[k] = r;
         }
-        // 144 bytes as nine 16-byte stores
-        const uint4 *src = reinterpret_cast<const uint4 *>(&s);
-        uint4 *dst = reinterpret_cast<uint4 *>(out + r);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) dst[k] = src[k];
+      }
+      __syncthreads();
+      const unsigned nrec = min(128u, n - r0);
+      const uint4 *src = reinterpret_cast<const uint4 *>(s_rec);
+      uint4 *dst = reinterpret_cast<uint4 *>(out + r0);
+      for (unsigned w = threadIdx.x; w < nrec * 9u; w += 128u) dst[w] = src[w];
+      __syncthreads();
     }
 }
 

@@ -236,5 +236,61 @@ class BinomRef:
         return p.value, q.value
 
 
+CALLREF_SO = os.path.join(HERE, "_ref", "libcallref.so")
+CALLB200_SO = os.path.join(HERE, "_ref", "libcallb200.so")
+
+
+class CallOracle:
+    """Callback-boundary oracle (oracle/call_harness.c): identical plp_col_t objects go through the reference's REAL
+    call_vars() -> call_snvs() -> report_var() -> vcf_write_var() (lofreq_call.c, vcf.c, fet.c compiled unmodified), or —
+    adapter=True, library _ref/libcallb200.so — through the product's drop-in callback lfb200_call_vars() + lfb200_flush()
+    (lofreq_b200/adapter/lofreq_adapter.c compiled against the reference's own headers).  Returns the raw VCF text."""
+
+    def __init__(self, adapter=False):
+        path = CALLB200_SO if adapter else CALLREF_SO
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.adapter = adapter
+        self.lib = C.CDLL(path)
+        f = self.lib.lfref_call_vars_vcf
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(_Conf), C.POINTER(_Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        g = self.lib.lfref_sb_qual
+        g.restype = C.c_int
+        g.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+
+    def sb_qual(self, ref_fw, ref_rv, alt_fw, alt_rv):
+        two = C.c_double()
+        return self.lib.lfref_sb_qual(int(ref_fw), int(ref_rv), int(alt_fw), int(alt_rv), C.byref(two)), two.value
+
+    def call_vars_vcf(self, batch, strand8, conf=None, pos=None, cons0=None, target="synthetic", adapter=None):
+        """-> (vcf text, bonf_subst, num_snv_tests).  strand8: int32 [n][8] = fw A,C,G,T then rv A,C,G,T."""
+        import tempfile
+        use_adapter = self.adapter if adapter is None else adapter
+        conf = default_conf() if conf is None else conf
+        cf = _Conf(**conf)
+        sb, keep, n = Oracle._mk_batch(batch)
+        s8 = np.ascontiguousarray(strand8, np.int32)
+        ps = None if pos is None else np.ascontiguousarray(pos, np.int32)
+        c0 = None if cons0 is None else np.ascontiguousarray(cons0, np.uint8)
+        with tempfile.NamedTemporaryFile(suffix=".vcf", delete=False) as tf:
+            path = tf.name
+        try:
+            rc = self.lib.lfref_call_vars_vcf(C.byref(cf), C.byref(sb), _ptr(s8), _ptr(ps), _ptr(c0), target.encode(), path.encode(),
+                                              None, None, None, 1 if use_adapter else 0)
+            if rc:
+                raise RuntimeError("lfref_call_vars_vcf returned %d" % rc)
+            with open(path) as f:
+                text = f.read()
+        finally:
+            os.unlink(path)
+        return text, cf.bonf_subst, cf.num_snv_tests
+
+
+def have_call_oracle(adapter=False):
+    return os.path.exists(CALLB200_SO if adapter else CALLREF_SO)
+
+
 def have_reference():
     return os.path.exists(REF_SO)

@@ -78,7 +78,7 @@ def column_depths(workload, c0, n_cols):
     return depth_table()[idx].astype(np.int64)
 
 
-def generate(workload, c0, n_cols, with_baq=False, seed=SEED, pad=16):
+def generate(workload, c0, n_cols, with_baq=False, seed=SEED, pad=16, with_strand=False):
     """Packed column batch (dict, see oracle/column_batch.h) for columns
     [c0, c0+n_cols) of the named workload."""
     w = WORKLOADS[workload]
@@ -93,6 +93,7 @@ def generate(workload, c0, n_cols, with_baq=False, seed=SEED, pad=16):
     mq_pl = np.zeros(total, np.uint8)
     baq_pl = np.zeros(total, np.uint8) if with_baq else None
     nt_cnt = np.zeros((n_cols, 4), np.int32)
+    strand8 = np.zeros((n_cols, 8), np.int32) if with_strand else None     # fw A,C,G,T then rv A,C,G,T (plp_col_t.fw_counts / rv_counts)
     ref = np.frombuffer(b"ACGT", dtype=np.uint8)[(np.arange(c0, c0 + n_cols) & 3)]
 
     # group columns by depth so the per-read work vectorises
@@ -130,10 +131,15 @@ def generate(workload, c0, n_cols, with_baq=False, seed=SEED, pad=16):
         baq_s = np.take_along_axis(baq, order, axis=1).astype(np.uint8)
         for g in range(4):
             nt_cnt[sel, g] = (nt == g).sum(axis=1)
+        if with_strand:
+            rv = ((he >> np.uint64(16)) & np.uint64(1)).astype(bool)        # strand = one bit of the read's hash
+            for g in range(4):
+                strand8[sel, g] = ((nt == g) & ~rv).sum(axis=1)
+                strand8[sel, 4 + g] = ((nt == g) & rv).sum(axis=1)
         idx = col_off[sel][:, None] + np.arange(d)[None, :]
         bq_pl[idx] = bq_s
         mq_pl[idx] = 60
         if with_baq:
             baq_pl[idx] = baq_s
     return dict(col_off=col_off, nt_cnt=nt_cnt, ref_base=ref.copy(), bq=bq_pl, mq=mq_pl,
-                baq=baq_pl, sq=None, coverage=None, depths=depths)
+                baq=baq_pl, sq=None, coverage=None, depths=depths, strand8=strand8)

@@ -537,9 +537,12 @@ def test_packed_kernel_classes(caller, port_oracle):
     assert got["job_counts"]["packed"] == 0
 
 
-def test_packed_scratch_pool_overflow(caller, port_oracle):
+def test_packed_scratch_pool_overflow(port_oracle):
     """more heavy reads than the scratch pool holds (16 reads per column of the batch, at least 1 Mi): the columns
-    that do not get a row take the per-column kernels, with the same results"""
+    that do not get a row take the per-column kernels, with the same results (fresh context: the pool of a used one
+    has grown to what earlier batches asked for)"""
+    import lofreq_b200
+    caller = lofreq_b200.Caller(0)
     rng = np.random.default_rng(3)
     e = (np.zeros(0, int),) * 3
     cols = []
@@ -553,6 +556,7 @@ def test_packed_scratch_pool_overflow(caller, port_oracle):
     compare_batch(got, want, "pool overflow")
     jc = got["job_counts"]
     assert 0 < jc["packed"] < 450 and jc["per_column"] + jc["mid"] > 0, jc
+    caller.close()
 
 
 def test_poissbin_rows_golden(caller):
