@@ -231,9 +231,8 @@ int lfb200_get_profile(lfb200_ctx *ctx, float *ms4);
 /* copy alt_counts | alt_raw_counts ([n_cols][6] ints) of the last screen into caller-owned device memory */
 int lfb200_copy_counts_device(lfb200_ctx *ctx, void *stream, int *dst_dev);
 /* which kernels the tested columns of the last finished batch (lfb200_sites_device / _end / lfb200_call_columns) took:
- * out[0] packed kernel (8 < K <= 256, several columns per warp), out[1] of those handed on to the fallback list,
- * out[2] one-warp / one-CTA-per-column kernels (K > 256, very deep columns, median override),
- * out[3] k_mid (K <= 8 survivors of the prune, unpackable K <= 32) */
+ * out[0] k_dp (8 < K <= 2048, several columns per warp), out[1] the per-column fallback k_heavy_all (columns k_dp or
+ * k_mid handed back), out[2] k_heavy_xl (K > 2048, one CTA per column), out[3] k_mid (K <= 8 survivors of the prune) */
 int lfb200_last_job_counts(lfb200_ctx *ctx, long long out[4]);
 /* measured DFMA/s of this GPU (8 independent chains per thread, ~20 ms): the fp64-pipe roofline denominator */
 double lfb200_dfma_peak(lfb200_ctx *ctx, void *stream);

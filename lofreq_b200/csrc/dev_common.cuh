@@ -187,14 +187,16 @@ __device__ __forceinline__ void mark_cand(const Workspace &ws, long long c)
     atomicAdd(&ws.candtile[c >> 8], 1u);
 }
 
-// packed job list (k_packed) of a column with largest alt count K and n reads; -1 = not packable.
-// list = depth bin * PK_NG + gi, G = 4 << gi lanes per column: the smallest G with G * PK_R >= K.
-__device__ __forceinline__ int packed_list(int K, int n)
+// k_dp job list of a column with largest alt count K (KS < K <= DP_MAXK) and n reads: class * DP_NBIN1 + depth bin
+__device__ __forceinline__ int dp_class(int K)
 {
-    if (K <= KS || K > PK_MAXK || n > PK_MAXN) return -1;
-    const int gi = K <= 4 * PK_R ? 0 : K <= 8 * PK_R ? 1 : K <= 16 * PK_R ? 2 : 3;
+    return K <= 32 ? 0 : K <= 64 ? 1 : K <= 128 ? 2 : K <= 256 ? 3 : K <= 512 ? 4 : K <= 1024 ? 5 : 6;
+}
+
+__device__ __forceinline__ int dp_list(int K, int n)
+{
     int bin = 0;
-    while (bin < PK_NB - 1 && n > (128 << bin)) ++bin;
-    return bin * PK_NG + gi;
+    while (bin < DP_NBIN - 1 && n > (128 << bin)) ++bin;
+    return dp_class(K) * DP_NBIN1 + bin;
 }
 }  // namespace lfb

@@ -1,0 +1,675 @@
+// k_dp: the O(depth*K) recurrence of pruned_calc_prob_dist (snpcaller.c:830-971) for every column with
+// 8 < K <= 2048, straight from the quality bytes — plp_to_errprobs (snpcaller.c:345-498), the tilt, the recurrence and
+// the per-allele tails in ONE kernel, several columns per warp.
+//
+// The recurrence over reads is strictly serial (row n needs row n-1), so a column can use at most K lanes x registers
+// of parallelism, and a warp that owns one K = 40 column would spend its issue slots on per-read bookkeeping instead
+// of on cells.  A warp therefore owns 32/G columns, G = 4, 8, 16 or 32 lanes each, R = 8, 16, 32 or 64 cells per
+// lane (G*R >= K), all of them advancing read by read in lock step: one parameter load + one shuffle + R DFMAs per
+// step serve every column of the warp.  Job lists per (G, R, depth bin) keep the columns of a warp alike.
+//
+// Per warp task:
+//   1. pre-pass over the column's bytes with 16-byte loads: reads kept and lambda = sum of the merged probabilities
+//      (G lanes per column).  Chernoff exponent of the tail > 300 nats -> the untilted cells of interest would leave
+//      the fp64 range -> saddlepoint tilt s: a histogram of the merged probabilities (160 buckets of 0.75 dB) built by
+//      the whole warp in shared memory, Newton on ln s over the buckets (the tolerance of the tilt is coarse: an
+//      error e costs about var*e^2/2 nats of ~700).
+//   2. the quality bytes of the next 128 reads of every column of the warp travel from HBM to shared memory with
+//      1-D bulk TMA copies (cp.async.bulk + mbarrier, double-buffered: stage k+1 is in flight while stage k is
+//      consumed); for each block of 32 reads the lanes of a column turn its bytes into the step parameters
+//      (o, 1/q), o = p*s/q, with the shared-memory copy of the glibc-pow LUT and the reference's merge order.
+//   3. the recurrence in odds form, E[k] += E[k-1]*o (one DFMA per cell), absorbing state T = T/q + E[K-1]*o,
+//      exact power-of-two rescaling per column every 32 reads, and the reference's early exit (snpcaller.c:916-958)
+//      on a lower bound of ln P(X >= K among the reads seen) built from the exponents of T and of the running
+//      product of q.
+//   4. ln P(X >= K), and the tails of the other alleles from the same (possibly tilted) row:
+//      P(X >= c) = sum_{k >= c} E[k] s^-k — all terms positive.
+// Columns this form cannot finish (a parameter above 2^20, a tail that needs the tilt after all, a low cell of a
+// strongly tilted row lost to underflow) go to the per-column fallback lists that k_heavy_all takes afterwards.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "internal.h"
+#include "dev_common.cuh"
+
+namespace lfb {
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v)
+{
+#pragma unroll
+    for (int m = G / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
+    return v;
+}
+
+template <int G>
+__device__ __forceinline__ int group_sum_i(int v)
+{
+#pragma unroll
+    for (int m = G / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
+    return v;
+}
+
+template <int G>
+__device__ __forceinline__ int group_max_i(int v)
+{
+#pragma unroll
+    for (int m = G / 2; m >= 1; m >>= 1) v = max(v, __shfl_xor_sync(FULL, v, m));
+    return v;
+}
+
+template <int G>
+__device__ __forceinline__ int group_min_i(int v)
+{
+#pragma unroll
+    for (int m = G / 2; m >= 1; m >>= 1) v = min(v, __shfl_xor_sync(FULL, v, m));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk TMA (cp.async.bulk), PTX ISA 8.x
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_inval(unsigned long long *bar)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is signalled on `bar`
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// layout of the dynamic shared memory
+// ------------------------------------------------------------------------------------------------
+constexpr int DP_WARPS = 4;
+constexpr int DP_S = 128;                   // reads per TMA stage and column
+constexpr int DP_SB = DP_S + 16;            // bytes per stage, column and plane: + the lead of an unaligned column
+constexpr int DP_NCOLMAX = 8;               // columns per warp at G = 4
+constexpr int DP_PAR = 33;                  // one parameter row: 32 reads, padded (banks)
+constexpr int DP_NHIST = 160;               // buckets of the tilt histogram: 4 per binade, 2^-40 .. 1
+
+struct DpWarpSmem {
+    unsigned long long bar[2];
+    double2 par[DP_NCOLMAX][DP_PAR];
+    union {
+        struct { float sum[DP_NHIST]; int cnt[DP_NHIST]; } hist;     // tilt histogram (whole warp, one column at a time)
+        int median_hist[256];                                         // def_alt_bq == -1 (warp_ref_median)
+    } u;
+    // followed by the byte stages: [2][DP_NCOLMAX][planes][DP_SB]
+};
+
+__host__ __device__ constexpr size_t dp_warp_bytes(int planes)
+{
+    return ((sizeof(DpWarpSmem) + 15) & ~(size_t)15) + (size_t)2 * DP_NCOLMAX * planes * DP_SB;
+}
+
+// processing order of the job lists: deepest bin first, widest class first; entry i is list DP_NL-1-i.
+// tbase[i] = first task of entry i, tbase[DP_NL] = number of tasks
+__device__ __forceinline__ int dp_cols_per_task(int cls) { return cls == 0 ? 8 : cls == 1 ? 4 : cls == 2 ? 2 : 1; }
+
+// whole CTA: every thread counts the tasks of one entry, thread 0 sums them up
+__device__ void dp_list_bases(const Workspace &ws, unsigned *tbase, int cls_lo, int cls_hi)
+{
+    for (int i = threadIdx.x; i < DP_NL; i += blockDim.x) {
+        const int li = DP_NL - 1 - i;
+        const int cls = li / DP_NBIN1;
+        unsigned tasks = 0;
+        if (cls >= cls_lo && cls <= cls_hi) {
+            const bool unbinned = (li % DP_NBIN1) == DP_NBIN;
+            const unsigned nj = unbinned ? ws.counters->n_pjobs[li] : min(ws.counters->n_pjobs[li], (unsigned)ws.pcap);
+            const unsigned ncol = dp_cols_per_task(cls);
+            tasks = (nj + ncol - 1) / ncol;
+        }
+        tbase[i + 1] = tasks;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned acc = 0;
+        tbase[0] = 0;
+        for (int i = 1; i <= DP_NL; ++i) {
+            acc += tbase[i];
+            tbase[i] = acc;
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ const int *dp_list_ptr(const Workspace &ws, int li)
+{
+    const int cls = li / DP_NBIN1, bin = li % DP_NBIN1;
+    return bin == DP_NBIN ? ws.ujobs + (long long)cls * ws.cap_cols : ws.pjobs + ((long long)cls * DP_NBIN + bin) * ws.pcap;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tilt: saddlepoint equation sum_n p_n s/(q_n + p_n s) = min(K, N - 1/2) on a histogram of the merged probabilities
+// ------------------------------------------------------------------------------------------------
+__device__ double warp_tilt(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &g, int K, int N, double lam,
+                            DpWarpSmem &sm)
+{
+    const int lane = lane_id();
+    for (int i = lane; i < DP_NHIST; i += 32) {
+        sm.u.hist.sum[i] = 0.f;
+        sm.u.hist.cnt[i] = 0;
+    }
+    __syncwarp();
+    const long long abase = g.off & ~15ll;
+    const int lead = (int)(g.off - abase);
+    const int nch = (lead + g.n + 15) >> 4;
+    for (int i = lane; i < nch; i += 32) {
+        Chunk16 ch;
+        load_chunk(cf, b, abase + 16ll * i, ch);
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+            const int pos = 16 * i - lead + k;
+            if (pos < 0 || pos >= g.n) continue;
+            bool is_alt;
+            int slot;
+            double jp;
+            if (!eval_read<true>(cf, s_lut, g, pos, byte_of(ch.bq, k), byte_of(ch.mq, k), byte_of(ch.baq, k), byte_of(ch.sq, k), is_alt, slot, jp))
+                continue;
+            const double p = jp < DEPS ? DEPS : jp;
+            int bk = (0x3ff00000 - __double2hiint(p)) >> 18;       // 4 buckets per binade below 1
+            bk = min(max(bk, 0), DP_NHIST - 1);
+            atomicAdd(&sm.u.hist.sum[bk], (float)p);
+            atomicAdd(&sm.u.hist.cnt[bk], 1);
+        }
+    }
+    __syncwarp();
+    // every lane keeps its 5 buckets: count and mean probability
+    float cb[DP_NHIST / 32], pb[DP_NHIST / 32];
+#pragma unroll
+    for (int k = 0; k < DP_NHIST / 32; ++k) {
+        const int c = sm.u.hist.cnt[lane + 32 * k];
+        cb[k] = (float)c;
+        pb[k] = c ? fminf(sm.u.hist.sum[lane + 32 * k] / (float)c, 1.f) : 0.f;
+    }
+    __syncwarp();
+    const double kt = fmin((double)K, (double)N - 0.5);
+    const double s0 = kt * fmax((double)N - lam, 1e-300) / (fmax(lam, 1e-300) * fmax((double)N - kt, 0.5));
+    double lo = 0.0, hi = 60.0;
+    double ls = fmin(log(fmax(s0, 1.0)), hi);
+    for (int it = 0; it < 40; ++it) {
+        const float sf = (float)exp(ls);
+        float gs = 0.f, ds = 0.f;
+#pragma unroll
+        for (int k = 0; k < DP_NHIST / 32; ++k) {
+            const float ps = pb[k] * sf;
+            const float w = __fdividef(ps, fmaxf(1.f - pb[k], 1e-30f) + ps);        // p s / (q + p s)
+            gs = fmaf(cb[k], w, gs);
+            ds = fmaf(cb[k] * w, 1.f - w, ds);                                        // derivative with respect to ln s
+        }
+        const double gsum = __shfl_sync(FULL, warp_sum((double)gs), 0) - kt;
+        const double d = __shfl_sync(FULL, warp_sum((double)ds), 0);
+        // an error e in ln s costs about d*e^2/2 nats of head-room (of ~700): stop once that is negligible
+        const double step = d > 0.0 ? gsum / d : 0.0;
+        if (d > 0.0 && fabs(step) * sqrt(fmax(d, 1.0)) < 0.5) {
+            ls = fmin(fmax(ls - step, 0.0), 60.0);
+            break;
+        }
+        if (gsum > 0.0) hi = fmin(hi, ls); else lo = fmax(lo, ls);
+        double nl = d > 0.0 ? ls - step : 0.5 * (lo + hi);
+        if (!(nl > lo && nl < hi)) nl = 0.5 * (lo + hi);
+        ls = nl;
+    }
+    return ls;
+}
+
+// lower bound of ln(x) for a positive normal double from its bits: x = m 2^e, ln m >= (m - 1) ln 2 on [1, 2)
+__device__ __forceinline__ double ln_lower(double x)
+{
+    const int hi = __double2hiint(x);
+    const int e = (hi >> 20) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    return ((double)e + (m - 1.0)) * LN2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one warp task: 32/G columns in lock step
+// ------------------------------------------------------------------------------------------------
+template <int G, int R>
+__device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &ws, const double *s_lut, DpWarpSmem &sm,
+                        unsigned char *stage_bytes, int planes, const int *list, unsigned j0, unsigned nj)
+{
+    constexpr int NCOL = 32 / G;
+    constexpr int RPL = 32 / G;                         // reads per lane and block of 32 reads
+    const int lane = lane_id(), grp = lane / G, gl = lane % G;
+    const int last = grp * G + G - 1;                   // the lane that owns the top cells and the absorbing state
+    bool have = j0 + grp < nj;
+    const long long c = have ? list[j0 + grp] : -1;
+    Geom g;
+    g.off = 0; g.n = 0; g.b1 = g.b2 = g.b3 = 0; g.ref_idx = -1; g.alt_bp = 0.0;
+    int cnt[3] = {0, 0, 0};
+    long long bonf = 1;
+    if (have) {
+        int cov;
+        load_geom(b, c, g, cov);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
+        bonf = ws.bonf_used[c];
+    }
+    const int K = max(cnt[0], max(cnt[1], cnt[2]));
+    // alt-base quality override (snpcaller.c:431-441)
+    if (cf.alt_bq_mode == 1) {
+        g.alt_bp = cf.alt_bq_prob;
+    } else if (cf.alt_bq_mode == 2) {
+        // median of the reference-base qualities: whole warp, one column at a time
+#pragma unroll 1
+        for (int ci = 0; ci < NCOL; ++ci) {
+            Geom gg;
+            gg.off = __shfl_sync(FULL, g.off, ci * G);
+            gg.n = __shfl_sync(FULL, g.n, ci * G);
+            gg.b1 = __shfl_sync(FULL, g.b1, ci * G);
+            gg.b2 = __shfl_sync(FULL, g.b2, ci * G);
+            gg.b3 = __shfl_sync(FULL, g.b3, ci * G);
+            gg.ref_idx = __shfl_sync(FULL, g.ref_idx, ci * G);
+            gg.alt_bp = 0.0;
+            if (!__shfl_sync(FULL, (int)have, ci * G)) continue;
+            setup_alt_bq(cf, b, s_lut, gg, sm.u.median_hist);
+            if (grp == ci) g.alt_bp = gg.alt_bp;
+        }
+    }
+
+    // ---- 1. reads kept and lambda, G lanes per column
+    int N = 0;
+    double lam = 0.0;
+    {
+        const long long abase = g.off & ~15ll;
+        const int lead = (int)(g.off - abase);
+        const int nch = have ? (lead + g.n + 15) >> 4 : 0;
+#pragma unroll 1
+        for (int i = gl; i < nch; i += G) {
+            Chunk16 ch;
+            load_chunk(cf, b, abase + 16ll * i, ch);
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+                const int pos = 16 * i - lead + k;
+                bool is_alt;
+                int slot;
+                double jp = 0.0;
+                const bool ok = pos >= 0 && pos < g.n &&
+                                eval_read<true>(cf, s_lut, g, pos, byte_of(ch.bq, k), byte_of(ch.mq, k), byte_of(ch.baq, k), byte_of(ch.sq, k),
+                                                is_alt, slot, jp);
+                if (ok) {
+                    lam += jp < DEPS ? DEPS : jp;
+                    ++N;
+                }
+            }
+        }
+        N = group_sum_i<G>(N);
+        lam = group_sum<G>(lam);
+    }
+    // Chernoff exponent of the tail: beyond ~300 nats the untilted cells of interest drift out of fp64 range
+    double ln_s = 0.0;
+    {
+        const double cher = (have && (double)K > lam) ? ((double)K * log((double)K / fmax(lam, 1e-300)) - (double)K + lam) : 0.0;
+        const bool need = have && cher > 300.0;
+        unsigned todo = __ballot_sync(FULL, need && gl == 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            Geom gg;
+            gg.off = __shfl_sync(FULL, g.off, src);
+            gg.n = __shfl_sync(FULL, g.n, src);
+            gg.b1 = __shfl_sync(FULL, g.b1, src);
+            gg.b2 = __shfl_sync(FULL, g.b2, src);
+            gg.b3 = __shfl_sync(FULL, g.b3, src);
+            gg.ref_idx = __shfl_sync(FULL, g.ref_idx, src);
+            gg.alt_bp = __shfl_sync(FULL, g.alt_bp, src);
+            const double ls = warp_tilt(cf, b, s_lut, gg, __shfl_sync(FULL, K, src), __shfl_sync(FULL, N, src), __shfl_sync(FULL, lam, src), sm);
+            if (lane / G == src / G) ln_s = ls;
+        }
+    }
+    const double s = (ln_s == 0.0) ? 1.0 : exp(ln_s);
+
+    // ---- 2./3. the recurrence, all columns of the warp in lock step
+    const int k0 = K - G * R + gl * R;                  // cell of register 0 (k < 0: padding, stays 0)
+    double E[R], T = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) E[r] = (have && k0 + r == 0) ? 1.0 : 0.0;
+    int e2 = 0;
+    const int n_mine = have ? g.n : 0;
+    const int nmax = __reduce_max_sync(FULL, n_mine);
+    const int lead = (int)(g.off & 15ll);
+    // the bytes of reads [ks*DP_S, (ks+1)*DP_S) of this group's column -> stage buffer ks & 1
+    auto issue = [&](int ks) {
+        if (gl == 0) {
+            unsigned long long *bar = &sm.bar[ks & 1];
+            const int r0 = ks * DP_S;
+            if (r0 < n_mine) {
+                const long long a0 = (g.off + r0) & ~15ll;
+                const unsigned nbytes = (unsigned)((lead + min(DP_S, n_mine - r0) + 15) & ~15);
+                mbar_arrive_expect_tx(bar, nbytes * (unsigned)planes);
+                unsigned char *dst = stage_bytes + ((size_t)((ks & 1) * DP_NCOLMAX + grp) * planes) * DP_SB;
+                int pl = 0;
+                tma_load_1d(dst + (size_t)(pl++) * DP_SB, b.bq + a0, nbytes, bar);
+                if (cf.use_mq) tma_load_1d(dst + (size_t)(pl++) * DP_SB, b.mq + a0, nbytes, bar);
+                if (cf.use_baq) tma_load_1d(dst + (size_t)(pl++) * DP_SB, b.baq + a0, nbytes, bar);
+                if (cf.use_sq) tma_load_1d(dst + (size_t)(pl++) * DP_SB, b.sq + a0, nbytes, bar);
+            } else {
+                mbar_arrive(bar);
+            }
+        }
+    };
+    if (lane == 0) {
+        mbar_init(&sm.bar[0], NCOL);
+        mbar_init(&sm.bar[1], NCOL);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    int issued = 0, waited = 0;
+    if (nmax > 0) { issue(0); issued = 1; }
+    const double thr_ln = log(cf.sig * (1.0 + 1e-9) / (double)bonf) + (double)K * ln_s;
+    bool dead = !have, fb = false;
+    double lq_acc = 0.0, qprod = 1.0;                   // ln of the product of q over this lane's reads = lq_acc + ln(qprod)
+    // step parameters of block nb -> sm.par (single buffer: written between two recurrence blocks)
+    auto make_params = [&](int nb) {
+        const int rbase = nb * 32;
+        if ((rbase % DP_S) == 0) {
+            const int ks = rbase / DP_S;
+            if ((ks + 1) * DP_S < nmax) {
+                __syncwarp();                           // every lane is done with the buffer stage ks+1 overwrites
+                issue(ks + 1);
+                issued = ks + 2;
+            }
+            mbar_wait(&sm.bar[ks & 1], (unsigned)(ks >> 1) & 1u);
+            waited = ks + 1;
+        }
+        const int ks = rbase / DP_S;
+        const unsigned char *src = stage_bytes + ((size_t)((ks & 1) * DP_NCOLMAX + grp) * planes) * DP_SB + lead + (rbase - ks * DP_S);
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+            const int t = gl + G * i;                   // read of this block
+            const int pos = rbase + t;
+            double2 e = make_double2(0.0, 1.0);         // neutral step: a filtered read leaves the row unchanged
+            if (!dead && pos < n_mine) {
+                int pl = 0;
+                const int bq = src[(size_t)(pl++) * DP_SB + t];
+                const int mq = cf.use_mq ? src[(size_t)(pl++) * DP_SB + t] : 0;
+                const int baq = cf.use_baq ? src[(size_t)(pl++) * DP_SB + t] : 0;
+                const int sq = cf.use_sq ? src[(size_t)(pl++) * DP_SB + t] : 0;
+                bool is_alt;
+                int slot;
+                double jp;
+                if (eval_read<true>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp)) {
+                    double p, q;
+                    guard_pq(jp, p, q);
+                    const double rq = 1.0 / q;
+                    const double o = p * s * rq;
+                    e = make_double2(o, rq);
+                    qprod *= q;
+                    // between two rescalings (32 reads) a cell may grow by (1 + o)^32 and the absorbing state by (1/q)^32
+                    bad |= (o > 1048576.0 || rq > 1048576.0);
+                }
+            }
+            sm.par[grp][t] = e;
+        }
+        if (qprod < 1e-200) {
+            lq_acc += log(qprod);
+            qprod = 1.0;
+        }
+        if (__any_sync(FULL, bad)) {
+            // this column cannot be held between two rescalings: the per-column kernel rescales after every read
+            const unsigned bm = __ballot_sync(FULL, bad);
+            const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+            if (bm & gm) { fb = true; dead = true; }
+            __syncwarp();
+            if (fb) {
+#pragma unroll
+                for (int i = 0; i < RPL; ++i) sm.par[grp][gl + G * i] = make_double2(0.0, 1.0);
+            }
+        }
+        __syncwarp();
+    };
+    if (nmax > 0) make_params(0);
+    for (int n0 = 0; n0 < nmax; n0 += 32) {
+        const double2 *pp = sm.par[grp];
+        // software-pipelined: the parameters of read j+1 and the boundary cell for read j+1 (the top cell right
+        // after its own update) are requested before the remaining R-1 cells of read j are updated
+        double2 c_next = pp[0];
+        double in_next = __shfl_up_sync(FULL, E[R - 1], 1);
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+            const double2 cc = c_next;
+            const double in = gl == 0 ? 0.0 : in_next;
+            c_next = pp[(j + 1) & 31];
+            const double top = E[R - 1];
+            T = fma(top, cc.x, T * cc.y);
+            E[R - 1] = fma(E[R - 2], cc.x, top);
+            in_next = __shfl_up_sync(FULL, E[R - 1], 1);
+#pragma unroll
+            for (int r = R - 2; r >= 1; --r) E[r] = fma(E[r - 1], cc.x, E[r]);
+            E[0] = fma(in, cc.x, E[0]);
+        }
+        // exact power-of-two rescaling, per column
+        int hi = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) hi = max(hi, __double2hiint(E[r]));
+        if (lane == last) hi = max(hi, __double2hiint(T));
+        hi = group_max_i<G>(hi);
+        const int ex = (hi >> 20) - 1023;
+        if (hi > 0 && (ex > 200 || ex < -200)) {
+            const double f = __hiloint2double((1023 - ex) << 20, 0);
+#pragma unroll
+            for (int r = 0; r < R; ++r) E[r] *= f;
+            T *= f;
+            e2 += ex;
+        }
+        // Early exit (the reference's, snpcaller.c:916-958): the tail over the reads seen so far can only grow, so once a
+        // lower bound of ln P(X >= K among them) = ln T + e2 ln 2 + sum ln q - K ln s passes ln(sig / bonf) the column is
+        // insignificant whatever follows.  Lower bounds of the logarithms from the bits of T and of the q products.
+        const double lq_lb = group_sum<G>(lq_acc + ln_lower(qprod));
+        const bool over = lane == last && T > 1e-300 && ln_lower(T) + (double)e2 * LN2 + lq_lb > thr_ln;
+        const bool over_g = __shfl_sync(FULL, (int)over, last) != 0;     // every lane takes part, dead or not
+        dead = dead || over_g;
+        __syncwarp();                                  // sm.par is rewritten now
+        if (__all_sync(FULL, dead || n0 + 32 >= n_mine)) break;      // nothing left to decide in this warp
+        make_params((n0 >> 5) + 1);
+    }
+    // a prefetched stage may still be in flight: it must land before the buffers and barriers are reused
+    if (issued > waited) mbar_wait(&sm.bar[(issued - 1) & 1], (unsigned)((issued - 1) >> 1) & 1u);
+    __syncwarp();
+    if (lane == 0) {
+        mbar_inval(&sm.bar[0]);
+        mbar_inval(&sm.bar[1]);
+    }
+    const double sum_lq = group_sum<G>(lq_acc + log(qprod));
+
+    // ---- 4. tails
+    int hiE = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) hiE = max(hiE, __double2hiint(E[r]));
+    hiE = group_max_i<G>(hiE);
+    const double Tl = __shfl_sync(FULL, T, last);
+    const double topl = __shfl_sync(FULL, E[R - 1], last);
+    const int hiT = __double2hiint(Tl);
+    const int peak = max(hiE, hiT) >> 20;
+    const int gap = peak - (hiT >> 20);
+    const bool ruled_out = dead && !fb;                 // early exit fired: insignificant for good
+    if (!ruled_out && ((gap > 580 && ln_s == 0.0) || gap > 900)) fb = true;     // needs the tilt after all / out of range
+    const double base = (double)e2 * LN2 + sum_lq;
+    const double lnT = log(Tl) + base - (double)K * ln_s;
+    const double lnKm1 = log(topl) + base - (double)(K - 1) * ln_s;
+    bool site = have && !fb && !dead;
+    if (site && lnT > -700.0 && exp(lnT) * (double)bonf > cf.sig * (1.0 + 1e-9)) site = false;   // snpcaller.c:1155
+    double lnp[3] = {0.0, 0.0, 0.0};
+    const double invs = (ln_s == 0.0) ? 1.0 : exp(-ln_s);
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {
+        const int ci = cnt[i];
+        if (!__any_sync(FULL, site && ci > 0 && ci < K)) {
+            if (ci == K) lnp[i] = lnT;
+            continue;
+        }
+        const bool mine = site && ci > 0 && ci < K;
+        // P(X >= ci) = sum_{k >= ci} E[k] s^-(k-ci) + T s^-(K-ci), times s^-ci and the common scale
+        double acc = 0.0;
+        int hc = 0x7fffffff;
+        if (mine) {
+            const int kk = max(k0, ci);
+            double f = (ln_s == 0.0) ? 1.0 : exp(-(double)(kk - ci) * ln_s);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (k0 + r >= ci) {
+                    acc = fma(E[r], f, acc);
+                    f *= invs;
+                }
+                if (k0 + r == ci) hc = __double2hiint(E[r]);
+            }
+            if (lane == last) acc = fma(T, (ln_s == 0.0) ? 1.0 : exp(-(double)(K - ci) * ln_s), acc);
+        }
+        acc = group_sum<G>(acc);
+        hc = group_min_i<G>(hc);
+        if (mine) {
+            // the leading cell must have stayed a normal number all along (rescaling keeps the peak within 2^+-200
+            // at the block boundaries and below 2^840 inside a block)
+            if ((hc >> 20) < 64 || peak - (hc >> 20) > 850) fb = true;
+            lnp[i] = log(acc) + base - (double)ci * ln_s;
+        } else if (ci == K) {
+            lnp[i] = lnT;
+        }
+    }
+    if (ruled_out) fb = false;
+    if (fb) site = false;
+    if (have && gl == 0) {
+        if (fb) {
+            const int cls = max(3, class_of(K));          // k_heavy_all: R = 8 .. 64 cells per lane
+            const unsigned slot = atomicAdd(&ws.counters->n_jobs[cls], 1u);
+            ws.jobs[(long long)cls * ws.cap_cols + slot] = (int)c;
+        } else if (site) {
+            Cand cd;
+            cd.col = c;
+            cd.bonf = bonf;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                cd.lnp[i] = cnt[i] > 0 ? lnp[i] : 0.0;
+                cd.cnt[i] = cnt[i];
+                cd.raw[i] = ws.cnt6[6 * c + 3 + i];
+            }
+            cd.ln_floor = fmin(lnT, lnKm1);
+            cd.flags = 0;
+            cd.pad = 0;
+            ws.cand[atomicAdd(&ws.counters->n_cand, 1u)] = cd;
+            mark_cand(ws, c);
+        }
+    }
+    __syncwarp();
+}
+
+// BIG = false: classes 0..5 (R = 8, 16, 32 cells per lane); BIG = true: class 6 (R = 64, its own register budget)
+template <bool BIG>
+__global__ void __launch_bounds__(32 * DP_WARPS, BIG ? 1 : 4) k_dp(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
+                                                                   const Lut *lut, const Workspace ws, int planes)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ double s_lut[768];
+    __shared__ unsigned s_tbase[DP_NL + 1];
+    constexpr int CLS_LO = BIG ? 6 : 0, CLS_HI = BIG ? 6 : 5;
+    dp_list_bases(ws, s_tbase, CLS_LO, CLS_HI);
+    const unsigned total = s_tbase[DP_NL];
+    if (total == 0) return;
+    load_lut(s_lut, lut);
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    unsigned char *wbase = dyn_smem + (size_t)wib * dp_warp_bytes(planes);
+    DpWarpSmem &sm = *reinterpret_cast<DpWarpSmem *>(wbase);
+    unsigned char *stage_bytes = wbase + ((sizeof(DpWarpSmem) + 15) & ~(size_t)15);
+    // the first task of every warp is dealt out statically — with about as many tasks as resident warps, a race for
+    // them leaves some SMs with six tasks per sub-partition and others with three — the rest dynamically
+    const unsigned nwarps = gridDim.x * DP_WARPS;
+    unsigned t = blockIdx.x * DP_WARPS + wib;
+    unsigned *next = BIG ? &ws.counters->next_ptask_big : &ws.counters->next_ptask;
+    for (;;) {
+        if (t >= total) break;
+        // entry of the processing order that holds task t
+        int lo = 0, hi = DP_NL - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_tbase[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        const int li = DP_NL - 1 - lo;
+        const int cls = li / DP_NBIN1;
+        const bool unbinned = (li % DP_NBIN1) == DP_NBIN;
+        const unsigned nj = unbinned ? ws.counters->n_pjobs[li] : min(ws.counters->n_pjobs[li], (unsigned)ws.pcap);
+        const unsigned j0 = (t - s_tbase[lo]) * (unsigned)dp_cols_per_task(cls);
+        const int *list = dp_list_ptr(ws, li);
+        if (BIG) {
+            dp_task<32, 64>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj);
+        } else {
+            switch (cls) {
+                case 0: dp_task<4, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
+                case 1: dp_task<8, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
+                case 2: dp_task<16, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
+                case 3: dp_task<32, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
+                case 4: dp_task<32, 16>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
+                default: dp_task<32, 32>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
+            }
+        }
+        if (lane == 0) t = nwarps + atomicAdd(next, 1u);
+        t = __shfl_sync(FULL, t, 0);
+    }
+}
+
+static size_t dp_smem_bytes(int planes) { return (size_t)DP_WARPS * dp_warp_bytes(planes); }
+
+int dp_smem_optin()
+{
+    // the largest configuration: all four quality planes
+    const int bytes = (int)dp_smem_bytes(4);
+    if (cudaFuncSetAttribute(k_dp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_dp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 1;
+    return 0;
+}
+
+constexpr int DP_CTAS_PER_SM = 4;
+
+// k_dp<false> on `st`, k_dp<true> (K > 1024, rare) beside it on `st_big`
+void launch_dp(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
+               cudaStream_t st_big)
+{
+    if (b.n_cols <= 0) return;
+    const int planes = 1 + (cf.use_mq ? 1 : 0) + (cf.use_baq ? 1 : 0) + (cf.use_sq ? 1 : 0);
+    const size_t smem = dp_smem_bytes(planes);
+    k_dp<false><<<ls.sms * DP_CTAS_PER_SM, 32 * DP_WARPS, smem, st>>>(cf, b, lut, ws, planes);
+    k_dp<true><<<ls.sms, 32 * DP_WARPS, smem, st_big>>>(cf, b, lut, ws, planes);
+}
+
+}  // namespace lfb

@@ -146,7 +146,7 @@ struct lfb200_ctx {
     cudaStream_t stream = nullptr;       // used by the host entry points
     Lut *d_lut = nullptr;
     // workspace of the current batch
-    DevBuf w_cnt6, w_tested, w_bonf, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_pinfo, w_pkscr, w_tilecount, w_iscand, w_candtile, w_candpre, w_perm;
+    DevBuf w_cnt6, w_tested, w_bonf, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_ujobs, w_tilecount, w_iscand, w_candtile, w_candpre, w_perm;
     Workspace ws{};
     // device copies of host batches (host entry point)
     DevBuf in_off, in_cnt, in_ref, in_cov, in_nb, in_bq, in_mq, in_baq, in_sq;
@@ -157,7 +157,6 @@ struct lfb200_ctx {
     Cand *h_cand = nullptr;              // pinned
     size_t h_cand_cap = 0;
     std::unique_ptr<WorkerPool> pool;
-    size_t scr_want = 0;                 // entries of the packed scratch pool the last batch would have needed
     int ensure_cand(size_t n)
     {
         if (n <= h_cand_cap) return 0;
@@ -355,7 +354,7 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_bonf, &ctx->w_blocksum, &ctx->w_jobs,
-                      &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_pinfo, &ctx->w_pkscr, &ctx->w_tilecount, &ctx->w_iscand, &ctx->w_candtile, &ctx->w_candpre, &ctx->w_perm, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
+                      &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_ujobs, &ctx->w_tilecount, &ctx->w_iscand, &ctx->w_candtile, &ctx->w_candpre, &ctx->w_perm, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
                       &ctx->in_bq, &ctx->in_mq, &ctx->in_baq, &ctx->in_sq, &ctx->p_ep, &ctx->p_off, &ctx->p_cnt,
                       &ctx->p_bonf, &ctx->p_out};
     for (DevBuf *b : bufs) b->release();
@@ -393,16 +392,11 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
         bad |= ctx->w_candtile.ensure(((nn + 255) / 256 + 1) * sizeof(unsigned int));
         if (!bad && ctx->w_candtile.p != before) cudaMemset(ctx->w_candtile.p, 0, ctx->w_candtile.cap);   // the scan keeps it zero afterwards
     }
-    // packed job lists hold a quarter of the batch each (a fuller list spills into the per-column lists); the pool
-    // of scratch rows (step parameters of the packed columns, 16 B per read) holds 64 reads per column of the
-    // batch, between 16 MB and 1 GB — when it runs out the remaining columns take the per-column kernels
-    const size_t pcap = std::max<size_t>(nn / 4, 4096);
-    // and grows to what the last batch asked for (deep, noisy columns: lfb200_ctx::scr_want), up to 4 GB
-    const size_t scr_cap = std::max(std::min<size_t>(std::max<size_t>(nn * 64, (size_t)1 << 20), (size_t)64 << 20),
-                                    std::min<size_t>(ctx->scr_want, (size_t)256 << 20));
-    bad |= ctx->w_pjobs.ensure(pcap * PK_NL * sizeof(int));
-    bad |= ctx->w_pinfo.ensure(pcap * PK_NL * sizeof(PkInfo));
-    bad |= ctx->w_pkscr.ensure(scr_cap * sizeof(double2));
+    // k_dp job lists: a binned list holds an eighth of the batch (a fuller one spills into its class's unbinned list,
+    // which holds the whole batch)
+    const size_t pcap = std::max<size_t>(nn / 8, 4096);
+    bad |= ctx->w_pjobs.ensure(pcap * DP_NCLS * DP_NBIN * sizeof(int));
+    bad |= ctx->w_ujobs.ensure(nn * DP_NCLS * sizeof(int));
     if (bad) return fail("out of device memory for a batch of %lld columns", n);
     Workspace &w = ctx->ws;
     w.cap_cols = n;
@@ -418,12 +412,9 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     w.candpre = (long long *)ctx->w_candpre.p;
     w.cand_perm = (int *)ctx->w_perm.p;
     w.counters = (Counters *)ctx->w_counters.p;
-    static const bool no_packed = getenv("LFB200_NO_PACKED") != nullptr;      // A/B timing of k_packed against k_mid / k_heavy<R>
-    w.pjobs = no_packed ? nullptr : (int *)ctx->w_pjobs.p;
+    w.pjobs = (int *)ctx->w_pjobs.p;
     w.pcap = (long long)pcap;
-    w.pinfo = (PkInfo *)ctx->w_pinfo.p;
-    w.pk_scratch = no_packed ? nullptr : (double2 *)ctx->w_pkscr.p;
-    w.pk_scr_cap = (long long)scr_cap;
+    w.ujobs = (int *)ctx->w_ujobs.p;
     return 0;
 }
 
@@ -702,9 +693,9 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
         sm.n_tested = (long long)c->n_tested;
         sm.n_unsupported = c->n_unsupported;
         n_cand = c->n_cand;
-        if ((long long)c->pk_scr_used > ctx->ws.pk_scr_cap) ctx->scr_want = (size_t)c->pk_scr_used + (size_t)c->pk_scr_used / 4;
-        for (int i = 0; i < NCLASS; ++i) if (i != CLS_FALLBACK && i != CLS_PRUNE2) sm.n_heavy += c->n_jobs[i];
-        for (int i = 0; i < PK_NL; ++i) sm.n_heavy += std::min<long long>(c->n_pjobs[i], ctx->ws.pcap);
+        sm.n_heavy = c->n_jobs[0] + c->n_jobs[CLS_XL];        // k_mid, k_heavy_xl
+        for (int i = 0; i < DP_NL; ++i)                        // k_dp (binned lists are capped, the excess is in the unbinned ones)
+            sm.n_heavy += (i % DP_NBIN1) == DP_NBIN ? (long long)c->n_pjobs[i] : std::min<long long>(c->n_pjobs[i], ctx->ws.pcap);
         lfb200_site_t *hs = ctx->h_sites;
         // the few sites with a comparison inside its guard band
         if (c->n_fix) {
@@ -890,9 +881,10 @@ extern "C" int lfb200_last_job_counts(lfb200_ctx *ctx, long long out[4])
     if (!ctx || !out) return fail("null argument");
     const Counters &c = *ctx->h_counters;          // copied back by the last sites_sync
     out[0] = out[1] = out[2] = out[3] = 0;
-    for (int i = 0; i < PK_NL; ++i) out[0] += std::min<long long>(c.n_pjobs[i], ctx->ws.pcap);
-    out[1] = c.n_jobs[CLS_FALLBACK];               // includes the few k_mid hands back
-    for (int i = 1; i < NCLASS; ++i) if (i != CLS_FALLBACK && i != CLS_PRUNE2) out[2] += c.n_jobs[i];
+    for (int i = 0; i < DP_NL; ++i)
+        out[0] += (i % DP_NBIN1) == DP_NBIN ? (long long)c.n_pjobs[i] : std::min<long long>(c.n_pjobs[i], ctx->ws.pcap);
+    out[1] = c.n_jobs[CLS_FALLBACK] + c.n_jobs[3] + c.n_jobs[4] + c.n_jobs[5] + c.n_jobs[6];     // k_heavy_all
+    out[2] = c.n_jobs[CLS_XL];
     out[3] = c.n_jobs[0];
     return 0;
 }

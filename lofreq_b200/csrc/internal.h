@@ -13,16 +13,14 @@ constexpr int CLS_XL = 7, CLS_FALLBACK = 8;
 constexpr int CLS_PRUNE2 = 9;       // K <= 8 columns still alive after the first reads of k_finalize's prune: k_prune2's input
 constexpr int MAXK_WARP = 2048;    // 32 lanes * 64 cells
 
-// k_packed (packed.cu): columns with 8 < K <= 256 share a warp — G = 4, 8, 16 or 32 lanes per column, PK_R cells per
-// lane, all columns of a warp advancing read by read in lock step.  Job lists per (G, depth bin) so that the columns
-// of a warp have similar depths; a list that overflows, or a column the packed form cannot hold, uses the k_mid /
-// k_heavy<R> lists instead.
-constexpr int PK_R = 8;            // cells per lane
-constexpr int PK_NG = 4;           // G = 4 << gi
-constexpr int PK_NB = 8;           // depth bins: <= 128, 256, ..., 16384 reads
-constexpr int PK_NL = PK_NG * PK_NB;
-constexpr int PK_MAXN = 16384;     // deepest column of the packed form
-constexpr int PK_MAXK = 32 * PK_R;
+// k_dp (dp_fused.cu): columns with 8 < K <= 2048 share a warp — G = 4, 8, 16 or 32 lanes per column, R = 8 .. 64 cells
+// per lane (class), all columns of a warp advancing read by read in lock step.  Job lists per (class, depth bin) so
+// that the columns of a warp have similar depths; a binned list that overflows spills into the class's unbinned list.
+constexpr int DP_NCLS = 7;         // (G, R): (4,8) (8,8) (16,8) (32,8) (32,16) (32,32) (32,64) -> K <= 32 .. 2048
+constexpr int DP_NBIN = 14;        // depth bins: <= 128, 256, ..., 2^20 reads (defaults.h:60: max depth 1e6)
+constexpr int DP_NBIN1 = DP_NBIN + 1;   // + the unbinned overflow list of the class
+constexpr int DP_NL = DP_NCLS * DP_NBIN1;
+constexpr int DP_MAXK = 2048;
 
 // what the kernels need from varcall_conf_t, pre-digested on the host
 struct DevConf {
@@ -95,22 +93,15 @@ struct Counters {
     unsigned int n_jobs[NCLASS];
     unsigned int next_job[NCLASS];
     unsigned int err_flags;
-    unsigned int n_pjobs[PK_NL];   // packed job lists (may exceed Workspace::pcap: the excess went to the other lists)
-    unsigned int next_ptask;
-    unsigned long long pk_scr_used; // entries of the scratch pool handed out so far
+    unsigned int n_pjobs[DP_NL];   // k_dp job lists, index class * DP_NBIN1 + bin (a binned count may exceed Workspace::pcap:
+                                   // the excess went to the class's unbinned list, bin == DP_NBIN)
+    unsigned int next_ptask, next_ptask_big;
     long long bonf_start_used;     // running factor the last test started from (host or device supplied)
     // written by k_emit_sites
     unsigned int n_fix;            // sites whose decision the host must repeat (may exceed EMIT_FIX_MAX: then all are rechecked)
     unsigned int emit_overflow;    // more sites than the host buffer holds: the host grows it and emits again
     unsigned int n_unsupported;    // columns with an alt count no kernel of this build takes
     unsigned int fix[EMIT_FIX_MAX];
-};
-
-// what k_pk_prep leaves for k_packed about one packed column
-struct PkInfo {
-    long long scr_off;             // its row in the scratch pool; -1 = not prepared (pool full: the column went to k_heavy<R>)
-    double ln_s;                   // tilt (0 = none)
-    double sum_lq;                 // sum over the kept reads of ln(1 - p)
 };
 
 struct Workspace {
@@ -127,11 +118,9 @@ struct Workspace {
     long long *candpre;            // [ceil(n/256)]: candidates before each tile
     int *cand_perm;                // [n]: cand_perm[rank in column order] = index into cand
     Counters *counters;
-    int *pjobs;                    // [PK_NL][pcap]
+    int *pjobs;                    // [DP_NCLS * DP_NBIN][pcap]
     long long pcap;
-    PkInfo *pinfo;                 // [PK_NL][pcap], written by k_pk_prep
-    double2 *pk_scratch;           // pool of rows: per read the step parameters (o, 1/q), rows padded to 32 reads
-    long long pk_scr_cap;          // entries
+    int *ujobs;                    // [DP_NCLS][n]: unbinned overflow lists
 };
 
 // stand-alone snpcaller problems (link-compatible path)
@@ -169,8 +158,10 @@ void launch_bonf_start_strided(const long long *counts, int stride, int rank, lo
                                cudaStream_t st);
 void launch_set_i64(long long *dst, long long v, cudaStream_t st);
 double measure_dfma_per_second(int sms, cudaStream_t st);
-// packed.cu
-void launch_packed(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
+// dp_fused.cu
+int dp_smem_optin();
+void launch_dp(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
+               cudaStream_t st_big);
 void launch_prob_jobs(int sms, const ProbBatch &pb, Cand *out, cudaStream_t st);
 // mailbox.cu: the per-batch count exchange between shards through shared host memory
 constexpr int MAIL_DEPTH = 64;

@@ -6,7 +6,7 @@
 //   snpcaller -> poissbin -> pruned_calc_prob_dist (snpcaller.c:830-1204)
 //                                           Poisson-binomial DP in log space, tail p-value per allele
 //
-// What runs here (DESIGN.md has the whole picture; packed.cu, poissbin.cu, mailbox.cu, binom.cu hold the rest):
+// What runs here (DESIGN.md has the whole picture; dp_fused.cu, poissbin.cu, mailbox.cu, binom.cu, fisher.cu hold the rest):
 //   k_screen    gates and alt counts: only the reads showing a non-reference base are looked at; a warp takes 32
 //               columns (lane per column for few alt reads, whole warp otherwise); tested columns per tile of 256.
 //   k_scan_blocks / k_finalize / k_prune2
@@ -560,29 +560,22 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant
     }
     const int K = max(cnt[0], max(cnt[1], cnt[2]));
     if (t && K > KS) {
-        // 8 < K <= 256: packed kernel (several columns per warp) unless the column is too deep for its scratch row, the
-        // median override needs a warp-wide histogram, or the list is full; everything else: one warp / CTA per column
-        bool routed = false;
-        if (K <= PK_MAXK && cf.alt_bq_mode != 2 && ws.pjobs) {
-            const int pl = packed_list(K, mg.n);
-            if (pl >= 0) {
-                // its row in the scratch pool (padded to 32 reads), then its slot in the list
-                const int npad = (mg.n + 31) & ~31;
-                const long long off = (long long)atomicAdd(&ws.counters->pk_scr_used, (unsigned long long)npad);
-                if (off + npad <= ws.pk_scr_cap) {
-                    const unsigned slot = atomicAdd(&ws.counters->n_pjobs[pl], 1u);
-                    if (slot < (unsigned)ws.pcap) {
-                        ws.pjobs[(long long)pl * ws.pcap + slot] = (int)c;
-                        ws.pinfo[(long long)pl * ws.pcap + slot].scr_off = off;
-                        routed = true;
-                    }
-                }
+        if (K <= DP_MAXK) {
+            // 8 < K <= 2048: k_dp, several columns per warp; job list by (class, depth bin), the class's unbinned list
+            // when the binned one is full
+            const int li = dp_list(K, mg.n);
+            const int cls = li / DP_NBIN1;
+            const unsigned slot = atomicAdd(&ws.counters->n_pjobs[li], 1u);
+            if (slot < (unsigned)ws.pcap) {
+                ws.pjobs[((long long)cls * DP_NBIN + (li % DP_NBIN1)) * ws.pcap + slot] = (int)c;
+            } else {
+                const unsigned s2 = atomicAdd(&ws.counters->n_pjobs[cls * DP_NBIN1 + DP_NBIN], 1u);
+                ws.ujobs[(long long)cls * ws.cap_cols + s2] = (int)c;
             }
-        }
-        if (!routed) {
-            const int cls = class_of(K);
-            const unsigned slot = atomicAdd(&ws.counters->n_jobs[cls], 1u);
-            ws.jobs[(long long)cls * ws.cap_cols + slot] = (int)c;
+        } else {
+            // one CTA per column
+            const unsigned slot = atomicAdd(&ws.counters->n_jobs[CLS_XL], 1u);
+            ws.jobs[(long long)CLS_XL * ws.cap_cols + slot] = (int)c;
         }
     }
     // ---- columns with K <= KS ----
@@ -1085,11 +1078,11 @@ __device__ bool run_problem(const Src &src, const int (&cnt)[3], long long bonf,
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_mid: columns with 8 < K <= 32, and the columns with K <= 8 that k_finalize's lane-per-column prune could
-// not rule out within PRUNE_CAP reads.  At this size the recurrence over reads (depth serial steps of a
-// 32-cell row) is slower than folding the reads in parallel — every lane its 16-byte chunks into a
-// distribution truncated at 2, 4, 8, 16 or 32 — and merging the 32 distributions by truncated convolution.
-// Untilted: if the tail leaves the fp64 range the column is handed to k_heavy<1>.
+// k_mid: the columns with K <= 8 that the lane-per-column prune of k_finalize / k_prune2 could not rule out within
+// PRUNE_CAP reads (true low-frequency variants, the first columns of a run).  At this size the recurrence over reads
+// (depth serial steps of a short row) is slower than folding the reads in parallel — every lane its 16-byte chunks into
+// a distribution truncated at 2, 4 or 8 — and merging the 32 distributions by truncated convolution.
+// Untilted: if the tail leaves the fp64 range the column is handed to the per-column fallback (k_heavy_all).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_mid(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, const Lut *lut,
                                              const Workspace ws)
@@ -1120,9 +1113,7 @@ __global__ void __launch_bounds__(128) k_mid(const __grid_constant__ DevConf cf,
         double tails[4];
         if (K <= 2) screen_small<2>(cf, b, lut_sa, g, cnt, K, tails);
         else if (K <= 4) screen_small<4>(cf, b, lut_sa, g, cnt, K, tails);
-        else if (K <= 8) screen_small<8>(cf, b, lut_sa, g, cnt, K, tails);
-        else if (K <= 16) screen_small<16>(cf, b, lut_sa, g, cnt, K, tails);
-        else screen_small<32>(cf, b, lut_sa, g, cnt, K, tails);
+        else screen_small<8>(cf, b, lut_sa, g, cnt, K, tails);
         double tK = cnt[0] == K ? tails[0] : cnt[1] == K ? tails[1] : tails[2];
         tK = __shfl_sync(FULL, tK, 0);
         const double fl = __shfl_sync(FULL, tails[3], 0);
@@ -1152,19 +1143,15 @@ __global__ void __launch_bounds__(128) k_mid(const __grid_constant__ DevConf cf,
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_heavy<R>: persistent warps pull columns of one register-tile class from a job list
+// k_heavy_all: the per-column fallback — one warp per column, K cells tiled over 32 lanes x R registers, every
+// repair the general routine knows (run_problem: tilt after the fact, rescaling after every read, separate runs for
+// the other alleles).  Takes what k_dp and k_mid hand back; normally every list is empty and the kernel leaves at once.
 // ------------------------------------------------------------------------------------------------
 template <int R>
-__global__ void __launch_bounds__(128) k_heavy(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, const Lut *lut,
-                                               const Workspace ws, int cls)
+__device__ void heavy_list(const DevConf &cf, const DevBatch &b, const double *s_lut, const Workspace &ws, int cls, double2 *s_par,
+                           int *s_hist, double *s_stage)
 {
-    __shared__ double s_lut[768];
-    __shared__ double2 s_par[4][32];
-    __shared__ int s_hist[4][256];
-    extern __shared__ double s_stage[];          // [4][STAGE_DOUBLES]
-    if (ws.counters->n_jobs[cls] == 0) return;                 // nothing listed: leave before the table is even loaded
-    load_lut(s_lut, lut);
-    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    const int lane = lane_id();
     const unsigned njobs = ws.counters->n_jobs[cls];
     const int *jobs = ws.jobs + (long long)cls * ws.cap_cols;
     for (;;) {
@@ -1174,19 +1161,19 @@ __global__ void __launch_bounds__(128) k_heavy(const __grid_constant__ DevConf c
         if (j >= njobs) break;
         const long long c = jobs[j];
         Staged<ByteSrc> src;
-        src.init(s_stage + wib * STAGE_DOUBLES);
+        src.init(s_stage);
         src.raw.cf = &cf;
         src.raw.b = &b;
         src.raw.lut = s_lut;
         int cov;
         load_geom(b, c, src.raw.g, cov);
-        setup_alt_bq(cf, b, s_lut, src.raw.g, s_hist[wib]);
+        setup_alt_bq(cf, b, s_lut, src.raw.g, s_hist);
         int cnt[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
         const long long bonf = ws.bonf_used[c];
         Cand cd;
-        const bool site = run_problem<R>(src, cnt, bonf, cf.sig, s_par[wib], cd);
+        const bool site = run_problem<R>(src, cnt, bonf, cf.sig, s_par, cd);
         if (site && lane == 0) {
             cd.col = c;
             cd.bonf = bonf;
@@ -1201,6 +1188,25 @@ __global__ void __launch_bounds__(128) k_heavy(const __grid_constant__ DevConf c
             mark_cand(ws, c);
         }
     }
+}
+
+__global__ void __launch_bounds__(128) k_heavy_all(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, const Lut *lut,
+                                                   const Workspace ws)
+{
+    __shared__ double s_lut[768];
+    __shared__ double2 s_par[4][32];
+    __shared__ int s_hist[4][256];
+    extern __shared__ double s_stage[];          // [4][STAGE_DOUBLES]
+    const Counters *cn = ws.counters;
+    if ((cn->n_jobs[3] | cn->n_jobs[4] | cn->n_jobs[5] | cn->n_jobs[6] | cn->n_jobs[CLS_FALLBACK]) == 0) return;
+    load_lut(s_lut, lut);
+    const int wib = threadIdx.x >> 5;
+    double *stg = s_stage + wib * STAGE_DOUBLES;
+    heavy_list<64>(cf, b, s_lut, ws, 6, s_par[wib], s_hist[wib], stg);
+    heavy_list<32>(cf, b, s_lut, ws, 5, s_par[wib], s_hist[wib], stg);
+    heavy_list<16>(cf, b, s_lut, ws, 4, s_par[wib], s_hist[wib], stg);
+    heavy_list<8>(cf, b, s_lut, ws, 3, s_par[wib], s_hist[wib], stg);
+    heavy_list<8>(cf, b, s_lut, ws, CLS_FALLBACK, s_par[wib], s_hist[wib], stg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1598,7 +1604,6 @@ constexpr int STAGE_BYTES = 4 * STAGE_DOUBLES * (int)sizeof(double);
 template <int R>
 static void stage_optin_one()
 {
-    cudaFuncSetAttribute(k_heavy<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES);
     cudaFuncSetAttribute(k_prob_jobs<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES);
 }
 
@@ -1613,6 +1618,8 @@ int launch_state_init(LaunchState &ls, int device)
     ls.sms = n;
     stage_optin_one<1>(); stage_optin_one<2>(); stage_optin_one<4>(); stage_optin_one<8>();
     stage_optin_one<16>(); stage_optin_one<32>(); stage_optin_one<64>();
+    cudaFuncSetAttribute(k_heavy_all, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES);
+    if (dp_smem_optin()) return 1;
     if (cudaEventCreateWithFlags(&ls.ev_fork, cudaEventDisableTiming) != cudaSuccess) return 1;
     if (cudaEventCreateWithFlags(&ls.ev_fork2, cudaEventDisableTiming) != cudaSuccess) return 1;
     for (int i = 0; i < NSIDE; ++i) {
@@ -1663,33 +1670,21 @@ void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, co
     k_finalize<<<nb, FIN_BLOCK, 0, st>>>(cf, b, lut, ws, bonf_start_dev);
     k_prune2<<<ls.sms * 2, 128, 0, st>>>(cf, b, lut, ws);
     if (after_finalize) cudaEventRecord(after_finalize, st);
-    // The register-tile classes are independent: run them side by side so that their warps share the SMs
-    // (each class alone has too few columns to hide its own latencies).
-    const int g = ls.sms * 4;
-    // k_mid (K <= 8 survivors, unpackable K <= 32) runs beside k_pk_prep -> k_packed.  Both hand the few columns they
-    // cannot finish to one fallback list, which k_heavy<8> (any K <= 256) takes afterwards, side by side with the
-    // per-column kernels for what k_finalize listed for them (K > 256, very deep columns, median override) — each
-    // class alone has too few columns to hide its own latencies; an empty list costs an early exit.
+    // Independent work side by side, so that the warps of the small kernels share the SMs with k_dp: k_mid (K <= 8
+    // survivors of the prune), k_dp<true> (1024 < K <= 2048, its own register budget), k_heavy_xl (K > 2048, one CTA per
+    // column); an empty list costs an early exit.  Then the per-column fallback for the few columns they hand back.
     cudaEventRecord(ls.ev_fork, st);
     cudaStreamWaitEvent(ls.side[0], ls.ev_fork, 0);
-    k_mid<<<g, 128, 0, ls.side[0]>>>(cf, b, lut, ws);
-    cudaEventRecord(ls.ev_join[0], ls.side[0]);
-    launch_packed(ls, cf, b, lut, ws, st);
-    cudaStreamWaitEvent(st, ls.ev_join[0], 0);
-    cudaEventRecord(ls.ev_fork2, st);
-    for (int i = 0; i < NSIDE; ++i) cudaStreamWaitEvent(ls.side[i], ls.ev_fork2, 0);
-    k_heavy_xl<<<ls.sms, XL_T, 0, ls.side[7]>>>(cf, b, lut, ws, CLS_XL);
-    k_heavy<64><<<g, 128, STAGE_BYTES, ls.side[6]>>>(cf, b, lut, ws, 6);
-    k_heavy<32><<<g, 128, STAGE_BYTES, ls.side[5]>>>(cf, b, lut, ws, 5);
-    k_heavy<16><<<g, 128, STAGE_BYTES, ls.side[4]>>>(cf, b, lut, ws, 4);
-    k_heavy<8><<<g, 128, STAGE_BYTES, ls.side[3]>>>(cf, b, lut, ws, 3);
-    k_heavy<4><<<g, 128, STAGE_BYTES, ls.side[2]>>>(cf, b, lut, ws, 2);
-    k_heavy<2><<<g, 128, STAGE_BYTES, ls.side[1]>>>(cf, b, lut, ws, 1);
-    k_heavy<8><<<g, 128, STAGE_BYTES, ls.side[0]>>>(cf, b, lut, ws, CLS_FALLBACK);
-    for (int i = 0; i < NSIDE; ++i) {
+    cudaStreamWaitEvent(ls.side[1], ls.ev_fork, 0);
+    cudaStreamWaitEvent(ls.side[2], ls.ev_fork, 0);
+    k_mid<<<ls.sms * 4, 128, 0, ls.side[0]>>>(cf, b, lut, ws);
+    k_heavy_xl<<<ls.sms, XL_T, 0, ls.side[2]>>>(cf, b, lut, ws, CLS_XL);
+    launch_dp(ls, cf, b, lut, ws, st, ls.side[1]);
+    for (int i = 0; i < 3; ++i) {
         cudaEventRecord(ls.ev_join[i], ls.side[i]);
         cudaStreamWaitEvent(st, ls.ev_join[i], 0);
     }
+    k_heavy_all<<<ls.sms, 128, STAGE_BYTES, st>>>(cf, b, lut, ws);
     // the sites in column order (see k_rank_cands)
     k_scan_blocks<<<1, 1024, 0, st>>>(ws.candtile, ws.candpre, nb, nullptr);
     k_rank_cands<<<ls.sms, 256, 0, st>>>(ws);

@@ -489,8 +489,8 @@ def test_deep_columns_cta_per_column_kernel(caller, port_oracle):
 
 
 def test_packed_kernel_classes(caller, port_oracle):
-    """8 < K <= 256: k_pk_prep + k_packed, 4/8/16/32 lanes per column, columns of one warp in lock step.
-    Every group width, tilted and untilted rows, secondary alleles read off a tilted row, ragged depths inside
+    """8 < K <= 2048: k_dp, 4/8/16/32 lanes per column and 8..64 cells per lane, columns of one warp in lock step.
+    Every class, tilted and untilted rows, secondary alleles read off a tilted row, ragged depths inside
     one warp, neutral steps for filtered reads, and the hand-over to the fallback list."""
     rng = np.random.default_rng(77)
 
@@ -499,7 +499,7 @@ def test_packed_kernel_classes(caller, port_oracle):
     e = (np.zeros(0, int),) * 3
     cols = []
     # every group width at several depths (each depth bin has its own job list), ragged inside a bin
-    for K in (9, 17, 32, 33, 50, 64, 65, 100, 128, 129, 200, 256):
+    for K in (9, 17, 32, 33, 50, 64, 65, 100, 128, 129, 200, 256, 257, 400, 512, 513, 1000, 1024, 1025, 1500, 2048):
         for depth in (K + 1, 2 * K + 37, 600, 1100, 3000):
             if depth <= K:
                 continue
@@ -531,31 +531,30 @@ def test_packed_kernel_classes(caller, port_oracle):
             jc = got["job_counts"]
             assert jc["packed"] >= 60, jc                      # the packed kernel really took them
             assert jc["fallback"] < jc["packed"] // 4, jc
-    # median override needs a warp-wide histogram per column: none of these may take the packed form
+    # median override (def_alt_bq = -1): the histogram of the reference-base qualities is built inside k_dp
     got = caller.call_columns(b, default_conf(def_alt_bq=-1))
     compare_batch(got, port_oracle.call_columns(b, default_conf(def_alt_bq=-1)), "packed median")
-    assert got["job_counts"]["packed"] == 0
+    assert got["job_counts"]["packed"] >= 60
 
 
-def test_packed_scratch_pool_overflow(port_oracle):
-    """more heavy reads than the scratch pool holds (16 reads per column of the batch, at least 1 Mi): the columns
-    that do not get a row take the per-column kernels, with the same results (fresh context: the pool of a used one
-    has grown to what earlier batches asked for)"""
+def test_dp_job_list_overflow(port_oracle):
+    """more columns of one (class, depth bin) than its job list holds (an eighth of the batch, at least 4096): the excess
+    goes to the class's unbinned list and is computed all the same"""
     import lofreq_b200
     caller = lofreq_b200.Caller(0)
     rng = np.random.default_rng(3)
     e = (np.zeros(0, int),) * 3
     cols = []
-    for i in range(450):
-        n, K = 2600 + int(rng.integers(0, 200)), int(rng.integers(20, 250))
+    for i in range(5000):
+        n, K = 100 + int(rng.integers(0, 28)), int(rng.integers(9, 33))
         cols.append(dict(ref="A", groups=[(rng.integers(25, 41, n - K), np.full(n - K, 60), np.full(n - K, 40)),
                                           (rng.integers(25, 41, K), np.full(K, 60), np.full(K, 40)), e, e]))
     b = _custom_batch(cols, pad=16)
     want = port_oracle.call_columns(b, default_conf())
     got = caller.call_columns(b, default_conf())
-    compare_batch(got, want, "pool overflow")
+    compare_batch(got, want, "job list overflow")
     jc = got["job_counts"]
-    assert 0 < jc["packed"] < 450 and jc["per_column"] + jc["mid"] > 0, jc
+    assert jc["packed"] == 5000 and int(want["called"].any(axis=1).sum()) > 4500, jc
     caller.close()
 
 

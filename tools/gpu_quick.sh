@@ -2,12 +2,12 @@
 # quick GPU pass: parity tests (verbose timing of the slowest) + smoke + a short bench
 mkdir -p gpurun_out
 nproc > gpurun_out/gpu.txt; nvidia-smi -L >> gpurun_out/gpu.txt
-( time timeout 1500 python -m pytest tests -m gpu -x -q -s --durations=8 ${PYTEST_ARGS:-} ) > gpurun_out/pytest_gpu.log 2>&1
+( time timeout 1500 python -m pytest tests -m gpu -q -s --durations=8 ${PYTEST_ARGS:-} ) > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-grep -E "vs (reference|port)|multi-GPU|passed|failed|error|rc=|s call" gpurun_out/pytest_gpu.log | tail -30
+grep -E "vs (reference|port)|multi-GPU|passed|failed|error|rc=|s call|FAILED" gpurun_out/pytest_gpu.log | tail -30
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 tail -2 gpurun_out/smoke.log
-timeout 600 python bench.py --steps ${STEPS:-100} --no-cpu > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"
+LFB200_HOST_TIMING=1 timeout 600 python bench.py --steps ${STEPS:-100} --no-cpu > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_quick.json'))
