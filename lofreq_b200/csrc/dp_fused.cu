@@ -14,7 +14,7 @@
 //      the fp64 range -> saddlepoint tilt s: a histogram of the merged probabilities (160 buckets of 0.75 dB) built by
 //      the whole warp in shared memory, Newton on ln s over the buckets (the tolerance of the tilt is coarse: an
 //      error e costs about var*e^2/2 nats of ~700).
-//   2. the quality bytes of the next 128 reads of every column of the warp travel from HBM to shared memory with
+//   2. the quality bytes of the next 64 reads of every column of the warp travel from HBM to shared memory with
 //      1-D bulk TMA copies (cp.async.bulk + mbarrier, double-buffered: stage k+1 is in flight while stage k is
 //      consumed); for each block of 32 reads the lanes of a column turn its bytes into the step parameters
 //      (o, 1/q), o = p*s/q, with the shared-memory copy of the glibc-pow LUT and the reference's merge order.
@@ -31,6 +31,7 @@
 #include <math.h>
 #include "internal.h"
 #include "dev_common.cuh"
+#include "screen_common.cuh"
 
 namespace lfb {
 
@@ -64,6 +65,51 @@ __device__ __forceinline__ int group_min_i(int v)
 #pragma unroll
     for (int m = G / 2; m >= 1; m >>= 1) v = min(v, __shfl_xor_sync(FULL, v, m));
     return v;
+}
+
+// distribution truncated at KS = 8 (P[k] = P(k errors), k < 8; T = P(>= 8 errors)) for the small counts of the other
+// alleles of a heavy column: one read folded in ...
+__device__ __forceinline__ void small_update(double (&P)[KS], double &T, double p, double q)
+{
+    T = fma(P[KS - 1], p, T);
+#pragma unroll
+    for (int k = KS - 1; k >= 1; --k) P[k] = fma(P[k - 1], p, P[k] * q);
+    P[0] = P[0] * q;
+}
+
+// ... and the G per-lane distributions of a column merged by truncated convolution (butterfly inside the group)
+template <int G>
+__device__ __forceinline__ void small_merge(double (&P)[KS], double &T)
+{
+#pragma unroll 1
+    for (int m = 1; m < G; m <<= 1) {
+        double bb[KS], cc[KS];
+        const double tb = __shfl_xor_sync(FULL, T, m);
+        double sum_a = 0.0, sum_b = 0.0;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            bb[k] = __shfl_xor_sync(FULL, P[k], m);
+            sum_a += P[k];
+            sum_b += bb[k];
+        }
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i <= k; ++i) acc = fma(P[i], bb[k - i], acc);
+            cc[k] = acc;
+        }
+        double t = T * (sum_b + tb) + tb * sum_a;
+        double asuf = 0.0;
+#pragma unroll
+        for (int j = 1; j < KS; ++j) {
+            asuf += P[KS - j];
+            t = fma(bb[j], asuf, t);
+        }
+#pragma unroll
+        for (int k = 0; k < KS; ++k) P[k] = cc[k];
+        T = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -121,7 +167,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // layout of the dynamic shared memory
 // ------------------------------------------------------------------------------------------------
 constexpr int DP_WARPS = 4;
-constexpr int DP_S = 128;                   // reads per TMA stage and column
+constexpr int DP_S = 64;                    // reads per TMA stage and column
 constexpr int DP_SB = DP_S + 16;            // bytes per stage, column and plane: + the lead of an unaligned column
 constexpr int DP_NCOLMAX = 8;               // columns per warp at G = 4
 constexpr int DP_PAR = 33;                  // one parameter row: 32 reads, padded (banks)
@@ -129,8 +175,9 @@ constexpr int DP_NHIST = 160;               // buckets of the tilt histogram: 4 
 
 struct DpWarpSmem {
     unsigned long long bar[2];
-    double2 par[DP_NCOLMAX][DP_PAR];
     union {
+        double2 par[DP_NCOLMAX][DP_PAR];                              // step parameters of the current block of 32 reads
+        // before the recurrence starts the same bytes serve the set-up of the task:
         struct { float sum[DP_NHIST]; int cnt[DP_NHIST]; } hist;     // tilt histogram (whole warp, one column at a time)
         int median_hist[256];                                         // def_alt_bq == -1 (warp_ref_median)
     } u;
@@ -284,7 +331,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         load_geom(b, c, g, cov);
 #pragma unroll
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
-        bonf = ws.bonf_used[c];
+        bonf = bonf_of(cf, ws.counters->bonf_start_used, ws.rank[c]);
     }
     const int K = max(cnt[0], max(cnt[1], cnt[2]));
     // alt-base quality override (snpcaller.c:431-441)
@@ -308,9 +355,20 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         }
     }
 
-    // ---- 1. reads kept and lambda, G lanes per column
+    // ---- 1. reads kept and lambda, G lanes per column.  Alleles of the column with a count of at most KS (a few
+    // sequencing errors beside the variant) get their tail here as well, exactly, from the distribution truncated at KS —
+    // on a strongly tilted row their cells would be lost to underflow.
     int N = 0;
     double lam = 0.0;
+    double small_tail[3] = {0.0, 0.0, 0.0};
+    bool use_small[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) use_small[i] = have && cnt[i] > 0 && cnt[i] <= KS && cnt[i] < K;
+    const bool want_small = use_small[0] || use_small[1] || use_small[2];
+    const bool any_small = __any_sync(FULL, want_small);
+    double P8[KS], T8 = 0.0;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) P8[k] = (k == 0) ? 1.0 : 0.0;
     {
         const long long abase = g.off & ~15ll;
         const int lead = (int)(g.off - abase);
@@ -331,11 +389,27 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
                 if (ok) {
                     lam += jp < DEPS ? DEPS : jp;
                     ++N;
+                    if (any_small && want_small) {
+                        double p, q;
+                        guard_pq(jp, p, q);
+                        small_update(P8, T8, p, q);
+                    }
                 }
             }
         }
         N = group_sum_i<G>(N);
         lam = group_sum<G>(lam);
+        if (any_small) {
+            small_merge<G>(P8, T8);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double tl = T8;
+#pragma unroll
+                for (int k = KS - 1; k >= 0; --k)
+                    if (k >= cnt[i]) tl += P8[k];
+                small_tail[i] = tl;
+            }
+        }
     }
     // Chernoff exponent of the tail: beyond ~300 nats the untilted cells of interest drift out of fp64 range
     double ln_s = 0.0;
@@ -441,7 +515,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
                     bad |= (o > 1048576.0 || rq > 1048576.0);
                 }
             }
-            sm.par[grp][t] = e;
+            sm.u.par[grp][t] = e;
         }
         if (qprod < 1e-200) {
             lq_acc += log(qprod);
@@ -455,14 +529,14 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
             __syncwarp();
             if (fb) {
 #pragma unroll
-                for (int i = 0; i < RPL; ++i) sm.par[grp][gl + G * i] = make_double2(0.0, 1.0);
+                for (int i = 0; i < RPL; ++i) sm.u.par[grp][gl + G * i] = make_double2(0.0, 1.0);
             }
         }
         __syncwarp();
     };
     if (nmax > 0) make_params(0);
     for (int n0 = 0; n0 < nmax; n0 += 32) {
-        const double2 *pp = sm.par[grp];
+        const double2 *pp = sm.u.par[grp];
         // software-pipelined: the parameters of read j+1 and the boundary cell for read j+1 (the top cell right
         // after its own update) are requested before the remaining R-1 cells of read j are updated
         double2 c_next = pp[0];
@@ -536,11 +610,12 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
 #pragma unroll 1
     for (int i = 0; i < 3; ++i) {
         const int ci = cnt[i];
-        if (!__any_sync(FULL, site && ci > 0 && ci < K)) {
+        if (use_small[i]) lnp[i] = log(small_tail[i]);
+        if (!__any_sync(FULL, site && ci > 0 && ci < K && !use_small[i])) {
             if (ci == K) lnp[i] = lnT;
             continue;
         }
-        const bool mine = site && ci > 0 && ci < K;
+        const bool mine = site && ci > 0 && ci < K && !use_small[i];
         // P(X >= ci) = sum_{k >= ci} E[k] s^-(k-ci) + T s^-(K-ci), times s^-ci and the common scale
         double acc = 0.0;
         int hc = 0x7fffffff;
@@ -595,15 +670,16 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
     __syncwarp();
 }
 
-// BIG = false: classes 0..5 (R = 8, 16, 32 cells per lane); BIG = true: class 6 (R = 64, its own register budget)
-template <bool BIG>
-__global__ void __launch_bounds__(32 * DP_WARPS, BIG ? 1 : 4) k_dp(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
-                                                                   const Lut *lut, const Workspace ws, int planes)
+// One kernel per register budget: RC = 0: R = 8 cells per lane (classes 0..3, K <= 256, the bulk of the columns; 6 CTAs
+// per SM), RC = 1: R = 16 and 32 (classes 4, 5, K <= 1024), RC = 2: R = 64 (class 6, K <= 2048).
+template <int RC>
+__global__ void __launch_bounds__(32 * DP_WARPS, RC == 0 ? 6 : RC == 1 ? 4 : 1)
+k_dp(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, const Lut *lut, const Workspace ws, int planes)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ double s_lut[768];
     __shared__ unsigned s_tbase[DP_NL + 1];
-    constexpr int CLS_LO = BIG ? 6 : 0, CLS_HI = BIG ? 6 : 5;
+    constexpr int CLS_LO = RC == 0 ? 0 : RC == 1 ? 4 : 6, CLS_HI = RC == 0 ? 3 : RC == 1 ? 5 : 6;
     dp_list_bases(ws, s_tbase, CLS_LO, CLS_HI);
     const unsigned total = s_tbase[DP_NL];
     if (total == 0) return;
@@ -616,7 +692,7 @@ __global__ void __launch_bounds__(32 * DP_WARPS, BIG ? 1 : 4) k_dp(const __grid_
     // them leaves some SMs with six tasks per sub-partition and others with three — the rest dynamically
     const unsigned nwarps = gridDim.x * DP_WARPS;
     unsigned t = blockIdx.x * DP_WARPS + wib;
-    unsigned *next = BIG ? &ws.counters->next_ptask_big : &ws.counters->next_ptask;
+    unsigned *next = &ws.counters->next_ptask[RC];
     for (;;) {
         if (t >= total) break;
         // entry of the processing order that holds task t
@@ -631,16 +707,17 @@ __global__ void __launch_bounds__(32 * DP_WARPS, BIG ? 1 : 4) k_dp(const __grid_
         const unsigned nj = unbinned ? ws.counters->n_pjobs[li] : min(ws.counters->n_pjobs[li], (unsigned)ws.pcap);
         const unsigned j0 = (t - s_tbase[lo]) * (unsigned)dp_cols_per_task(cls);
         const int *list = dp_list_ptr(ws, li);
-        if (BIG) {
+        if (RC == 2) {
             dp_task<32, 64>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj);
+        } else if (RC == 1) {
+            if (cls == 4) dp_task<32, 16>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj);
+            else dp_task<32, 32>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj);
         } else {
             switch (cls) {
                 case 0: dp_task<4, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
                 case 1: dp_task<8, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
                 case 2: dp_task<16, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
-                case 3: dp_task<32, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
-                case 4: dp_task<32, 16>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
-                default: dp_task<32, 32>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
+                default: dp_task<32, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
             }
         }
         if (lane == 0) t = nwarps + atomicAdd(next, 1u);
@@ -654,22 +731,22 @@ int dp_smem_optin()
 {
     // the largest configuration: all four quality planes
     const int bytes = (int)dp_smem_bytes(4);
-    if (cudaFuncSetAttribute(k_dp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 1;
-    if (cudaFuncSetAttribute(k_dp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_dp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_dp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_dp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 1;
     return 0;
 }
 
-constexpr int DP_CTAS_PER_SM = 4;
-
-// k_dp<false> on `st`, k_dp<true> (K > 1024, rare) beside it on `st_big`
+// k_dp<0> on `st`; k_dp<1> (256 < K <= 1024) and k_dp<2> (K > 1024) beside it
 void launch_dp(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
-               cudaStream_t st_big)
+               cudaStream_t st1, cudaStream_t st2)
 {
     if (b.n_cols <= 0) return;
     const int planes = 1 + (cf.use_mq ? 1 : 0) + (cf.use_baq ? 1 : 0) + (cf.use_sq ? 1 : 0);
     const size_t smem = dp_smem_bytes(planes);
-    k_dp<false><<<ls.sms * DP_CTAS_PER_SM, 32 * DP_WARPS, smem, st>>>(cf, b, lut, ws, planes);
-    k_dp<true><<<ls.sms, 32 * DP_WARPS, smem, st_big>>>(cf, b, lut, ws, planes);
+    k_dp<0><<<ls.sms * 6, 32 * DP_WARPS, smem, st>>>(cf, b, lut, ws, planes);
+    k_dp<1><<<ls.sms * 4, 32 * DP_WARPS, smem, st1>>>(cf, b, lut, ws, planes);
+    k_dp<2><<<ls.sms, 32 * DP_WARPS, smem, st2>>>(cf, b, lut, ws, planes);
 }
 
 }  // namespace lfb

@@ -146,7 +146,7 @@ struct lfb200_ctx {
     cudaStream_t stream = nullptr;       // used by the host entry points
     Lut *d_lut = nullptr;
     // workspace of the current batch
-    DevBuf w_cnt6, w_tested, w_bonf, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_ujobs, w_tilecount, w_iscand, w_candtile, w_candpre, w_perm;
+    DevBuf w_cnt6, w_tested, w_bonf, w_rank, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_ujobs, w_iscand, w_candtile, w_candpre, w_perm;
     Workspace ws{};
     // device copies of host batches (host entry point)
     DevBuf in_off, in_cnt, in_ref, in_cov, in_nb, in_bq, in_mq, in_baq, in_sq;
@@ -195,6 +195,7 @@ struct lfb200_ctx {
     cudaEvent_t ev_done = nullptr;       // recorded after the sites and the counters of a test have been written
     DevConf last_dc{};                   // configuration of the last test (to emit again after growing h_sites)
     bool test_enqueued = false;
+    bool bonf_used_valid = false;        // ws.bonf_used has been materialised for the current batch
     int site_pvalues = 1;                // lfb200_set_site_pvalues
     int ensure_sites(size_t n)
     {
@@ -353,8 +354,8 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_bonf, &ctx->w_blocksum, &ctx->w_jobs,
-                      &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_ujobs, &ctx->w_tilecount, &ctx->w_iscand, &ctx->w_candtile, &ctx->w_candpre, &ctx->w_perm, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
+    DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_bonf, &ctx->w_rank, &ctx->w_blocksum, &ctx->w_jobs,
+                      &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_ujobs, &ctx->w_iscand, &ctx->w_candtile, &ctx->w_candpre, &ctx->w_perm, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
                       &ctx->in_bq, &ctx->in_mq, &ctx->in_baq, &ctx->in_sq, &ctx->p_ep, &ctx->p_off, &ctx->p_cnt,
                       &ctx->p_bonf, &ctx->p_out};
     for (DevBuf *b : bufs) b->release();
@@ -377,11 +378,7 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     bad |= ctx->w_tested.ensure(nn + 1024);
     bad |= ctx->w_bonf.ensure(nn * sizeof(long long));
     bad |= ctx->w_blocksum.ensure(((nn + 255) / 256 + 1) * sizeof(long long));
-    {
-        const void *before = ctx->w_tilecount.p;
-        bad |= ctx->w_tilecount.ensure(((nn + 255) / 256 + 1) * sizeof(unsigned int));
-        if (!bad && ctx->w_tilecount.p != before) cudaMemset(ctx->w_tilecount.p, 0, ctx->w_tilecount.cap);   // k_scan_blocks keeps it zero afterwards
-    }
+    bad |= ctx->w_rank.ensure(nn * sizeof(int));
     bad |= ctx->w_jobs.ensure(nn * NCLASS * sizeof(int));
     bad |= ctx->w_cand.ensure(nn * sizeof(Cand));
     bad |= ctx->w_iscand.ensure(((nn + 255) / 256 + 1) * 256);
@@ -404,7 +401,7 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     w.tested = (unsigned char *)ctx->w_tested.p;
     w.bonf_used = (long long *)ctx->w_bonf.p;
     w.blocksum = (long long *)ctx->w_blocksum.p;
-    w.tilecount = (unsigned int *)ctx->w_tilecount.p;
+    w.rank = (int *)ctx->w_rank.p;
     w.jobs = (int *)ctx->w_jobs.p;
     w.cand = (Cand *)ctx->w_cand.p;
     w.is_cand = (unsigned char *)ctx->w_iscand.p;
@@ -540,10 +537,10 @@ extern "C" int lfb200_screen_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, 
     ctx->have_batch = true;
     ctx->n_tested = -1;
     cudaStream_t st = (cudaStream_t)stream;
+    ctx->bonf_used_valid = false;
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
-    launch_screen(ctx->ls, dc, ctx->cur, ctx->d_lut, ctx->ws, st);
+    launch_front(ctx->ls, dc, ctx->cur, ctx->d_lut, ctx->ws, st);
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
-    launch_scan(ctx->cur, ctx->ws, st);
     if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
     CU(cudaGetLastError());
     return 0;
@@ -904,7 +901,18 @@ extern "C" int lfb200_device_results(lfb200_ctx *ctx, const int **alt_counts, co
     if (alt_counts) *alt_counts = ctx->ws.cnt6;
     if (alt_raw_counts) *alt_raw_counts = ctx->ws.cnt6 + 3;
     if (tested) *tested = ctx->ws.tested;
-    if (bonf_used) *bonf_used = ctx->ws.bonf_used;
+    if (bonf_used) {
+        // the factors live as ranks + a start value on the device; the dense array is written when somebody asks for it
+        if (!ctx->test_enqueued) return fail("bonf_used is available after lfb200_test_device");
+        if (!ctx->bonf_used_valid) {
+            CU(cudaSetDevice(ctx->device));
+            CU(cudaEventSynchronize(ctx->ev_done));
+            launch_bonf_used(ctx->ls, ctx->last_dc, ctx->ws, ctx->cur.n_cols, ctx->stream);
+            CU(cudaStreamSynchronize(ctx->stream));
+            ctx->bonf_used_valid = true;
+        }
+        *bonf_used = ctx->ws.bonf_used;
+    }
     return 0;
 }
 
@@ -997,7 +1005,11 @@ extern "C" int lfb200_call_columns(lfb200_ctx *ctx, lfb200_conf_t *conf, const l
                 }
         }
         if (dense->tested && nn) CU(cudaMemcpyAsync(dense->tested, ctx->ws.tested, nn, cudaMemcpyDeviceToHost, st));
-        if (dense->bonf_used && nn) CU(cudaMemcpyAsync(dense->bonf_used, ctx->ws.bonf_used, nn * 8, cudaMemcpyDeviceToHost, st));
+        if (dense->bonf_used && nn) {
+            launch_bonf_used(ctx->ls, ctx->last_dc, ctx->ws, n, st);
+            ctx->bonf_used_valid = true;
+            CU(cudaMemcpyAsync(dense->bonf_used, ctx->ws.bonf_used, nn * 8, cudaMemcpyDeviceToHost, st));
+        }
         CU(cudaStreamSynchronize(st));
         for (size_t c = 0; c < nn * 3; ++c) {
             if (dense->lnp) dense->lnp[c] = 0.0;

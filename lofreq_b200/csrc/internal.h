@@ -95,8 +95,9 @@ struct Counters {
     unsigned int err_flags;
     unsigned int n_pjobs[DP_NL];   // k_dp job lists, index class * DP_NBIN1 + bin (a binned count may exceed Workspace::pcap:
                                    // the excess went to the class's unbinned list, bin == DP_NBIN)
-    unsigned int next_ptask, next_ptask_big;
+    unsigned int next_ptask[3];    // k_dp<RC>
     long long bonf_start_used;     // running factor the last test started from (host or device supplied)
+    unsigned int front_ticket;     // tiles handed out by k_front
     // written by k_emit_sites
     unsigned int n_fix;            // sites whose decision the host must repeat (may exceed EMIT_FIX_MAX: then all are rechecked)
     unsigned int emit_overflow;    // more sites than the host buffer holds: the host grows it and emits again
@@ -108,9 +109,9 @@ struct Workspace {
     long long cap_cols;
     int *cnt6;                     // [n][6]: alt_counts[3], alt_raw_counts[3]
     unsigned char *tested;         // [n]
-    long long *bonf_used;          // [n]
-    long long *blocksum;           // [ceil(n/256)]: tested columns before each tile of 256 columns
-    unsigned int *tilecount;       // [ceil(n/256)]: tested columns per tile, accumulated by k_screen, zeroed again by the scan
+    int *rank;                     // [n]: 1-based rank among the tested columns of the batch, 0 = untested (k_front)
+    long long *bonf_used;          // [n]: materialised on request (k_bonf_used)
+    long long *blocksum;           // [ceil(n/256)]: tile states of k_front's look-back (status | tested columns up to the tile)
     int *jobs;                     // [NCLASS][n]
     Cand *cand;                    // [n]
     unsigned char *is_cand;        // [n rounded up to 256]: column emitted a candidate
@@ -147,8 +148,9 @@ int launch_state_init(LaunchState &ls, int device);
 void launch_state_destroy(LaunchState &ls);
 
 // launchers (snv_kernels.cu)
-void launch_screen(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
-void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st);
+// front.cu: gates, alt counts, running count, first stage of the prune, job lists — one pass
+void launch_front(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
+void launch_bonf_used(const LaunchState &ls, const DevConf &cf, const Workspace &ws, long long n, cudaStream_t st);
 void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
                  cudaEvent_t after_finalize, const long long *bonf_start_dev);
 // sites in column order, decided on the device, into (mapped pinned) host memory
@@ -161,7 +163,7 @@ double measure_dfma_per_second(int sms, cudaStream_t st);
 // dp_fused.cu
 int dp_smem_optin();
 void launch_dp(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
-               cudaStream_t st_big);
+               cudaStream_t st1, cudaStream_t st2);
 void launch_prob_jobs(int sms, const ProbBatch &pb, Cand *out, cudaStream_t st);
 // mailbox.cu: the per-batch count exchange between shards through shared host memory
 constexpr int MAIL_DEPTH = 64;

@@ -1,0 +1,110 @@
+// Device helpers of the stream side (k_front, k_prune2): column metadata, alt-read counting, the lane-per-column prune.
+#pragma once
+#include "dev_common.cuh"
+
+namespace lfb {
+
+constexpr int FIN_BLOCK = 256;      // columns per tile of the prefix sums = per CTA of k_front
+constexpr int PRUNE_CAP1 = 8;       // reads k_front itself looks at (K <= 3 is decided by then); the rest of the prune is k_prune2's
+constexpr int PRUNE_CAP = 32;       // reads the lane-per-column prune looks at before it hands the column to k_mid
+
+// running Bonferroni factor of the tested column with 1-based rank `rank` in a batch that starts from `start`
+// (lofreq_call.c:794-800: the first tested column sets 3 when bonf_subst was 1, else += 3)
+__device__ __forceinline__ long long bonf_of(const DevConf &cf, long long start, long long rank)
+{
+    return cf.bonf_dynamic ? ((start == 1 ? 0 : start) + 3 * rank) : start;
+}
+
+// [lo, hi) of the reads showing the reference base
+__device__ __forceinline__ void ref_range(const Geom &g, int &lo, int &hi)
+{
+    lo = g.ref_idx == 0 ? 0 : g.ref_idx == 1 ? g.b1 : g.ref_idx == 2 ? g.b2 : g.b3;
+    hi = g.ref_idx == 0 ? g.b1 : g.ref_idx == 1 ? g.b2 : g.ref_idx == 2 ? g.b3 : g.n;
+}
+
+struct RawGeom {        // the per-column metadata as loaded, one column ahead of its use
+    long long off;
+    int4 cnt;
+    int cov, nb;
+    char ref;
+};
+
+__device__ __forceinline__ void load_raw(const DevBatch &b, long long c, RawGeom &r)
+{
+    r.cnt = __ldg(reinterpret_cast<const int4 *>(b.nt_cnt) + c);
+    r.off = __ldg(b.col_off + c);
+    r.ref = __ldg(b.ref_base + c);
+    r.cov = b.coverage ? __ldg(b.coverage + c) : -1;
+    r.nb = b.num_bases ? __ldg(b.num_bases + c) : -1;
+}
+
+// k_screen: gates and alt counts.  Only reads that show a non-reference base decide whether a column is
+// tested and what K is (snpcaller.c:418-420,489), so only those bytes are touched.  A warp takes 32
+// consecutive columns: metadata, gates and columns with at most 8 non-reference reads run lane-per-column;
+// the rare columns with more (variant sites) are then counted by the whole warp.
+__device__ __forceinline__ void count_alt_read(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &g,
+                                               int ref_lo, int ref_hi, int i, int (&cnt)[3], int (&raw)[3])
+{
+    const int pos = i < ref_lo ? i : i - ref_lo + ref_hi;
+    const long long a = g.off + pos;
+    const int bq = b.bq[a];
+    int mq = 0, baq = 0, sq = 0;
+    if (cf.jq_filters) {
+        if (cf.use_mq) mq = b.mq[a];
+        if (cf.use_baq) baq = b.baq[a];
+        if (cf.use_sq) sq = b.sq[a];
+    }
+    bool is_alt;
+    int slot;
+    double jp;
+    const bool ok = eval_read<false>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp);
+    raw[0] += slot == 0;              // raw counts precede every filter (snpcaller.c:418-420)
+    raw[1] += slot == 1;
+    raw[2] += slot == 2;
+    if (ok) {
+        cnt[0] += slot == 0;
+        cnt[1] += slot == 1;
+        cnt[2] += slot == 2;
+    }
+}
+
+// The reference's early exit (snpcaller.c:916-958), one lane per column: walk the first `cap` reads until
+// P(X >= K among the reads seen) > limit = sig / bonf.  Returns true when the column is still alive after `cap` reads.
+// Cells are kept top-aligned (register 7 = cell K-1, padding below cell 0 stays 0), so one code path serves every
+// K <= KS.  Lanes with live == false only take part in the votes.
+__device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &mg, int K,
+                                           double limit, int cap_reads, bool live)
+{
+    double R[KS], T = 0.0;
+#pragma unroll
+    for (int j = 0; j < KS; ++j) R[j] = (j == KS - K) ? 1.0 : 0.0;
+    const int cap = min(mg.n, cap_reads);
+    // the reads come in aligned 16-byte chunks per plane: one load per plane covers what most columns need
+    const long long ca = mg.off & ~15ll;
+    const int lead = (int)(mg.off - ca);
+    Chunk16 ch;
+    ch.bq = ch.mq = ch.baq = ch.sq = make_uint4(0, 0, 0, 0);
+    if (live && cap > 0) load_chunk(cf, b, ca, ch);
+#pragma unroll 1
+    for (int i = 0; __any_sync(FULL, live && i < cap); ++i) {
+        if (!(live && i < cap)) continue;
+        const int idx = lead + i, j = idx & 15;
+        if (j == 0 && i > 0) load_chunk(cf, b, ca + idx, ch);
+        bool is_alt;
+        int slot;
+        double jp;
+        if (!eval_read<true>(cf, s_lut, mg, i, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j), byte_of(ch.sq, j),
+                             is_alt, slot, jp))
+            continue;
+        double p, q;
+        guard_pq(jp, p, q);
+        T = fma(R[KS - 1], p, T);
+#pragma unroll
+        for (int j2 = KS - 1; j2 >= 1; --j2) R[j2] = fma(R[j2 - 1], p, R[j2] * q);
+        R[0] = R[0] * q;
+        if (T > limit) live = false;          // clearly insignificant: snpcaller() leaves LDBL_MAX everywhere (snpcaller.c:1155)
+    }
+    return live;
+}
+
+}  // namespace lfb

@@ -9,7 +9,7 @@
 // What runs here (DESIGN.md has the whole picture; dp_fused.cu, poissbin.cu, mailbox.cu, binom.cu, fisher.cu hold the rest):
 //   k_screen    gates and alt counts: only the reads showing a non-reference base are looked at; a warp takes 32
 //               columns (lane per column for few alt reads, whole warp otherwise); tested columns per tile of 256.
-//   k_scan_blocks / k_finalize / k_prune2
+//   k_front (front.cu) / k_prune2
 //               running Bonferroni factor = prefix sum over the tested flags (lofreq_call.c:794-800); the reference's
 //               early exit, one lane per column, in two stages; job lists for everything that survives.
 //   k_mid       K <= 8 survivors: the exact distribution truncated at K, evaluated in linear space on 32 disjoint read
@@ -29,6 +29,7 @@
 #include <float.h>
 #include "internal.h"
 #include "dev_common.cuh"
+#include "screen_common.cuh"
 
 namespace lfb {
 // ------------------------------------------------------------------------------------------------
@@ -135,13 +136,6 @@ __device__ __forceinline__ void small_tails(const double (&P)[KV], double T, con
 // ------------------------------------------------------------------------------------------------
 // k_screen
 // ------------------------------------------------------------------------------------------------
-// [lo, hi) of the reads showing the reference base
-__device__ __forceinline__ void ref_range(const Geom &g, int &lo, int &hi)
-{
-    lo = g.ref_idx == 0 ? 0 : g.ref_idx == 1 ? g.b1 : g.ref_idx == 2 ? g.b2 : g.b3;
-    hi = g.ref_idx == 0 ? g.b1 : g.ref_idx == 1 ? g.b2 : g.ref_idx == 2 ? g.b3 : g.n;
-}
-
 // merged error probability of a read that shows the reference base and passed the bq filter
 // (merge_srcq_mapq_baq_and_bq with the terms of absent planes dropped: x*0, +0 and *1 are exact)
 __device__ __forceinline__ double ref_read_prob(const DevConf &cf, const double *lut, int bq, int mq, int baq, int sq)
@@ -291,136 +285,9 @@ __device__ __noinline__ void screen_small(const DevConf &cf, const DevBatch &b, 
     small_tails<KV>(P, T, cnt, K, tails);
 }
 
-struct RawGeom {        // the per-column metadata as loaded, one column ahead of its use
-    long long off;
-    int4 cnt;
-    int cov, nb;
-    char ref;
-};
-
-__device__ __forceinline__ void load_raw(const DevBatch &b, long long c, RawGeom &r)
-{
-    r.cnt = __ldg(reinterpret_cast<const int4 *>(b.nt_cnt) + c);
-    r.off = __ldg(b.col_off + c);
-    r.ref = __ldg(b.ref_base + c);
-    r.cov = b.coverage ? __ldg(b.coverage + c) : -1;
-    r.nb = b.num_bases ? __ldg(b.num_bases + c) : -1;
-}
-
-// k_screen: gates and alt counts.  Only reads that show a non-reference base decide whether a column is
-// tested and what K is (snpcaller.c:418-420,489), so only those bytes are touched.  A warp takes 32
-// consecutive columns: metadata, gates and columns with at most 8 non-reference reads run lane-per-column;
-// the rare columns with more (variant sites) are then counted by the whole warp.
-__device__ __forceinline__ void count_alt_read(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &g,
-                                               int ref_lo, int ref_hi, int i, int (&cnt)[3], int (&raw)[3])
-{
-    const int pos = i < ref_lo ? i : i - ref_lo + ref_hi;
-    const long long a = g.off + pos;
-    const int bq = b.bq[a];
-    int mq = 0, baq = 0, sq = 0;
-    if (cf.jq_filters) {
-        if (cf.use_mq) mq = b.mq[a];
-        if (cf.use_baq) baq = b.baq[a];
-        if (cf.use_sq) sq = b.sq[a];
-    }
-    bool is_alt;
-    int slot;
-    double jp;
-    const bool ok = eval_read<false>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp);
-    raw[0] += slot == 0;              // raw counts precede every filter (snpcaller.c:418-420)
-    raw[1] += slot == 1;
-    raw[2] += slot == 2;
-    if (ok) {
-        cnt[0] += slot == 0;
-        cnt[1] += slot == 1;
-        cnt[2] += slot == 2;
-    }
-}
-
-constexpr int FIN_BLOCK = 256;      // columns per tile of the prefix sum = per CTA of k_finalize
-
-__global__ void __launch_bounds__(256, 4) k_screen(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
-                                                   const Lut *lut, const Workspace ws)
-{
-    __shared__ double s_lut[768];
-    __shared__ int s_hist[8][256];
-    load_lut(s_lut, lut);
-    const int lane = lane_id();
-    const int wib = threadIdx.x >> 5;
-    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    // the median override (def_alt_bq == -1) needs a warp-wide histogram: no lane-per-column path then
-    const int serial_max = cf.alt_bq_mode == 2 ? 0 : 8;
-
-    RawGeom nxt;
-    nxt.off = 0; nxt.cnt = make_int4(0, 0, 0, 0); nxt.cov = -1; nxt.nb = -1; nxt.ref = 'N';
-    if (warp0 * 32 + lane < b.n_cols) load_raw(b, warp0 * 32 + lane, nxt);
-    for (long long base = warp0 * 32; base < b.n_cols; base += nwarps * 32) {
-        const long long c_mine = base + lane;
-        const RawGeom cur = nxt;
-        if (c_mine + nwarps * 32 < b.n_cols) load_raw(b, c_mine + nwarps * 32, nxt);   // next group's metadata in flight
-        // ---- lane per column ----
-        Geom mg;
-        mg.off = cur.off;
-        mg.b1 = cur.cnt.x;
-        mg.b2 = mg.b1 + cur.cnt.y;
-        mg.b3 = mg.b2 + cur.cnt.z;
-        mg.n = mg.b3 + cur.cnt.w;
-        mg.ref_idx = ref_index(cur.ref);
-        mg.alt_bp = cf.alt_bq_prob;
-        const int m_cov = cur.cov < 0 ? mg.n : cur.cov;
-        const int m_nb = cur.nb < 0 ? mg.n : cur.nb;           // plp_col_t.num_bases
-        const bool m_gate = c_mine < b.n_cols && mg.ref_idx >= 0 && !(m_nb * 2 < m_cov) && !(m_nb < cf.min_cov);   // lofreq_call.c:892,931,747,754
-        int m_lo, m_hi;
-        ref_range(mg, m_lo, m_hi);
-        const int m_alt = m_gate ? mg.n - (m_hi - m_lo) : 0;
-        int cnt[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
-        if (m_alt > 0 && m_alt <= serial_max)
-            for (int i = 0; i < m_alt; ++i) count_alt_read(cf, b, s_lut, mg, m_lo, m_hi, i, cnt, raw);
-        // ---- whole warp per column with many non-reference reads ----
-        unsigned todo = __ballot_sync(FULL, m_alt > serial_max);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            Geom g;
-            g.off = __shfl_sync(FULL, mg.off, src);
-            g.b1 = __shfl_sync(FULL, mg.b1, src);
-            g.b2 = __shfl_sync(FULL, mg.b2, src);
-            g.b3 = __shfl_sync(FULL, mg.b3, src);
-            g.n = __shfl_sync(FULL, mg.n, src);
-            g.ref_idx = __shfl_sync(FULL, mg.ref_idx, src);
-            g.alt_bp = 0.0;
-            int ref_lo, ref_hi;
-            ref_range(g, ref_lo, ref_hi);
-            const int n_alt = g.n - (ref_hi - ref_lo);
-            setup_alt_bq(cf, b, s_lut, g, s_hist[wib]);
-            int wc[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
-            for (int i = lane; i < n_alt; i += 32) count_alt_read(cf, b, s_lut, g, ref_lo, ref_hi, i, wc, wr);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                wc[i] = __reduce_add_sync(FULL, wc[i]);
-                wr[i] = __reduce_add_sync(FULL, wr[i]);
-                if (lane == src) { cnt[i] = wc[i]; raw[i] = wr[i]; }
-            }
-        }
-        if (c_mine < b.n_cols) {
-            int2 *o = reinterpret_cast<int2 *>(ws.cnt6 + 6 * c_mine);
-            o[0] = make_int2(cnt[0], cnt[1]);
-            o[1] = make_int2(cnt[2], raw[0]);
-            o[2] = make_int2(raw[1], raw[2]);
-            // no alt read left after filtering -> not a test (lofreq_call.c:768-780)
-            ws.tested[c_mine] = (cnt[0] | cnt[1] | cnt[2]) ? 1 : 0;
-        }
-        // tested columns per tile of FIN_BLOCK columns (a warp's 32 columns lie in one tile): input of the prefix sum
-        const unsigned tb = __ballot_sync(FULL, c_mine < b.n_cols && (cnt[0] | cnt[1] | cnt[2]) != 0);
-        if (lane == 0 && tb) atomicAdd(&ws.tilecount[base / FIN_BLOCK], (unsigned)__popc(tb));
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // running Bonferroni: prefix sum over tested flags, then the significance screen
 // ------------------------------------------------------------------------------------------------
-constexpr int PRUNE_CAP = 32;       // reads the lane-per-column prune of k_finalize looks at before it hands the column on
 
 // exclusive scan of the per-tile counts k_screen accumulated, one block; the counts are zeroed for the next batch
 __global__ void __launch_bounds__(1024) k_scan_blocks(unsigned int *tilecount, long long *blocksum, int nb, unsigned long long *total)
@@ -462,150 +329,17 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(unsigned int *tilecount, l
     if (threadIdx.x == 0 && total) *total = (unsigned long long)s_carry;
 }
 
-// The reference's early exit (snpcaller.c:916-958), one lane per column: walk the first `cap` reads until
-// P(X >= K among the reads seen) > limit = sig / bonf.  Returns true when the column is still alive after `cap` reads.
-// Cells are kept top-aligned (register 7 = cell K-1, padding below cell 0 stays 0), so one code path serves every
-// K <= KS.  Lanes with live == false only take part in the votes.
-__device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &mg, int K,
-                                           double limit, int cap_reads, bool live)
-{
-    double R[KS], T = 0.0;
-#pragma unroll
-    for (int j = 0; j < KS; ++j) R[j] = (j == KS - K) ? 1.0 : 0.0;
-    const int cap = min(mg.n, cap_reads);
-    // the reads come in aligned 16-byte chunks per plane: one load per plane covers what most columns need
-    const long long ca = mg.off & ~15ll;
-    const int lead = (int)(mg.off - ca);
-    Chunk16 ch;
-    ch.bq = ch.mq = ch.baq = ch.sq = make_uint4(0, 0, 0, 0);
-    if (live && cap > 0) load_chunk(cf, b, ca, ch);
-#pragma unroll 1
-    for (int i = 0; __any_sync(FULL, live && i < cap); ++i) {
-        if (!(live && i < cap)) continue;
-        const int idx = lead + i, j = idx & 15;
-        if (j == 0 && i > 0) load_chunk(cf, b, ca + idx, ch);
-        bool is_alt;
-        int slot;
-        double jp;
-        if (!eval_read<true>(cf, s_lut, mg, i, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j), byte_of(ch.sq, j),
-                             is_alt, slot, jp))
-            continue;
-        double p, q;
-        guard_pq(jp, p, q);
-        T = fma(R[KS - 1], p, T);
-#pragma unroll
-        for (int j2 = KS - 1; j2 >= 1; --j2) R[j2] = fma(R[j2 - 1], p, R[j2] * q);
-        R[0] = R[0] * q;
-        if (T > limit) live = false;          // clearly insignificant: snpcaller() leaves LDBL_MAX everywhere (snpcaller.c:1155)
-    }
-    return live;
-}
-
-constexpr int PRUNE_CAP1 = 8;       // reads k_finalize itself looks at (K <= 3 is decided by then); the rest of the prune is k_prune2's
-
-__global__ void __launch_bounds__(FIN_BLOCK, 4) k_finalize(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
-                                                        const Lut *lut, const Workspace ws, const long long *bonf_start_dev)
-{
-    __shared__ int s_warp[32];
-    __shared__ double s_lut[768];
-    load_lut(s_lut, lut);
-    const long long n = b.n_cols;
-    // the running factor this batch continues from: the caller's conf, or a value another shard's count
-    // exchange left in device memory (no host round trip)
-    const long long bonf_start = bonf_start_dev ? *bonf_start_dev : cf.bonf_start;
-    if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters->bonf_start_used = bonf_start;
-    // one CTA per tile of FIN_BLOCK columns (CTAs that pull tiles from a counter, loading the table once, measured slower)
-    const long long tile = blockIdx.x;
-    const long long c = tile * FIN_BLOCK + threadIdx.x;
-    const int lane = lane_id(), w = threadIdx.x >> 5;
-    // everything the column may need is requested at once, whether or not it turns out to be tested: the kernel is
-    // bound by the chain of dependent loads (flag -> counts -> geometry -> quality bytes), not by bytes
-    int t = 0;
-    int2 a0 = make_int2(0, 0), a1 = make_int2(0, 0);
-    Geom mg;
-    mg.off = 0; mg.b1 = mg.b2 = mg.b3 = mg.n = 0; mg.ref_idx = -1; mg.alt_bp = cf.alt_bq_prob;
-    if (c < n) {
-        t = ws.tested[c];
-        const int2 *in = reinterpret_cast<const int2 *>(ws.cnt6 + 6 * c);
-        a0 = in[0];
-        a1 = in[1];
-        int cov;
-        load_geom(b, c, mg, cov);
-        mg.alt_bp = cf.alt_bq_prob;
-    }
-    const unsigned bal = __ballot_sync(FULL, t);
-    if (lane == 0) s_warp[w] = __popc(bal);
-    __syncthreads();
-    if (w == 0) {
-        int z = lane < FIN_BLOCK / 32 ? s_warp[lane] : 0;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(FULL, z, d);
-            if (lane >= d) z += y;
-        }
-        s_warp[lane] = z;
-    }
-    __syncthreads();
-    long long bonf = 0;
-    if (t) {
-        // 1-based rank of this column among the tested columns of the batch
-        const long long rank = ws.blocksum[tile] + (w ? s_warp[w - 1] : 0) + __popc(bal & ((2u << lane) - 1u));
-        // lofreq_call.c:794-800: first tested column sets 3 when bonf_subst was 1, else += 3
-        bonf = cf.bonf_dynamic ? ((bonf_start == 1 ? 0 : bonf_start) + 3 * rank) : bonf_start;
-    }
-    if (c < n) ws.bonf_used[c] = bonf;
-    int cnt[3] = {0, 0, 0};
-    if (t) {
-        cnt[0] = a0.x; cnt[1] = a0.y; cnt[2] = a1.x;
-    }
-    const int K = max(cnt[0], max(cnt[1], cnt[2]));
-    if (t && K > KS) {
-        if (K <= DP_MAXK) {
-            // 8 < K <= 2048: k_dp, several columns per warp; job list by (class, depth bin), the class's unbinned list
-            // when the binned one is full
-            const int li = dp_list(K, mg.n);
-            const int cls = li / DP_NBIN1;
-            const unsigned slot = atomicAdd(&ws.counters->n_pjobs[li], 1u);
-            if (slot < (unsigned)ws.pcap) {
-                ws.pjobs[((long long)cls * DP_NBIN + (li % DP_NBIN1)) * ws.pcap + slot] = (int)c;
-            } else {
-                const unsigned s2 = atomicAdd(&ws.counters->n_pjobs[cls * DP_NBIN1 + DP_NBIN], 1u);
-                ws.ujobs[(long long)cls * ws.cap_cols + s2] = (int)c;
-            }
-        } else {
-            // one CTA per column
-            const unsigned slot = atomicAdd(&ws.counters->n_jobs[CLS_XL], 1u);
-            ws.jobs[(long long)CLS_XL * ws.cap_cols + slot] = (int)c;
-        }
-    }
-    // ---- columns with K <= KS ----
-    // (1) prune, lane per column, in two stages.  With the Bonferroni factors of a real run the early exit fires after a
-    //     handful of reads (K = 1: one; K = 3: ~6; K = 4: ~27 at depth-500 Q30), so almost every column ends here
-    //     without a warp ever being dedicated to it.  A warp runs as long as its slowest lane, and the few columns
-    //     with K >= 4 would keep 31 finished lanes waiting: this kernel stops after PRUNE_CAP1 reads and lists what is
-    //     still alive for k_prune2, whose warps are full of such columns.
-    bool small = t && K <= KS;
-    const double limit = small ? cf.sig * (1.0 + 1e-9) / (double)bonf : 0.0;   // margin: borderline columns go to the host
-    if (cf.alt_bq_mode != 2) {          // the median override needs a warp-wide histogram: no lane-serial prune
-        small = lane_prune(cf, b, s_lut, mg, K, limit, PRUNE_CAP1, small);
-        if (small) {
-            const unsigned slot = atomicAdd(&ws.counters->n_jobs[CLS_PRUNE2], 1u);
-            ws.jobs[(long long)CLS_PRUNE2 * ws.cap_cols + slot] = (int)c;
-        }
-    } else if (small) {
-        // every small column joins the columns with 8 < K <= 32 in k_mid's job list: full evaluation, whole warp
-        const unsigned slot = atomicAdd(&ws.counters->n_jobs[0], 1u);
-        ws.jobs[slot] = (int)c;
-    }
-}
-
 // (2) second stage of the prune: the columns k_finalize could not rule out within PRUNE_CAP1 reads, one lane each, up to
 //     PRUNE_CAP reads (from the first read again: eight reads are cheaper to redo than to carry).  The survivors (true
 //     low-frequency variants, the first columns of a run) join k_mid's job list.
 __global__ void __launch_bounds__(128) k_prune2(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, const Lut *lut,
-                                                const Workspace ws)
+                                                const Workspace ws, const long long *bonf_start_dev)
 {
     __shared__ double s_lut[768];
+    // the exact factor this batch continues from: k_front used the caller's conf; region shards on other GPUs may have
+    // added to it since (lfb200_comm_exchange leaves the sum in device memory, no host round trip)
+    const long long start = bonf_start_dev ? *bonf_start_dev : cf.bonf_start;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && bonf_start_dev) ws.counters->bonf_start_used = start;
     const unsigned njobs = ws.counters->n_jobs[CLS_PRUNE2];
     if (njobs == 0) return;
     load_lut(s_lut, lut);
@@ -625,7 +359,7 @@ __global__ void __launch_bounds__(128) k_prune2(const __grid_constant__ DevConf 
             const int2 *in = reinterpret_cast<const int2 *>(ws.cnt6 + 6 * c);
             const int2 a0 = in[0], a1 = in[1];
             K = max(a0.x, max(a0.y, a1.x));
-            limit = cf.sig * (1.0 + 1e-9) / (double)ws.bonf_used[c];
+            limit = cf.sig * (1.0 + 1e-9) / (double)bonf_of(cf, start, ws.rank[c]);
         }
         live = lane_prune(cf, b, s_lut, mg, K, limit, PRUNE_CAP, live);
         if (live) {
@@ -1109,7 +843,7 @@ __global__ void __launch_bounds__(128) k_mid(const __grid_constant__ DevConf cf,
 #pragma unroll
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
         const int K = max(cnt[0], max(cnt[1], cnt[2]));
-        const long long bonf = ws.bonf_used[c];
+        const long long bonf = bonf_of(cf, ws.counters->bonf_start_used, ws.rank[c]);
         double tails[4];
         if (K <= 2) screen_small<2>(cf, b, lut_sa, g, cnt, K, tails);
         else if (K <= 4) screen_small<4>(cf, b, lut_sa, g, cnt, K, tails);
@@ -1171,7 +905,7 @@ __device__ void heavy_list(const DevConf &cf, const DevBatch &b, const double *s
         int cnt[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
-        const long long bonf = ws.bonf_used[c];
+        const long long bonf = bonf_of(cf, ws.counters->bonf_start_used, ws.rank[c]);
         Cand cd;
         const bool site = run_problem<R>(src, cnt, bonf, cf.sig, s_par, cd);
         if (site && lane == 0) {
@@ -1495,7 +1229,7 @@ __global__ void __launch_bounds__(XL_T, 1) k_heavy_xl(const __grid_constant__ De
 #pragma unroll
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
         const int K = max(cnt[0], max(cnt[1], cnt[2]));
-        const long long bonf = ws.bonf_used[c];
+        const long long bonf = bonf_of(cf, ws.counters->bonf_start_used, ws.rank[c]);
         Cand cd;
         if (K > XL_T * XL_R) {
             // no kernel of this build takes an alt count this large: the column is reported as a site whose alleles carry
@@ -1641,22 +1375,6 @@ void launch_state_destroy(LaunchState &ls)
     ls = LaunchState();
 }
 
-void launch_screen(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st)
-{
-    if (b.n_cols <= 0) return;
-    // one resident wave: 4 CTAs of 8 warps per SM, every warp strides over groups of 32 columns
-    const long long want = (b.n_cols + 255) / 256;
-    const int grid = (int)(want < (long long)ls.sms * 4 ? want : (long long)ls.sms * 4);
-    k_screen<<<grid, 256, 0, st>>>(cf, b, lut, ws);
-}
-
-void launch_scan(const DevBatch &b, const Workspace &ws, cudaStream_t st)
-{
-    if (b.n_cols <= 0) return;
-    const int nb = (int)((b.n_cols + FIN_BLOCK - 1) / FIN_BLOCK);
-    k_scan_blocks<<<1, 1024, 0, st>>>(ws.tilecount, ws.blocksum, nb, &ws.counters->n_tested);
-}
-
 __global__ void k_rank_cands(const Workspace ws);
 
 void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
@@ -1664,11 +1382,8 @@ void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, co
 {
     if (b.n_cols <= 0) return;
     const int nb = (int)((b.n_cols + FIN_BLOCK - 1) / FIN_BLOCK);
-    // n_tested (first 8 bytes) belongs to the scan; everything after it is per-test state
-    cudaMemsetAsync(reinterpret_cast<char *>(ws.counters) + 8, 0, sizeof(Counters) - 8, st);
-    cudaMemsetAsync(ws.is_cand, 0, (size_t)nb * FIN_BLOCK, st);
-    k_finalize<<<nb, FIN_BLOCK, 0, st>>>(cf, b, lut, ws, bonf_start_dev);
-    k_prune2<<<ls.sms * 2, 128, 0, st>>>(cf, b, lut, ws);
+    // second stage of the prune with the exact factor (k_front, in the screen phase, did the first)
+    k_prune2<<<ls.sms * 2, 128, 0, st>>>(cf, b, lut, ws, bonf_start_dev);
     if (after_finalize) cudaEventRecord(after_finalize, st);
     // Independent work side by side, so that the warps of the small kernels share the SMs with k_dp: k_mid (K <= 8
     // survivors of the prune), k_dp<true> (1024 < K <= 2048, its own register budget), k_heavy_xl (K > 2048, one CTA per
@@ -1677,10 +1392,11 @@ void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, co
     cudaStreamWaitEvent(ls.side[0], ls.ev_fork, 0);
     cudaStreamWaitEvent(ls.side[1], ls.ev_fork, 0);
     cudaStreamWaitEvent(ls.side[2], ls.ev_fork, 0);
+    cudaStreamWaitEvent(ls.side[3], ls.ev_fork, 0);
     k_mid<<<ls.sms * 4, 128, 0, ls.side[0]>>>(cf, b, lut, ws);
     k_heavy_xl<<<ls.sms, XL_T, 0, ls.side[2]>>>(cf, b, lut, ws, CLS_XL);
-    launch_dp(ls, cf, b, lut, ws, st, ls.side[1]);
-    for (int i = 0; i < 3; ++i) {
+    launch_dp(ls, cf, b, lut, ws, st, ls.side[1], ls.side[3]);
+    for (int i = 0; i < 4; ++i) {
         cudaEventRecord(ls.ev_join[i], ls.side[i]);
         cudaStreamWaitEvent(st, ls.ev_join[i], 0);
     }

@@ -1,5 +1,5 @@
 #!/bin/bash
-# quick GPU pass: parity tests (verbose timing of the slowest) + smoke + a short bench
+# quick GPU pass: parity tests (verbose timing of the slowest) + smoke + a short bench (+ optional ncu launch list: NCU=1)
 mkdir -p gpurun_out
 nproc > gpurun_out/gpu.txt; nvidia-smi -L >> gpurun_out/gpu.txt
 ( time timeout 1500 python -m pytest tests -m gpu -q -s --durations=8 ${PYTEST_ARGS:-} ) > gpurun_out/pytest_gpu.log 2>&1
@@ -15,3 +15,12 @@ print(d['value'], d['ms_per_step'], d['roofline']['phase_ms'], d['config']['site
 print('e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'in_place', d['e2e']['in_place']['value'], 'frac', d['roofline']['frac'])
 PY
 tail -3 gpurun_out/bench_quick.err
+if [ -n "${NCU:-}" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_bench.log 2>&1
+  echo "launch list rc=$?"
+  python tools/launch_summary.py gpurun_out/launches.csv | tail -25
+fi
+if [ -n "${NCUFULL:-}" ]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCUFULL}" -s ${NCUSKIP:-6} -c ${NCUCOUNT:-4} -f -o gpurun_out/prof_r2 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
+  echo "full rc=$?"; ls -la gpurun_out/prof_r2.ncu-rep
+fi
