@@ -171,14 +171,13 @@ constexpr int DP_S = 64;                    // reads per TMA stage and column
 constexpr int DP_SB = DP_S + 16;            // bytes per stage, column and plane: + the lead of an unaligned column
 constexpr int DP_NCOLMAX = 8;               // columns per warp at G = 4
 constexpr int DP_PAR = 33;                  // one parameter row: 32 reads, padded (banks)
-constexpr int DP_NHIST = 160;               // buckets of the tilt histogram: 4 per binade, 2^-40 .. 1
 
 struct DpWarpSmem {
     unsigned long long bar[2];
     union {
         double2 par[DP_NCOLMAX][DP_PAR];                              // step parameters of the current block of 32 reads
         // before the recurrence starts the same bytes serve the set-up of the task:
-        struct { float sum[DP_NHIST]; int cnt[DP_NHIST]; } hist;     // tilt histogram (whole warp, one column at a time)
+        unsigned char hist_bytes[DP_NCOLMAX * 512];                   // ColHist per column of the warp (tilt)
         int median_hist[256];                                         // def_alt_bq == -1 (warp_ref_median)
     } u;
     // followed by the byte stages: [2][DP_NCOLMAX][planes][DP_SB]
@@ -189,15 +188,16 @@ __host__ __device__ constexpr size_t dp_warp_bytes(int planes)
     return ((sizeof(DpWarpSmem) + 15) & ~(size_t)15) + (size_t)2 * DP_NCOLMAX * planes * DP_SB;
 }
 
-// processing order of the job lists: deepest bin first, widest class first; entry i is list DP_NL-1-i.
-// tbase[i] = first task of entry i, tbase[DP_NL] = number of tasks
+// processing order of the job lists (longest tasks first): the unbinned lists, then bin by bin from the deepest, and
+// inside a bin the classes with the most columns per warp first.  tbase[i] = first task of entry i, tbase[DP_NL] = all
+__device__ __forceinline__ int dp_entry_list(int i) { return (i % DP_NCLS) * DP_NBIN1 + (DP_NBIN1 - 1 - i / DP_NCLS); }
 __device__ __forceinline__ int dp_cols_per_task(int cls) { return cls == 0 ? 8 : cls == 1 ? 4 : cls == 2 ? 2 : 1; }
 
 // whole CTA: every thread counts the tasks of one entry, thread 0 sums them up
 __device__ void dp_list_bases(const Workspace &ws, unsigned *tbase, int cls_lo, int cls_hi)
 {
     for (int i = threadIdx.x; i < DP_NL; i += blockDim.x) {
-        const int li = DP_NL - 1 - i;
+        const int li = dp_entry_list(i);
         const int cls = li / DP_NBIN1;
         unsigned tasks = 0;
         if (cls >= cls_lo && cls <= cls_hi) {
@@ -227,77 +227,95 @@ __device__ __forceinline__ const int *dp_list_ptr(const Workspace &ws, int li)
 }
 
 // ------------------------------------------------------------------------------------------------
-// tilt: saddlepoint equation sum_n p_n s/(q_n + p_n s) = min(K, N - 1/2) on a histogram of the merged probabilities
+// one read of plp_to_errprobs (snpcaller.c:399-491)
 // ------------------------------------------------------------------------------------------------
-__device__ double warp_tilt(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &g, int K, int N, double lam,
-                            DpWarpSmem &sm)
+// UNIFORM: the configuration treats reference and alt reads alike (the defaults: min_alt_bq <= min_bq, no def_alt_bq /
+// def_alt_jq, no jq filters) — no position bookkeeping; plain_merge: only bq and mq are merged (sp = bap = 0: the dropped
+// terms of merge_srcq_mapq_baq_and_bq are exact zeros and ones)
+struct EvalMode {
+    bool uniform, plain_merge;
+};
+
+__device__ __forceinline__ bool dp_eval(const DevConf &cf, const EvalMode &em, const double *s_lut, const Geom &g, int pos, int bq, int mq,
+                                        int baq, int sq, double &jp)
 {
-    const int lane = lane_id();
-    for (int i = lane; i < DP_NHIST; i += 32) {
-        sm.u.hist.sum[i] = 0.f;
-        sm.u.hist.cnt[i] = 0;
-    }
-    __syncwarp();
-    const long long abase = g.off & ~15ll;
-    const int lead = (int)(g.off - abase);
-    const int nch = (lead + g.n + 15) >> 4;
-    for (int i = lane; i < nch; i += 32) {
-        Chunk16 ch;
-        load_chunk(cf, b, abase + 16ll * i, ch);
-#pragma unroll 1
-        for (int k = 0; k < 16; ++k) {
-            const int pos = 16 * i - lead + k;
-            if (pos < 0 || pos >= g.n) continue;
-            bool is_alt;
-            int slot;
-            double jp;
-            if (!eval_read<true>(cf, s_lut, g, pos, byte_of(ch.bq, k), byte_of(ch.mq, k), byte_of(ch.baq, k), byte_of(ch.sq, k), is_alt, slot, jp))
-                continue;
-            const double p = jp < DEPS ? DEPS : jp;
-            int bk = (0x3ff00000 - __double2hiint(p)) >> 18;       // 4 buckets per binade below 1
-            bk = min(max(bk, 0), DP_NHIST - 1);
-            atomicAdd(&sm.u.hist.sum[bk], (float)p);
-            atomicAdd(&sm.u.hist.cnt[bk], 1);
+    if (em.uniform) {
+        if (bq < cf.min_bq) return false;
+        const double bp = s_lut[bq];
+        if (em.plain_merge) {
+            if (!cf.use_mq) { jp = bp; return true; }
+            const double mp = s_lut[256 + mq];
+            jp = __dadd_rn(mp, __dmul_rn(__dsub_rn(1.0, mp), bp));
+            return true;
         }
+        jp = merge4(cf.use_sq ? s_lut[512 + sq] : 0.0, cf.use_mq ? s_lut[256 + mq] : 0.0, cf.use_baq ? s_lut[512 + baq] : 0.0, bp);
+        return true;
     }
-    __syncwarp();
-    // every lane keeps its 5 buckets: count and mean probability
-    float cb[DP_NHIST / 32], pb[DP_NHIST / 32];
-#pragma unroll
-    for (int k = 0; k < DP_NHIST / 32; ++k) {
-        const int c = sm.u.hist.cnt[lane + 32 * k];
-        cb[k] = (float)c;
-        pb[k] = c ? fminf(sm.u.hist.sum[lane + 32 * k] / (float)c, 1.f) : 0.f;
-    }
-    __syncwarp();
+    bool is_alt;
+    int slot;
+    return eval_read<true>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tilt: saddlepoint equation sum_n p_n s/(q_n + p_n s) = min(K, N - 1/2), solved on a histogram of the merged
+// probabilities of the column (64 buckets, two per binade: inside a bucket p varies by at most 41 %, and the bucket
+// mean stands for it — the tolerance of the tilt is coarse: an error e in ln s costs about var * e^2 / 2 nats of ~700)
+// ------------------------------------------------------------------------------------------------
+constexpr int DP_NB = 64;
+struct ColHist {
+    float sum[DP_NB];
+    int cnt[DP_NB];
+};
+
+__device__ __forceinline__ int hist_bucket(double p)
+{
+    const int bk = (0x3ff00000 - __double2hiint(p)) >> 19;
+    return min(max(bk, 0), DP_NB - 1);
+}
+
+// Newton on ln s, the G lanes of a column over its histogram; columns that need no tilt idle along (need == false)
+template <int G>
+__device__ __forceinline__ double group_tilt(const ColHist &h, bool need, int K, int N, double lam)
+{
+    const int gl = lane_id() % G;
     const double kt = fmin((double)K, (double)N - 0.5);
     const double s0 = kt * fmax((double)N - lam, 1e-300) / (fmax(lam, 1e-300) * fmax((double)N - kt, 0.5));
     double lo = 0.0, hi = 60.0;
     double ls = fmin(log(fmax(s0, 1.0)), hi);
+    bool conv = !need;
+#pragma unroll 1
     for (int it = 0; it < 40; ++it) {
+        if (__all_sync(FULL, conv)) break;
         const float sf = (float)exp(ls);
         float gs = 0.f, ds = 0.f;
-#pragma unroll
-        for (int k = 0; k < DP_NHIST / 32; ++k) {
-            const float ps = pb[k] * sf;
-            const float w = __fdividef(ps, fmaxf(1.f - pb[k], 1e-30f) + ps);        // p s / (q + p s)
-            gs = fmaf(cb[k], w, gs);
-            ds = fmaf(cb[k] * w, 1.f - w, ds);                                        // derivative with respect to ln s
+        if (!conv) {
+#pragma unroll 1
+            for (int k = gl; k < DP_NB; k += G) {
+                const int c = h.cnt[k];
+                if (c == 0) continue;
+                const float pb = fminf(h.sum[k] / (float)c, 1.f);
+                const float ps = pb * sf;
+                const float w = __fdividef(ps, fmaxf(1.f - pb, 1e-30f) + ps);        // p s / (q + p s)
+                gs = fmaf((float)c, w, gs);
+                ds = fmaf((float)c * w, 1.f - w, ds);                                  // derivative with respect to ln s
+            }
         }
-        const double gsum = __shfl_sync(FULL, warp_sum((double)gs), 0) - kt;
-        const double d = __shfl_sync(FULL, warp_sum((double)ds), 0);
+        const double gsum = group_sum<G>((double)gs) - kt;
+        const double d = group_sum<G>((double)ds);
+        if (conv) continue;
         // an error e in ln s costs about d*e^2/2 nats of head-room (of ~700): stop once that is negligible
         const double step = d > 0.0 ? gsum / d : 0.0;
         if (d > 0.0 && fabs(step) * sqrt(fmax(d, 1.0)) < 0.5) {
             ls = fmin(fmax(ls - step, 0.0), 60.0);
-            break;
+            conv = true;
+            continue;
         }
         if (gsum > 0.0) hi = fmin(hi, ls); else lo = fmax(lo, ls);
         double nl = d > 0.0 ? ls - step : 0.5 * (lo + hi);
         if (!(nl > lo && nl < hi)) nl = 0.5 * (lo + hi);
         ls = nl;
     }
-    return ls;
+    return need ? ls : 0.0;
 }
 
 // lower bound of ln(x) for a positive normal double from its bits: x = m 2^e, ln m >= (m - 1) ln 2 on [1, 2)
@@ -355,95 +373,10 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         }
     }
 
-    // ---- 1. reads kept and lambda, G lanes per column.  Alleles of the column with a count of at most KS (a few
-    // sequencing errors beside the variant) get their tail here as well, exactly, from the distribution truncated at KS —
-    // on a strongly tilted row their cells would be lost to underflow.
-    int N = 0;
-    double lam = 0.0;
-    double small_tail[3] = {0.0, 0.0, 0.0};
-    bool use_small[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) use_small[i] = have && cnt[i] > 0 && cnt[i] <= KS && cnt[i] < K;
-    const bool want_small = use_small[0] || use_small[1] || use_small[2];
-    const bool any_small = __any_sync(FULL, want_small);
-    double P8[KS], T8 = 0.0;
-#pragma unroll
-    for (int k = 0; k < KS; ++k) P8[k] = (k == 0) ? 1.0 : 0.0;
-    {
-        const long long abase = g.off & ~15ll;
-        const int lead = (int)(g.off - abase);
-        const int nch = have ? (lead + g.n + 15) >> 4 : 0;
-#pragma unroll 1
-        for (int i = gl; i < nch; i += G) {
-            Chunk16 ch;
-            load_chunk(cf, b, abase + 16ll * i, ch);
-#pragma unroll 4
-            for (int k = 0; k < 16; ++k) {
-                const int pos = 16 * i - lead + k;
-                bool is_alt;
-                int slot;
-                double jp = 0.0;
-                const bool ok = pos >= 0 && pos < g.n &&
-                                eval_read<true>(cf, s_lut, g, pos, byte_of(ch.bq, k), byte_of(ch.mq, k), byte_of(ch.baq, k), byte_of(ch.sq, k),
-                                                is_alt, slot, jp);
-                if (ok) {
-                    lam += jp < DEPS ? DEPS : jp;
-                    ++N;
-                    if (any_small && want_small) {
-                        double p, q;
-                        guard_pq(jp, p, q);
-                        small_update(P8, T8, p, q);
-                    }
-                }
-            }
-        }
-        N = group_sum_i<G>(N);
-        lam = group_sum<G>(lam);
-        if (any_small) {
-            small_merge<G>(P8, T8);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                double tl = T8;
-#pragma unroll
-                for (int k = KS - 1; k >= 0; --k)
-                    if (k >= cnt[i]) tl += P8[k];
-                small_tail[i] = tl;
-            }
-        }
-    }
-    // Chernoff exponent of the tail: beyond ~300 nats the untilted cells of interest drift out of fp64 range
-    double ln_s = 0.0;
-    {
-        const double cher = (have && (double)K > lam) ? ((double)K * log((double)K / fmax(lam, 1e-300)) - (double)K + lam) : 0.0;
-        const bool need = have && cher > 300.0;
-        unsigned todo = __ballot_sync(FULL, need && gl == 0);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            Geom gg;
-            gg.off = __shfl_sync(FULL, g.off, src);
-            gg.n = __shfl_sync(FULL, g.n, src);
-            gg.b1 = __shfl_sync(FULL, g.b1, src);
-            gg.b2 = __shfl_sync(FULL, g.b2, src);
-            gg.b3 = __shfl_sync(FULL, g.b3, src);
-            gg.ref_idx = __shfl_sync(FULL, g.ref_idx, src);
-            gg.alt_bp = __shfl_sync(FULL, g.alt_bp, src);
-            const double ls = warp_tilt(cf, b, s_lut, gg, __shfl_sync(FULL, K, src), __shfl_sync(FULL, N, src), __shfl_sync(FULL, lam, src), sm);
-            if (lane / G == src / G) ln_s = ls;
-        }
-    }
-    const double s = (ln_s == 0.0) ? 1.0 : exp(ln_s);
-
-    // ---- 2./3. the recurrence, all columns of the warp in lock step
-    const int k0 = K - G * R + gl * R;                  // cell of register 0 (k < 0: padding, stays 0)
-    double E[R], T = 0.0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) E[r] = (have && k0 + r == 0) ? 1.0 : 0.0;
-    int e2 = 0;
+    // the bytes of reads [ks*DP_S, (ks+1)*DP_S) of this group's column -> stage buffer ks & 1
     const int n_mine = have ? g.n : 0;
     const int nmax = __reduce_max_sync(FULL, n_mine);
     const int lead = (int)(g.off & 15ll);
-    // the bytes of reads [ks*DP_S, (ks+1)*DP_S) of this group's column -> stage buffer ks & 1
     auto issue = [&](int ks) {
         if (gl == 0) {
             unsigned long long *bar = &sm.bar[ks & 1];
@@ -469,8 +402,115 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         fence_barrier_init();
     }
     __syncwarp();
+    // the first stage travels while the pre-pass runs
     int issued = 0, waited = 0;
     if (nmax > 0) { issue(0); issued = 1; }
+
+    EvalMode em;
+    em.uniform = cf.min_bq >= 0 && cf.min_alt_bq <= cf.min_bq && cf.alt_bq_mode == 0 && !cf.def_alt_jq_on && !cf.jq_filters;
+    em.plain_merge = !(cf.use_baq | cf.use_sq);
+
+    // ---- 1. pre-pass, G lanes per column, 16-byte loads: reads kept, lambda, the histogram of the merged probabilities
+    // (for the tilt).  Alleles of the column with a count of at most KS (a few sequencing errors beside the variant) get
+    // their tail here as well, exactly, from the distribution truncated at KS — on a strongly tilted row their cells
+    // would be lost to underflow.
+    int N = 0;
+    double lam = 0.0;
+    double small_tail[3] = {0.0, 0.0, 0.0};
+    bool use_small[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) use_small[i] = have && cnt[i] > 0 && cnt[i] <= KS && cnt[i] < K;
+    const bool want_small = use_small[0] || use_small[1] || use_small[2];
+    const bool any_small = __any_sync(FULL, want_small);
+    double P8[KS], T8 = 0.0;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) P8[k] = (k == 0) ? 1.0 : 0.0;
+    ColHist &hist = *reinterpret_cast<ColHist *>(sm.u.hist_bytes + grp * sizeof(ColHist));
+    for (int i = gl; i < DP_NB; i += G) {
+        hist.sum[i] = 0.f;
+        hist.cnt[i] = 0;
+    }
+    __syncwarp();
+    {
+        // runs of reads that fall into the same bucket (uniform qualities: all of them) are summed in registers first
+        int run_b = -1, run_c = 0;
+        float run_s = 0.f;
+        auto flush = [&]() {
+            if (run_b >= 0) {
+                atomicAdd(&hist.sum[run_b], run_s);
+                atomicAdd(&hist.cnt[run_b], run_c);
+            }
+        };
+        const long long abase = g.off & ~15ll;
+        const int nch = have ? (lead + g.n + 15) >> 4 : 0;
+#pragma unroll 1
+        for (int i = gl; i < nch; i += G) {
+            Chunk16 ch;
+            load_chunk(cf, b, abase + 16ll * i, ch);
+            const int pos0 = 16 * i - lead;
+            const bool inside = pos0 >= 0 && pos0 + 16 <= g.n;
+#pragma unroll 1
+            for (int wd = 0; wd < 4; ++wd) {
+                const unsigned wbq = wd == 0 ? ch.bq.x : wd == 1 ? ch.bq.y : wd == 2 ? ch.bq.z : ch.bq.w;
+                const unsigned wmq = wd == 0 ? ch.mq.x : wd == 1 ? ch.mq.y : wd == 2 ? ch.mq.z : ch.mq.w;
+                const unsigned wbaq = wd == 0 ? ch.baq.x : wd == 1 ? ch.baq.y : wd == 2 ? ch.baq.z : ch.baq.w;
+                const unsigned wsq = wd == 0 ? ch.sq.x : wd == 1 ? ch.sq.y : wd == 2 ? ch.sq.z : ch.sq.w;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int pos = pos0 + 4 * wd + j;
+                    double jp = 0.0;
+                    const bool ok = (inside || (pos >= 0 && pos < g.n)) &&
+                                    dp_eval(cf, em, s_lut, g, pos, (wbq >> (8 * j)) & 0xff, (wmq >> (8 * j)) & 0xff, (wbaq >> (8 * j)) & 0xff,
+                                            (wsq >> (8 * j)) & 0xff, jp);
+                    if (!ok) continue;
+                    const double p = jp < DEPS ? DEPS : jp;
+                    lam += p;
+                    ++N;
+                    const int bk = hist_bucket(p);
+                    if (bk != run_b) {
+                        flush();
+                        run_b = bk;
+                        run_s = 0.f;
+                        run_c = 0;
+                    }
+                    run_s += (float)p;
+                    ++run_c;
+                    if (any_small && want_small) {
+                        double pp_, qq_;
+                        guard_pq(jp, pp_, qq_);
+                        small_update(P8, T8, pp_, qq_);
+                    }
+                }
+            }
+        }
+        flush();
+        N = group_sum_i<G>(N);
+        lam = group_sum<G>(lam);
+        if (any_small) {
+            small_merge<G>(P8, T8);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double tl = T8;
+#pragma unroll
+                for (int k = KS - 1; k >= 0; --k)
+                    if (k >= cnt[i]) tl += P8[k];
+                small_tail[i] = tl;
+            }
+        }
+    }
+    __syncwarp();
+    // Chernoff exponent of the tail: beyond ~300 nats the untilted cells of interest drift out of fp64 range
+    const double cher = (have && (double)K > lam) ? ((double)K * log((double)K / fmax(lam, 1e-300)) - (double)K + lam) : 0.0;
+    const double ln_s = group_tilt<G>(hist, have && cher > 300.0, K, N, lam);
+    __syncwarp();                                       // the histograms give way to the step parameters
+    const double s = (ln_s == 0.0) ? 1.0 : exp(ln_s);
+
+    // ---- 2./3. the recurrence, all columns of the warp in lock step
+    const int k0 = K - G * R + gl * R;                  // cell of register 0 (k < 0: padding, stays 0)
+    double E[R], T = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) E[r] = (have && k0 + r == 0) ? 1.0 : 0.0;
+    int e2 = 0;
     const double thr_ln = log(cf.sig * (1.0 + 1e-9) / (double)bonf) + (double)K * ln_s;
     bool dead = !have, fb = false;
     double lq_acc = 0.0, qprod = 1.0;                   // ln of the product of q over this lane's reads = lq_acc + ln(qprod)
@@ -501,10 +541,8 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
                 const int mq = cf.use_mq ? src[(size_t)(pl++) * DP_SB + t] : 0;
                 const int baq = cf.use_baq ? src[(size_t)(pl++) * DP_SB + t] : 0;
                 const int sq = cf.use_sq ? src[(size_t)(pl++) * DP_SB + t] : 0;
-                bool is_alt;
-                int slot;
                 double jp;
-                if (eval_read<true>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp)) {
+                if (dp_eval(cf, em, s_lut, g, pos, bq, mq, baq, sq, jp)) {
                     double p, q;
                     guard_pq(jp, p, q);
                     const double rq = 1.0 / q;
@@ -701,7 +739,7 @@ k_dp(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, con
             const int mid = (lo + hi + 1) >> 1;
             if (s_tbase[mid] <= t) lo = mid; else hi = mid - 1;
         }
-        const int li = DP_NL - 1 - lo;
+        const int li = dp_entry_list(lo);
         const int cls = li / DP_NBIN1;
         const bool unbinned = (li % DP_NBIN1) == DP_NBIN;
         const unsigned nj = unbinned ? ws.counters->n_pjobs[li] : min(ws.counters->n_pjobs[li], (unsigned)ws.pcap);

@@ -53,9 +53,8 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_front(const __grid_constant__ 
     __shared__ int s_warp[32];
     __shared__ long long s_excl;
     __shared__ unsigned s_tile;
-    load_lut(s_lut, lut);
     if (threadIdx.x == 0) s_tile = atomicAdd(&ws.counters->front_ticket, 1u);
-    __syncthreads();
+    load_lut(s_lut, lut);            // (ends with the barrier that also publishes the ticket)
     const long long tile = s_tile;
     const long long n = b.n_cols;
     const long long c = tile * FIN_BLOCK + threadIdx.x;
@@ -121,6 +120,12 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_front(const __grid_constant__ 
         ws.tested[c] = (unsigned char)t;
     }
 
+    // the first 16 reads of a column the prune will walk: requested now, used after the look-back
+    const int K = max(cnt[0], max(cnt[1], cnt[2]));
+    Chunk16 first;
+    first.bq = first.mq = first.baq = first.sq = make_uint4(0, 0, 0, 0);
+    if (t && K <= KS && cf.alt_bq_mode != 2 && mg.n > 0) load_chunk(cf, b, mg.off & ~15ll, first);
+
     // ---- B. rank among the tested columns of the batch ----
     const unsigned bal = __ballot_sync(FULL, t);
     if (lane == 0) s_warp[w] = __popc(bal);
@@ -137,23 +142,33 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_front(const __grid_constant__ 
         long long excl = 0;
         if (tile > 0) {
             if (lane == 0) st_release_gpu(&state[tile], TS_AGG | (unsigned long long)total);
-            // look back over the tiles before this one, 32 at a time, nearest first
+            // Look back over the tiles before this one, 256 at a time, nearest first: every lane takes 8 consecutive
+            // tiles (8 loads in flight), so a whole resident wave of tiles is covered in two or three L2 round trips.
             long long base = tile - 1;
             for (;;) {
-                const long long idx = base - lane;
-                unsigned long long v = TS_PREFIX;                         // before the first tile: prefix 0
-                if (idx >= 0) {
-                    v = ld_acquire_gpu(&state[idx]);
-                    while ((v >> 62) == 0) v = ld_acquire_gpu(&state[idx]);
+                unsigned long long v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const long long idx = base - (lane * 8 + k);
+                    v[k] = idx >= 0 ? ld_acquire_gpu(&state[idx]) : TS_PREFIX;       // before the first tile: prefix 0
                 }
-                const unsigned pm = __ballot_sync(FULL, (v >> 62) == 2);
-                const int stop = pm ? __ffs(pm) - 1 : 32;                  // nearest tile whose inclusive prefix is known
-                long long add = lane <= stop ? (long long)(v & TS_MASK) : 0;
+                long long add = 0;
+                bool found = false;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const long long idx = base - (lane * 8 + k);
+                    while ((v[k] >> 62) == 0) v[k] = ld_acquire_gpu(&state[idx]);      // not counted yet: wait for its aggregate
+                    if (!found) add += (long long)(v[k] & TS_MASK);
+                    found = found || (v[k] >> 62) == 2;                                  // nearest tile whose inclusive prefix is known
+                }
+                const unsigned pm = __ballot_sync(FULL, found);
+                const int stop = pm ? __ffs(pm) - 1 : 32;
+                if (lane > stop) add = 0;
 #pragma unroll
                 for (int m = 16; m >= 1; m >>= 1) add += __shfl_xor_sync(FULL, add, m);
                 excl += add;
                 if (pm) break;
-                base -= 32;
+                base -= 256;
             }
         }
         if (lane == 0) {
@@ -174,7 +189,6 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_front(const __grid_constant__ 
     if (c < n) ws.rank[c] = rank;
 
     // ---- C. routing and the first stage of the prune ----
-    const int K = max(cnt[0], max(cnt[1], cnt[2]));
     if (t && K > KS) {
         if (K <= DP_MAXK) {
             // 8 < K <= 2048: k_dp, several columns per warp; job list by (class, depth bin), the class's unbinned list
@@ -200,7 +214,7 @@ __global__ void __launch_bounds__(FIN_BLOCK, 4) k_front(const __grid_constant__ 
     bool small = t && K <= KS;
     const double limit = small ? cf.sig * (1.0 + 1e-9) / (double)bonf : 0.0;   // margin: borderline columns go to the host
     if (cf.alt_bq_mode != 2) {          // the median override needs a warp-wide histogram: no lane-serial prune
-        small = lane_prune(cf, b, s_lut, mg, K, limit, PRUNE_CAP1, small);
+        small = lane_prune(cf, b, s_lut, mg, K, limit, PRUNE_CAP1, small, &first);
         if (small) {
             const unsigned slot = atomicAdd(&ws.counters->n_jobs[CLS_PRUNE2], 1u);
             ws.jobs[(long long)CLS_PRUNE2 * ws.cap_cols + slot] = (int)c;

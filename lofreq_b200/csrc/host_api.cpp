@@ -708,6 +708,10 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
         }
         if (dbg) t2 = now();
         // long double images of the p-values, for callers that want them (lfb200_set_site_pvalues)
+        if (!ctx->site_pvalues && n_cand) {
+            // the device does not write the p-value bytes: clear what an earlier batch may have left there
+            for (long long i = 0; i < n_cand; ++i) memset((void *)hs[i].pvalue, 0, sizeof(hs[i].pvalue));
+        }
         if (ctx->site_pvalues && n_cand) {
             if (n_cand < 1024) {
                 for (long long i = 0; i < n_cand; ++i) fill_pvalues(hs[i]);

@@ -10,6 +10,7 @@ constexpr int KS = 8;              // columns whose largest alt count is <= KS a
 constexpr int NCLASS = 10;         // job lists: 0 = K <= 32 (k_mid), 1..6 = register tiles R = 2..64 (k_heavy<R>), 7 = XL (CTA per
                                    // column), 8 = K <= 32 columns k_mid hands back to k_heavy<1> (tail outside the untilted range)
 constexpr int CLS_XL = 7, CLS_FALLBACK = 8;
+constexpr int CLS_XLFB = 1;         // K > 2048 columns k_xl hands to k_heavy_xl (a step parameter above 2^20: rescaling after every read)
 constexpr int CLS_PRUNE2 = 9;       // K <= 8 columns still alive after the first reads of k_finalize's prune: k_prune2's input
 constexpr int MAXK_WARP = 2048;    // 32 lanes * 64 cells
 
@@ -165,6 +166,9 @@ int dp_smem_optin();
 void launch_dp(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
                cudaStream_t st1, cudaStream_t st2);
 void launch_prob_jobs(int sms, const ProbBatch &pb, Cand *out, cudaStream_t st);
+// xl.cu: K > 2048, one CTA per column, the row spread over 8 warps running as a wavefront over the reads
+int xl_smem_optin();
+void launch_xl(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
 // mailbox.cu: the per-batch count exchange between shards through shared host memory
 constexpr int MAIL_DEPTH = 64;
 struct MailSlot {

@@ -73,7 +73,7 @@ __device__ __forceinline__ void count_alt_read(const DevConf &cf, const DevBatch
 // Cells are kept top-aligned (register 7 = cell K-1, padding below cell 0 stays 0), so one code path serves every
 // K <= KS.  Lanes with live == false only take part in the votes.
 __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &mg, int K,
-                                           double limit, int cap_reads, bool live)
+                                           double limit, int cap_reads, bool live, const Chunk16 *first = nullptr)
 {
     double R[KS], T = 0.0;
 #pragma unroll
@@ -84,7 +84,8 @@ __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b,
     const int lead = (int)(mg.off - ca);
     Chunk16 ch;
     ch.bq = ch.mq = ch.baq = ch.sq = make_uint4(0, 0, 0, 0);
-    if (live && cap > 0) load_chunk(cf, b, ca, ch);
+    if (first) ch = *first;                     // the caller requested the first chunk ahead of time
+    else if (live && cap > 0) load_chunk(cf, b, ca, ch);
 #pragma unroll 1
     for (int i = 0; __any_sync(FULL, live && i < cap); ++i) {
         if (!(live && i < cap)) continue;

@@ -1353,7 +1353,7 @@ int launch_state_init(LaunchState &ls, int device)
     stage_optin_one<1>(); stage_optin_one<2>(); stage_optin_one<4>(); stage_optin_one<8>();
     stage_optin_one<16>(); stage_optin_one<32>(); stage_optin_one<64>();
     cudaFuncSetAttribute(k_heavy_all, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES);
-    if (dp_smem_optin()) return 1;
+    if (dp_smem_optin() || xl_smem_optin()) return 1;
     if (cudaEventCreateWithFlags(&ls.ev_fork, cudaEventDisableTiming) != cudaSuccess) return 1;
     if (cudaEventCreateWithFlags(&ls.ev_fork2, cudaEventDisableTiming) != cudaSuccess) return 1;
     for (int i = 0; i < NSIDE; ++i) {
@@ -1385,21 +1385,22 @@ void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, co
     // second stage of the prune with the exact factor (k_front, in the screen phase, did the first)
     k_prune2<<<ls.sms * 2, 128, 0, st>>>(cf, b, lut, ws, bonf_start_dev);
     if (after_finalize) cudaEventRecord(after_finalize, st);
-    // Independent work side by side, so that the warps of the small kernels share the SMs with k_dp: k_mid (K <= 8
-    // survivors of the prune), k_dp<true> (1024 < K <= 2048, its own register budget), k_heavy_xl (K > 2048, one CTA per
-    // column); an empty list costs an early exit.  Then the per-column fallback for the few columns they hand back.
+    // Independent work side by side, so that the warps of the small kernels share the SMs with k_dp<0>: k_mid (K <= 8
+    // survivors of the prune), k_dp<1>, k_dp<2> (256 < K <= 2048, their own register budgets), k_xl (K > 2048, one CTA
+    // per column); an empty list costs an early exit.  Then the per-column fallbacks for the few columns they hand back.
     cudaEventRecord(ls.ev_fork, st);
     cudaStreamWaitEvent(ls.side[0], ls.ev_fork, 0);
     cudaStreamWaitEvent(ls.side[1], ls.ev_fork, 0);
     cudaStreamWaitEvent(ls.side[2], ls.ev_fork, 0);
     cudaStreamWaitEvent(ls.side[3], ls.ev_fork, 0);
     k_mid<<<ls.sms * 4, 128, 0, ls.side[0]>>>(cf, b, lut, ws);
-    k_heavy_xl<<<ls.sms, XL_T, 0, ls.side[2]>>>(cf, b, lut, ws, CLS_XL);
+    launch_xl(ls, cf, b, lut, ws, ls.side[2]);
     launch_dp(ls, cf, b, lut, ws, st, ls.side[1], ls.side[3]);
     for (int i = 0; i < 4; ++i) {
         cudaEventRecord(ls.ev_join[i], ls.side[i]);
         cudaStreamWaitEvent(st, ls.ev_join[i], 0);
     }
+    k_heavy_xl<<<ls.sms, XL_T, 0, st>>>(cf, b, lut, ws, CLS_XLFB);
     k_heavy_all<<<ls.sms, 128, STAGE_BYTES, st>>>(cf, b, lut, ws);
     // the sites in column order (see k_rank_cands)
     k_scan_blocks<<<1, 1024, 0, st>>>(ws.candtile, ws.candpre, nb, nullptr);
@@ -1550,7 +1551,12 @@ __global__ void __launch_bounds__(128) k_emit_sites(const __grid_constant__ DevC
       const unsigned nrec = min(128u, n - r0);
       const uint4 *src = reinterpret_cast<const uint4 *>(s_rec);
       uint4 *dst = reinterpret_cast<uint4 *>(out + r0);
-      for (unsigned w = threadIdx.x; w < nrec * 9u; w += 128u) dst[w] = src[w];
+      // words 3..5 of a record are the long double p-values: the host's business, never written from here
+      for (unsigned w = threadIdx.x; w < nrec * 6u; w += 128u) {
+          const unsigned rec = w / 6u, k = w - rec * 6u;
+          const unsigned at = rec * 9u + (k < 3u ? k : k + 3u);
+          dst[at] = src[at];
+      }
       __syncthreads();
     }
 }

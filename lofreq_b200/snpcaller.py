@@ -239,6 +239,7 @@ class Caller:
         out["n_sites"] = sm.n_sites
         out["n_tested"] = sm.n_tested
         out["n_heavy"] = sm.n_heavy
+        out["n_unsupported"] = sm.n_unsupported
         jc = (C.c_longlong * 4)()
         capi.check(self.lib.lfb200_last_job_counts(self._ctx, jc))
         out["job_counts"] = dict(packed=jc[0], fallback=jc[1], per_column=jc[2], mid=jc[3])

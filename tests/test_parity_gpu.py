@@ -488,6 +488,34 @@ def test_deep_columns_cta_per_column_kernel(caller, port_oracle):
         assert_lnp_close(got, want, status_of(want), "deep snpcaller")
 
 
+def test_alt_count_beyond_every_kernel_is_reported_not_dropped(caller, port_oracle):
+    """a column whose largest alt count exceeds what the kernels take (16384) comes back as a site with status
+    LFB200_ST_UNSUPPORTED; the other columns of the batch are computed and the Bonferroni state advances as if nothing
+    had happened (it used to fail the whole batch)"""
+    rng = np.random.default_rng(12)
+
+    def grp(n, qlo=20, qhi=41):
+        return (rng.integers(qlo, qhi, n), np.full(n, 60), rng.integers(30, 61, n))
+    e = (np.zeros(0, int),) * 3
+    cols = [dict(ref="A", groups=[grp(400), grp(60), e, e]),
+            dict(ref="C", groups=[grp(17000), grp(300), grp(4), e]),      # K = 17000 > 16384
+            dict(ref="G", groups=[grp(3), e, grp(500), grp(45)]),
+            dict(ref="T", groups=[e, e, e, grp(80)])]
+    b = _custom_batch(cols, pad=16)
+    want = port_oracle.call_columns(b, default_conf())
+    got = caller.call_columns(b, default_conf())
+    assert got["n_unsupported"] == 1
+    for k in ("alt_counts", "alt_raw_counts", "tested", "bonf_used"):
+        assert np.array_equal(got[k], want[k]), k
+    assert got["bonf_subst"] == want["bonf_subst"] and got["num_snv_tests"] == want["num_snv_tests"]
+    ok = np.array([0, 2, 3])
+    assert np.array_equal(got["called"][ok], want["called"][ok]) and np.array_equal(got["qual"][ok], want["qual"][ok])
+    assert_lnp_close(got["pvalues"][ok], want["pvalues"][ok], status_of(want["pvalues"][ok]), "beside the unsupported column")
+    assert got["status"][1].tolist() == [3, 3, 3] and not got["called"][1].any()
+    s = got["sites"]
+    assert (s["flags"][s["col"] == 1] & 2).all()
+
+
 def test_packed_kernel_classes(caller, port_oracle):
     """8 < K <= 2048: k_dp, 4/8/16/32 lanes per column and 8..64 cells per lane, columns of one warp in lock step.
     Every class, tilted and untilted rows, secondary alleles read off a tilted row, ragged depths inside
