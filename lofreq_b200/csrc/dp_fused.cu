@@ -726,10 +726,15 @@ k_dp(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, con
     unsigned char *wbase = dyn_smem + (size_t)wib * dp_warp_bytes(planes);
     DpWarpSmem &sm = *reinterpret_cast<DpWarpSmem *>(wbase);
     unsigned char *stage_bytes = wbase + ((sizeof(DpWarpSmem) + 15) & ~(size_t)15);
-    // the first task of every warp is dealt out statically — with about as many tasks as resident warps, a race for
-    // them leaves some SMs with six tasks per sub-partition and others with three — the rest dynamically
+    // The first task of every warp is dealt out statically — with about as many tasks as resident warps, a race for
+    // them leaves some SMs with six tasks per sub-partition and others with three — the rest dynamically.  The tasks are
+    // sorted by length (depth bin, then columns per warp); warp w of CTA b takes task w * Q + b, so that every CTA — and
+    // with it every SM — gets a cross-section of the lengths instead of four neighbours of the sorted order.
     const unsigned nwarps = gridDim.x * DP_WARPS;
-    unsigned t = blockIdx.x * DP_WARPS + wib;
+    const unsigned nstatic = min(total, nwarps);
+    const unsigned Q = (nstatic + DP_WARPS - 1) / DP_WARPS;
+    unsigned t = blockIdx.x < Q ? wib * Q + blockIdx.x : total;
+    if (t >= nstatic) t = total;
     unsigned *next = &ws.counters->next_ptask[RC];
     for (;;) {
         if (t >= total) break;

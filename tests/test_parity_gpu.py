@@ -511,7 +511,7 @@ def test_alt_count_beyond_every_kernel_is_reported_not_dropped(caller, port_orac
     ok = np.array([0, 2, 3])
     assert np.array_equal(got["called"][ok], want["called"][ok]) and np.array_equal(got["qual"][ok], want["qual"][ok])
     assert_lnp_close(got["pvalues"][ok], want["pvalues"][ok], status_of(want["pvalues"][ok]), "beside the unsupported column")
-    assert got["status"][1].tolist() == [3, 3, 3] and not got["called"][1].any()
+    assert got["status"][1].tolist() == [3, 3, 1] and not got["called"][1].any()      # the third allele has no reads: LDBL_MAX as ever
     s = got["sites"]
     assert (s["flags"][s["col"] == 1] & 2).all()
 
