@@ -349,7 +349,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         load_geom(b, c, g, cov);
 #pragma unroll
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
-        bonf = bonf_of(cf, ws.counters->bonf_start_used, ws.rank[c]);
+        bonf = bonf_of(cf, ws.counters->bonf_start_used, col_rank(ws, c));
     }
     const int K = max(cnt[0], max(cnt[1], cnt[2]));
     // alt-base quality override (snpcaller.c:431-441)
@@ -726,15 +726,10 @@ k_dp(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, con
     unsigned char *wbase = dyn_smem + (size_t)wib * dp_warp_bytes(planes);
     DpWarpSmem &sm = *reinterpret_cast<DpWarpSmem *>(wbase);
     unsigned char *stage_bytes = wbase + ((sizeof(DpWarpSmem) + 15) & ~(size_t)15);
-    // The first task of every warp is dealt out statically — with about as many tasks as resident warps, a race for
-    // them leaves some SMs with six tasks per sub-partition and others with three — the rest dynamically.  The tasks are
-    // sorted by length (depth bin, then columns per warp); warp w of CTA b takes task w * Q + b, so that every CTA — and
-    // with it every SM — gets a cross-section of the lengths instead of four neighbours of the sorted order.
+    // the first task of every warp is dealt out statically — with about as many tasks as resident warps, a race for
+    // them leaves some SMs with six tasks per sub-partition and others with three — the rest dynamically
     const unsigned nwarps = gridDim.x * DP_WARPS;
-    const unsigned nstatic = min(total, nwarps);
-    const unsigned Q = (nstatic + DP_WARPS - 1) / DP_WARPS;
-    unsigned t = blockIdx.x < Q ? wib * Q + blockIdx.x : total;
-    if (t >= nstatic) t = total;
+    unsigned t = blockIdx.x * DP_WARPS + wib;
     unsigned *next = &ws.counters->next_ptask[RC];
     for (;;) {
         if (t >= total) break;

@@ -22,6 +22,7 @@ constexpr int DP_NBIN = 14;        // depth bins: <= 128, 256, ..., 2^20 reads (
 constexpr int DP_NBIN1 = DP_NBIN + 1;   // + the unbinned overflow list of the class
 constexpr int DP_NL = DP_NCLS * DP_NBIN1;
 constexpr int DP_MAXK = 2048;
+constexpr int FRONT_MAXROUNDS = 64;  // round counters of k_front (rounds beyond share the last one)
 
 // what the kernels need from varcall_conf_t, pre-digested on the host
 struct DevConf {
@@ -98,7 +99,7 @@ struct Counters {
                                    // the excess went to the class's unbinned list, bin == DP_NBIN)
     unsigned int next_ptask[3];    // k_dp<RC>
     long long bonf_start_used;     // running factor the last test started from (host or device supplied)
-    unsigned int front_ticket;     // tiles handed out by k_front
+    unsigned long long front_round[FRONT_MAXROUNDS];   // tested columns counted so far per round of k_front (lower bounds for its prune)
     // written by k_emit_sites
     unsigned int n_fix;            // sites whose decision the host must repeat (may exceed EMIT_FIX_MAX: then all are rechecked)
     unsigned int emit_overflow;    // more sites than the host buffer holds: the host grows it and emits again
@@ -110,9 +111,10 @@ struct Workspace {
     long long cap_cols;
     int *cnt6;                     // [n][6]: alt_counts[3], alt_raw_counts[3]
     unsigned char *tested;         // [n]
-    int *rank;                     // [n]: 1-based rank among the tested columns of the batch, 0 = untested (k_front)
+    int *rank;                     // [n]: 1-based rank among the tested columns of its tile of 256 columns, 0 = untested (k_front);
+                                   // rank in the batch = blocksum[tile] + rank (col_rank)
     long long *bonf_used;          // [n]: materialised on request (k_bonf_used)
-    long long *blocksum;           // [ceil(n/256)]: tile states of k_front's look-back (status | tested columns up to the tile)
+    long long *blocksum;           // [ceil(n/256)]: tested columns per tile (k_front), then before each tile (k_scan_tiles)
     int *jobs;                     // [NCLASS][n]
     Cand *cand;                    // [n]
     unsigned char *is_cand;        // [n rounded up to 256]: column emitted a candidate

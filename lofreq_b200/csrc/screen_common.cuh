@@ -15,6 +15,13 @@ __device__ __forceinline__ long long bonf_of(const DevConf &cf, long long start,
     return cf.bonf_dynamic ? ((start == 1 ? 0 : start) + 3 * rank) : start;
 }
 
+// 1-based rank of a tested column among the tested columns of the batch (0 = untested): prefix of its tile + rank inside it
+__device__ __forceinline__ long long col_rank(const Workspace &ws, long long c)
+{
+    const int r = ws.rank[c];
+    return r ? ws.blocksum[c >> 8] + r : 0;
+}
+
 // [lo, hi) of the reads showing the reference base
 __device__ __forceinline__ void ref_range(const Geom &g, int &lo, int &hi)
 {

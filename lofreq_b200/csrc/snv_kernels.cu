@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(128) k_prune2(const __grid_constant__ DevConf 
             const int2 *in = reinterpret_cast<const int2 *>(ws.cnt6 + 6 * c);
             const int2 a0 = in[0], a1 = in[1];
             K = max(a0.x, max(a0.y, a1.x));
-            limit = cf.sig * (1.0 + 1e-9) / (double)bonf_of(cf, start, ws.rank[c]);
+            limit = cf.sig * (1.0 + 1e-9) / (double)bonf_of(cf, start, col_rank(ws, c));
         }
         live = lane_prune(cf, b, s_lut, mg, K, limit, PRUNE_CAP, live);
         if (live) {
@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(128) k_mid(const __grid_constant__ DevConf cf,
 #pragma unroll
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
         const int K = max(cnt[0], max(cnt[1], cnt[2]));
-        const long long bonf = bonf_of(cf, ws.counters->bonf_start_used, ws.rank[c]);
+        const long long bonf = bonf_of(cf, ws.counters->bonf_start_used, col_rank(ws, c));
         double tails[4];
         if (K <= 2) screen_small<2>(cf, b, lut_sa, g, cnt, K, tails);
         else if (K <= 4) screen_small<4>(cf, b, lut_sa, g, cnt, K, tails);
@@ -905,7 +905,7 @@ __device__ void heavy_list(const DevConf &cf, const DevBatch &b, const double *s
         int cnt[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
-        const long long bonf = bonf_of(cf, ws.counters->bonf_start_used, ws.rank[c]);
+        const long long bonf = bonf_of(cf, ws.counters->bonf_start_used, col_rank(ws, c));
         Cand cd;
         const bool site = run_problem<R>(src, cnt, bonf, cf.sig, s_par, cd);
         if (site && lane == 0) {
@@ -1229,7 +1229,7 @@ __global__ void __launch_bounds__(XL_T, 1) k_heavy_xl(const __grid_constant__ De
 #pragma unroll
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
         const int K = max(cnt[0], max(cnt[1], cnt[2]));
-        const long long bonf = bonf_of(cf, ws.counters->bonf_start_used, ws.rank[c]);
+        const long long bonf = bonf_of(cf, ws.counters->bonf_start_used, col_rank(ws, c));
         Cand cd;
         if (K > XL_T * XL_R) {
             // no kernel of this build takes an alt count this large: the column is reported as a site whose alleles carry

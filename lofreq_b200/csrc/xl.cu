@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(XLT, 1) k_xl(const __grid_constant__ DevConf c
 #pragma unroll
         for (int i = 0; i < 3; ++i) cnt[i] = ws.cnt6[6 * c + i];
         const int K = max(cnt[0], max(cnt[1], cnt[2]));
-        const long long bonf = bonf_of(cf, ws.counters->bonf_start_used, ws.rank[c]);
+        const long long bonf = bonf_of(cf, ws.counters->bonf_start_used, col_rank(ws, c));
         Cand cd;
         cd.flags = 0;
         cd.lnp[0] = cd.lnp[1] = cd.lnp[2] = 0.0;
