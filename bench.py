@@ -167,15 +167,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-STREAM_KERNELS = ("k_screen", "k_scan_blocks", "k_finalize", "k_prune2")
-HEAVY_KERNELS = ("k_mid", "k_pk_prep", "k_packed", "k_heavy")      # k_heavy<R>, k_heavy_xl
+STREAM_KERNELS = ("k_front", "k_prune2")
+HEAVY_KERNELS = ("k_mid", "k_dp", "k_xl", "k_heavy")               # k_dp<0..2>, k_xl, k_heavy_all, k_heavy_xl
+KERNELS_PER_STEP = 12      # k_front, k_prune2, k_mid, k_xl, k_dp<0>, k_dp<1>, k_dp<2>, k_heavy_xl, k_heavy_all, k_scan_blocks, k_rank_cands, k_emit_sites
 
 
-def ncu_traffic(names):
+def ncu_traffic(names, wl="C2"):
     """dram__bytes_read.sum + dram__bytes_write.sum per step of the named kernels, from the committed `ncu --set full`
-    capture of one step of this workload (profiles/r1_step_kernels.json, written by tools/ncu_extract.py); None when
-    the capture is not there."""
-    p = os.path.join(ROOT, "profiles", "r1_step_kernels.json")
+    capture of one step of this workload (profiles/r2_step_kernels_<workload>.json, written by tools/ncu_extract.py in
+    the same gpurun as the round's bench: tools/gpu_profile_round.sh); None when the capture is not there."""
+    p = os.path.join(ROOT, "profiles", "r2_step_kernels_%s.json" % wl)
     try:
         with open(p) as f:
             ks = json.load(f)
@@ -263,7 +264,7 @@ def run_ours(args):
     sts = [C.c_void_p(s_.cuda_stream) for s_ in streams]
 
     # this rank's region shard: columns [rank*n, (rank+1)*n)
-    t = synth.generate_device(wl, rank * n, n, with_baq=False, device=str(dev))
+    t = synth.generate_device(wl, rank * n, n, with_baq=args.baq, device=str(dev))
     torch.cuda.synchronize()
     db = caller.device_batch(t)
     max_sites = n
@@ -408,13 +409,14 @@ def run_ours(args):
 
     # ---- e2e: host buffers through lfb200_call_columns ----------------------------------------
     total = t["total_bytes"]
+    n_planes = 3 if args.baq else 2
+    planes = [("bq", t["bq"][: total + 16]), ("mq", t["mq"][: total + 16])] + ([("baq", t["baq"][: total + 16])] if args.baq else [])
     hb_t = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in
-            (("col_off", t["col_off"]), ("nt_cnt", t["nt_cnt"]), ("ref_base", t["ref_base"]),
-             ("bq", t["bq"][: total + 16]), ("mq", t["mq"][: total + 16]))}
+            [("col_off", t["col_off"]), ("nt_cnt", t["nt_cnt"]), ("ref_base", t["ref_base"])] + planes}
     torch.cuda.synchronize()
     hb = capi.Batch(n, hb_t["col_off"].data_ptr(), hb_t["nt_cnt"].data_ptr(), hb_t["ref_base"].data_ptr(), None,
-                    hb_t["bq"].data_ptr(), hb_t["mq"].data_ptr(), None, None, None)
-    h2d = 8 * (n + 1) + 16 * n + n + 2 * total
+                    hb_t["bq"].data_ptr(), hb_t["mq"].data_ptr(), hb_t["baq"].data_ptr() if args.baq else None, None, None)
+    h2d = 8 * (n + 1) + 16 * n + n + n_planes * total
 
     def step_e2e():
         cf = lofreq_b200.varcall_conf()
@@ -423,8 +425,9 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, 5))
 
     def time_e2e(mode):
-        """mode 0: the call copies the planes to the device; mode 1: the kernels read the pinned planes in place
-        over PCIe (lfb200_set_host_planes) and only the per-column metadata is copied"""
+        """mode 1 (the default of lfb200_call_columns): planes that lie in pinned host memory are read in place over PCIe
+        by the kernels — only the reads that decide a column cross the bus — and only the per-column metadata is copied;
+        mode 0: every plane is copied to the device first"""
         capi.check(lib.lfb200_set_host_planes(caller._ctx, mode))
         for _ in range(2):
             step_e2e()
@@ -443,9 +446,9 @@ def run_ours(args):
     else:
         e2e_copy_s, sites_copy, tests_copy = time_e2e(0)
         e2e_s, sites_map, tests_map = time_e2e(1)
-        capi.check(lib.lfb200_set_host_planes(caller._ctx, 0))
+        capi.check(lib.lfb200_set_host_planes(caller._ctx, 1))
         assert (sites_copy, tests_copy) == (sites_map, tests_map), "in-place and copied planes disagree"
-    e2e_value = world * n / e2e_copy_s            # headline: every input byte is copied host -> device inside the timed region
+    e2e_value = world * n / e2e_s                 # headline: the entry point with its defaults on pinned host buffers
     d2h = 128 + int(sm.n_sites) * 80
     h2d_meta = 8 * (n + 1) + 16 * n + n
 
@@ -458,10 +461,10 @@ def run_ours(args):
     # cells = sum_n (min(n, K-1) + 1) + (depth - K).
     peak, peak_src = measured_peaks()
     ph = prof.mean(axis=0) * 1e-3
-    t_stream = float(ph[0] + ph[1] + ph[2])
-    bytes_algo = algorithmic_bytes(int(t["depths"].sum().item()), n)
-    hbm = {"bound": "hbm", "kernel": "k_screen + k_scan_blocks + k_finalize + k_prune2", "achieved": bytes_algo / t_stream / 1e9,
-           "peak": peak, "unit": "GB/s", "frac": bytes_algo / t_stream / 1e9 / peak, "traffic": ncu_traffic(STREAM_KERNELS), "peak_source": peak_src,
+    t_stream = float(ph[0] + ph[2])
+    bytes_algo = algorithmic_bytes(int(t["depths"].sum().item()), n, planes=n_planes)
+    hbm = {"bound": "hbm", "kernel": "k_front + k_prune2", "achieved": bytes_algo / t_stream / 1e9,
+           "peak": peak, "unit": "GB/s", "frac": bytes_algo / t_stream / 1e9 / peak, "traffic": ncu_traffic(STREAM_KERNELS, wl), "peak_source": peak_src,
            "note": "algorithmic bytes = every quality byte the configuration merges (SURVEY.md 8d); the early-exit prune reads far fewer "
                    "(see traffic), so a fraction above 1 means bytes skipped, not bandwidth above peak",
            "algorithmic_bytes_per_launch": bytes_algo, "kernel_ms": t_stream * 1e3}
@@ -479,17 +482,17 @@ def run_ours(args):
     dfma = lib.lfb200_dfma_peak(callers[0]._ctx, sts[0])
     fp64_peak = 2.0 * dfma / 1e12
     t_heavy = float(ph[3])
-    fp64 = {"bound": "fp64", "kernel": "k_pk_prep + k_packed (8 < K <= 256, several columns per warp) beside k_mid; k_heavy<R> for the rest", "achieved": flops_algo / t_heavy / 1e12,
+    fp64 = {"bound": "fp64", "kernel": "k_dp<0..2> (8 < K <= 2048, several columns per warp, bytes staged by bulk TMA) beside k_mid and k_xl (K > 2048, wavefront of 8 warps per column)", "achieved": flops_algo / t_heavy / 1e12,
             "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops_algo / t_heavy / 1e12 / fp64_peak if fp64_peak else None,
-            "traffic": ncu_traffic(HEAVY_KERNELS), "peak_source": "DFMA microbenchmark run in this process (lfb200_dfma_peak); MEASURED_PEAKS.json has no fp64 entry",
+            "traffic": ncu_traffic(HEAVY_KERNELS, wl), "peak_source": "DFMA microbenchmark run in this process (lfb200_dfma_peak); MEASURED_PEAKS.json has no fp64 entry",
             "algorithmic_flops_per_launch": flops_algo, "kernel_ms": t_heavy * 1e3, "columns": int(heavy.sum().item())}
     if hbm["traffic"] is not None:
         hbm["traffic_frac"] = hbm["traffic"] / t_stream / 1e9 / peak      # measured DRAM bytes / time / peak: the real pressure
-    # the dominant kernel of the step is k_packed (profiles/r1_summary.md), so the fp64 side is the headline roofline
-    # and the stream side rides along as `other` (the two sides take about the same time on C2)
+    # the dominant kernel of the step is k_dp<0> (profiles/r2_summary.md), so the fp64 side is the headline roofline
+    # and the stream side rides along as `other`
     roofline = dict(fp64)
-    roofline["phase_ms"] = {"k_screen": float(ph[0] * 1e3), "prefix_sum": float(ph[1] * 1e3), "k_finalize": float(ph[2] * 1e3),
-                            "k_heavy": float(ph[3] * 1e3)}
+    roofline["phase_ms"] = {"k_front": float(ph[0] * 1e3), "k_prune2": float(ph[2] * 1e3),
+                            "heavy": float(ph[3] * 1e3)}
     roofline["other"] = hbm
 
     if rank == 0:
@@ -500,24 +503,36 @@ def run_ours(args):
             cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": kind,
                    "sample": "first %d columns of the same workload, %.1f s, single thread (the reference is "
                              "single-threaded; all-core number: --impl reference)" % (args.cpu_sample, s)}
+            # the literal `lofreq call` of the metric: the reference's own prebuilt 2.1.4 binary on a synthetic BAM of the same
+            # column model (BAM decode + pileup + test), without BAQ like this workload's planes
+            try:
+                from oracle import cli_baseline
+                if cli_baseline.have_cli() and wl in DEPTH:
+                    cpu["cli"] = cli_baseline.run_cli(20000 if DEPTH[wl] <= 500 else 4000, depth=DEPTH[wl], baq=False)
+            except Exception as e:          # the CLI leg is a reported extra: never fails the bench
+                cpu["cli"] = {"unavailable": str(e)[:200]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_desc(wl, n) + " per GPU (region shard = rank*cols)",
                            "cols_per_gpu": n, "depth": DEPTH.get(wl), "l2": "inputs larger than L2 (%.2f GB per step)" % (2 * total / 1e9),
-                           "value_region": "screen + prefix sum + significance test + O(depth*K) kernels + D2H of sites + long double finishing, inputs resident in HBM; %d contexts so that the host finishing of one batch overlaps the kernels of the next" % NC + "",
+                           "planes": "bq+mq" + ("+baq" if args.baq else " (no BAQ plane: SURVEY 8d core benchmark; --baq adds it)"),
+                           "value_region": "k_front (gates, counts, running Bonferroni, prune) + O(depth*K) kernels + per-site decision (status / called / QUAL) on the device + sites in column order into pinned host memory + host wait, inputs resident in HBM; long double p-value images not requested (lfb200_set_site_pvalues 0); %d contexts = batches in flight" % NC + "",
                            "tested_columns": int(n_tested), "sites": int(n_sites), "heavy_columns": int(n_heavy),
                            "sites_all_ranks": final_sites,
                            "bonf_subst_final_this_rank": int(sm.bonf_subst_final)},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_copy_s * 1e3, "steps": e2e_steps,
-                        "h2d_mode": "lfb200_call_columns on pinned host buffers (its default, host plane mode 0): every plane and the "
-                                    "per-column metadata are copied to the device, then screen/test/sites; PCIe-bound",
-                        "in_place": {"value": world * n / e2e_s, "ms_per_step": e2e_s * 1e3, "h2d_bytes_copied_per_step": h2d_meta,
-                                     "h2d_mode": "optional host plane mode 1 (lfb200_set_host_planes): the kernels read the pinned quality "
-                                                 "planes in place over PCIe, so only the reads that decide a column cross the bus; "
-                                                 "only the per-column metadata is copied"}},
-                "gpu_launches": 17 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_meta, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "copies_declared": True,
+                        "h2d_bytes_mapped_per_step": n_planes * total,
+                        "h2d_mode": "lfb200_call_columns with its defaults on pinned host buffers (host plane mode 1): the per-column "
+                                    "metadata is copied (h2d_bytes_per_step); the quality planes (h2d_bytes_mapped_per_step) lie in "
+                                    "pinned memory and are read in place over PCIe by the kernels, so only the reads that decide a "
+                                    "column cross the bus; sites come back through pinned memory; identical results in both modes "
+                                    "(asserted every run)",
+                        "copy_mode": {"value": world * n / e2e_copy_s, "ms_per_step": e2e_copy_s * 1e3, "h2d_bytes_per_step": h2d,
+                                      "h2d_mode": "host plane mode 0 (lfb200_set_host_planes): every plane is copied to the device "
+                                                  "first; PCIe-bound (the round-1 headline)"}},
+                "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 else 0)) * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "wall_ms_per_step": wall * 1e3 / args.steps}
         emit(line)
     if world > 1:
@@ -533,7 +548,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"])
-    ap.add_argument("--cols", type=int, default=1_000_000, help="columns per GPU")
+    ap.add_argument("--cols", type=int, default=1_000_000, help="columns per GPU and step (batch size)")
+    ap.add_argument("--baq", action="store_true", help="add a BAQ plane (general 4-way merge) to the workload")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="columns of the single-thread cpu_baseline sample")
     ap.add_argument("--ref-cols-per-proc", type=int, default=30_000)
     ap.add_argument("--contexts", type=int, default=0, help="contexts (batches in flight) per GPU; default 2")

@@ -149,10 +149,10 @@ void lfb200_init_conf(lfb200_conf_t *conf);
 int lfb200_call_columns(lfb200_ctx *ctx, lfb200_conf_t *conf, const lfb200_batch_t *host_batch,
                         const lfb200_dense_out_t *dense, lfb200_site_t *sites, long long max_sites,
                         lfb200_summary_t *summary);
-/* How lfb200_call_columns (and the column builder) hands the quality planes to the device: 0 = bulk copy
- * (default); 1 = planes that lie in pinned host memory (cudaHostAlloc / cudaHostRegister) are read in place
- * over PCIe — the kernels only touch the reads that decide a column, so far fewer bytes cross the bus; planes
- * in pageable memory are still copied.  Results are identical. */
+/* How lfb200_call_columns (and the column builder) hands the quality planes to the device: 1 (default) = planes that
+ * lie in pinned host memory (cudaHostAlloc / cudaHostRegister) are read in place over PCIe — the kernels only touch the
+ * reads that decide a column, so far fewer bytes cross the bus than a bulk copy moves; planes in pageable memory are
+ * copied; 0 = every plane is copied to the device first.  Results are identical. */
 int lfb200_set_host_planes(lfb200_ctx *ctx, int mode);
 
 /* Device-resident batch, two phases so that region shards on several GPUs can
@@ -225,7 +225,8 @@ int lfb200_sites_buffer(lfb200_ctx *ctx, const lfb200_site_t **sites);
 int lfb200_set_site_pvalues(lfb200_ctx *ctx, int on);
 void lfb200_site_fill_pvalues(lfb200_site_t *sites, long long n);
 /* optional per-phase device timing with CUDA events on the launching stream (benchmark / roofline):
- * ms4 = { k_screen, prefix-sum kernels, k_finalize, k_heavy<*> } of the last screen + test */
+ * ms4 = { k_front + k_scan_tiles, 0, k_prune2, the O(depth*K) kernels (k_mid | k_dp<0..2> | k_xl, then the fallbacks) }
+ * of the last screen + test */
 int lfb200_set_profiling(lfb200_ctx *ctx, int on);
 int lfb200_get_profile(lfb200_ctx *ctx, float *ms4);
 /* copy alt_counts | alt_raw_counts ([n_cols][6] ints) of the last screen into caller-owned device memory */

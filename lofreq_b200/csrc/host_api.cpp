@@ -186,7 +186,7 @@ struct lfb200_ctx {
     char fin_err[512] = "";
     void finisher_loop();
     void *comm_state = nullptr;          // owned by shard_comm.cpp
-    int host_planes = 0;                 // lfb200_set_host_planes
+    int host_planes = 1;                 // lfb200_set_host_planes: pinned planes are read in place unless the caller says otherwise
     LaunchState ls;                      // side streams / events / SM count of this context's device
     // sites of the last test, written by k_emit_sites in column order straight into mapped pinned memory
     lfb200_site_t *h_sites = nullptr;
@@ -568,8 +568,8 @@ static int test_device_impl(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *st
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (ctx->profiling) cudaEventRecord(ctx->ev[3], st);
-    launch_test(ctx->ls, dc, ctx->cur, ctx->d_lut, ctx->ws, st, ctx->profiling ? ctx->ev[4] : nullptr, bonf_start_dev);
-    if (ctx->profiling) cudaEventRecord(ctx->ev[5], st);
+    launch_test(ctx->ls, dc, ctx->cur, ctx->d_lut, ctx->ws, st, ctx->profiling ? ctx->ev[4] : nullptr, ctx->profiling ? ctx->ev[5] : nullptr,
+                bonf_start_dev);
     // the sites, decided on the device, in column order into pinned host memory; then the counters; then the event the
     // host waits for: nothing of this needs the host before lfb200_sites_*
     ctx->last_dc = dc;

@@ -155,7 +155,7 @@ void launch_state_destroy(LaunchState &ls);
 void launch_front(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st);
 void launch_bonf_used(const LaunchState &ls, const DevConf &cf, const Workspace &ws, long long n, cudaStream_t st);
 void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
-                 cudaEvent_t after_finalize, const long long *bonf_start_dev);
+                 cudaEvent_t after_finalize, cudaEvent_t after_heavy, const long long *bonf_start_dev);
 // sites in column order, decided on the device, into (mapped pinned) host memory
 void launch_emit_sites(const LaunchState &ls, const DevConf &cf, const Workspace &ws, SiteRec *out, unsigned cap, cudaStream_t st);
 void launch_bonf_start(const long long *counts, int rank, long long bonf_subst, long long *start, cudaStream_t st);

@@ -1378,7 +1378,7 @@ void launch_state_destroy(LaunchState &ls)
 __global__ void k_rank_cands(const Workspace ws);
 
 void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
-                 cudaEvent_t after_finalize, const long long *bonf_start_dev)
+                 cudaEvent_t after_finalize, cudaEvent_t after_heavy, const long long *bonf_start_dev)
 {
     if (b.n_cols <= 0) return;
     const int nb = (int)((b.n_cols + FIN_BLOCK - 1) / FIN_BLOCK);
@@ -1402,6 +1402,7 @@ void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, co
     }
     k_heavy_xl<<<ls.sms, XL_T, 0, st>>>(cf, b, lut, ws, CLS_XLFB);
     k_heavy_all<<<ls.sms, 128, STAGE_BYTES, st>>>(cf, b, lut, ws);
+    if (after_heavy) cudaEventRecord(after_heavy, st);
     // the sites in column order (see k_rank_cands)
     k_scan_blocks<<<1, 1024, 0, st>>>(ws.candtile, ws.candpre, nb, nullptr);
     k_rank_cands<<<ls.sms, 256, 0, st>>>(ws);

@@ -12,7 +12,7 @@ python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_quick.json'))
 print(d['value'], d['ms_per_step'], d['roofline']['phase_ms'], d['config']['sites'], d['config']['heavy_columns'], d['config']['tested_columns'])
-print('e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'in_place', d['e2e']['in_place']['value'], 'frac', d['roofline']['frac'])
+print('e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'copy_mode', d['e2e']['copy_mode']['value'], 'frac', d['roofline']['frac'])
 PY
 tail -3 gpurun_out/bench_quick.err
 if [ -n "${NCU:-}" ]; then
