@@ -67,47 +67,47 @@ __device__ __forceinline__ int group_min_i(int v)
     return v;
 }
 
-// distribution truncated at KS = 8 (P[k] = P(k errors), k < 8; T = P(>= 8 errors)) for the small counts of the other
-// alleles of a heavy column: one read folded in ...
-__device__ __forceinline__ void small_update(double (&P)[KS], double &T, double p, double q)
+// distribution truncated at KSM = 16 (P[k] = P(k errors), k < 16; T = P(>= 16 errors)) for the small counts of the other
+// alleles of a heavy column (a few sequencing errors beside the variant): one read folded in ...
+constexpr int KSM = 16;
+__device__ __forceinline__ void small_update(double (&P)[KSM], double &T, double p, double q)
 {
-    T = fma(P[KS - 1], p, T);
+    T = fma(P[KSM - 1], p, T);
 #pragma unroll
-    for (int k = KS - 1; k >= 1; --k) P[k] = fma(P[k - 1], p, P[k] * q);
+    for (int k = KSM - 1; k >= 1; --k) P[k] = fma(P[k - 1], p, P[k] * q);
     P[0] = P[0] * q;
 }
 
 // ... and the G per-lane distributions of a column merged by truncated convolution (butterfly inside the group)
 template <int G>
-__device__ __forceinline__ void small_merge(double (&P)[KS], double &T)
+__device__ __forceinline__ void small_merge(double (&P)[KSM], double &T)
 {
 #pragma unroll 1
     for (int m = 1; m < G; m <<= 1) {
-        double bb[KS], cc[KS];
+        // c[k] = sum_i P[i] b[k-i]; the partner's cells are fetched one at a time inside the convolution
+        double cc[KSM];
         const double tb = __shfl_xor_sync(FULL, T, m);
         double sum_a = 0.0, sum_b = 0.0;
 #pragma unroll
-        for (int k = 0; k < KS; ++k) {
-            bb[k] = __shfl_xor_sync(FULL, P[k], m);
+        for (int k = 0; k < KSM; ++k) {
+            cc[k] = 0.0;
             sum_a += P[k];
-            sum_b += bb[k];
         }
+        double t = 0.0, asuf = 0.0;
 #pragma unroll
-        for (int k = 0; k < KS; ++k) {
-            double acc = 0.0;
+        for (int j = 0; j < KSM; ++j) {
+            const double bj = __shfl_xor_sync(FULL, P[j], m);
+            sum_b += bj;
 #pragma unroll
-            for (int i = 0; i <= k; ++i) acc = fma(P[i], bb[k - i], acc);
-            cc[k] = acc;
+            for (int k = j; k < KSM; ++k) cc[k] = fma(P[k - j], bj, cc[k]);
+            if (j >= 1) {
+                asuf += P[KSM - j];
+                t = fma(bj, asuf, t);
+            }
         }
-        double t = T * (sum_b + tb) + tb * sum_a;
-        double asuf = 0.0;
+        t += T * (sum_b + tb) + tb * sum_a;
 #pragma unroll
-        for (int j = 1; j < KS; ++j) {
-            asuf += P[KS - j];
-            t = fma(bb[j], asuf, t);
-        }
-#pragma unroll
-        for (int k = 0; k < KS; ++k) P[k] = cc[k];
+        for (int k = 0; k < KSM; ++k) P[k] = cc[k];
         T = t;
     }
 }
@@ -318,6 +318,57 @@ __device__ __forceinline__ double group_tilt(const ColHist &h, bool need, int K,
     return need ? ls : 0.0;
 }
 
+// P(X >= c) for the counts c0, c1, c2 (<= KSM) of one column, exactly: every lane of the column's group folds its 16-byte
+// chunks of reads into a distribution truncated at KSM, the G distributions are merged by truncated convolution.
+// Whole warp (the shuffles of the merge); lanes with want == false only take part.  Its own register allocation: the
+// recurrence's registers are not live here.
+template <int G>
+__device__ __noinline__ void small_tails_sweep(const DevConf &cf, const DevBatch &b, const EvalMode &em, const double *s_lut, const Geom &g,
+                                               int lead, bool want, int c0, int c1, int c2, double (&tails)[3])
+{
+    const int gl = lane_id() % G;
+    double P[KSM], TS = 0.0;
+#pragma unroll
+    for (int k = 0; k < KSM; ++k) P[k] = (k == 0) ? 1.0 : 0.0;
+    const long long abase = g.off & ~15ll;
+    const int nch = want ? (lead + g.n + 15) >> 4 : 0;
+#pragma unroll 1
+    for (int i = gl; i < nch; i += G) {
+        Chunk16 ch;
+        load_chunk(cf, b, abase + 16ll * i, ch);
+        const int pos0 = 16 * i - lead;
+#pragma unroll 1
+        for (int wd = 0; wd < 4; ++wd) {
+            const unsigned wbq = wd == 0 ? ch.bq.x : wd == 1 ? ch.bq.y : wd == 2 ? ch.bq.z : ch.bq.w;
+            const unsigned wmq = wd == 0 ? ch.mq.x : wd == 1 ? ch.mq.y : wd == 2 ? ch.mq.z : ch.mq.w;
+            const unsigned wbaq = wd == 0 ? ch.baq.x : wd == 1 ? ch.baq.y : wd == 2 ? ch.baq.z : ch.baq.w;
+            const unsigned wsq = wd == 0 ? ch.sq.x : wd == 1 ? ch.sq.y : wd == 2 ? ch.sq.z : ch.sq.w;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                const int pos = pos0 + 4 * wd + j;
+                double jp = 0.0;
+                if (pos < 0 || pos >= g.n ||
+                    !dp_eval(cf, em, s_lut, g, pos, (wbq >> (8 * j)) & 0xff, (wmq >> (8 * j)) & 0xff, (wbaq >> (8 * j)) & 0xff, (wsq >> (8 * j)) & 0xff, jp))
+                    continue;
+                double p, q;
+                guard_pq(jp, p, q);
+                small_update(P, TS, p, q);
+            }
+        }
+    }
+    small_merge<G>(P, TS);
+    double t0 = TS, t1 = TS, t2 = TS;
+#pragma unroll
+    for (int k = KSM - 1; k >= 0; --k) {      // small terms first
+        if (k >= c0) t0 += P[k];
+        if (k >= c1) t1 += P[k];
+        if (k >= c2) t2 += P[k];
+    }
+    tails[0] = t0;
+    tails[1] = t1;
+    tails[2] = t2;
+}
+
 // lower bound of ln(x) for a positive normal double from its bits: x = m 2^e, ln m >= (m - 1) ln 2 on [1, 2)
 __device__ __forceinline__ double ln_lower(double x)
 {
@@ -410,21 +461,13 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
     em.uniform = cf.min_bq >= 0 && cf.min_alt_bq <= cf.min_bq && cf.alt_bq_mode == 0 && !cf.def_alt_jq_on && !cf.jq_filters;
     em.plain_merge = !(cf.use_baq | cf.use_sq);
 
-    // ---- 1. pre-pass, G lanes per column, 16-byte loads: reads kept, lambda, the histogram of the merged probabilities
-    // (for the tilt).  Alleles of the column with a count of at most KS (a few sequencing errors beside the variant) get
-    // their tail here as well, exactly, from the distribution truncated at KS — on a strongly tilted row their cells
-    // would be lost to underflow.
+    // ---- 1. pre-pass, G lanes per column, 16-byte loads: reads kept, lambda and the histogram of the merged probabilities —
+    // what the tilt needs.  Most columns need no tilt (and many are ruled out by the early exit after a fraction of their
+    // reads), so the sweep first takes a sample of 64 reads per lane; only a column whose estimated Chernoff exponent comes
+    // near the limit is swept to the end.  (A wrong guess costs speed, not correctness: an untilted row that turns out to
+    // need the tilt is handed to the per-column fallback.)
     int N = 0;
     double lam = 0.0;
-    double small_tail[3] = {0.0, 0.0, 0.0};
-    bool use_small[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) use_small[i] = have && cnt[i] > 0 && cnt[i] <= KS && cnt[i] < K;
-    const bool want_small = use_small[0] || use_small[1] || use_small[2];
-    const bool any_small = __any_sync(FULL, want_small);
-    double P8[KS], T8 = 0.0;
-#pragma unroll
-    for (int k = 0; k < KS; ++k) P8[k] = (k == 0) ? 1.0 : 0.0;
     ColHist &hist = *reinterpret_cast<ColHist *>(sm.u.hist_bytes + grp * sizeof(ColHist));
     for (int i = gl; i < DP_NB; i += G) {
         hist.sum[i] = 0.f;
@@ -440,62 +483,63 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
                 atomicAdd(&hist.sum[run_b], run_s);
                 atomicAdd(&hist.cnt[run_b], run_c);
             }
+            run_b = -1;
         };
         const long long abase = g.off & ~15ll;
         const int nch = have ? (lead + g.n + 15) >> 4 : 0;
+        auto sweep = [&](int i0, int i1) {
 #pragma unroll 1
-        for (int i = gl; i < nch; i += G) {
-            Chunk16 ch;
-            load_chunk(cf, b, abase + 16ll * i, ch);
-            const int pos0 = 16 * i - lead;
-            const bool inside = pos0 >= 0 && pos0 + 16 <= g.n;
+            for (int i = i0; i < i1; i += G) {
+                Chunk16 ch;
+                load_chunk(cf, b, abase + 16ll * i, ch);
+                const int pos0 = 16 * i - lead;
+                const bool inside = pos0 >= 0 && pos0 + 16 <= g.n;
 #pragma unroll 1
-            for (int wd = 0; wd < 4; ++wd) {
-                const unsigned wbq = wd == 0 ? ch.bq.x : wd == 1 ? ch.bq.y : wd == 2 ? ch.bq.z : ch.bq.w;
-                const unsigned wmq = wd == 0 ? ch.mq.x : wd == 1 ? ch.mq.y : wd == 2 ? ch.mq.z : ch.mq.w;
-                const unsigned wbaq = wd == 0 ? ch.baq.x : wd == 1 ? ch.baq.y : wd == 2 ? ch.baq.z : ch.baq.w;
-                const unsigned wsq = wd == 0 ? ch.sq.x : wd == 1 ? ch.sq.y : wd == 2 ? ch.sq.z : ch.sq.w;
+                for (int wd = 0; wd < 4; ++wd) {
+                    const unsigned wbq = wd == 0 ? ch.bq.x : wd == 1 ? ch.bq.y : wd == 2 ? ch.bq.z : ch.bq.w;
+                    const unsigned wmq = wd == 0 ? ch.mq.x : wd == 1 ? ch.mq.y : wd == 2 ? ch.mq.z : ch.mq.w;
+                    const unsigned wbaq = wd == 0 ? ch.baq.x : wd == 1 ? ch.baq.y : wd == 2 ? ch.baq.z : ch.baq.w;
+                    const unsigned wsq = wd == 0 ? ch.sq.x : wd == 1 ? ch.sq.y : wd == 2 ? ch.sq.z : ch.sq.w;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int pos = pos0 + 4 * wd + j;
-                    double jp = 0.0;
-                    const bool ok = (inside || (pos >= 0 && pos < g.n)) &&
-                                    dp_eval(cf, em, s_lut, g, pos, (wbq >> (8 * j)) & 0xff, (wmq >> (8 * j)) & 0xff, (wbaq >> (8 * j)) & 0xff,
-                                            (wsq >> (8 * j)) & 0xff, jp);
-                    if (!ok) continue;
-                    const double p = jp < DEPS ? DEPS : jp;
-                    lam += p;
-                    ++N;
-                    const int bk = hist_bucket(p);
-                    if (bk != run_b) {
-                        flush();
-                        run_b = bk;
-                        run_s = 0.f;
-                        run_c = 0;
-                    }
-                    run_s += (float)p;
-                    ++run_c;
-                    if (any_small && want_small) {
-                        double pp_, qq_;
-                        guard_pq(jp, pp_, qq_);
-                        small_update(P8, T8, pp_, qq_);
+                    for (int j = 0; j < 4; ++j) {
+                        const int pos = pos0 + 4 * wd + j;
+                        double jp = 0.0;
+                        const bool ok = (inside || (pos >= 0 && pos < g.n)) &&
+                                        dp_eval(cf, em, s_lut, g, pos, (wbq >> (8 * j)) & 0xff, (wmq >> (8 * j)) & 0xff, (wbaq >> (8 * j)) & 0xff,
+                                                (wsq >> (8 * j)) & 0xff, jp);
+                        if (!ok) continue;
+                        const double p = jp < DEPS ? DEPS : jp;
+                        lam += p;
+                        ++N;
+                        const int bk = hist_bucket(p);
+                        if (bk != run_b) {
+                            flush();
+                            run_b = bk;
+                            run_s = 0.f;
+                            run_c = 0;
+                        }
+                        run_s += (float)p;
+                        ++run_c;
                     }
                 }
             }
-        }
+        };
+        constexpr int SAMPLE_CHUNKS = 4;                 // per lane: 64 reads
+        const int i_mid = min(nch, gl + SAMPLE_CHUNKS * G);
+        sweep(gl, i_mid);
+        const int n_s = group_sum_i<G>(N);
+        const double lam_s = group_sum<G>(lam);
+        const int covered = min(SAMPLE_CHUNKS * G * 16, lead + g.n);            // positions the sample has looked at
+        const double lam_est = have && covered > 0 ? lam_s * (double)(lead + g.n) / (double)covered : 0.0;
+        const double cher_est = (have && (double)K > lam_est) ? ((double)K * log((double)K / fmax(lam_est, 1e-300)) - (double)K + lam_est) : 0.0;
+        const bool full = have && nch > SAMPLE_CHUNKS * G && cher_est > 100.0;
+        if (full) sweep(gl + SAMPLE_CHUNKS * G, nch);
         flush();
         N = group_sum_i<G>(N);
         lam = group_sum<G>(lam);
-        if (any_small) {
-            small_merge<G>(P8, T8);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                double tl = T8;
-#pragma unroll
-                for (int k = KS - 1; k >= 0; --k)
-                    if (k >= cnt[i]) tl += P8[k];
-                small_tail[i] = tl;
-            }
+        if (have && !full && nch > SAMPLE_CHUNKS * G) {                 // estimates: no tilt will be computed from them
+            lam = lam_est;
+            N = (int)((double)n_s * (double)(lead + g.n) / (double)covered);
         }
     }
     __syncwarp();
@@ -643,17 +687,19 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
     const double lnKm1 = log(topl) + base - (double)(K - 1) * ln_s;
     bool site = have && !fb && !dead;
     if (site && lnT > -700.0 && exp(lnT) * (double)bonf > cf.sig * (1.0 + 1e-9)) site = false;   // snpcaller.c:1155
-    double lnp[3] = {0.0, 0.0, 0.0};
+    double lnp0 = 0.0, lnp1 = 0.0, lnp2 = 0.0;
+    bool use_small[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) use_small[i] = site && cnt[i] > 0 && cnt[i] <= KSM && cnt[i] < K;
+    const bool want_small = use_small[0] || use_small[1] || use_small[2];
     const double invs = (ln_s == 0.0) ? 1.0 : exp(-ln_s);
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
         const int ci = cnt[i];
-        if (use_small[i]) lnp[i] = log(small_tail[i]);
-        if (!__any_sync(FULL, site && ci > 0 && ci < K && !use_small[i])) {
-            if (ci == K) lnp[i] = lnT;
-            continue;
-        }
+        double &out = i == 0 ? lnp0 : i == 1 ? lnp1 : lnp2;
+        if (ci == K) out = lnT;
         const bool mine = site && ci > 0 && ci < K && !use_small[i];
+        if (!__any_sync(FULL, mine)) continue;
         // P(X >= ci) = sum_{k >= ci} E[k] s^-(k-ci) + T s^-(K-ci), times s^-ci and the common scale
         double acc = 0.0;
         int hc = 0x7fffffff;
@@ -676,10 +722,18 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
             // the leading cell must have stayed a normal number all along (rescaling keeps the peak within 2^+-200
             // at the block boundaries and below 2^840 inside a block)
             if ((hc >> 20) < 64 || peak - (hc >> 20) > 850) fb = true;
-            lnp[i] = log(acc) + base - (double)ci * ln_s;
-        } else if (ci == K) {
-            lnp[i] = lnT;
+            out = log(acc) + base - (double)ci * ln_s;
         }
+    }
+    // Alleles of a site with a count of at most KSM (a few sequencing errors beside the variant): their tail exactly, from
+    // the distribution truncated at KSM — on a strongly tilted row their cells would be lost to underflow.  After the row
+    // has been read (its registers are free now); only columns that are sites get here.
+    if (__any_sync(FULL, want_small)) {
+        double t3[3];
+        small_tails_sweep<G>(cf, b, em, s_lut, g, lead, want_small, cnt[0], cnt[1], cnt[2], t3);
+        if (use_small[0]) lnp0 = log(t3[0]);
+        if (use_small[1]) lnp1 = log(t3[1]);
+        if (use_small[2]) lnp2 = log(t3[2]);
     }
     if (ruled_out) fb = false;
     if (fb) site = false;
@@ -692,9 +746,11 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
             Cand cd;
             cd.col = c;
             cd.bonf = bonf;
+            cd.lnp[0] = cnt[0] > 0 ? lnp0 : 0.0;
+            cd.lnp[1] = cnt[1] > 0 ? lnp1 : 0.0;
+            cd.lnp[2] = cnt[2] > 0 ? lnp2 : 0.0;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                cd.lnp[i] = cnt[i] > 0 ? lnp[i] : 0.0;
                 cd.cnt[i] = cnt[i];
                 cd.raw[i] = ws.cnt6[6 * c + 3 + i];
             }

@@ -6,7 +6,8 @@ namespace lfb {
 
 constexpr int FIN_BLOCK = 256;      // columns per tile of the prefix sums = per CTA of k_front
 constexpr int PRUNE_CAP1 = 8;       // reads k_front itself looks at (K <= 3 is decided by then); the rest of the prune is k_prune2's
-constexpr int PRUNE_CAP = 32;       // reads the lane-per-column prune looks at before it hands the column to k_mid
+constexpr int PRUNE_CAP = 32;       // reads the lane-per-column prune looks at before it hands the column to k_mid ...
+constexpr int PRUNE_EXT = 256;      // ... unless the tail reached by then says the early exit is within reach (lane_prune)
 
 // running Bonferroni factor of the tested column with 1-based rank `rank` in a batch that starts from `start`
 // (lofreq_call.c:794-800: the first tested column sets 3 when bonf_subst was 1, else += 3)
@@ -79,13 +80,17 @@ __device__ __forceinline__ void count_alt_read(const DevConf &cf, const DevBatch
 // P(X >= K among the reads seen) > limit = sig / bonf.  Returns true when the column is still alive after `cap` reads.
 // Cells are kept top-aligned (register 7 = cell K-1, padding below cell 0 stays 0), so one code path serves every
 // K <= KS.  Lanes with live == false only take part in the votes.
+// ext_reads > cap_reads: a column still alive after cap_reads reads goes on up to ext_reads when the tail it has reached
+// says it will get there — P(X >= K among n reads) grows about like n^K, so ext_reads / cap_reads = 8 more reads can
+// close a gap of 8^K (deep, noisy columns: insignificant, but only after a hundred reads).
 __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &mg, int K,
-                                           double limit, int cap_reads, bool live, const Chunk16 *first = nullptr)
+                                           double limit, int cap_reads, bool live, const Chunk16 *first = nullptr, int ext_reads = 0)
 {
     double R[KS], T = 0.0;
 #pragma unroll
     for (int j = 0; j < KS; ++j) R[j] = (j == KS - K) ? 1.0 : 0.0;
-    const int cap = min(mg.n, cap_reads);
+    int cap = min(mg.n, cap_reads);
+    const int cap2 = min(mg.n, ext_reads);
     // the reads come in aligned 16-byte chunks per plane: one load per plane covers what most columns need
     const long long ca = mg.off & ~15ll;
     const int lead = (int)(mg.off - ca);
@@ -111,6 +116,7 @@ __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b,
         for (int j2 = KS - 1; j2 >= 1; --j2) R[j2] = fma(R[j2 - 1], p, R[j2] * q);
         R[0] = R[0] * q;
         if (T > limit) live = false;          // clearly insignificant: snpcaller() leaves LDBL_MAX everywhere (snpcaller.c:1155)
+        if (live && i + 1 == cap && cap < cap2 && T * __hiloint2double((1023 + 3 * K) << 20, 0) >= limit) cap = cap2;
     }
     return live;
 }

@@ -131,12 +131,12 @@ __device__ XlOut xl_run(const DevConf &cf, const DevBatch &b, const Geom &g, int
         fetch(0);
         for (int blk = 0; blk < nblk; ++blk) {
             // ---- wait: input from the warp below, room in the warp above
-            if (lane == 0) {
-                if (w > 0)
-                    while (ld_volatile(&sh.done[w - 1]) <= blk && !ld_volatile(&sh.stop)) {}
-                if (!is_last)
-                    while (ld_volatile(&sh.done[w + 1]) < blk - 1 && !ld_volatile(&sh.stop)) {}
-            }
+            // (every lane polls the same word: the warp stays converged, which the shuffles of the recurrence rely on —
+            // a one-lane spin loop leaves the warp split and every later shuffle takes the slow divergent path)
+            if (w > 0)
+                while (ld_volatile(&sh.done[w - 1]) <= blk && !ld_volatile(&sh.stop)) {}
+            if (!is_last)
+                while (ld_volatile(&sh.done[w + 1]) < blk - 1 && !ld_volatile(&sh.stop)) {}
             __syncwarp();
             if (ld_volatile(&sh.stop)) break;
             __threadfence_block();
