@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdlib.h>
 #include "internal.h"
 #include "dev_common.cuh"
 #include "screen_common.cuh"
@@ -70,44 +71,45 @@ __device__ __forceinline__ int group_min_i(int v)
 // distribution truncated at KSM = 16 (P[k] = P(k errors), k < 16; T = P(>= 16 errors)) for the small counts of the other
 // alleles of a heavy column (a few sequencing errors beside the variant): one read folded in ...
 constexpr int KSM = 16;
-__device__ __forceinline__ void small_update(double (&P)[KSM], double &T, double p, double q)
+template <int KV>
+__device__ __forceinline__ void small_update(double (&P)[KV], double &T, double p, double q)
 {
-    T = fma(P[KSM - 1], p, T);
+    T = fma(P[KV - 1], p, T);
 #pragma unroll
-    for (int k = KSM - 1; k >= 1; --k) P[k] = fma(P[k - 1], p, P[k] * q);
+    for (int k = KV - 1; k >= 1; --k) P[k] = fma(P[k - 1], p, P[k] * q);
     P[0] = P[0] * q;
 }
 
 // ... and the G per-lane distributions of a column merged by truncated convolution (butterfly inside the group)
-template <int G>
-__device__ __forceinline__ void small_merge(double (&P)[KSM], double &T)
+template <int G, int KV>
+__device__ __forceinline__ void small_merge(double (&P)[KV], double &T)
 {
 #pragma unroll 1
     for (int m = 1; m < G; m <<= 1) {
         // c[k] = sum_i P[i] b[k-i]; the partner's cells are fetched one at a time inside the convolution
-        double cc[KSM];
+        double cc[KV];
         const double tb = __shfl_xor_sync(FULL, T, m);
         double sum_a = 0.0, sum_b = 0.0;
 #pragma unroll
-        for (int k = 0; k < KSM; ++k) {
+        for (int k = 0; k < KV; ++k) {
             cc[k] = 0.0;
             sum_a += P[k];
         }
         double t = 0.0, asuf = 0.0;
 #pragma unroll
-        for (int j = 0; j < KSM; ++j) {
+        for (int j = 0; j < KV; ++j) {
             const double bj = __shfl_xor_sync(FULL, P[j], m);
             sum_b += bj;
 #pragma unroll
-            for (int k = j; k < KSM; ++k) cc[k] = fma(P[k - j], bj, cc[k]);
+            for (int k = j; k < KV; ++k) cc[k] = fma(P[k - j], bj, cc[k]);
             if (j >= 1) {
-                asuf += P[KSM - j];
+                asuf += P[KV - j];
                 t = fma(bj, asuf, t);
             }
         }
         t += T * (sum_b + tb) + tb * sum_a;
 #pragma unroll
-        for (int k = 0; k < KSM; ++k) P[k] = cc[k];
+        for (int k = 0; k < KV; ++k) P[k] = cc[k];
         T = t;
     }
 }
@@ -322,14 +324,14 @@ __device__ __forceinline__ double group_tilt(const ColHist &h, bool need, int K,
 // chunks of reads into a distribution truncated at KSM, the G distributions are merged by truncated convolution.
 // Whole warp (the shuffles of the merge); lanes with want == false only take part.  Its own register allocation: the
 // recurrence's registers are not live here.
-template <int G>
+template <int G, int KV>
 __device__ __noinline__ void small_tails_sweep(const DevConf &cf, const DevBatch &b, const EvalMode &em, const double *s_lut, const Geom &g,
                                                int lead, bool want, int c0, int c1, int c2, double (&tails)[3])
 {
     const int gl = lane_id() % G;
-    double P[KSM], TS = 0.0;
+    double P[KV], TS = 0.0;
 #pragma unroll
-    for (int k = 0; k < KSM; ++k) P[k] = (k == 0) ? 1.0 : 0.0;
+    for (int k = 0; k < KV; ++k) P[k] = (k == 0) ? 1.0 : 0.0;
     const long long abase = g.off & ~15ll;
     const int nch = want ? (lead + g.n + 15) >> 4 : 0;
 #pragma unroll 1
@@ -352,14 +354,14 @@ __device__ __noinline__ void small_tails_sweep(const DevConf &cf, const DevBatch
                     continue;
                 double p, q;
                 guard_pq(jp, p, q);
-                small_update(P, TS, p, q);
+                small_update<KV>(P, TS, p, q);
             }
         }
     }
-    small_merge<G>(P, TS);
+    small_merge<G, KV>(P, TS);
     double t0 = TS, t1 = TS, t2 = TS;
 #pragma unroll
-    for (int k = KSM - 1; k >= 0; --k) {      // small terms first
+    for (int k = KV - 1; k >= 0; --k) {      // small terms first
         if (k >= c0) t0 += P[k];
         if (k >= c1) t1 += P[k];
         if (k >= c2) t2 += P[k];
@@ -688,17 +690,14 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
     bool site = have && !fb && !dead;
     if (site && lnT > -700.0 && exp(lnT) * (double)bonf > cf.sig * (1.0 + 1e-9)) site = false;   // snpcaller.c:1155
     double lnp0 = 0.0, lnp1 = 0.0, lnp2 = 0.0;
-    bool use_small[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) use_small[i] = site && cnt[i] > 0 && cnt[i] <= KSM && cnt[i] < K;
-    const bool want_small = use_small[0] || use_small[1] || use_small[2];
     const double invs = (ln_s == 0.0) ? 1.0 : exp(-ln_s);
+    bool sweep_for[3] = {false, false, false};
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const int ci = cnt[i];
         double &out = i == 0 ? lnp0 : i == 1 ? lnp1 : lnp2;
         if (ci == K) out = lnT;
-        const bool mine = site && ci > 0 && ci < K && !use_small[i];
+        const bool mine = site && ci > 0 && ci < K;
         if (!__any_sync(FULL, mine)) continue;
         // P(X >= ci) = sum_{k >= ci} E[k] s^-(k-ci) + T s^-(K-ci), times s^-ci and the common scale
         double acc = 0.0;
@@ -720,20 +719,28 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         hc = group_min_i<G>(hc);
         if (mine) {
             // the leading cell must have stayed a normal number all along (rescaling keeps the peak within 2^+-200
-            // at the block boundaries and below 2^840 inside a block)
-            if ((hc >> 20) < 64 || peak - (hc >> 20) > 850) fb = true;
+            // at the block boundaries and below 2^840 inside a block); a small count whose cells were lost on a strongly
+            // tilted row is computed exactly below, a large one sends the column to the per-column fallback
+            if ((hc >> 20) < 64 || peak - (hc >> 20) > 850) {
+                if (ci <= KSM) sweep_for[i] = true; else fb = true;
+            }
             out = log(acc) + base - (double)ci * ln_s;
         }
     }
-    // Alleles of a site with a count of at most KSM (a few sequencing errors beside the variant): their tail exactly, from
-    // the distribution truncated at KSM — on a strongly tilted row their cells would be lost to underflow.  After the row
-    // has been read (its registers are free now); only columns that are sites get here.
+    // Alleles with a count of at most KSM (a few sequencing errors beside the variant) that could not be read off the
+    // row: their tail exactly, from the distribution truncated at KSM.  After the row has been read (its registers are
+    // free now); rare on shallow data, the rule on deep noisy columns.
+    const bool want_small = !fb && (sweep_for[0] || sweep_for[1] || sweep_for[2]);
     if (__any_sync(FULL, want_small)) {
         double t3[3];
-        small_tails_sweep<G>(cf, b, em, s_lut, g, lead, want_small, cnt[0], cnt[1], cnt[2], t3);
-        if (use_small[0]) lnp0 = log(t3[0]);
-        if (use_small[1]) lnp1 = log(t3[1]);
-        if (use_small[2]) lnp2 = log(t3[2]);
+        int maxc = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (sweep_for[i]) maxc = max(maxc, cnt[i]);
+        if (__reduce_max_sync(FULL, want_small ? maxc : 0) <= 8) small_tails_sweep<G, 8>(cf, b, em, s_lut, g, lead, want_small, cnt[0], cnt[1], cnt[2], t3);
+        else small_tails_sweep<G, KSM>(cf, b, em, s_lut, g, lead, want_small, cnt[0], cnt[1], cnt[2], t3);
+        if (want_small && sweep_for[0]) lnp0 = log(t3[0]);
+        if (want_small && sweep_for[1]) lnp1 = log(t3[1]);
+        if (want_small && sweep_for[2]) lnp2 = log(t3[2]);
     }
     if (ruled_out) fb = false;
     if (fb) site = false;
@@ -838,7 +845,8 @@ void launch_dp(const LaunchState &ls, const DevConf &cf, const DevBatch &b, cons
     if (b.n_cols <= 0) return;
     const int planes = 1 + (cf.use_mq ? 1 : 0) + (cf.use_baq ? 1 : 0) + (cf.use_sq ? 1 : 0);
     const size_t smem = dp_smem_bytes(planes);
-    k_dp<0><<<ls.sms * 6, 32 * DP_WARPS, smem, st>>>(cf, b, lut, ws, planes);
+    static const int dp0_ctas = getenv("LFB200_DP0_CTAS") ? atoi(getenv("LFB200_DP0_CTAS")) : 6;
+    k_dp<0><<<ls.sms * dp0_ctas, 32 * DP_WARPS, smem, st>>>(cf, b, lut, ws, planes);
     k_dp<1><<<ls.sms * 4, 32 * DP_WARPS, smem, st1>>>(cf, b, lut, ws, planes);
     k_dp<2><<<ls.sms, 32 * DP_WARPS, smem, st2>>>(cf, b, lut, ws, planes);
 }

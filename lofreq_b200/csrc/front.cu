@@ -28,6 +28,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <float.h>
+#include <stdlib.h>
 #include "internal.h"
 #include "dev_common.cuh"
 #include "screen_common.cuh"
@@ -250,7 +251,8 @@ void launch_front(const LaunchState &ls, const DevConf &cf, const DevBatch &b, c
     // per-batch state: counters (job lists, round counts), candidate marks
     cudaMemsetAsync(ws.counters, 0, sizeof(Counters), st);
     cudaMemsetAsync(ws.is_cand, 0, (size_t)nb * FIN_BLOCK, st);
-    const int grid = nb < ls.sms * FRONT_CTAS_PER_SM ? nb : ls.sms * FRONT_CTAS_PER_SM;
+    static const int front_ctas = getenv("LFB200_FRONT_CTAS") ? atoi(getenv("LFB200_FRONT_CTAS")) : FRONT_CTAS_PER_SM;
+    const int grid = nb < ls.sms * front_ctas ? nb : ls.sms * front_ctas;
     k_front<<<grid, FIN_BLOCK, 0, st>>>(cf, b, lut, ws);
     k_scan_tiles<<<1, 1024, 0, st>>>(ws.blocksum, nb, &ws.counters->n_tested);
 }

@@ -6,8 +6,7 @@ namespace lfb {
 
 constexpr int FIN_BLOCK = 256;      // columns per tile of the prefix sums = per CTA of k_front
 constexpr int PRUNE_CAP1 = 8;       // reads k_front itself looks at (K <= 3 is decided by then); the rest of the prune is k_prune2's
-constexpr int PRUNE_CAP = 32;       // reads the lane-per-column prune looks at before it hands the column to k_mid ...
-constexpr int PRUNE_EXT = 256;      // ... unless the tail reached by then says the early exit is within reach (lane_prune)
+constexpr int PRUNE_CAP = 32;       // reads the lane-per-column prune looks at before it hands the column to k_mid (4x / 8x more when the exit is within reach)
 
 // running Bonferroni factor of the tested column with 1-based rank `rank` in a batch that starts from `start`
 // (lofreq_call.c:794-800: the first tested column sets 3 when bonf_subst was 1, else += 3)
@@ -80,29 +79,40 @@ __device__ __forceinline__ void count_alt_read(const DevConf &cf, const DevBatch
 // P(X >= K among the reads seen) > limit = sig / bonf.  Returns true when the column is still alive after `cap` reads.
 // Cells are kept top-aligned (register 7 = cell K-1, padding below cell 0 stays 0), so one code path serves every
 // K <= KS.  Lanes with live == false only take part in the votes.
-// ext_reads > cap_reads: a column still alive after cap_reads reads goes on up to ext_reads when the tail it has reached
-// says it will get there — P(X >= K among n reads) grows about like n^K, so ext_reads / cap_reads = 8 more reads can
-// close a gap of 8^K (deep, noisy columns: insignificant, but only after a hundred reads).
+// ext: a column still alive after cap_reads reads goes on when the tail it has reached says the early exit is within
+// reach — P(X >= K among n reads) grows about like n^K, so f times more reads close a gap of f^K.  Shallow columns
+// (where evaluating everything in k_mid is cheap) get f = 4, deep ones (k_mid would walk thousands of reads) f = 8.
 __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &mg, int K,
-                                           double limit, int cap_reads, bool live, const Chunk16 *first = nullptr, int ext_reads = 0)
+                                           double limit, int cap_reads, bool live, const Chunk16 *first = nullptr, bool ext = false)
 {
     double R[KS], T = 0.0;
 #pragma unroll
     for (int j = 0; j < KS; ++j) R[j] = (j == KS - K) ? 1.0 : 0.0;
     int cap = min(mg.n, cap_reads);
-    const int cap2 = min(mg.n, ext_reads);
-    // the reads come in aligned 16-byte chunks per plane: one load per plane covers what most columns need
+    const int fshift = mg.n >= 1024 ? 3 : 2;
+    const int cap2 = ext ? min(mg.n, cap_reads << fshift) : 0;
+    // the reads come in aligned 16-byte chunks per plane: one load per plane covers what most columns need; the chunk
+    // after the current one is requested while the current one is walked
     const long long ca = mg.off & ~15ll;
     const int lead = (int)(mg.off - ca);
-    Chunk16 ch;
+    Chunk16 ch, nx;
     ch.bq = ch.mq = ch.baq = ch.sq = make_uint4(0, 0, 0, 0);
+    nx = ch;
     if (first) ch = *first;                     // the caller requested the first chunk ahead of time
     else if (live && cap > 0) load_chunk(cf, b, ca, ch);
+    if (ext && live && lead + cap > 16) load_chunk(cf, b, ca + 16, nx);
 #pragma unroll 1
     for (int i = 0; __any_sync(FULL, live && i < cap); ++i) {
         if (!(live && i < cap)) continue;
         const int idx = lead + i, j = idx & 15;
-        if (j == 0 && i > 0) load_chunk(cf, b, ca + idx, ch);
+        if (j == 0 && i > 0) {
+            if (ext) {
+                ch = nx;
+                if (idx + 16 < lead + max(cap, cap2)) load_chunk(cf, b, ca + idx + 16, nx);
+            } else {
+                load_chunk(cf, b, ca + idx, ch);
+            }
+        }
         bool is_alt;
         int slot;
         double jp;
@@ -116,7 +126,7 @@ __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b,
         for (int j2 = KS - 1; j2 >= 1; --j2) R[j2] = fma(R[j2 - 1], p, R[j2] * q);
         R[0] = R[0] * q;
         if (T > limit) live = false;          // clearly insignificant: snpcaller() leaves LDBL_MAX everywhere (snpcaller.c:1155)
-        if (live && i + 1 == cap && cap < cap2 && T * __hiloint2double((1023 + 3 * K) << 20, 0) >= limit) cap = cap2;
+        if (live && i + 1 == cap && cap < cap2 && T * __hiloint2double((1023 + fshift * K) << 20, 0) >= limit) cap = cap2;
     }
     return live;
 }
