@@ -690,7 +690,16 @@ static int sites_sync(lfb200_ctx *ctx, lfb200_conf_t *conf, void *stream, lfb200
         sm.n_tested = (long long)c->n_tested;
         sm.n_unsupported = c->n_unsupported;
         n_cand = c->n_cand;
-        sm.n_heavy = c->n_jobs[0] + c->n_jobs[CLS_XL];        // k_mid, k_heavy_xl
+        {
+            // side streams for the next batch on this context only where this batch had work for them
+            unsigned long long dp1 = 0, dp2 = 0;
+            for (int bin = 0; bin < DP_NBIN1; ++bin) {
+                dp1 += c->n_pjobs[4 * DP_NBIN1 + bin] + c->n_pjobs[5 * DP_NBIN1 + bin];
+                dp2 += c->n_pjobs[6 * DP_NBIN1 + bin];
+            }
+            ctx->ls.side_mask = (c->n_jobs[0] >= 256 ? 1u : 0u) | (dp1 ? 2u : 0u) | (c->n_jobs[CLS_XL] ? 4u : 0u) | (dp2 ? 8u : 0u);
+        }
+        sm.n_heavy = c->n_jobs[0] + c->n_jobs[CLS_XL];        // k_mid, k_xl
         for (int i = 0; i < DP_NL; ++i)                        // k_dp (binned lists are capped, the excess is in the unbinned ones)
             sm.n_heavy += (i % DP_NBIN1) == DP_NBIN ? (long long)c->n_pjobs[i] : std::min<long long>(c->n_pjobs[i], ctx->ws.pcap);
         lfb200_site_t *hs = ctx->h_sites;

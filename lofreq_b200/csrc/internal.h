@@ -146,6 +146,9 @@ struct LaunchState {
     cudaStream_t side[NSIDE] = {};
     cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[NSIDE] = {};
     bool ready = false;
+    // which of k_mid (1), k_dp<1> (2), k_xl (4), k_dp<2> (8) get a side stream for the next test: those whose job list
+    // was not empty in this context's previous batch (everything, before the first batch)
+    unsigned side_mask = 0xfu;
 };
 int launch_state_init(LaunchState &ls, int device);
 void launch_state_destroy(LaunchState &ls);

@@ -1388,18 +1388,26 @@ void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, co
     // Independent work side by side, so that the warps of the small kernels share the SMs with k_dp<0>: k_mid (K <= 8
     // survivors of the prune), k_dp<1>, k_dp<2> (256 < K <= 2048, their own register budgets), k_xl (K > 2048, one CTA
     // per column); an empty list costs an early exit.  Then the per-column fallbacks for the few columns they hand back.
-    cudaEventRecord(ls.ev_fork, st);
-    cudaStreamWaitEvent(ls.side[0], ls.ev_fork, 0);
-    cudaStreamWaitEvent(ls.side[1], ls.ev_fork, 0);
-    cudaStreamWaitEvent(ls.side[2], ls.ev_fork, 0);
-    cudaStreamWaitEvent(ls.side[3], ls.ev_fork, 0);
-    k_mid<<<ls.sms * 4, 128, 0, ls.side[0]>>>(cf, b, lut, ws);
-    launch_xl(ls, cf, b, lut, ws, ls.side[2]);
-    launch_dp(ls, cf, b, lut, ws, st, ls.side[1], ls.side[3]);
-    for (int i = 0; i < 4; ++i) {
-        cudaEventRecord(ls.ev_join[i], ls.side[i]);
-        cudaStreamWaitEvent(st, ls.ev_join[i], 0);
+    // A kernel whose list was empty in the context's previous batch is simply queued behind k_dp<0> (side_mask): on data
+    // without deep columns that saves the fork/join events — host time per batch is what limits 8 GPUs on one box.
+    const unsigned m = ls.side_mask;
+    cudaStream_t s_mid = (m & 1u) ? ls.side[0] : st, s_dp1 = (m & 2u) ? ls.side[1] : st, s_xl = (m & 4u) ? ls.side[2] : st,
+                 s_dp2 = (m & 8u) ? ls.side[3] : st;
+    if (m) {
+        cudaEventRecord(ls.ev_fork, st);
+        for (int i = 0; i < 4; ++i)
+            if (m & (1u << i)) cudaStreamWaitEvent(ls.side[i], ls.ev_fork, 0);
     }
+    if (m & 1u) k_mid<<<ls.sms * 4, 128, 0, s_mid>>>(cf, b, lut, ws);
+    if (m & 4u) launch_xl(ls, cf, b, lut, ws, s_xl);
+    launch_dp(ls, cf, b, lut, ws, st, s_dp1, s_dp2);
+    if (!(m & 1u)) k_mid<<<ls.sms * 4, 128, 0, st>>>(cf, b, lut, ws);
+    if (!(m & 4u)) launch_xl(ls, cf, b, lut, ws, st);
+    for (int i = 0; i < 4; ++i)
+        if (m & (1u << i)) {
+            cudaEventRecord(ls.ev_join[i], ls.side[i]);
+            cudaStreamWaitEvent(st, ls.ev_join[i], 0);
+        }
     k_heavy_xl<<<ls.sms, XL_T, 0, st>>>(cf, b, lut, ws, CLS_XLFB);
     k_heavy_all<<<ls.sms, 128, STAGE_BYTES, st>>>(cf, b, lut, ws);
     if (after_heavy) cudaEventRecord(after_heavy, st);
