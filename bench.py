@@ -129,10 +129,13 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark(self):
+        """lines from here on belong to the timed region (the ones before: warm-up, also under load, kept as a fallback)"""
+        self.mark_at = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -140,7 +143,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines[getattr(self, "mark_at", 0):]
+        if len(lines) < 2:                      # a very short timed region: the warm-up lines were taken under the same load
+            lines = self.lines[max(0, len(self.lines) - 8):]
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -355,10 +361,14 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     # ---- value: resident inputs -------------------------------------------------------------
-    run_steps(max(args.warmup, 3))
+    # the clock sampler starts before the warm-up: with 8 busy GPUs nvidia-smi needs tens of milliseconds for its first
+    # line, and the timed region of a short run is not much longer
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
+    run_steps(max(args.warmup, 3))
+    run_steps(20)                      # (untimed) keeps the GPU under load until the sampler has lines
+    barrier()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(streams[0])
     for k_ in host_t:
@@ -544,7 +554,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"])
