@@ -284,6 +284,8 @@ int lfb200_sb_qual_batch(lfb200_ctx *ctx, long long n, const lfb200_dp4_t *dp4, 
 /* the INFO string of a SNV record exactly as vcf_var_sprintf_info writes it (vcf.c:608-629):
  * "DP=%d;AF=%f;SB=%d;DP4=%d,%d,%d,%d;HQA=%d"; returns its length or -1 when buf is too small */
 int lfb200_format_snv_info(char *buf, unsigned long size, int dp, float af, int sb, const lfb200_dp4_t *dp4, int hqa);
+/* the INFO string of an indel record (vcf.c:608-629, indel branch): "DP=%d;AF=%f;SB=%d;DP4=%d,%d,%d,%d;INDEL;HRUN=%d" */
+int lfb200_format_indel_info(char *buf, unsigned long size, int dp, float af, int sb, const lfb200_dp4_t *dp4, int hrun);
 /* the record line as vcf_write_var writes it (vcf.c:469-495): CHROM POS(1-based) . REF ALT QUAL . INFO \n */
 int lfb200_format_snv_record(char *buf, unsigned long size, const char *chrom, long pos0, char ref, char alt, int qual,
                              const char *info);

@@ -1671,6 +1671,14 @@ extern "C" int lfb200_format_snv_info(char *buf, unsigned long size, int dp, flo
     return (k < 0 || (unsigned long)k >= size) ? -1 : k;
 }
 
+extern "C" int lfb200_format_indel_info(char *buf, unsigned long size, int dp, float af, int sb, const lfb200_dp4_t *dp4, int hrun)
+{
+    if (!buf || !dp4) return -1;
+    const int k = snprintf(buf, size, "DP=%d;AF=%f;SB=%d;DP4=%d,%d,%d,%d;INDEL;HRUN=%d", dp, af, sb, dp4->ref_fw, dp4->ref_rv,
+                           dp4->alt_fw, dp4->alt_rv, hrun);                    // vcf.c:615-622
+    return (k < 0 || (unsigned long)k >= size) ? -1 : k;
+}
+
 extern "C" int lfb200_format_snv_record(char *buf, unsigned long size, const char *chrom, long pos0, char ref, char alt, int qual,
                                         const char *info)
 {

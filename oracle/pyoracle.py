@@ -236,8 +236,72 @@ class BinomRef:
         return p.value, q.value
 
 
+class _Indels(C.Structure):
+    """oracle_indels_t of oracle/call_harness.c"""
+    _fields_ = [("n_events", C.c_longlong), ("ev_col", C.c_void_p), ("ev_is_del", C.c_void_p), ("ev_key", C.c_void_p),
+                ("ev_read_off", C.c_void_p), ("ev_q", C.c_void_p), ("ev_aq", C.c_void_p), ("ev_mq", C.c_void_p), ("ev_sq", C.c_void_p),
+                ("ev_rv", C.c_void_p), ("non_off", C.c_void_p), ("non_iq", C.c_void_p), ("non_dq", C.c_void_p), ("non_mq", C.c_void_p),
+                ("hrun", C.c_void_p), ("num_tails", C.c_void_p), ("non_ins_fw_rv", C.c_void_p), ("non_del_fw_rv", C.c_void_p)]
+
+
+MAX_INDELSIZE = 256          # utils.h
+
+
+def synth_indels(n_cols, depths, seed=7, frac=0.06):
+    """Synthetic indel events for the columns of a batch (test input for the call_indels path): per column the reads
+    without an indel (insertion / deletion / mapping quality each), and for a fraction of the columns 1-3 events (key,
+    reads with indel quality, alignment quality, mapping quality, strand) — low-AF single-base A/T pairs included, which
+    the reference's poly-AT filter ignores (lofreq_call.c:650-680)."""
+    rng = np.random.default_rng(seed)
+    depths = np.asarray(depths, np.int64)
+    ev_col, ev_is_del, keys, ev_reads = [], [], [], []
+    for c in np.flatnonzero(rng.random(n_cols) < frac):
+        kind = rng.integers(0, 4)
+        evs = []
+        if kind == 3:                                    # poly-AT pair: ins X and del X, both rare
+            b = "AT"[int(rng.integers(0, 2))]
+            evs = [(0, b, int(rng.integers(1, 4))), (1, b, int(rng.integers(1, 4)))]
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                key = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, int(rng.integers(1, 6))))
+                evs.append((int(rng.integers(0, 2)), key, int(rng.integers(1, max(2, min(40, depths[c] // 8))))))
+        seen = set()
+        for is_del, key, cnt in sorted(evs):               # insertions first (the harness wants them grouped per column)
+            if (is_del, key) in seen:
+                continue
+            seen.add((is_del, key))
+            ev_col.append(int(c)); ev_is_del.append(is_del); keys.append(key); ev_reads.append(cnt)
+    order = sorted(range(len(ev_col)), key=lambda i: (ev_col[i], ev_is_del[i], i))
+    ev_col = [ev_col[i] for i in order]; ev_is_del = [ev_is_del[i] for i in order]
+    keys = [keys[i] for i in order]; ev_reads = [ev_reads[i] for i in order]
+    # reads without an indel: what is left of the column's depth (plp_to_ins/del_errprobs size their vector by coverage_plp)
+    used = np.zeros(n_cols, np.int64)
+    for c, r in zip(ev_col, ev_reads):
+        used[c] += r
+    non_off = np.zeros(n_cols + 1, np.int64)
+    non_off[1:] = np.cumsum(np.maximum(depths - used, 0))
+    tot = int(non_off[-1])
+    ind = dict(non_off=non_off, non_iq=rng.integers(25, 46, tot).astype(np.int32), non_dq=rng.integers(25, 46, tot).astype(np.int32),
+               non_mq=np.where(rng.random(tot) < 0.01, 255, rng.integers(20, 61, tot)).astype(np.int32),
+               hrun=rng.integers(1, 6, n_cols).astype(np.int32), num_tails=rng.integers(0, 5, n_cols).astype(np.int32),
+               non_ins_fw_rv=rng.integers(0, 200, (n_cols, 2)).astype(np.int32), non_del_fw_rv=rng.integers(0, 200, (n_cols, 2)).astype(np.int32))
+    ne = len(ev_col)
+    ro = np.zeros(ne + 1, np.int64)
+    ro[1:] = np.cumsum(ev_reads)
+    nr = int(ro[-1])
+    kb = np.zeros((ne, MAX_INDELSIZE), np.uint8)
+    for i, k in enumerate(keys):
+        kb[i, :len(k)] = np.frombuffer(k.encode(), np.uint8)
+    ind.update(n_events=ne, ev_col=np.array(ev_col, np.int64), ev_is_del=np.array(ev_is_del, np.uint8), ev_key=kb, ev_read_off=ro,
+               ev_q=rng.integers(15, 46, nr).astype(np.int32), ev_aq=np.where(rng.random(nr) < 0.05, -1, rng.integers(5, 61, nr)).astype(np.int32),
+               ev_mq=np.where(rng.random(nr) < 0.02, 255, rng.integers(20, 61, nr)).astype(np.int32), ev_sq=np.full(nr, -1, np.int32),
+               ev_rv=rng.integers(0, 2, nr).astype(np.uint8))
+    return ind
+
+
 CALLREF_SO = os.path.join(HERE, "_ref", "libcallref.so")
 CALLB200_SO = os.path.join(HERE, "_ref", "libcallb200.so")
+CALLSWAP_SO = os.path.join(HERE, "_ref", "libcallswap.so")
 
 
 class CallOracle:
@@ -246,8 +310,10 @@ class CallOracle:
     adapter=True, library _ref/libcallb200.so — through the product's drop-in callback lfb200_call_vars() + lfb200_flush()
     (lofreq_b200/adapter/lofreq_adapter.c compiled against the reference's own headers).  Returns the raw VCF text."""
 
-    def __init__(self, adapter=False):
-        path = CALLB200_SO if adapter else CALLREF_SO
+    def __init__(self, adapter=False, swap=False):
+        """swap=True: _ref/libcallswap.so — the reference's own call_vars() on top of the GPU-backed snpcaller() /
+        plp_to_errprobs() / poissbin() symbols (lofreq_b200/adapter/snpcaller_shim.c)"""
+        path = CALLSWAP_SO if swap else CALLB200_SO if adapter else CALLREF_SO
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.adapter = adapter
@@ -264,8 +330,9 @@ class CallOracle:
         two = C.c_double()
         return self.lib.lfref_sb_qual(int(ref_fw), int(ref_rv), int(alt_fw), int(alt_rv), C.byref(two)), two.value
 
-    def call_vars_vcf(self, batch, strand8, conf=None, pos=None, cons0=None, target="synthetic", adapter=None):
-        """-> (vcf text, bonf_subst, num_snv_tests).  strand8: int32 [n][8] = fw A,C,G,T then rv A,C,G,T."""
+    def call_vars_vcf(self, batch, strand8, conf=None, pos=None, cons0=None, target="synthetic", adapter=None, indels=None):
+        """-> (vcf text, bonf_subst, num_snv_tests[, bonf_indel, num_indel_tests] with indels).  strand8: int32 [n][8] = fw
+        A,C,G,T then rv A,C,G,T.  indels: dict from synth_indels() — switches --call-indels on (conf.no_indels = 0)."""
         import tempfile
         use_adapter = self.adapter if adapter is None else adapter
         conf = default_conf() if conf is None else conf
@@ -277,19 +344,34 @@ class CallOracle:
         with tempfile.NamedTemporaryFile(suffix=".vcf", delete=False) as tf:
             path = tf.name
         try:
+            ind_p, bi, nit, hold = None, C.c_longlong(1), C.c_longlong(0), []
+            if indels is not None:
+                st = _Indels()
+                st.n_events = int(indels["n_events"])
+                for k, dt in (("ev_col", np.int64), ("ev_is_del", np.uint8), ("ev_key", np.uint8), ("ev_read_off", np.int64), ("ev_q", np.int32),
+                              ("ev_aq", np.int32), ("ev_mq", np.int32), ("ev_sq", np.int32), ("ev_rv", np.uint8), ("non_off", np.int64),
+                              ("non_iq", np.int32), ("non_dq", np.int32), ("non_mq", np.int32), ("hrun", np.int32), ("num_tails", np.int32),
+                              ("non_ins_fw_rv", np.int32), ("non_del_fw_rv", np.int32)):
+                    a = np.ascontiguousarray(indels[k], dt)
+                    hold.append(a)
+                    setattr(st, k, a.ctypes.data)
+                ind_p = C.cast(C.pointer(st), C.c_void_p)
             rc = self.lib.lfref_call_vars_vcf(C.byref(cf), C.byref(sb), _ptr(s8), _ptr(ps), _ptr(c0), target.encode(), path.encode(),
-                                              None, None, None, 1 if use_adapter else 0)
+                                              ind_p, C.cast(C.byref(bi), C.c_void_p), C.cast(C.byref(nit), C.c_void_p),
+                                              1 if use_adapter else 0)
             if rc:
                 raise RuntimeError("lfref_call_vars_vcf returned %d" % rc)
             with open(path) as f:
                 text = f.read()
         finally:
             os.unlink(path)
+        if indels is not None:
+            return text, cf.bonf_subst, cf.num_snv_tests, bi.value, nit.value
         return text, cf.bonf_subst, cf.num_snv_tests
 
 
-def have_call_oracle(adapter=False):
-    return os.path.exists(CALLB200_SO if adapter else CALLREF_SO)
+def have_call_oracle(adapter=False, swap=False):
+    return os.path.exists(CALLSWAP_SO if swap else CALLB200_SO if adapter else CALLREF_SO)
 
 
 def have_reference():

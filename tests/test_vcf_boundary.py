@@ -110,6 +110,49 @@ def test_adapter_gates_and_live_reference():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("flag_over", [{}, dict(flag=2), dict(bonf_dynamic=0)])
+def test_adapter_call_indels_bookkeeping(flag_over):
+    """--call-indels through the adapter: the bookkeeping of call_indels() (lofreq_call.c:618-726: min_cov
+    gate, poly-AT filter, one test per event in hash order, running bonf_indel, num_indel_tests), the tests batched
+    through lfb200_indel_tests, INDEL records interleaved with the substitution records in the reference's order —
+    VCF text, bonf_indel and num_indel_tests identical to the reference's call_vars()"""
+    if not (have_call_oracle(adapter=True) and have_call_oracle()):
+        pytest.skip("callback oracle not built")
+    from oracle.pyoracle import synth_indels
+    n = 3000
+    b = synth_np.generate("C4", 88000, n, with_baq=True, with_strand=True)
+    ind = synth_indels(n, b["nt_cnt"].sum(axis=1), seed=11, frac=0.08)
+    conf = default_conf(**flag_over)
+    want = CallOracle().call_vars_vcf(b, b["strand8"], dict(conf), indels=ind, target="chr7")
+    os.environ["LFB200_BATCH_COLS"] = "700"
+    try:
+        got = CallOracle(adapter=True).call_vars_vcf(b, b["strand8"], dict(conf), indels=ind, target="chr7")
+    finally:
+        os.environ.pop("LFB200_BATCH_COLS", None)
+    assert got[0].splitlines() == want[0].splitlines()
+    assert got[1:] == want[1:]
+    n_indel = sum("INDEL" in ln for ln in want[0].splitlines())
+    assert n_indel > 50 and want[4] > 150 and want[3] == (want[4] + 1 if conf["bonf_dynamic"] else 1)
+
+
+@pytest.mark.gpu
+def test_link_level_swap_of_snpcaller_symbols():
+    """lofreq_b200/adapter/snpcaller_shim.c: the reference's UNMODIFIED call_vars() / call_snvs() (lofreq_call.c) linked
+    against the un-prefixed snpcaller() / plp_to_errprobs() / poissbin() of the shim (every column two GPU round trips) writes
+    the VCF text of the reference"""
+    if not have_call_oracle(swap=True):
+        pytest.skip("oracle/_ref/libcallswap.so not built (needs the reference tree)")
+    name, wl, c0, n, baq, over = CASES[0]
+    n = 1500
+    b = synth_np.generate(wl, c0, n, with_baq=baq, with_strand=True)
+    got, bonf, tests = CallOracle(swap=True).call_vars_vcf(b, b["strand8"], default_conf(**over), pos=np.arange(c0, c0 + n) % 100000,
+                                                           adapter=False)
+    want = [ln for ln in Z["vcf_" + name].tobytes().decode().splitlines() if int(ln.split("\t")[1]) <= n]
+    assert got.splitlines() == want and len(want) >= 10
+    assert tests == 3 * int(bonf // 3) and bonf > 1000
+
+
+@pytest.mark.gpu
 def test_sb_qual_kernel_matches_report_var():
     """lfb200_sb_qual_batch (k_sb_qual: Fisher's exact test per DP4 table on the device) == PROB_TO_PHREDQUAL_SAFE of
     kt_fisher_exact's two-tailed p as report_var() computes it (lofreq_call.c:108-125, fet.c:62-101), INT_MAX case included"""
