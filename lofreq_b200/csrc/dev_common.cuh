@@ -84,6 +84,44 @@ __device__ __forceinline__ bool eval_read(const DevConf &cf, const double *lut, 
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// one read of plp_to_errprobs (snpcaller.c:399-491)
+// ------------------------------------------------------------------------------------------------
+// UNIFORM: the configuration treats reference and alt reads alike (the defaults: min_alt_bq <= min_bq, no def_alt_bq /
+// def_alt_jq, no jq filters) — no position bookkeeping; plain_merge: only bq and mq are merged (sp = bap = 0: the dropped
+// terms of merge_srcq_mapq_baq_and_bq are exact zeros and ones)
+struct EvalMode {
+    bool uniform, plain_merge;
+};
+
+__device__ __forceinline__ EvalMode eval_mode(const DevConf &cf)
+{
+    EvalMode em;
+    em.uniform = cf.min_bq >= 0 && cf.min_alt_bq <= cf.min_bq && cf.alt_bq_mode == 0 && !cf.def_alt_jq_on && !cf.jq_filters;
+    em.plain_merge = !(cf.use_baq | cf.use_sq);
+    return em;
+}
+
+__device__ __forceinline__ bool dp_eval(const DevConf &cf, const EvalMode &em, const double *s_lut, const Geom &g, int pos, int bq, int mq,
+                                        int baq, int sq, double &jp)
+{
+    if (em.uniform) {
+        if (bq < cf.min_bq) return false;
+        const double bp = s_lut[bq];
+        if (em.plain_merge) {
+            if (!cf.use_mq) { jp = bp; return true; }
+            const double mp = s_lut[256 + mq];
+            jp = __dadd_rn(mp, __dmul_rn(__dsub_rn(1.0, mp), bp));
+            return true;
+        }
+        jp = merge4(cf.use_sq ? s_lut[512 + sq] : 0.0, cf.use_mq ? s_lut[256 + mq] : 0.0, cf.use_baq ? s_lut[512 + baq] : 0.0, bp);
+        return true;
+    }
+    bool is_alt;
+    int slot;
+    return eval_read<true>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp);
+}
+
 __device__ __forceinline__ void load_lut(double *s_lut, const Lut *lut)
 {
     const double *src = reinterpret_cast<const double *>(lut);

@@ -229,36 +229,6 @@ __device__ __forceinline__ const int *dp_list_ptr(const Workspace &ws, int li)
 }
 
 // ------------------------------------------------------------------------------------------------
-// one read of plp_to_errprobs (snpcaller.c:399-491)
-// ------------------------------------------------------------------------------------------------
-// UNIFORM: the configuration treats reference and alt reads alike (the defaults: min_alt_bq <= min_bq, no def_alt_bq /
-// def_alt_jq, no jq filters) — no position bookkeeping; plain_merge: only bq and mq are merged (sp = bap = 0: the dropped
-// terms of merge_srcq_mapq_baq_and_bq are exact zeros and ones)
-struct EvalMode {
-    bool uniform, plain_merge;
-};
-
-__device__ __forceinline__ bool dp_eval(const DevConf &cf, const EvalMode &em, const double *s_lut, const Geom &g, int pos, int bq, int mq,
-                                        int baq, int sq, double &jp)
-{
-    if (em.uniform) {
-        if (bq < cf.min_bq) return false;
-        const double bp = s_lut[bq];
-        if (em.plain_merge) {
-            if (!cf.use_mq) { jp = bp; return true; }
-            const double mp = s_lut[256 + mq];
-            jp = __dadd_rn(mp, __dmul_rn(__dsub_rn(1.0, mp), bp));
-            return true;
-        }
-        jp = merge4(cf.use_sq ? s_lut[512 + sq] : 0.0, cf.use_mq ? s_lut[256 + mq] : 0.0, cf.use_baq ? s_lut[512 + baq] : 0.0, bp);
-        return true;
-    }
-    bool is_alt;
-    int slot;
-    return eval_read<true>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp);
-}
-
-// ------------------------------------------------------------------------------------------------
 // tilt: saddlepoint equation sum_n p_n s/(q_n + p_n s) = min(K, N - 1/2), solved on a histogram of the merged
 // probabilities of the column (64 buckets, two per binade: inside a bucket p varies by at most 41 %, and the bucket
 // mean stands for it — the tolerance of the tilt is coarse: an error e in ln s costs about var * e^2 / 2 nats of ~700)
@@ -459,9 +429,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
     int issued = 0, waited = 0;
     if (nmax > 0) { issue(0); issued = 1; }
 
-    EvalMode em;
-    em.uniform = cf.min_bq >= 0 && cf.min_alt_bq <= cf.min_bq && cf.alt_bq_mode == 0 && !cf.def_alt_jq_on && !cf.jq_filters;
-    em.plain_merge = !(cf.use_baq | cf.use_sq);
+    const EvalMode em = eval_mode(cf);
 
     // ---- 1. pre-pass, G lanes per column, 16-byte loads: reads kept, lambda and the histogram of the merged probabilities —
     // what the tilt needs.  Most columns need no tilt (and many are ruled out by the early exit after a fraction of their

@@ -99,8 +99,18 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
         if (m_alt > 0 && cf.alt_bq_mode != 2) load_chunk(cf, b, mg.off & ~15ll, first);
         // ---- alt counts ----
         int cnt[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
-        if (m_alt > 0 && m_alt <= serial_max)
-            for (int i = 0; i < m_alt; ++i) count_alt_read(cf, b, s_lut, mg, m_lo, m_hi, i, cnt, raw);
+        if (m_alt > 0 && m_alt <= serial_max) {
+            // the base qualities of the first four non-reference reads are requested together: one memory latency per
+            // round instead of one per read
+            int bq4[4] = {-1, -1, -1, -1};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < m_alt) bq4[i] = b.bq[mg.off + (i < m_lo ? i : i - m_lo + m_hi)];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < m_alt) count_alt_read(cf, b, s_lut, mg, m_lo, m_hi, i, cnt, raw, bq4[i]);
+            for (int i = 4; i < m_alt; ++i) count_alt_read(cf, b, s_lut, mg, m_lo, m_hi, i, cnt, raw);
+        }
         // whole warp per column with many non-reference reads
         unsigned todo = __ballot_sync(FULL, m_alt > serial_max);
         while (todo) {
@@ -184,9 +194,13 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
         const double limit = small ? cf.sig * (1.0 + 1e-9) / (double)bonf : 0.0;   // margin: borderline columns go to the host
         if (cf.alt_bq_mode != 2) {          // the median override needs a warp-wide histogram: no lane-serial prune
             small = lane_prune(cf, b, s_lut, mg, K, limit, PRUNE_CAP1, small, &first);
-            if (small) {
-                const unsigned slot = atomicAdd(&ws.counters->n_jobs[CLS_PRUNE2], 1u);
-                ws.jobs[(long long)CLS_PRUNE2 * ws.cap_cols + slot] = (int)c;
+            // one atomic per warp for the survivors' slots
+            const unsigned sm_ = __ballot_sync(FULL, small);
+            if (sm_) {
+                unsigned base = 0;
+                if (lane == __ffs(sm_) - 1) base = atomicAdd(&ws.counters->n_jobs[CLS_PRUNE2], (unsigned)__popc(sm_));
+                base = __shfl_sync(FULL, base, __ffs(sm_) - 1);
+                if (small) ws.jobs[(long long)CLS_PRUNE2 * ws.cap_cols + base + __popc(sm_ & ((1u << lane) - 1u))] = (int)c;
             }
         } else if (small) {
             // every small column joins k_mid's job list: full evaluation, whole warp

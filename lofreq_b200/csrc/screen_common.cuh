@@ -50,11 +50,11 @@ __device__ __forceinline__ void load_raw(const DevBatch &b, long long c, RawGeom
 // consecutive columns: metadata, gates and columns with at most 8 non-reference reads run lane-per-column;
 // the rare columns with more (variant sites) are then counted by the whole warp.
 __device__ __forceinline__ void count_alt_read(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &g,
-                                               int ref_lo, int ref_hi, int i, int (&cnt)[3], int (&raw)[3])
+                                               int ref_lo, int ref_hi, int i, int (&cnt)[3], int (&raw)[3], int bq_ready = -1)
 {
     const int pos = i < ref_lo ? i : i - ref_lo + ref_hi;
     const long long a = g.off + pos;
-    const int bq = b.bq[a];
+    const int bq = bq_ready >= 0 ? bq_ready : b.bq[a];
     int mq = 0, baq = 0, sq = 0;
     if (cf.jq_filters) {
         if (cf.use_mq) mq = b.mq[a];
@@ -79,18 +79,20 @@ __device__ __forceinline__ void count_alt_read(const DevConf &cf, const DevBatch
 // P(X >= K among the reads seen) > limit = sig / bonf.  Returns true when the column is still alive after `cap` reads.
 // Cells are kept top-aligned (register 7 = cell K-1, padding below cell 0 stays 0), so one code path serves every
 // K <= KS.  Lanes with live == false only take part in the votes.
-// ext: a column still alive after cap_reads reads goes on when the tail it has reached says the early exit is within
-// reach — P(X >= K among n reads) grows about like n^K, so f times more reads close a gap of f^K.  Shallow columns
-// (where evaluating everything in k_mid is cheap) get f = 4, deep ones (k_mid would walk thousands of reads) f = 8.
+// ext: a deep column still alive after cap_reads reads goes on when the tail it has reached says the early exit is
+// within reach — P(X >= K among n reads) grows about like n^K, so 8 times more reads close a gap of 8^K.
 __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &mg, int K,
                                            double limit, int cap_reads, bool live, const Chunk16 *first = nullptr, bool ext = false)
 {
     double R[KS], T = 0.0;
 #pragma unroll
     for (int j = 0; j < KS; ++j) R[j] = (j == KS - K) ? 1.0 : 0.0;
+    const EvalMode em = eval_mode(cf);
     int cap = min(mg.n, cap_reads);
-    const int fshift = mg.n >= 1024 ? 3 : 2;
-    const int cap2 = ext ? min(mg.n, cap_reads << fshift) : 0;
+    // only deep columns go on: below ~2000 reads evaluating everything in k_mid (beside k_dp) is cheaper than a longer
+    // lane-serial walk on the critical path
+    const int fshift = 3;
+    const int cap2 = (ext && mg.n >= 2048) ? min(mg.n, cap_reads << fshift) : 0;
     // the reads come in aligned 16-byte chunks per plane: one load per plane covers what most columns need; the chunk
     // after the current one is requested while the current one is walked
     const long long ca = mg.off & ~15ll;
@@ -113,12 +115,8 @@ __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b,
                 load_chunk(cf, b, ca + idx, ch);
             }
         }
-        bool is_alt;
-        int slot;
         double jp;
-        if (!eval_read<true>(cf, s_lut, mg, i, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j), byte_of(ch.sq, j),
-                             is_alt, slot, jp))
-            continue;
+        if (!dp_eval(cf, em, s_lut, mg, i, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j), byte_of(ch.sq, j), jp)) continue;
         double p, q;
         guard_pq(jp, p, q);
         T = fma(R[KS - 1], p, T);
