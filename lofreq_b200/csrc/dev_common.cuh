@@ -208,6 +208,25 @@ __device__ __forceinline__ void load_chunk(const DevConf &cf, const DevBatch &b,
     ch.sq = cf.use_sq ? ldg16(b.sq + a) : zero;
 }
 
+// the same 16 bytes from an address that is only 8-byte aligned
+// (the upper half only when the column reaches into it: the planes are readable up to the 16-byte boundary past their
+// last read, not further)
+__device__ __forceinline__ uint4 ldg8x2(const unsigned char *p, bool hi_too)
+{
+    const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(p));
+    const uint2 hi = hi_too ? __ldg(reinterpret_cast<const uint2 *>(p) + 1) : make_uint2(0u, 0u);
+    return make_uint4(lo.x, lo.y, hi.x, hi.y);
+}
+
+__device__ __forceinline__ void load_chunk8(const DevConf &cf, const DevBatch &b, long long a, bool hi_too, Chunk16 &ch)
+{
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    ch.bq = ldg8x2(b.bq + a, hi_too);
+    ch.mq = cf.use_mq ? ldg8x2(b.mq + a, hi_too) : zero;
+    ch.baq = cf.use_baq ? ldg8x2(b.baq + a, hi_too) : zero;
+    ch.sq = cf.use_sq ? ldg8x2(b.sq + a, hi_too) : zero;
+}
+
 __device__ __forceinline__ int class_of(int K)
 {
     const int need = (K + 31) >> 5;          // cells per lane

@@ -8,20 +8,22 @@
 // handful of reads, without a warp ever being dedicated to it.
 //
 // Persistent CTAs, thread per column, tile = 256 consecutive columns; CTA b takes tiles b, b + G, b + 2G, ... (round
-// k = tiles [kG, (k+1)G)).  No CTA ever waits for another one:
+// k = tiles [kG, (k+1)G)).  No CTA ever waits for another one, and no warp for another warp (the kernel has no barrier:
+// a warp whose 32 columns are dull runs ahead into the next round while its neighbours still walk theirs):
 //   * the exact place of a column in the running count needs the tested columns of ALL tiles before it.  The prune
 //     does not: it only needs a factor that is not larger than the true one (a column ruled out under a smaller
-//     factor is ruled out under the larger one).  Every CTA adds the tested columns of its tile to a counter of its
-//     round; a column of round k uses start + 3 * (whatever the counters of rounds < k hold at that moment — all
-//     of it belongs to tiles before this one — + its rank inside its own tile).  After the first round that is
-//     within a fraction of the exact factor.
-//   * the exact ranks are tile prefix + rank inside the tile: k_front leaves the per-tile counts and the local ranks,
-//     k_scan_tiles (one CTA) turns the counts into exclusive prefixes.  Everything that survives the prune is decided
-//     with the exact factor afterwards (k_prune2 and later: col_rank()).
+//     factor is ruled out under the larger one).  The tested columns of a tile are added to a counter of its round
+//     (the last of the tile's warps to get there adds them); a column of round k uses start + 3 * (whatever the
+//     counters of rounds < k hold at that moment — all of it belongs to tiles before this one — + its rank among the
+//     32 columns of its warp).  After the first round that is within a fraction of the exact factor.
+//   * the exact ranks are tile prefix + tested columns of the warps before it in the tile + rank inside the warp:
+//     k_front leaves the per-warp counts (a byte each, eight per tile) and the ranks inside the warp (a byte each),
+//     k_scan_tiles (one CTA) turns the counts into exclusive tile prefixes.  Everything that survives the prune is
+//     decided with the exact factor afterwards (k_prune2 and later: col_rank()).
 // Per round and tile: metadata (requested a round earlier), gates; the alt reads and the first 16 reads of every column
 // that has alt reads are requested together; alt counts — lane per column for up to 8 non-reference reads, the whole
-// warp for the rare columns with more (variant sites); one barrier for the per-warp counts; routing (K > 8 -> job list
-// of k_dp / k_xl) and the prune over the first PRUNE_CAP1 reads, survivors to k_prune2's list.
+// warp for the rare columns with more (variant sites); routing (K > 8 -> job list of k_dp / k_xl) and the prune over
+// the first PRUNE_CAP1 reads, survivors to k_prune2's list.
 // When region shards on several GPUs continue each other's count (lfb200_comm_exchange), the shards before this one add
 // to the start AFTER this pass — one more reason why the factor used here is a lower bound.
 #include <cuda_runtime.h>
@@ -35,23 +37,37 @@
 
 namespace lfb {
 
-constexpr int FRONT_CTAS_PER_SM = 4;
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+#ifndef LFB_FRONT_CTAS
+#define LFB_FRONT_CTAS 3
+#endif
+constexpr int FRONT_CTAS_PER_SM = LFB_FRONT_CTAS;
+#ifndef LFB_KS1
+#define LFB_KS1 4
+#endif
+constexpr int KS1 = LFB_KS1;          // largest alt count the first stage of the prune walks itself
 
 __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
                                                                         const Lut *lut, const Workspace ws)
 {
     __shared__ double s_lut[768];
     __shared__ int s_hist[FIN_BLOCK / 32][256];
-    __shared__ int s_warp[2][FIN_BLOCK / 32];
-    __shared__ long long s_before[2];
-    load_lut(s_lut, lut);
+    __shared__ unsigned int s_round[FRONT_MAXROUNDS];     // per round of this CTA: (warps arrived << 16) + tested columns
+    for (int i = threadIdx.x; i < FRONT_MAXROUNDS; i += blockDim.x) s_round[i] = 0;
+    load_lut(s_lut, lut);                                 // ends with the kernel's only barrier
     const long long n = b.n_cols;
     const long long ntiles = (n + FIN_BLOCK - 1) / FIN_BLOCK;
     const int lane = lane_id(), w = threadIdx.x >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters->bonf_start_used = cf.bonf_start;
     // the median override (def_alt_bq == -1) needs a warp-wide histogram: no lane-per-column path then
     const int serial_max = cf.alt_bq_mode == 2 ? 0 : 8;
-    unsigned long long *round_cnt = ws.counters->front_round;
+    unsigned int *round_cnt = ws.counters->front_round;
 
     RawGeom nxt;
     nxt.off = 0; nxt.cnt = make_int4(0, 0, 0, 0); nxt.cov = -1; nxt.nb = -1; nxt.ref = 'N';
@@ -59,8 +75,8 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
         const long long c0 = (long long)blockIdx.x * FIN_BLOCK + threadIdx.x;
         if (c0 < n) load_raw(b, c0, nxt);
     }
-    int round = 0, par = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++round, par ^= 1) {
+    int round = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++round) {
         const long long c = tile * FIN_BLOCK + threadIdx.x;
         const RawGeom raw_g = nxt;
         {
@@ -69,15 +85,10 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
             if (cn < n) load_raw(b, cn, nxt);                  // next round's metadata in flight
         }
         // What the rounds before this one have counted so far — every tile of an earlier round lies before this tile, so any
-        // snapshot of their counters is a lower bound of the tested columns before it.  Requested now, used after the barrier.
-        if (threadIdx.x < 32) {
-            long long acc = 0;
-            for (int j = lane; j < min(round, FRONT_MAXROUNDS); j += 32)
-                acc += (long long)*reinterpret_cast<volatile unsigned long long *>(&round_cnt[j]);
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(FULL, acc, m);
-            if (lane == 0) s_before[par] = acc;
-        }
+        // snapshot of their counters is a lower bound of the tested columns before it.  Requested now, used after the counts.
+        // (lane j takes the counter of round j; summed where the factor is needed)
+        unsigned int before_l = 0;
+        if (lane < min(round, FRONT_MAXROUNDS)) before_l = ld_relaxed_u32(&round_cnt[lane]);
         // ---- metadata, gates ----
         Geom mg;
         mg.off = raw_g.off;
@@ -93,10 +104,11 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
         int m_lo, m_hi;
         ref_range(mg, m_lo, m_hi);
         const int m_alt = m_gate ? mg.n - (m_hi - m_lo) : 0;
-        // the first 16 reads of a column the prune may walk: requested together with its alt reads
+        // the first PRUNE_CAP1 reads of a column the prune may walk (16 bytes per plane from the 8-byte boundary below the
+        // column hold them wherever the column starts): requested together with its alt reads
         Chunk16 first;
         first.bq = first.mq = first.baq = first.sq = make_uint4(0, 0, 0, 0);
-        if (m_alt > 0 && cf.alt_bq_mode != 2) load_chunk(cf, b, mg.off & ~15ll, first);
+        if (m_alt > 0 && cf.alt_bq_mode != 2) load_chunk8(cf, b, mg.off & ~7ll, (mg.off & ~7ll) + 8 < mg.off + mg.n, first);
         // ---- alt counts ----
         int cnt[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
         if (m_alt > 0 && m_alt <= serial_max) {
@@ -146,25 +158,22 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
             o[2] = make_int2(raw[1], raw[2]);
             ws.tested[c] = (unsigned char)t;
         }
-        // ---- rank inside the tile; the tile's count for the exact prefix (k_scan_tiles) and for the rounds after this one
+        // ---- rank inside the warp; the warp's count for the exact prefix (k_scan_tiles, col_rank) and, through the CTA's
+        // counter of the round, for the rounds after this one
         const unsigned bal = __ballot_sync(FULL, t);
-        if (lane == 0) s_warp[par][w] = __popc(bal);
-        __syncthreads();                                       // the only barrier of the round
-        int wbefore = 0, ttotal = 0;
-#pragma unroll
-        for (int i = 0; i < FIN_BLOCK / 32; ++i) {
-            const int v = s_warp[par][i];
-            if (i < w) wbefore += v;
-            ttotal += v;
+        const int lrank = t ? __popc(bal & ((2u << lane) - 1u)) : 0;      // 1-based among the tested columns of the warp
+        if (c < n) ws.rank[c] = (unsigned char)lrank;
+        if (lane == 0) {
+            ws.wcount[tile * (FIN_BLOCK / 32) + w] = (unsigned char)__popc(bal);
+            if (round < FRONT_MAXROUNDS) {
+                // the warps of a CTA drift apart by whole rounds; the last one of this round hands the tile's count on
+                const unsigned v = atomicAdd(&s_round[round], (1u << 16) + (unsigned)__popc(bal)) + (1u << 16) + (unsigned)__popc(bal);
+                if ((v >> 16) == FIN_BLOCK / 32 && (v & 0xffffu)) atomicAdd(&round_cnt[round], v & 0xffffu);
+            }
         }
-        const int lrank = t ? wbefore + __popc(bal & ((2u << lane) - 1u)) : 0;      // 1-based among the tested columns of the tile
-        if (c < n) ws.rank[c] = lrank;
-        if (threadIdx.x == 0) {
-            ws.blocksum[tile] = ttotal;
-            if (ttotal) atomicAdd(&round_cnt[min(round, FRONT_MAXROUNDS - 1)], (unsigned long long)ttotal);
-        }
+        const long long before = (long long)__reduce_add_sync(FULL, before_l);
         // factor for the prune: never larger than the true one
-        const long long bonf = t ? bonf_of(cf, cf.bonf_start, s_before[par] + lrank) : 0;
+        const long long bonf = t ? bonf_of(cf, cf.bonf_start, before + lrank) : 0;
 
         // ---- routing and the first stage of the prune ----
         const int K = max(cnt[0], max(cnt[1], cnt[2]));
@@ -193,7 +202,9 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
         bool small = t && K <= KS;
         const double limit = small ? cf.sig * (1.0 + 1e-9) / (double)bonf : 0.0;   // margin: borderline columns go to the host
         if (cf.alt_bq_mode != 2) {          // the median override needs a warp-wide histogram: no lane-serial prune
-            small = lane_prune(cf, b, s_lut, mg, K, limit, PRUNE_CAP1, small, &first);
+            // (K > KS1 cannot be ruled out within PRUNE_CAP1 reads under any real factor: listed without a walk)
+            const bool alive = lane_prune<KS1>(cf, b, s_lut, mg, K, limit, PRUNE_CAP1, small && K <= KS1, &first, false, 8);
+            small = small && (K > KS1 || alive);
             // one atomic per warp for the survivors' slots
             const unsigned sm_ = __ballot_sync(FULL, small);
             if (sm_) {
@@ -210,8 +221,9 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
     }
 }
 
-// exclusive prefix over the per-tile counts k_front left in blocksum[], one CTA; total -> counters->n_tested
-__global__ void __launch_bounds__(1024) k_scan_tiles(long long *blocksum, int nb, unsigned long long *total)
+// exclusive prefix over the tiles' tested columns (the eight per-warp bytes k_front left per tile), one CTA;
+// total -> counters->n_tested
+__global__ void __launch_bounds__(1024) k_scan_tiles(const unsigned char *wcount, long long *blocksum, int nb, unsigned long long *total)
 {
     __shared__ long long s_w[32];
     __shared__ long long s_carry;
@@ -220,7 +232,11 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(long long *blocksum, int nb
     const int lane = lane_id(), w = threadIdx.x >> 5;
     for (int base = 0; base < nb; base += 1024) {
         const int i = base + threadIdx.x;
-        const long long v = (i < nb) ? blocksum[i] : 0;
+        long long v = 0;
+        if (i < nb) {
+            const uint2 x8 = reinterpret_cast<const uint2 *>(wcount)[i];
+            v = __vsadu4(x8.x, 0u) + __vsadu4(x8.y, 0u);
+        }
         long long x = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -268,7 +284,7 @@ void launch_front(const LaunchState &ls, const DevConf &cf, const DevBatch &b, c
     static const int front_ctas = getenv("LFB200_FRONT_CTAS") ? atoi(getenv("LFB200_FRONT_CTAS")) : FRONT_CTAS_PER_SM;
     const int grid = nb < ls.sms * front_ctas ? nb : ls.sms * front_ctas;
     k_front<<<grid, FIN_BLOCK, 0, st>>>(cf, b, lut, ws);
-    k_scan_tiles<<<1, 1024, 0, st>>>(ws.blocksum, nb, &ws.counters->n_tested);
+    k_scan_tiles<<<1, 1024, 0, st>>>(ws.wcount, ws.blocksum, nb, &ws.counters->n_tested);
 }
 
 void launch_bonf_used(const LaunchState &ls, const DevConf &cf, const Workspace &ws, long long n, cudaStream_t st)

@@ -146,7 +146,7 @@ struct lfb200_ctx {
     cudaStream_t stream = nullptr;       // used by the host entry points
     Lut *d_lut = nullptr;
     // workspace of the current batch
-    DevBuf w_cnt6, w_tested, w_bonf, w_rank, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_ujobs, w_iscand, w_candtile, w_candpre, w_perm;
+    DevBuf w_cnt6, w_tested, w_bonf, w_rank, w_wcount, w_blocksum, w_jobs, w_cand, w_counters, w_pjobs, w_ujobs, w_iscand, w_candtile, w_candpre, w_perm;
     Workspace ws{};
     // device copies of host batches (host entry point)
     DevBuf in_off, in_cnt, in_ref, in_cov, in_nb, in_bq, in_mq, in_baq, in_sq;
@@ -354,7 +354,7 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_bonf, &ctx->w_rank, &ctx->w_blocksum, &ctx->w_jobs,
+    DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_bonf, &ctx->w_rank, &ctx->w_wcount, &ctx->w_blocksum, &ctx->w_jobs,
                       &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_ujobs, &ctx->w_iscand, &ctx->w_candtile, &ctx->w_candpre, &ctx->w_perm, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
                       &ctx->in_bq, &ctx->in_mq, &ctx->in_baq, &ctx->in_sq, &ctx->p_ep, &ctx->p_off, &ctx->p_cnt,
                       &ctx->p_bonf, &ctx->p_out};
@@ -378,7 +378,8 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     bad |= ctx->w_tested.ensure(nn + 1024);
     bad |= ctx->w_bonf.ensure(nn * sizeof(long long));
     bad |= ctx->w_blocksum.ensure(((nn + 255) / 256 + 1) * sizeof(long long));
-    bad |= ctx->w_rank.ensure(nn * sizeof(int));
+    bad |= ctx->w_rank.ensure(nn);
+    bad |= ctx->w_wcount.ensure(((nn + 255) / 256 + 1) * 8);
     bad |= ctx->w_jobs.ensure(nn * NCLASS * sizeof(int));
     bad |= ctx->w_cand.ensure(nn * sizeof(Cand));
     bad |= ctx->w_iscand.ensure(((nn + 255) / 256 + 1) * 256);
@@ -401,7 +402,8 @@ static int ensure_workspace(lfb200_ctx *ctx, long long n)
     w.tested = (unsigned char *)ctx->w_tested.p;
     w.bonf_used = (long long *)ctx->w_bonf.p;
     w.blocksum = (long long *)ctx->w_blocksum.p;
-    w.rank = (int *)ctx->w_rank.p;
+    w.rank = (unsigned char *)ctx->w_rank.p;
+    w.wcount = (unsigned char *)ctx->w_wcount.p;
     w.jobs = (int *)ctx->w_jobs.p;
     w.cand = (Cand *)ctx->w_cand.p;
     w.is_cand = (unsigned char *)ctx->w_iscand.p;

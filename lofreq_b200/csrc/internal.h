@@ -22,7 +22,7 @@ constexpr int DP_NBIN = 14;        // depth bins: <= 128, 256, ..., 2^20 reads (
 constexpr int DP_NBIN1 = DP_NBIN + 1;   // + the unbinned overflow list of the class
 constexpr int DP_NL = DP_NCLS * DP_NBIN1;
 constexpr int DP_MAXK = 2048;
-constexpr int FRONT_MAXROUNDS = 64;  // round counters of k_front (rounds beyond share the last one)
+constexpr int FRONT_MAXROUNDS = 32;  // round counters of k_front (later rounds count nothing: the prune's factor stays a lower bound)
 
 // what the kernels need from varcall_conf_t, pre-digested on the host
 struct DevConf {
@@ -99,7 +99,7 @@ struct Counters {
                                    // the excess went to the class's unbinned list, bin == DP_NBIN)
     unsigned int next_ptask[3];    // k_dp<RC>
     long long bonf_start_used;     // running factor the last test started from (host or device supplied)
-    unsigned long long front_round[FRONT_MAXROUNDS];   // tested columns counted so far per round of k_front (lower bounds for its prune)
+    unsigned int front_round[FRONT_MAXROUNDS];   // tested columns counted so far per round of k_front (lower bounds for its prune)
     // written by k_emit_sites
     unsigned int n_fix;            // sites whose decision the host must repeat (may exceed EMIT_FIX_MAX: then all are rechecked)
     unsigned int emit_overflow;    // more sites than the host buffer holds: the host grows it and emits again
@@ -111,10 +111,11 @@ struct Workspace {
     long long cap_cols;
     int *cnt6;                     // [n][6]: alt_counts[3], alt_raw_counts[3]
     unsigned char *tested;         // [n]
-    int *rank;                     // [n]: 1-based rank among the tested columns of its tile of 256 columns, 0 = untested (k_front);
-                                   // rank in the batch = blocksum[tile] + rank (col_rank)
+    unsigned char *rank;           // [n]: 1-based rank among the tested columns of its warp's 32 columns, 0 = untested (k_front);
+                                   // rank in the batch = blocksum[tile] + wcount[warps before it in the tile] + rank (col_rank)
+    unsigned char *wcount;         // [ceil(n/256)][8]: tested columns per warp of a tile (k_front)
     long long *bonf_used;          // [n]: materialised on request (k_bonf_used)
-    long long *blocksum;           // [ceil(n/256)]: tested columns per tile (k_front), then before each tile (k_scan_tiles)
+    long long *blocksum;           // [ceil(n/256)]: tested columns before each tile (k_scan_tiles)
     int *jobs;                     // [NCLASS][n]
     Cand *cand;                    // [n]
     unsigned char *is_cand;        // [n rounded up to 256]: column emitted a candidate

@@ -15,11 +15,17 @@ __device__ __forceinline__ long long bonf_of(const DevConf &cf, long long start,
     return cf.bonf_dynamic ? ((start == 1 ? 0 : start) + 3 * rank) : start;
 }
 
-// 1-based rank of a tested column among the tested columns of the batch (0 = untested): prefix of its tile + rank inside it
+// 1-based rank of a tested column among the tested columns of the batch (0 = untested): prefix of its tile of 256
+// columns + tested columns of the warps before its own in the tile + rank among its warp's 32 columns
 __device__ __forceinline__ long long col_rank(const Workspace &ws, long long c)
 {
     const int r = ws.rank[c];
-    return r ? ws.blocksum[c >> 8] + r : 0;
+    if (!r) return 0;
+    const uint2 x8 = __ldg(reinterpret_cast<const uint2 *>(ws.wcount) + (c >> 8));
+    const int wi = (int)(c >> 5) & 7;
+    const unsigned lo = wi >= 4 ? x8.x : (x8.x & ((1u << (8 * wi)) - 1u));
+    const unsigned hi = wi > 4 ? (x8.y & ((1u << (8 * (wi - 4))) - 1u)) : 0u;
+    return ws.blocksum[c >> 8] + (long long)(__vsadu4(lo, 0u) + __vsadu4(hi, 0u)) + r;
 }
 
 // [lo, hi) of the reads showing the reference base
@@ -77,16 +83,18 @@ __device__ __forceinline__ void count_alt_read(const DevConf &cf, const DevBatch
 
 // The reference's early exit (snpcaller.c:916-958), one lane per column: walk the first `cap` reads until
 // P(X >= K among the reads seen) > limit = sig / bonf.  Returns true when the column is still alive after `cap` reads.
-// Cells are kept top-aligned (register 7 = cell K-1, padding below cell 0 stays 0), so one code path serves every
-// K <= KS.  Lanes with live == false only take part in the votes.
+// Cells are kept top-aligned (register KP-1 = cell K-1, padding below cell 0 stays 0), so one code path serves every
+// K <= KP.  Lanes with live == false only take part in the votes.
 // ext: a deep column still alive after cap_reads reads goes on when the tail it has reached says the early exit is
 // within reach — P(X >= K among n reads) grows about like n^K, so 8 times more reads close a gap of 8^K.
+template <int KP>
 __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &mg, int K,
-                                           double limit, int cap_reads, bool live, const Chunk16 *first = nullptr, bool ext = false)
+                                           double limit, int cap_reads, bool live, const Chunk16 *first = nullptr, bool ext = false,
+                                           int first_align = 16)
 {
-    double R[KS], T = 0.0;
+    double R[KP], T = 0.0;
 #pragma unroll
-    for (int j = 0; j < KS; ++j) R[j] = (j == KS - K) ? 1.0 : 0.0;
+    for (int j = 0; j < KP; ++j) R[j] = (j == KP - K) ? 1.0 : 0.0;
     const EvalMode em = eval_mode(cf);
     int cap = min(mg.n, cap_reads);
     // only deep columns go on: below ~2000 reads evaluating everything in k_mid (beside k_dp) is cheaper than a longer
@@ -95,7 +103,9 @@ __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b,
     const int cap2 = (ext && mg.n >= 2048) ? min(mg.n, cap_reads << fshift) : 0;
     // the reads come in aligned 16-byte chunks per plane: one load per plane covers what most columns need; the chunk
     // after the current one is requested while the current one is walked
-    const long long ca = mg.off & ~15ll;
+    // (first_align == 8: the caller's first chunk starts at the 8-byte boundary below the column and cap_reads <= 9, so
+    // the walk never leaves it)
+    const long long ca = mg.off & ~(long long)(first_align - 1);
     const int lead = (int)(mg.off - ca);
     Chunk16 ch, nx;
     ch.bq = ch.mq = ch.baq = ch.sq = make_uint4(0, 0, 0, 0);
@@ -119,9 +129,9 @@ __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b,
         if (!dp_eval(cf, em, s_lut, mg, i, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j), byte_of(ch.sq, j), jp)) continue;
         double p, q;
         guard_pq(jp, p, q);
-        T = fma(R[KS - 1], p, T);
+        T = fma(R[KP - 1], p, T);
 #pragma unroll
-        for (int j2 = KS - 1; j2 >= 1; --j2) R[j2] = fma(R[j2 - 1], p, R[j2] * q);
+        for (int j2 = KP - 1; j2 >= 1; --j2) R[j2] = fma(R[j2 - 1], p, R[j2] * q);
         R[0] = R[0] * q;
         if (T > limit) live = false;          // clearly insignificant: snpcaller() leaves LDBL_MAX everywhere (snpcaller.c:1155)
         if (live && i + 1 == cap && cap < cap2 && T * __hiloint2double((1023 + fshift * K) << 20, 0) >= limit) cap = cap2;

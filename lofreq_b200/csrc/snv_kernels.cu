@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(128) k_prune2(const __grid_constant__ DevConf 
             K = max(a0.x, max(a0.y, a1.x));
             limit = cf.sig * (1.0 + 1e-9) / (double)bonf_of(cf, start, col_rank(ws, c));
         }
-        live = lane_prune(cf, b, s_lut, mg, K, limit, PRUNE_CAP, live, nullptr, true);
+        live = lane_prune<KS>(cf, b, s_lut, mg, K, limit, PRUNE_CAP, live, nullptr, true);
         if (live) {
             const unsigned slot = atomicAdd(&ws.counters->n_jobs[0], 1u);
             ws.jobs[slot] = (int)c;

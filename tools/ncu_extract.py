@@ -21,6 +21,11 @@ def main():
     for r in rows[2:]:
         d = {"kernel": r[hdr.index("Kernel Name")]}
         for h, u, v in zip(hdr, units, r):
+            if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio") or h.startswith("smsp__average_warp_latency_issue_stalled"):
+                try:
+                    d.setdefault("stall", {})[h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "")] = round(float(v.replace(",", "")), 3)
+                except ValueError:
+                    pass
             if h in KEYS:
                 try:
                     x = float(v.replace(",", ""))
@@ -36,6 +41,9 @@ def main():
     with open(out, "w") as f:
         json.dump(res, f, indent=1)
     for d in res:
+        if d.get("stall"):
+            top = sorted(d["stall"].items(), key=lambda kv: -kv[1])[:6]
+            print("   stalls (warps per issue):", ", ".join("%s %.2f" % kv for kv in top))
         print("%-60s %8.1f us  dram %.1f MB" % (d["kernel"][:60], d.get("gpu__time_duration.sum [us]", 0),
                                               (d.get("dram__bytes_read.sum [bytes]", 0) + d.get("dram__bytes_write.sum [bytes]", 0)) / 1e6))
 
