@@ -27,6 +27,7 @@
 // Columns this form cannot finish (a parameter above 2^20, a tail that needs the tilt after all, a low cell of a
 // strongly tilted row lost to underflow) go to the per-column fallback lists that k_heavy_all takes afterwards.
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <math.h>
 #include <stdlib.h>
@@ -247,7 +248,7 @@ __device__ __forceinline__ int hist_bucket(double p)
 
 // Newton on ln s, the G lanes of a column over its histogram; columns that need no tilt idle along (need == false)
 template <int G>
-__device__ __forceinline__ double group_tilt(const ColHist &h, bool need, int K, int N, double lam)
+__device__ __forceinline__ double group_tilt(const ColHist &h, bool need, int K, int N, double lam, double scale)
 {
     const int gl = lane_id() % G;
     const double kt = fmin((double)K, (double)N - 0.5);
@@ -272,8 +273,8 @@ __device__ __forceinline__ double group_tilt(const ColHist &h, bool need, int K,
                 ds = fmaf((float)c * w, 1.f - w, ds);                                  // derivative with respect to ln s
             }
         }
-        const double gsum = group_sum<G>((double)gs) - kt;
-        const double d = group_sum<G>((double)ds);
+        const double gsum = group_sum<G>((double)gs) * scale - kt;       // the histogram holds a sample: scale = reads / sampled reads
+        const double d = group_sum<G>((double)ds) * scale;
         if (conv) continue;
         // an error e in ln s costs about d*e^2/2 nats of head-room (of ~700): stop once that is negligible
         const double step = d > 0.0 ? gsum / d : 0.0;
@@ -354,12 +355,15 @@ __device__ __forceinline__ double ln_lower(double x)
 // one warp task: 32/G columns in lock step
 // ------------------------------------------------------------------------------------------------
 template <int G, int R>
-__device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &ws, const double *s_lut, DpWarpSmem &sm,
+__device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &ws, const double *s_lut, const Lut *lut, DpWarpSmem &sm,
                         unsigned char *stage_bytes, int planes, const int *list, unsigned j0, unsigned nj)
 {
     constexpr int NCOL = 32 / G;
     constexpr int RPL = 32 / G;                         // reads per lane and block of 32 reads
     const int lane = lane_id(), grp = lane / G, gl = lane % G;
+#ifdef LFB_DP_PROF
+    long long pf_t0 = clock64(), pf_par = 0, pf_loop = 0, pf_chk = 0, pf_a, pf_setup, pf_pre, pf_tilt, pf_main;
+#endif
     const int last = grp * G + G - 1;                   // the lane that owns the top cells and the absorbing state
     bool have = j0 + grp < nj;
     const long long c = have ? list[j0 + grp] : -1;
@@ -430,14 +434,18 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
     if (nmax > 0) { issue(0); issued = 1; }
 
     const EvalMode em = eval_mode(cf);
+#ifdef LFB_DP_PROF
+    pf_setup = clock64();
+#endif
 
-    // ---- 1. pre-pass, G lanes per column, 16-byte loads: reads kept, lambda and the histogram of the merged probabilities —
-    // what the tilt needs.  Most columns need no tilt (and many are ruled out by the early exit after a fraction of their
-    // reads), so the sweep first takes a sample of 64 reads per lane; only a column whose estimated Chernoff exponent comes
-    // near the limit is swept to the end.  (A wrong guess costs speed, not correctness: an untilted row that turns out to
-    // need the tilt is handed to the per-column fallback.)
+    // ---- 1. pre-pass, G lanes per column, 16-byte loads: what the tilt needs — the number of reads kept, lambda and the
+    // histogram of the merged probabilities — estimated from a sample of 8 .. 32 chunks of 16 reads spread evenly over the
+    // column (the reads are grouped by base, and error reads are of lower quality than the rest: a prefix would not do).
+    // The tilt is a free parameter of the recurrence — the results do not depend on it, only the numeric range the cells
+    // stay in — so an estimate is enough: a relative error e of lambda costs about K e^2 / 2 nats of ~700, and a row that
+    // leaves the range all the same is detected (gap tests below) and handed to the per-column kernel.
     int N = 0;
-    double lam = 0.0;
+    double lam = 0.0, scale = 1.0;
     ColHist &hist = *reinterpret_cast<ColHist *>(sm.u.hist_bytes + grp * sizeof(ColHist));
     for (int i = gl; i < DP_NB; i += G) {
         hist.sum[i] = 0.f;
@@ -455,70 +463,71 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
             }
             run_b = -1;
         };
+        constexpr int SAMPLE = G >= 8 ? G : 8;           // chunks per column
         const long long abase = g.off & ~15ll;
         const int nch = have ? (lead + g.n + 15) >> 4 : 0;
-        auto sweep = [&](int i0, int i1) {
+        const int m = min(nch, SAMPLE);
+        int seen = 0;                                    // positions of the column the sample has looked at
 #pragma unroll 1
-            for (int i = i0; i < i1; i += G) {
-                Chunk16 ch;
-                load_chunk(cf, b, abase + 16ll * i, ch);
-                const int pos0 = 16 * i - lead;
-                const bool inside = pos0 >= 0 && pos0 + 16 <= g.n;
+        for (int k = gl; k < m; k += G) {
+            const int i = nch <= SAMPLE ? k : (int)(((long long)k * nch) / SAMPLE);
+            Chunk16 ch;
+            load_chunk(cf, b, abase + 16ll * i, ch);
+            const int pos0 = 16 * i - lead;
+            const bool inside = pos0 >= 0 && pos0 + 16 <= g.n;
+            seen += min(pos0 + 16, g.n) - max(pos0, 0);
 #pragma unroll 1
-                for (int wd = 0; wd < 4; ++wd) {
-                    const unsigned wbq = wd == 0 ? ch.bq.x : wd == 1 ? ch.bq.y : wd == 2 ? ch.bq.z : ch.bq.w;
-                    const unsigned wmq = wd == 0 ? ch.mq.x : wd == 1 ? ch.mq.y : wd == 2 ? ch.mq.z : ch.mq.w;
-                    const unsigned wbaq = wd == 0 ? ch.baq.x : wd == 1 ? ch.baq.y : wd == 2 ? ch.baq.z : ch.baq.w;
-                    const unsigned wsq = wd == 0 ? ch.sq.x : wd == 1 ? ch.sq.y : wd == 2 ? ch.sq.z : ch.sq.w;
+            for (int wd = 0; wd < 4; ++wd) {
+                const unsigned wbq = wd == 0 ? ch.bq.x : wd == 1 ? ch.bq.y : wd == 2 ? ch.bq.z : ch.bq.w;
+                const unsigned wmq = wd == 0 ? ch.mq.x : wd == 1 ? ch.mq.y : wd == 2 ? ch.mq.z : ch.mq.w;
+                const unsigned wbaq = wd == 0 ? ch.baq.x : wd == 1 ? ch.baq.y : wd == 2 ? ch.baq.z : ch.baq.w;
+                const unsigned wsq = wd == 0 ? ch.sq.x : wd == 1 ? ch.sq.y : wd == 2 ? ch.sq.z : ch.sq.w;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int pos = pos0 + 4 * wd + j;
-                        double jp = 0.0;
-                        const bool ok = (inside || (pos >= 0 && pos < g.n)) &&
-                                        dp_eval(cf, em, s_lut, g, pos, (wbq >> (8 * j)) & 0xff, (wmq >> (8 * j)) & 0xff, (wbaq >> (8 * j)) & 0xff,
-                                                (wsq >> (8 * j)) & 0xff, jp);
-                        if (!ok) continue;
-                        const double p = jp < DEPS ? DEPS : jp;
-                        lam += p;
-                        ++N;
-                        const int bk = hist_bucket(p);
-                        if (bk != run_b) {
-                            flush();
-                            run_b = bk;
-                            run_s = 0.f;
-                            run_c = 0;
-                        }
-                        run_s += (float)p;
-                        ++run_c;
+                for (int j = 0; j < 4; ++j) {
+                    const int pos = pos0 + 4 * wd + j;
+                    double jp = 0.0;
+                    const bool ok = (inside || (pos >= 0 && pos < g.n)) &&
+                                    dp_eval(cf, em, s_lut, g, pos, (wbq >> (8 * j)) & 0xff, (wmq >> (8 * j)) & 0xff, (wbaq >> (8 * j)) & 0xff,
+                                            (wsq >> (8 * j)) & 0xff, jp);
+                    if (!ok) continue;
+                    const double p = jp < DEPS ? DEPS : jp;
+                    lam += p;
+                    ++N;
+                    const int bk = hist_bucket(p);
+                    if (bk != run_b) {
+                        flush();
+                        run_b = bk;
+                        run_s = 0.f;
+                        run_c = 0;
                     }
+                    run_s += (float)p;
+                    ++run_c;
                 }
             }
-        };
-        constexpr int SAMPLE_CHUNKS = 4;                 // per lane: 64 reads
-        const int i_mid = min(nch, gl + SAMPLE_CHUNKS * G);
-        sweep(gl, i_mid);
-        const int n_s = group_sum_i<G>(N);
-        const double lam_s = group_sum<G>(lam);
-        const int covered = min(SAMPLE_CHUNKS * G * 16, lead + g.n);            // positions the sample has looked at
-        const double lam_est = have && covered > 0 ? lam_s * (double)(lead + g.n) / (double)covered : 0.0;
-        const double cher_est = (have && (double)K > lam_est) ? ((double)K * log((double)K / fmax(lam_est, 1e-300)) - (double)K + lam_est) : 0.0;
-        const bool full = have && nch > SAMPLE_CHUNKS * G && cher_est > 100.0;
-        if (full) sweep(gl + SAMPLE_CHUNKS * G, nch);
+        }
         flush();
         N = group_sum_i<G>(N);
         lam = group_sum<G>(lam);
-        if (have && !full && nch > SAMPLE_CHUNKS * G) {                 // estimates: no tilt will be computed from them
-            lam = lam_est;
-            N = (int)((double)n_s * (double)(lead + g.n) / (double)covered);
+        seen = group_sum_i<G>(seen);
+        if (have && seen > 0 && seen < g.n) {
+            scale = (double)g.n / (double)seen;
+            lam *= scale;
+            N = (int)((double)N * scale);
         }
     }
     __syncwarp();
+#ifdef LFB_DP_PROF
+    pf_pre = clock64();
+#endif
     // Chernoff exponent of the tail: beyond ~300 nats the untilted cells of interest drift out of fp64 range
     const double cher = (have && (double)K > lam) ? ((double)K * log((double)K / fmax(lam, 1e-300)) - (double)K + lam) : 0.0;
-    const double ln_s = group_tilt<G>(hist, have && cher > 300.0, K, N, lam);
+    const double ln_s = group_tilt<G>(hist, have && cher > 300.0, K, N, lam, scale);
     __syncwarp();                                       // the histograms give way to the step parameters
     const double s = (ln_s == 0.0) ? 1.0 : exp(ln_s);
 
+#ifdef LFB_DP_PROF
+    pf_tilt = clock64();
+#endif
     // ---- 2./3. the recurrence, all columns of the warp in lock step
     const int k0 = K - G * R + gl * R;                  // cell of register 0 (k < 0: padding, stays 0)
     double E[R], T = 0.0;
@@ -544,6 +553,44 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         const int ks = rbase / DP_S;
         const unsigned char *src = stage_bytes + ((size_t)((ks & 1) * DP_NCOLMAX + grp) * planes) * DP_SB + lead + (rbase - ks * DP_S);
         bool bad = false;
+        if (em.uniform && em.plain_merge) {
+            // The default configuration (bq and mq merged, reference and alt reads alike), straight-line: 1 / q of a (bq, mq)
+            // pair is the product of two table entries, so nothing here waits for a division, and the reads of a lane are
+            // independent chains the scheduler interleaves.  (The relative error of that product, ~4e-16, enters T once per
+            // read; a q of zero — probability 1 — gives inf and sends the column to the per-column kernel like any step too
+            // large to hold between two rescalings.)
+            constexpr int CH = RPL < 4 ? RPL : 4;
+#pragma unroll
+            for (int i0 = 0; i0 < RPL; i0 += CH) {
+                int bqv[CH], mqv[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    const int t = gl + G * (i0 + u);
+                    bqv[u] = src[t];
+                    mqv[u] = cf.use_mq ? src[DP_SB + t] : 255;
+                }
+                double bpv[CH], mpv[CH], rqv[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    bpv[u] = s_lut[bqv[u]];
+                    mpv[u] = s_lut[256 + mqv[u]];
+                    rqv[u] = __ldg(&lut->rbq[bqv[u]]) * __ldg(&lut->rmq[mqv[u]]);
+                }
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    const int t = gl + G * (i0 + u);
+                    const bool ok = !dead && rbase + t < n_mine && bqv[u] >= cf.min_bq;
+                    const double jp = __dadd_rn(mpv[u], __dmul_rn(__dsub_rn(1.0, mpv[u]), bpv[u]));
+                    double p, q;
+                    guard_pq(jp, p, q);
+                    const double rq = rqv[u];
+                    const double o = p * s * rq;
+                    bad |= ok && !(o <= 1048576.0 && rq <= 1048576.0);
+                    qprod *= ok ? q : 1.0;
+                    sm.u.par[grp][t] = ok ? make_double2(o, rq) : make_double2(0.0, 1.0);
+                }
+            }
+        } else {
 #pragma unroll
         for (int i = 0; i < RPL; ++i) {
             const int t = gl + G * i;                   // read of this block
@@ -569,6 +616,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
             }
             sm.u.par[grp][t] = e;
         }
+        }
         if (qprod < 1e-200) {
             lq_acc += log(qprod);
             qprod = 1.0;
@@ -586,8 +634,17 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         }
         __syncwarp();
     };
+#ifdef LFB_DP_PROF
+    pf_a = clock64();
+#endif
     if (nmax > 0) make_params(0);
+#ifdef LFB_DP_PROF
+    pf_par += clock64() - pf_a;
+#endif
     for (int n0 = 0; n0 < nmax; n0 += 32) {
+#ifdef LFB_DP_PROF
+        pf_a = clock64();
+#endif
         const double2 *pp = sm.u.par[grp];
         // software-pipelined: the parameters of read j+1 and the boundary cell for read j+1 (the top cell right
         // after its own update) are requested before the remaining R-1 cells of read j are updated
@@ -606,6 +663,9 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
             for (int r = R - 2; r >= 1; --r) E[r] = fma(E[r - 1], cc.x, E[r]);
             E[0] = fma(in, cc.x, E[0]);
         }
+#ifdef LFB_DP_PROF
+        pf_loop += clock64() - pf_a; pf_a = clock64();
+#endif
         // exact power-of-two rescaling, per column
         int hi = 0;
 #pragma unroll
@@ -628,9 +688,18 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         const bool over_g = __shfl_sync(FULL, (int)over, last) != 0;     // every lane takes part, dead or not
         dead = dead || over_g;
         __syncwarp();                                  // sm.par is rewritten now
+#ifdef LFB_DP_PROF
+        pf_chk += clock64() - pf_a; pf_a = clock64();
+#endif
         if (__all_sync(FULL, dead || n0 + 32 >= n_mine)) break;      // nothing left to decide in this warp
         make_params((n0 >> 5) + 1);
+#ifdef LFB_DP_PROF
+        pf_par += clock64() - pf_a;
+#endif
     }
+#ifdef LFB_DP_PROF
+    pf_main = clock64();
+#endif
     // a prefetched stage may still be in flight: it must land before the buffers and barriers are reused
     if (issued > waited) mbar_wait(&sm.bar[(issued - 1) & 1], (unsigned)((issued - 1) >> 1) & 1u);
     __syncwarp();
@@ -737,6 +806,11 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         }
     }
     __syncwarp();
+#ifdef LFB_DP_PROF
+    if (lane == 0 && (blockIdx.x % 97) == 0)
+        printf("dp_task G=%d R=%d blk %d nmax %d: setup %lld pre %lld tilt %lld main %lld (par %lld loop %lld chk %lld) tails %lld total %lld start %lld\n", G, R, blockIdx.x, nmax,
+               pf_setup - pf_t0, pf_pre - pf_setup, pf_tilt - pf_pre, pf_main - pf_tilt, pf_par, pf_loop, pf_chk, (long long)clock64() - pf_main, (long long)clock64() - pf_t0, pf_t0);
+#endif
 }
 
 // One kernel per register budget: RC = 0: R = 8 cells per lane (classes 0..3, K <= 256, the bulk of the columns; 6 CTAs
@@ -777,16 +851,16 @@ k_dp(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, con
         const unsigned j0 = (t - s_tbase[lo]) * (unsigned)dp_cols_per_task(cls);
         const int *list = dp_list_ptr(ws, li);
         if (RC == 2) {
-            dp_task<32, 64>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj);
+            dp_task<32, 64>(cf, b, ws, s_lut, lut, sm, stage_bytes, planes, list, j0, nj);
         } else if (RC == 1) {
-            if (cls == 4) dp_task<32, 16>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj);
-            else dp_task<32, 32>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj);
+            if (cls == 4) dp_task<32, 16>(cf, b, ws, s_lut, lut, sm, stage_bytes, planes, list, j0, nj);
+            else dp_task<32, 32>(cf, b, ws, s_lut, lut, sm, stage_bytes, planes, list, j0, nj);
         } else {
             switch (cls) {
-                case 0: dp_task<4, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
-                case 1: dp_task<8, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
-                case 2: dp_task<16, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
-                default: dp_task<32, 8>(cf, b, ws, s_lut, sm, stage_bytes, planes, list, j0, nj); break;
+                case 0: dp_task<4, 8>(cf, b, ws, s_lut, lut, sm, stage_bytes, planes, list, j0, nj); break;
+                case 1: dp_task<8, 8>(cf, b, ws, s_lut, lut, sm, stage_bytes, planes, list, j0, nj); break;
+                case 2: dp_task<16, 8>(cf, b, ws, s_lut, lut, sm, stage_bytes, planes, list, j0, nj); break;
+                default: dp_task<32, 8>(cf, b, ws, s_lut, lut, sm, stage_bytes, planes, list, j0, nj); break;
             }
         }
         if (lane == 0) t = nwarps + atomicAdd(next, 1u);

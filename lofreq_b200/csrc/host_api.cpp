@@ -227,6 +227,10 @@ static void build_lut(Lut &l)
     l.mq[0] = 0.5;      // MQ0_ERRPROB, snpcaller.c:64,315
     l.mq[255] = 0.0;    // unknown -> -1 -> probability 0, snpcaller.c:451-453,311
     l.aq[255] = 0.0;    // -1: quality not available (plp.c:961)
+    for (int q = 0; q < 256; ++q) {
+        l.rbq[q] = 1.0 / (1.0 - l.bq[q]);
+        l.rmq[q] = 1.0 / (1.0 - l.mq[q]);
+    }
 }
 
 // PROB_TO_PHREDQUAL_SAFE (utils.h:46)
