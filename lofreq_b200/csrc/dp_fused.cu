@@ -56,6 +56,7 @@ __device__ __forceinline__ int group_sum_i(int v)
 template <int G>
 __device__ __forceinline__ int group_max_i(int v)
 {
+    if (G == 32) return __reduce_max_sync(FULL, v);
 #pragma unroll
     for (int m = G / 2; m >= 1; m >>= 1) v = max(v, __shfl_xor_sync(FULL, v, m));
     return v;
@@ -170,25 +171,30 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // layout of the dynamic shared memory
 // ------------------------------------------------------------------------------------------------
 constexpr int DP_WARPS = 4;
-constexpr int DP_S = 64;                    // reads per TMA stage and column
-constexpr int DP_SB = DP_S + 16;            // bytes per stage, column and plane: + the lead of an unaligned column
 constexpr int DP_NCOLMAX = 8;               // columns per warp at G = 4
-constexpr int DP_PAR = 33;                  // one parameter row: 32 reads, padded (banks)
+// A warp works in superblocks of 8 G reads of each of its 32 / G columns (32 reads at G = 4 .. 256 at G = 32): 256
+// (column, read) pairs, 8 per lane, whatever the class.  The step parameters of a superblock are made in one go (the
+// latency of a parameter's dependent chain is paid once per 8 reads of a lane), the recurrence then runs over it in blocks
+// of 32 reads.  One TMA stage holds one superblock (two at G = 4).
+constexpr int DP_PAR_ENTRIES = 264;         // parameter rows: 32 / G rows of 8 G + 1 entries
+constexpr int DP_STAGE_ROWS = 640;          // bytes per stage and plane: 32 / G rows of (reads per stage + 16) bytes, at most 8 * 80
+__host__ __device__ constexpr int dp_superblock(int G) { return 8 * G; }
+__host__ __device__ constexpr int dp_stage_reads(int G) { return G == 4 ? 64 : 8 * G; }
 
 struct DpWarpSmem {
     unsigned long long bar[2];
     union {
-        double2 par[DP_NCOLMAX][DP_PAR];                              // step parameters of the current block of 32 reads
+        double2 par[DP_PAR_ENTRIES];                                  // step parameters of the current superblock
         // before the recurrence starts the same bytes serve the set-up of the task:
         unsigned char hist_bytes[DP_NCOLMAX * 512];                   // ColHist per column of the warp (tilt)
         int median_hist[256];                                         // def_alt_bq == -1 (warp_ref_median)
     } u;
-    // followed by the byte stages: [2][DP_NCOLMAX][planes][DP_SB]
+    // followed by the byte stages: [2][planes][DP_STAGE_ROWS]
 };
 
 __host__ __device__ constexpr size_t dp_warp_bytes(int planes)
 {
-    return ((sizeof(DpWarpSmem) + 15) & ~(size_t)15) + (size_t)2 * DP_NCOLMAX * planes * DP_SB;
+    return ((sizeof(DpWarpSmem) + 15) & ~(size_t)15) + (size_t)2 * planes * DP_STAGE_ROWS;
 }
 
 // processing order of the job lists (longest tasks first): the unbinned lists, then bin by bin from the deepest, and
@@ -362,7 +368,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
     constexpr int RPL = 32 / G;                         // reads per lane and block of 32 reads
     const int lane = lane_id(), grp = lane / G, gl = lane % G;
 #ifdef LFB_DP_PROF
-    long long pf_t0 = clock64(), pf_par = 0, pf_loop = 0, pf_chk = 0, pf_a, pf_setup, pf_pre, pf_tilt, pf_main;
+    long long pf_t0 = clock64(), pf_par = 0, pf_loop = 0, pf_chk = 0, pf_a, pf_setup, pf_pre, pf_tilt, pf_main, pf_w = 0, pf_e = 0, pf_b;
 #endif
     const int last = grp * G + G - 1;                   // the lane that owns the top cells and the absorbing state
     bool have = j0 + grp < nj;
@@ -400,24 +406,26 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         }
     }
 
-    // the bytes of reads [ks*DP_S, (ks+1)*DP_S) of this group's column -> stage buffer ks & 1
+    // the bytes of reads [ks*ST, (ks+1)*ST) of this group's column -> stage buffer ks & 1
+    constexpr int SB = dp_superblock(G), ST = dp_stage_reads(G), ROW = ST + 16;     // ROW: + the lead of an unaligned column
+    static_assert(NCOL * ROW <= DP_STAGE_ROWS && NCOL * (SB + 1) <= DP_PAR_ENTRIES, "shared memory layout");
     const int n_mine = have ? g.n : 0;
     const int nmax = __reduce_max_sync(FULL, n_mine);
     const int lead = (int)(g.off & 15ll);
     auto issue = [&](int ks) {
         if (gl == 0) {
             unsigned long long *bar = &sm.bar[ks & 1];
-            const int r0 = ks * DP_S;
+            const int r0 = ks * ST;
             if (r0 < n_mine) {
                 const long long a0 = (g.off + r0) & ~15ll;
-                const unsigned nbytes = (unsigned)((lead + min(DP_S, n_mine - r0) + 15) & ~15);
+                const unsigned nbytes = (unsigned)((lead + min(ST, n_mine - r0) + 15) & ~15);
                 mbar_arrive_expect_tx(bar, nbytes * (unsigned)planes);
-                unsigned char *dst = stage_bytes + ((size_t)((ks & 1) * DP_NCOLMAX + grp) * planes) * DP_SB;
+                unsigned char *dst = stage_bytes + (size_t)(ks & 1) * planes * DP_STAGE_ROWS + grp * ROW;
                 int pl = 0;
-                tma_load_1d(dst + (size_t)(pl++) * DP_SB, b.bq + a0, nbytes, bar);
-                if (cf.use_mq) tma_load_1d(dst + (size_t)(pl++) * DP_SB, b.mq + a0, nbytes, bar);
-                if (cf.use_baq) tma_load_1d(dst + (size_t)(pl++) * DP_SB, b.baq + a0, nbytes, bar);
-                if (cf.use_sq) tma_load_1d(dst + (size_t)(pl++) * DP_SB, b.sq + a0, nbytes, bar);
+                tma_load_1d(dst + (size_t)(pl++) * DP_STAGE_ROWS, b.bq + a0, nbytes, bar);
+                if (cf.use_mq) tma_load_1d(dst + (size_t)(pl++) * DP_STAGE_ROWS, b.mq + a0, nbytes, bar);
+                if (cf.use_baq) tma_load_1d(dst + (size_t)(pl++) * DP_STAGE_ROWS, b.baq + a0, nbytes, bar);
+                if (cf.use_sq) tma_load_1d(dst + (size_t)(pl++) * DP_STAGE_ROWS, b.sq + a0, nbytes, bar);
             } else {
                 mbar_arrive(bar);
             }
@@ -537,21 +545,29 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
     const double thr_ln = log(cf.sig * (1.0 + 1e-9) / (double)bonf) + (double)K * ln_s;
     bool dead = !have, fb = false;
     double lq_acc = 0.0, qprod = 1.0;                   // ln of the product of q over this lane's reads = lq_acc + ln(qprod)
-    // step parameters of block nb -> sm.par (single buffer: written between two recurrence blocks)
-    auto make_params = [&](int nb) {
-        const int rbase = nb * 32;
-        if ((rbase % DP_S) == 0) {
-            const int ks = rbase / DP_S;
-            if ((ks + 1) * DP_S < nmax) {
-                __syncwarp();                           // every lane is done with the buffer stage ks+1 overwrites
+    double lq_sb = 0.0;                                 // lower bound of the column's sum of ln q up to the end of the current superblock
+    double2 *const prow = sm.u.par + grp * (SB + 1);
+    // step parameters of superblock sb -> sm.par (single buffer: written between two superblocks)
+    auto make_params = [&](int sb) {
+        const int rbase = sb * SB;
+#ifdef LFB_DP_PROF
+        pf_b = clock64();
+#endif
+        if ((rbase % ST) == 0) {
+            const int ks = rbase / ST;
+            // (the buffer stage ks+1 overwrites held stage ks-1: every lane left it before the last __syncwarp)
+            if ((ks + 1) * ST < nmax) {
                 issue(ks + 1);
                 issued = ks + 2;
             }
             mbar_wait(&sm.bar[ks & 1], (unsigned)(ks >> 1) & 1u);
             waited = ks + 1;
         }
-        const int ks = rbase / DP_S;
-        const unsigned char *src = stage_bytes + ((size_t)((ks & 1) * DP_NCOLMAX + grp) * planes) * DP_SB + lead + (rbase - ks * DP_S);
+#ifdef LFB_DP_PROF
+        pf_w += clock64() - pf_b; pf_b = clock64();
+#endif
+        const int ks = rbase / ST;
+        const unsigned char *src = stage_bytes + (size_t)(ks & 1) * planes * DP_STAGE_ROWS + grp * ROW + lead + (rbase - ks * ST);
         bool bad = false;
         if (em.uniform && em.plain_merge) {
             // The default configuration (bq and mq merged, reference and alt reads alike), straight-line: 1 / q of a (bq, mq)
@@ -559,25 +575,24 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
             // independent chains the scheduler interleaves.  (The relative error of that product, ~4e-16, enters T once per
             // read; a q of zero — probability 1 — gives inf and sends the column to the per-column kernel like any step too
             // large to hold between two rescalings.)
-            constexpr int CH = RPL < 4 ? RPL : 4;
 #pragma unroll
-            for (int i0 = 0; i0 < RPL; i0 += CH) {
-                int bqv[CH], mqv[CH];
+            for (int i0 = 0; i0 < 8; i0 += 4) {
+                int bqv[4], mqv[4];
 #pragma unroll
-                for (int u = 0; u < CH; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     const int t = gl + G * (i0 + u);
                     bqv[u] = src[t];
-                    mqv[u] = cf.use_mq ? src[DP_SB + t] : 255;
+                    mqv[u] = cf.use_mq ? src[DP_STAGE_ROWS + t] : 255;
                 }
-                double bpv[CH], mpv[CH], rqv[CH];
+                double bpv[4], mpv[4], rqv[4];
 #pragma unroll
-                for (int u = 0; u < CH; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     bpv[u] = s_lut[bqv[u]];
                     mpv[u] = s_lut[256 + mqv[u]];
                     rqv[u] = __ldg(&lut->rbq[bqv[u]]) * __ldg(&lut->rmq[mqv[u]]);
                 }
 #pragma unroll
-                for (int u = 0; u < CH; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     const int t = gl + G * (i0 + u);
                     const bool ok = !dead && rbase + t < n_mine && bqv[u] >= cf.min_bq;
                     const double jp = __dadd_rn(mpv[u], __dmul_rn(__dsub_rn(1.0, mpv[u]), bpv[u]));
@@ -585,38 +600,41 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
                     guard_pq(jp, p, q);
                     const double rq = rqv[u];
                     const double o = p * s * rq;
+                    // between two rescalings (32 reads) a cell may grow by (1 + o)^32 and the absorbing state by (1/q)^32
                     bad |= ok && !(o <= 1048576.0 && rq <= 1048576.0);
                     qprod *= ok ? q : 1.0;
-                    sm.u.par[grp][t] = ok ? make_double2(o, rq) : make_double2(0.0, 1.0);
+                    prow[t] = ok ? make_double2(o, rq) : make_double2(0.0, 1.0);     // neutral step: the row stays as it is
                 }
             }
         } else {
-#pragma unroll
-        for (int i = 0; i < RPL; ++i) {
-            const int t = gl + G * i;                   // read of this block
-            const int pos = rbase + t;
-            double2 e = make_double2(0.0, 1.0);         // neutral step: a filtered read leaves the row unchanged
-            if (!dead && pos < n_mine) {
-                int pl = 0;
-                const int bq = src[(size_t)(pl++) * DP_SB + t];
-                const int mq = cf.use_mq ? src[(size_t)(pl++) * DP_SB + t] : 0;
-                const int baq = cf.use_baq ? src[(size_t)(pl++) * DP_SB + t] : 0;
-                const int sq = cf.use_sq ? src[(size_t)(pl++) * DP_SB + t] : 0;
-                double jp;
-                if (dp_eval(cf, em, s_lut, g, pos, bq, mq, baq, sq, jp)) {
-                    double p, q;
-                    guard_pq(jp, p, q);
-                    const double rq = 1.0 / q;
-                    const double o = p * s * rq;
-                    e = make_double2(o, rq);
-                    qprod *= q;
-                    // between two rescalings (32 reads) a cell may grow by (1 + o)^32 and the absorbing state by (1/q)^32
-                    bad |= (o > 1048576.0 || rq > 1048576.0);
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                const int t = gl + G * i;                   // read of this superblock
+                const int pos = rbase + t;
+                double2 e = make_double2(0.0, 1.0);
+                if (!dead && pos < n_mine) {
+                    int pl = 0;
+                    const int bq = src[(size_t)(pl++) * DP_STAGE_ROWS + t];
+                    const int mq = cf.use_mq ? src[(size_t)(pl++) * DP_STAGE_ROWS + t] : 0;
+                    const int baq = cf.use_baq ? src[(size_t)(pl++) * DP_STAGE_ROWS + t] : 0;
+                    const int sq = cf.use_sq ? src[(size_t)(pl++) * DP_STAGE_ROWS + t] : 0;
+                    double jp;
+                    if (dp_eval(cf, em, s_lut, g, pos, bq, mq, baq, sq, jp)) {
+                        double p, q;
+                        guard_pq(jp, p, q);
+                        const double rq = 1.0 / q;
+                        const double o = p * s * rq;
+                        e = make_double2(o, rq);
+                        qprod *= q;
+                        bad |= (o > 1048576.0 || rq > 1048576.0);
+                    }
                 }
+                prow[t] = e;
             }
-            sm.u.par[grp][t] = e;
         }
-        }
+#ifdef LFB_DP_PROF
+        pf_e += clock64() - pf_b;
+#endif
         if (qprod < 1e-200) {
             lq_acc += log(qprod);
             qprod = 1.0;
@@ -629,9 +647,12 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
             __syncwarp();
             if (fb) {
 #pragma unroll
-                for (int i = 0; i < RPL; ++i) sm.u.par[grp][gl + G * i] = make_double2(0.0, 1.0);
+                for (int i = 0; i < 8; ++i) prow[gl + G * i] = make_double2(0.0, 1.0);
             }
         }
+        // The early exit below wants a lower bound of the sum of ln q over the reads seen; the sum up to the end of this
+        // superblock is one (every term is negative), and costs one reduction per superblock instead of one per block.
+        lq_sb = group_sum<G>(lq_acc + ln_lower(qprod));
         __syncwarp();
     };
 #ifdef LFB_DP_PROF
@@ -645,7 +666,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
 #ifdef LFB_DP_PROF
         pf_a = clock64();
 #endif
-        const double2 *pp = sm.u.par[grp];
+        const double2 *pp = prow + (n0 % SB);
         // software-pipelined: the parameters of read j+1 and the boundary cell for read j+1 (the top cell right
         // after its own update) are requested before the remaining R-1 cells of read j are updated
         double2 c_next = pp[0];
@@ -654,7 +675,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         for (int j = 0; j < 32; ++j) {
             const double2 cc = c_next;
             const double in = gl == 0 ? 0.0 : in_next;
-            c_next = pp[(j + 1) & 31];
+            c_next = pp[j + 1];                          // (entry SB of the row is padding)
             const double top = E[R - 1];
             T = fma(top, cc.x, T * cc.y);
             E[R - 1] = fma(E[R - 2], cc.x, top);
@@ -683,16 +704,17 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         // Early exit (the reference's, snpcaller.c:916-958): the tail over the reads seen so far can only grow, so once a
         // lower bound of ln P(X >= K among them) = ln T + e2 ln 2 + sum ln q - K ln s passes ln(sig / bonf) the column is
         // insignificant whatever follows.  Lower bounds of the logarithms from the bits of T and of the q products.
-        const double lq_lb = group_sum<G>(lq_acc + ln_lower(qprod));
-        const bool over = lane == last && T > 1e-300 && ln_lower(T) + (double)e2 * LN2 + lq_lb > thr_ln;
+        const bool over = lane == last && T > 1e-300 && ln_lower(T) + (double)e2 * LN2 + lq_sb > thr_ln;
         const bool over_g = __shfl_sync(FULL, (int)over, last) != 0;     // every lane takes part, dead or not
         dead = dead || over_g;
-        __syncwarp();                                  // sm.par is rewritten now
 #ifdef LFB_DP_PROF
         pf_chk += clock64() - pf_a; pf_a = clock64();
 #endif
         if (__all_sync(FULL, dead || n0 + 32 >= n_mine)) break;      // nothing left to decide in this warp
-        make_params((n0 >> 5) + 1);
+        if (((n0 + 32) % SB) == 0) {
+            __syncwarp();                              // sm.par is rewritten now
+            make_params((n0 + 32) / SB);
+        }
 #ifdef LFB_DP_PROF
         pf_par += clock64() - pf_a;
 #endif
@@ -807,9 +829,9 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
     }
     __syncwarp();
 #ifdef LFB_DP_PROF
-    if (lane == 0 && (blockIdx.x % 97) == 0)
-        printf("dp_task G=%d R=%d blk %d nmax %d: setup %lld pre %lld tilt %lld main %lld (par %lld loop %lld chk %lld) tails %lld total %lld start %lld\n", G, R, blockIdx.x, nmax,
-               pf_setup - pf_t0, pf_pre - pf_setup, pf_tilt - pf_pre, pf_main - pf_tilt, pf_par, pf_loop, pf_chk, (long long)clock64() - pf_main, (long long)clock64() - pf_t0, pf_t0);
+    if (lane == 0 && (blockIdx.x % 5) == 0)
+        printf("dp_task G=%d R=%d blk %d nmax %d: setup %lld pre %lld tilt %lld main %lld (par %lld loop %lld chk %lld) tails %lld total %lld start %lld parwait %lld pareval %lld\n", G, R, blockIdx.x, nmax,
+               pf_setup - pf_t0, pf_pre - pf_setup, pf_tilt - pf_pre, pf_main - pf_tilt, pf_par, pf_loop, pf_chk, (long long)clock64() - pf_main, (long long)clock64() - pf_t0, pf_t0, pf_w, pf_e);
 #endif
 }
 
