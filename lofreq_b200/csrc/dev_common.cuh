@@ -102,6 +102,18 @@ __device__ __forceinline__ EvalMode eval_mode(const DevConf &cf)
     return em;
 }
 
+// the general read (alt-specific filters and overrides); k_dp keeps it out of line (LFB_EVAL_INLINE, dp_fused.cu)
+#ifndef LFB_EVAL_INLINE
+#define LFB_EVAL_INLINE __forceinline__
+#endif
+static __device__ LFB_EVAL_INLINE bool eval_read_general(const DevConf &cf, const double *s_lut, const Geom &g, int pos, int bq, int mq, int baq, int sq,
+                                                      double &jp)
+{
+    bool is_alt;
+    int slot;
+    return eval_read<true>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp);
+}
+
 __device__ __forceinline__ bool dp_eval(const DevConf &cf, const EvalMode &em, const double *s_lut, const Geom &g, int pos, int bq, int mq,
                                         int baq, int sq, double &jp)
 {
@@ -117,9 +129,7 @@ __device__ __forceinline__ bool dp_eval(const DevConf &cf, const EvalMode &em, c
         jp = merge4(cf.use_sq ? s_lut[512 + sq] : 0.0, cf.use_mq ? s_lut[256 + mq] : 0.0, cf.use_baq ? s_lut[512 + baq] : 0.0, bp);
         return true;
     }
-    bool is_alt;
-    int slot;
-    return eval_read<true>(cf, s_lut, g, pos, bq, mq, baq, sq, is_alt, slot, jp);
+    return eval_read_general(cf, s_lut, g, pos, bq, mq, baq, sq, jp);
 }
 
 __device__ __forceinline__ void load_lut(double *s_lut, const Lut *lut)

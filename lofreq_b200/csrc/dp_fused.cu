@@ -31,11 +31,18 @@
 #include <stdint.h>
 #include <math.h>
 #include <stdlib.h>
+#define LFB_EVAL_INLINE __noinline__      // one copy of the general read evaluation per kernel: see dlog below
 #include "internal.h"
 #include "dev_common.cuh"
 #include "screen_common.cuh"
 
 namespace lfb {
+
+// One copy of the logarithm and the exponential for everything outside the recurrence: k_dp is four (G, R) instances of a long
+// task, and a warp runs most of a task's code once — what it executes is bounded by instruction fetch, so the code the
+// instances can share is kept out of line.
+static __device__ __noinline__ double dlog(double x) { return log(x); }
+static __device__ __noinline__ double dexp(double x) { return exp(x); }
 
 template <int G>
 __device__ __forceinline__ double group_sum(double v)
@@ -56,10 +63,13 @@ __device__ __forceinline__ int group_sum_i(int v)
 template <int G>
 __device__ __forceinline__ int group_max_i(int v)
 {
-    if (G == 32) return __reduce_max_sync(FULL, v);
+    if constexpr (G == 32) {
+        return __reduce_max_sync(FULL, v);
+    } else {
 #pragma unroll
-    for (int m = G / 2; m >= 1; m >>= 1) v = max(v, __shfl_xor_sync(FULL, v, m));
-    return v;
+        for (int m = G / 2; m >= 1; m >>= 1) v = max(v, __shfl_xor_sync(FULL, v, m));
+        return v;
+    }
 }
 
 template <int G>
@@ -260,12 +270,12 @@ __device__ __forceinline__ double group_tilt(const ColHist &h, bool need, int K,
     const double kt = fmin((double)K, (double)N - 0.5);
     const double s0 = kt * fmax((double)N - lam, 1e-300) / (fmax(lam, 1e-300) * fmax((double)N - kt, 0.5));
     double lo = 0.0, hi = 60.0;
-    double ls = fmin(log(fmax(s0, 1.0)), hi);
+    double ls = fmin(dlog(fmax(s0, 1.0)), hi);
     bool conv = !need;
 #pragma unroll 1
     for (int it = 0; it < 40; ++it) {
         if (__all_sync(FULL, conv)) break;
-        const float sf = (float)exp(ls);
+        const float sf = (float)dexp(ls);
         float gs = 0.f, ds = 0.f;
         if (!conv) {
 #pragma unroll 1
@@ -365,7 +375,6 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
                         unsigned char *stage_bytes, int planes, const int *list, unsigned j0, unsigned nj)
 {
     constexpr int NCOL = 32 / G;
-    constexpr int RPL = 32 / G;                         // reads per lane and block of 32 reads
     const int lane = lane_id(), grp = lane / G, gl = lane % G;
 #ifdef LFB_DP_PROF
     long long pf_t0 = clock64(), pf_par = 0, pf_loop = 0, pf_chk = 0, pf_a, pf_setup, pf_pre, pf_tilt, pf_main, pf_w = 0, pf_e = 0, pf_b;
@@ -528,10 +537,10 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
     pf_pre = clock64();
 #endif
     // Chernoff exponent of the tail: beyond ~300 nats the untilted cells of interest drift out of fp64 range
-    const double cher = (have && (double)K > lam) ? ((double)K * log((double)K / fmax(lam, 1e-300)) - (double)K + lam) : 0.0;
+    const double cher = (have && (double)K > lam) ? ((double)K * dlog((double)K / fmax(lam, 1e-300)) - (double)K + lam) : 0.0;
     const double ln_s = group_tilt<G>(hist, have && cher > 300.0, K, N, lam, scale);
     __syncwarp();                                       // the histograms give way to the step parameters
-    const double s = (ln_s == 0.0) ? 1.0 : exp(ln_s);
+    const double s = (ln_s == 0.0) ? 1.0 : dexp(ln_s);
 
 #ifdef LFB_DP_PROF
     pf_tilt = clock64();
@@ -542,7 +551,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
 #pragma unroll
     for (int r = 0; r < R; ++r) E[r] = (have && k0 + r == 0) ? 1.0 : 0.0;
     int e2 = 0;
-    const double thr_ln = log(cf.sig * (1.0 + 1e-9) / (double)bonf) + (double)K * ln_s;
+    const double thr_ln = dlog(cf.sig * (1.0 + 1e-9) / (double)bonf) + (double)K * ln_s;
     bool dead = !have, fb = false;
     double lq_acc = 0.0, qprod = 1.0;                   // ln of the product of q over this lane's reads = lq_acc + ln(qprod)
     double lq_sb = 0.0;                                 // lower bound of the column's sum of ln q up to the end of the current superblock
@@ -636,7 +645,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         pf_e += clock64() - pf_b;
 #endif
         if (qprod < 1e-200) {
-            lq_acc += log(qprod);
+            lq_acc += dlog(qprod);
             qprod = 1.0;
         }
         if (__any_sync(FULL, bad)) {
@@ -729,7 +738,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         mbar_inval(&sm.bar[0]);
         mbar_inval(&sm.bar[1]);
     }
-    const double sum_lq = group_sum<G>(lq_acc + log(qprod));
+    const double sum_lq = group_sum<G>(lq_acc + dlog(qprod));
 
     // ---- 4. tails
     int hiE = 0;
@@ -744,12 +753,12 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
     const bool ruled_out = dead && !fb;                 // early exit fired: insignificant for good
     if (!ruled_out && ((gap > 580 && ln_s == 0.0) || gap > 900)) fb = true;     // needs the tilt after all / out of range
     const double base = (double)e2 * LN2 + sum_lq;
-    const double lnT = log(Tl) + base - (double)K * ln_s;
-    const double lnKm1 = log(topl) + base - (double)(K - 1) * ln_s;
+    const double lnT = dlog(Tl) + base - (double)K * ln_s;
+    const double lnKm1 = dlog(topl) + base - (double)(K - 1) * ln_s;
     bool site = have && !fb && !dead;
-    if (site && lnT > -700.0 && exp(lnT) * (double)bonf > cf.sig * (1.0 + 1e-9)) site = false;   // snpcaller.c:1155
+    if (site && lnT > -700.0 && dexp(lnT) * (double)bonf > cf.sig * (1.0 + 1e-9)) site = false;   // snpcaller.c:1155
     double lnp0 = 0.0, lnp1 = 0.0, lnp2 = 0.0;
-    const double invs = (ln_s == 0.0) ? 1.0 : exp(-ln_s);
+    const double invs = (ln_s == 0.0) ? 1.0 : dexp(-ln_s);
     bool sweep_for[3] = {false, false, false};
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -763,7 +772,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         int hc = 0x7fffffff;
         if (mine) {
             const int kk = max(k0, ci);
-            double f = (ln_s == 0.0) ? 1.0 : exp(-(double)(kk - ci) * ln_s);
+            double f = (ln_s == 0.0) ? 1.0 : dexp(-(double)(kk - ci) * ln_s);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (k0 + r >= ci) {
@@ -772,7 +781,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
                 }
                 if (k0 + r == ci) hc = __double2hiint(E[r]);
             }
-            if (lane == last) acc = fma(T, (ln_s == 0.0) ? 1.0 : exp(-(double)(K - ci) * ln_s), acc);
+            if (lane == last) acc = fma(T, (ln_s == 0.0) ? 1.0 : dexp(-(double)(K - ci) * ln_s), acc);
         }
         acc = group_sum<G>(acc);
         hc = group_min_i<G>(hc);
@@ -783,7 +792,7 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
             if ((hc >> 20) < 64 || peak - (hc >> 20) > 850) {
                 if (ci <= KSM) sweep_for[i] = true; else fb = true;
             }
-            out = log(acc) + base - (double)ci * ln_s;
+            out = dlog(acc) + base - (double)ci * ln_s;
         }
     }
     // Alleles with a count of at most KSM (a few sequencing errors beside the variant) that could not be read off the
@@ -797,9 +806,9 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         for (int i = 0; i < 3; ++i) if (sweep_for[i]) maxc = max(maxc, cnt[i]);
         if (__reduce_max_sync(FULL, want_small ? maxc : 0) <= 8) small_tails_sweep<G, 8>(cf, b, em, s_lut, g, lead, want_small, cnt[0], cnt[1], cnt[2], t3);
         else small_tails_sweep<G, KSM>(cf, b, em, s_lut, g, lead, want_small, cnt[0], cnt[1], cnt[2], t3);
-        if (want_small && sweep_for[0]) lnp0 = log(t3[0]);
-        if (want_small && sweep_for[1]) lnp1 = log(t3[1]);
-        if (want_small && sweep_for[2]) lnp2 = log(t3[2]);
+        if (want_small && sweep_for[0]) lnp0 = dlog(t3[0]);
+        if (want_small && sweep_for[1]) lnp1 = dlog(t3[1]);
+        if (want_small && sweep_for[2]) lnp2 = dlog(t3[2]);
     }
     if (ruled_out) fb = false;
     if (fb) site = false;
