@@ -141,8 +141,86 @@ struct DevBuf {
     }
 };
 
+// The launches of a phase (screen: 4, test: ~20 with the fork / join events of the side streams) as one CUDA graph.  A
+// pipeline that sends batches of one shape through the same buffers (a resident batch timed again and again; a builder
+// that refills its planes) repeats the same launch sequence byte for byte: the second time in a row a sequence is seen it
+// is captured, from then on replayed with one cudaGraphLaunch — host time per batch is what limits 8 processes sharing
+// one box's cores.  Anything else (a new configuration, a running Bonferroni factor passed by value, grown buffers)
+// simply takes the plain launches.
+struct GraphCache {
+    std::vector<unsigned char> key, seen;
+    cudaGraphExec_t exec = nullptr;
+    bool disabled = false;
+    void release()
+    {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr;
+        key.clear();
+        seen.clear();
+    }
+};
+
+struct KeyBuilder {
+    std::vector<unsigned char> v;
+    template <class T> void add(const T &x)
+    {
+        const unsigned char *p = reinterpret_cast<const unsigned char *>(&x);
+        v.insert(v.end(), p, p + sizeof(T));
+    }
+};
+
+template <class F> static int run_graphed(GraphCache &gc, bool allowed, const std::vector<unsigned char> &key, cudaStream_t st, F &&enqueue)
+{
+    static const bool off = getenv("LFB200_NO_GRAPH") != nullptr;
+    if (off || !allowed || gc.disabled || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
+        enqueue();
+        return 0;
+    }
+    if (gc.exec && key == gc.key) {
+        if (cudaGraphLaunch(gc.exec, st) == cudaSuccess) return 0;
+        cudaGetLastError();
+        gc.disabled = true;
+        enqueue();
+        return 0;
+    }
+    if (key != gc.seen) {
+        gc.seen = key;
+        enqueue();
+        return 0;
+    }
+    // the same sequence twice in a row: capture it (nothing runs during the capture), then launch what was captured
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        gc.disabled = true;
+        enqueue();
+        return 0;
+    }
+    enqueue();
+    cudaError_t rc = cudaStreamEndCapture(st, &g);
+    cudaGraphExec_t ex = nullptr;
+    if (rc == cudaSuccess && g) rc = cudaGraphInstantiate(&ex, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (rc != cudaSuccess || !ex) {
+        cudaGetLastError();
+        gc.disabled = true;
+        enqueue();
+        return 0;
+    }
+    if (gc.exec) cudaGraphExecDestroy(gc.exec);
+    gc.exec = ex;
+    gc.key = key;
+    if (cudaGraphLaunch(gc.exec, st) != cudaSuccess) {
+        cudaGetLastError();
+        gc.disabled = true;
+        enqueue();
+    }
+    return 0;
+}
+
 struct lfb200_ctx {
     int device = 0;
+    GraphCache g_front, g_test;
     cudaStream_t stream = nullptr;       // used by the host entry points
     Lut *d_lut = nullptr;
     // workspace of the current batch
@@ -368,6 +446,8 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     if (ctx->h_cand) cudaFreeHost(ctx->h_cand);
     if (ctx->h_sites) cudaFreeHost(ctx->h_sites);
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    ctx->g_front.release();
+    ctx->g_test.release();
     launch_state_destroy(ctx->ls);
     ctx->pool.reset();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -536,6 +616,7 @@ extern "C" int lfb200_screen_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, 
     }
     CU(cudaSetDevice(ctx->device));
     DevConf dc;
+    memset(&dc, 0, sizeof(dc));
     if (make_devconf(conf, b, dc)) return 1;
     if (ensure_workspace(ctx, b->n_cols)) return 1;
     ctx->test_enqueued = false;
@@ -545,7 +626,12 @@ extern "C" int lfb200_screen_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, 
     cudaStream_t st = (cudaStream_t)stream;
     ctx->bonf_used_valid = false;
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
-    launch_front(ctx->ls, dc, ctx->cur, ctx->d_lut, ctx->ws, st);
+    {
+        KeyBuilder kb;
+        kb.add(dc); kb.add(ctx->cur); kb.add(ctx->ws); kb.add(ctx->d_lut); kb.add(st);
+        run_graphed(ctx->g_front, !ctx->profiling && ctx->cur.n_cols > 0, kb.v, st,
+                    [&]() { launch_front(ctx->ls, dc, ctx->cur, ctx->d_lut, ctx->ws, st); });
+    }
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
     if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
     CU(cudaGetLastError());
@@ -570,20 +656,31 @@ static int test_device_impl(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *st
     memset(&hb, 0, sizeof(hb));
     hb.mq = ctx->cur.mq; hb.baq = ctx->cur.baq; hb.sq = ctx->cur.sq;
     DevConf dc;
+    memset(&dc, 0, sizeof(dc));
     if (make_devconf(conf, &hb, dc)) return 1;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (ctx->profiling) cudaEventRecord(ctx->ev[3], st);
-    launch_test(ctx->ls, dc, ctx->cur, ctx->d_lut, ctx->ws, st, ctx->profiling ? ctx->ev[4] : nullptr, ctx->profiling ? ctx->ev[5] : nullptr,
-                bonf_start_dev);
     // the sites, decided on the device, in column order into pinned host memory; then the counters; then the event the
     // host waits for: nothing of this needs the host before lfb200_sites_*
     ctx->last_dc = dc;
     ctx->test_enqueued = false;
-    if (ctx->cur.n_cols > 0) {
-        if (ctx->ensure_sites(std::max<size_t>(65536, (size_t)ctx->cur.n_cols / 16))) return fail("out of pinned host memory");
-        launch_emit_sites(ctx->ls, dc, ctx->ws, ctx->d_sites, (unsigned)std::min<size_t>(ctx->h_sites_cap, 0xffffffffu), st);
-        CU(cudaMemcpyAsync(ctx->h_counters, ctx->ws.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    if (ctx->cur.n_cols > 0 && ctx->ensure_sites(std::max<size_t>(65536, (size_t)ctx->cur.n_cols / 16))) return fail("out of pinned host memory");
+    {
+        const unsigned site_cap = (unsigned)std::min<size_t>(ctx->h_sites_cap, 0xffffffffu);
+        KeyBuilder kb;
+        kb.add(dc); kb.add(ctx->cur); kb.add(ctx->ws); kb.add(ctx->d_lut); kb.add(st); kb.add(ctx->ls.side_mask); kb.add(bonf_start_dev);
+        kb.add(ctx->d_sites); kb.add(site_cap); kb.add(ctx->h_counters);
+        bool bad = false;
+        run_graphed(ctx->g_test, !ctx->profiling && ctx->cur.n_cols > 0, kb.v, st, [&]() {
+            launch_test(ctx->ls, dc, ctx->cur, ctx->d_lut, ctx->ws, st, ctx->profiling ? ctx->ev[4] : nullptr, ctx->profiling ? ctx->ev[5] : nullptr,
+                        bonf_start_dev);
+            if (ctx->cur.n_cols > 0) {
+                launch_emit_sites(ctx->ls, dc, ctx->ws, ctx->d_sites, site_cap, st);
+                if (cudaMemcpyAsync(ctx->h_counters, ctx->ws.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st) != cudaSuccess) bad = true;
+            }
+        });
+        if (bad) { cudaGetLastError(); return fail("could not queue the copy of the counters"); }
     }
     CU(cudaEventRecord(ctx->ev_done, st));
     ctx->test_enqueued = true;
