@@ -175,7 +175,7 @@ def measured_peaks():
 
 STREAM_KERNELS = ("k_front", "k_prune2")
 HEAVY_KERNELS = ("k_mid", "k_dp", "k_xl", "k_heavy")               # k_dp<0..2>, k_xl, k_heavy_all, k_heavy_xl
-KERNELS_PER_STEP = 12      # k_front, k_prune2, k_mid, k_xl, k_dp<0>, k_dp<1>, k_dp<2>, k_heavy_xl, k_heavy_all, k_scan_blocks, k_rank_cands, k_emit_sites
+KERNELS_PER_STEP = 13      # (N > 1: + the count exchange and k_set_start) k_front, k_scan_tiles, k_prune2, k_mid, k_xl, k_dp<0>, k_dp<1>, k_dp<2>, k_heavy_xl, k_heavy_all, k_scan_blocks, k_rank_cands, k_emit_sites
 
 
 def ncu_traffic(names, wl="C2"):
@@ -542,7 +542,7 @@ def run_ours(args):
                         "copy_mode": {"value": world * n / e2e_copy_s, "ms_per_step": e2e_copy_s * 1e3, "h2d_bytes_per_step": h2d,
                                       "h2d_mode": "host plane mode 0 (lfb200_set_host_planes): every plane is copied to the device "
                                                   "first; PCIe-bound (the round-1 headline)"}},
-                "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 else 0)) * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_launches": (KERNELS_PER_STEP + (2 if world > 1 else 0)) * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "wall_ms_per_step": wall * 1e3 / args.steps}
         emit(line)
     if world > 1:

@@ -339,7 +339,6 @@ __global__ void __launch_bounds__(128) k_prune2(const __grid_constant__ DevConf 
     // the exact factor this batch continues from: k_front used the caller's conf; region shards on other GPUs may have
     // added to it since (lfb200_comm_exchange leaves the sum in device memory, no host round trip)
     const long long start = bonf_start_dev ? *bonf_start_dev : cf.bonf_start;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && bonf_start_dev) ws.counters->bonf_start_used = start;
     const unsigned njobs = ws.counters->n_jobs[CLS_PRUNE2];
     if (njobs == 0) return;
     load_lut(s_lut, lut);
@@ -1377,31 +1376,46 @@ void launch_state_destroy(LaunchState &ls)
 
 __global__ void k_rank_cands(const Workspace ws);
 
+// the exact factor a shard's batch continues from (the shards before it have added to what k_front saw): every kernel of
+// the test phase reads it from the counters
+__global__ void k_set_start(const Workspace ws, const long long *bonf_start_dev) { ws.counters->bonf_start_used = *bonf_start_dev; }
+
 void launch_test(const LaunchState &ls, const DevConf &cf, const DevBatch &b, const Lut *lut, const Workspace &ws, cudaStream_t st,
                  cudaEvent_t after_finalize, cudaEvent_t after_heavy, const long long *bonf_start_dev)
 {
     if (b.n_cols <= 0) return;
     const int nb = (int)((b.n_cols + FIN_BLOCK - 1) / FIN_BLOCK);
-    // second stage of the prune with the exact factor (k_front, in the screen phase, did the first)
-    k_prune2<<<ls.sms * 2, 128, 0, st>>>(cf, b, lut, ws, bonf_start_dev);
-    if (after_finalize) cudaEventRecord(after_finalize, st);
-    // Independent work side by side, so that the warps of the small kernels share the SMs with k_dp<0>: k_mid (K <= 8
-    // survivors of the prune), k_dp<1>, k_dp<2> (256 < K <= 2048, their own register budgets), k_xl (K > 2048, one CTA
-    // per column); an empty list costs an early exit.  Then the per-column fallbacks for the few columns they hand back.
+    // Independent work side by side, so that the warps of the small kernels share the SMs with k_dp<0>: the second stage of
+    // the prune with the exact factor (k_front, in the screen phase, did the first) and k_mid for what survives it (K <= 8);
+    // k_dp<1>, k_dp<2> (256 < K <= 2048, their own register budgets), k_xl (K > 2048, one CTA per column); an empty list
+    // costs an early exit.  Then the per-column fallbacks for the few columns they hand back.  k_dp<0>, the longest, goes
+    // first on the launching stream: nothing it needs comes from the prune.
     // A kernel whose list was empty in the context's previous batch is simply queued behind k_dp<0> (side_mask): on data
     // without deep columns that saves the fork/join events — host time per batch is what limits 8 GPUs on one box.
     const unsigned m = ls.side_mask;
     cudaStream_t s_mid = (m & 1u) ? ls.side[0] : st, s_dp1 = (m & 2u) ? ls.side[1] : st, s_xl = (m & 4u) ? ls.side[2] : st,
                  s_dp2 = (m & 8u) ? ls.side[3] : st;
+    const bool timed = after_finalize != nullptr;       // per-phase timing (lfb200_set_profiling): the prune alone, first
+    if (bonf_start_dev) k_set_start<<<1, 1, 0, st>>>(ws, bonf_start_dev);
+    if (timed) {
+        k_prune2<<<ls.sms * 2, 128, 0, st>>>(cf, b, lut, ws, bonf_start_dev);
+        cudaEventRecord(after_finalize, st);
+    }
     if (m) {
         cudaEventRecord(ls.ev_fork, st);
         for (int i = 0; i < 4; ++i)
             if (m & (1u << i)) cudaStreamWaitEvent(ls.side[i], ls.ev_fork, 0);
     }
-    if (m & 1u) k_mid<<<ls.sms * 4, 128, 0, s_mid>>>(cf, b, lut, ws);
+    if (m & 1u) {
+        if (!timed) k_prune2<<<ls.sms * 2, 128, 0, s_mid>>>(cf, b, lut, ws, bonf_start_dev);
+        k_mid<<<ls.sms * 4, 128, 0, s_mid>>>(cf, b, lut, ws);
+    }
     if (m & 4u) launch_xl(ls, cf, b, lut, ws, s_xl);
     launch_dp(ls, cf, b, lut, ws, st, s_dp1, s_dp2);
-    if (!(m & 1u)) k_mid<<<ls.sms * 4, 128, 0, st>>>(cf, b, lut, ws);
+    if (!(m & 1u)) {
+        if (!timed) k_prune2<<<ls.sms * 2, 128, 0, st>>>(cf, b, lut, ws, bonf_start_dev);
+        k_mid<<<ls.sms * 4, 128, 0, st>>>(cf, b, lut, ws);
+    }
     if (!(m & 4u)) launch_xl(ls, cf, b, lut, ws, st);
     for (int i = 0; i < 4; ++i)
         if (m & (1u << i)) {
