@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 KREG='^k_(front|scan_tiles|prune2|mid|dp|xl|heavy_xl|heavy_all|scan_blocks|rank_cands|emit_sites)'
 for wl in ${1:-C2 C3 C5}; do
   timeout 900 python bench.py --workload $wl --steps ${STEPS:-200} --cpu-sample ${CPUS:-20000} > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err; echo "$wl bench rc=$?"
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$KREG" -s 26 -c 13 -f -o /tmp/prof_step_$wl python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full_$wl.log 2>&1
+  LFB200_NO_GRAPH=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$KREG" -s 26 -c 13 -f -o /tmp/prof_step_$wl python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full_$wl.log 2>&1
   echo "$wl ncu rc=$?"
   python tools/ncu_extract.py /tmp/prof_step_$wl.ncu-rep gpurun_out/r2_step_kernels_$wl.json > gpurun_out/r2_step_kernels_$wl.txt 2>&1
   for k in k_dp k_front k_prune2 k_xl; do python tools/ncu_lines.py /tmp/prof_step_$wl.ncu-rep $k 25 > gpurun_out/r2_lines_${wl}_$k.txt 2>&1; done

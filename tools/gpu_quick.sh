@@ -16,7 +16,7 @@ print('e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'copy_mode', d['e2e']['
 PY
 tail -3 gpurun_out/bench_quick.err
 if [ -n "${NCU:-}" ]; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_bench.log 2>&1
+  LFB200_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_bench.log 2>&1
   echo "launch list rc=$?"
   python tools/launch_summary.py gpurun_out/launches.csv | tail -25
 fi

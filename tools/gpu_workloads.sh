@@ -15,7 +15,7 @@ except Exception as e:
 PY
   tail -2 gpurun_out/bench_$tag.err
   if [ -n "${NCU:-}" ]; then
-    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --workload $wl $extra --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_$tag.log 2>&1
+    LFB200_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --workload $wl $extra --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_$tag.log 2>&1
     python tools/launch_summary.py gpurun_out/launches_$tag.csv 2>/dev/null | head -16
   fi
 done
