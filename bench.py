@@ -366,7 +366,22 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     run_steps(max(args.warmup, 3))
-    run_steps(20)                      # (untimed) keeps the GPU under load until the sampler has lines
+
+    def agree(flag):
+        """the same answer on every rank (the batches of a step are exchanged between the ranks: all run the same count)"""
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(int(t.item()))
+
+    def under_load_until(enough, limit_s):
+        """untimed steps that keep the GPU under the same load until the sampler has what `enough` asks for"""
+        t_end = time.perf_counter() + limit_s
+        while agree(sampler.proc is not None and not enough() and time.perf_counter() < t_end):
+            run_steps(20)
+
+    under_load_until(lambda: len(sampler.lines) >= 1, 5.0)      # nvidia-smi needs a while for its first line
     barrier()
     sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -379,6 +394,8 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - t0
     dev_ms = e0.elapsed_time(e1)
+    # a timed region shorter than the sampling period: the same load goes on (untimed) until the sampler has two lines of it
+    under_load_until(lambda: len(sampler.lines) - sampler.mark_at >= 2, 3.0)
     if os.environ.get("LFB200_HOST_TIMING"):
         print("host seconds in the launching thread (timed steps):", host_t, "wall of timed steps", wall, file=sys.stderr)
     clocks = sampler.stop()

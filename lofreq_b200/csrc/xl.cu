@@ -34,6 +34,8 @@ struct XlEdge {
     int pad;
 };
 
+constexpr int XL_SORT_MAX = 512;
+
 struct XlSm {
     double lut[768];
     double2 par[XLW][32];
@@ -49,6 +51,10 @@ struct XlSm {
     int med_hist[256];
     double bcast[4];
     unsigned job;
+    // longest-first order of the job list (a few hundred columns of very different cost on 148 CTAs: taken in arrival order
+    // the last CTA to start a deep column decides the kernel's duration)
+    float cost[XL_SORT_MAX];
+    unsigned short order[XL_SORT_MAX];
 };
 
 __device__ __forceinline__ double xl_block_sum(double v, XlSm &sh)
@@ -332,13 +338,33 @@ __global__ void __launch_bounds__(XLT, 1) k_xl(const __grid_constant__ DevConf c
     load_lut(sh.lut, lut);
     const int *jobs = ws.jobs + (long long)CLS_XL * ws.cap_cols;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // every CTA works out the same longest-first order (cost ~ reads x cells); a long list balances by itself
+    const bool sorted = njobs <= XL_SORT_MAX;
+    if (sorted) {
+        for (unsigned j = tid; j < njobs; j += XLT) {
+            const long long c = jobs[j];
+            const int4 nt = __ldg(reinterpret_cast<const int4 *>(b.nt_cnt) + c);
+            const int k = max(ws.cnt6[6 * c], max(ws.cnt6[6 * c + 1], ws.cnt6[6 * c + 2]));
+            sh.cost[j] = (float)(nt.x + nt.y + nt.z + nt.w) * (float)k;
+        }
+        __syncthreads();
+        for (unsigned j = tid; j < njobs; j += XLT) {
+            const float mine = sh.cost[j];
+            unsigned r = 0;
+            for (unsigned i = 0; i < njobs; ++i) {
+                const float o = sh.cost[i];
+                r += (o > mine || (o == mine && i < j)) ? 1u : 0u;
+            }
+            sh.order[r] = (unsigned short)j;
+        }
+    }
     for (;;) {
         __syncthreads();
         if (tid == 0) sh.job = atomicAdd(&ws.counters->next_job[CLS_XL], 1u);
         __syncthreads();
         const unsigned j = sh.job;
         if (j >= njobs) break;
-        const long long c = jobs[j];
+        const long long c = jobs[sorted ? sh.order[j] : j];
         Geom g;
         int cov;
         load_geom(b, c, g, cov);
