@@ -177,22 +177,17 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
 
         // ---- routing and the first stage of the prune ----
         const int K = max(cnt[0], max(cnt[1], cnt[2]));
+        // K > KS: a slot in a job list of k_dp / k_xl.  The slot is requested here and used after the prune walk below, which
+        // hides the round trip of the atomic.
+        unsigned slot_a = 0;
+        int li = -1;
         if (t && K > KS) {
             if (K <= DP_MAXK) {
-                // 8 < K <= 2048: k_dp, several columns per warp; job list by (class, depth bin), the class's unbinned list
-                // when the binned one is full
-                const int li = dp_list(K, mg.n);
-                const int cls = li / DP_NBIN1;
-                const unsigned slot = atomicAdd(&ws.counters->n_pjobs[li], 1u);
-                if (slot < (unsigned)ws.pcap) {
-                    ws.pjobs[((long long)cls * DP_NBIN + (li % DP_NBIN1)) * ws.pcap + slot] = (int)c;
-                } else {
-                    const unsigned s2 = atomicAdd(&ws.counters->n_pjobs[cls * DP_NBIN1 + DP_NBIN], 1u);
-                    ws.ujobs[(long long)cls * ws.cap_cols + s2] = (int)c;
-                }
+                // 8 < K <= 2048: k_dp, several columns per warp; job list by (class, depth bin)
+                li = dp_list(K, mg.n);
+                slot_a = atomicAdd(&ws.counters->n_pjobs[li], 1u);
             } else {
-                const unsigned slot = atomicAdd(&ws.counters->n_jobs[CLS_XL], 1u);      // one CTA per column
-                ws.jobs[(long long)CLS_XL * ws.cap_cols + slot] = (int)c;
+                slot_a = atomicAdd(&ws.counters->n_jobs[CLS_XL], 1u);      // one CTA per column
             }
         }
         // K <= KS: with the Bonferroni factors of a real run the early exit fires after a handful of reads (K = 1: one;
@@ -217,6 +212,20 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
             // every small column joins k_mid's job list: full evaluation, whole warp
             const unsigned slot = atomicAdd(&ws.counters->n_jobs[0], 1u);
             ws.jobs[slot] = (int)c;
+        }
+        if (t && K > KS) {
+            if (li >= 0) {
+                // the class's unbinned list when the binned one is full
+                const int cls = li / DP_NBIN1;
+                if (slot_a < (unsigned)ws.pcap) {
+                    ws.pjobs[((long long)cls * DP_NBIN + (li % DP_NBIN1)) * ws.pcap + slot_a] = (int)c;
+                } else {
+                    const unsigned s2 = atomicAdd(&ws.counters->n_pjobs[cls * DP_NBIN1 + DP_NBIN], 1u);
+                    ws.ujobs[(long long)cls * ws.cap_cols + s2] = (int)c;
+                }
+            } else {
+                ws.jobs[(long long)CLS_XL * ws.cap_cols + slot_a] = (int)c;
+            }
         }
     }
 }
