@@ -162,7 +162,8 @@ int lfb200_set_host_planes(lfb200_ctx *ctx, int mode);
  * stream is a cudaStream_t (or NULL).
  *   screen : gates (lofreq_call.c:747,754,892,931), alt counts and raw counts
  *            from the reads showing a non-reference base, tested flags and the
- *            number of tested columns per tile
+ *            place of every tested column in the running count, and the first
+ *            stage of the early exit under a lower bound of the factor
  *   ntested: number of tested columns found by screen (synchronises)
  *   test   : running Bonferroni from conf->bonf_subst (or from device memory),
  *            the reference's early exit lane-per-column, the O(depth*K) kernels for
@@ -172,7 +173,12 @@ int lfb200_set_host_planes(lfb200_ctx *ctx, int mode);
  *   sites  : wait for the test, re-decide the few guard-band sites in long
  *            double, fill the long double p-values when asked for (synchronises)
  * One batch per context at a time: screen fails while a lfb200_sites_begin
- * request is pending on the same context. */
+ * request is pending on the same context.
+ * When a phase is queued with the same arguments, buffers and stream as the
+ * time before (a resident batch timed repeatedly, a builder refilling its
+ * planes), its launches are captured once and replayed as a CUDA graph; this
+ * needs a stream other than the legacy default stream and can be switched off
+ * with LFB200_NO_GRAPH=1 in the environment.  Results do not depend on it. */
 int lfb200_screen_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, const lfb200_batch_t *dev_batch, void *stream);
 int lfb200_ntested_device(lfb200_ctx *ctx, void *stream, long long *n_tested);
 int lfb200_test_device(lfb200_ctx *ctx, const lfb200_conf_t *conf, void *stream);
