@@ -241,6 +241,8 @@ int lfb200_copy_counts_device(lfb200_ctx *ctx, void *stream, int *dst_dev);
  * out[0] k_dp (8 < K <= 2048, several columns per warp), out[1] the per-column fallback k_heavy_all (columns k_dp or
  * k_mid handed back), out[2] k_heavy_xl (K > 2048, one CTA per column), out[3] k_mid (K <= 8 survivors of the prune) */
 int lfb200_last_job_counts(lfb200_ctx *ctx, long long out[4]);
+/* how many phases of this context were queued by replaying a captured CUDA graph so far (diagnostics) */
+long long lfb200_graph_replays(lfb200_ctx *ctx);
 /* measured DFMA/s of this GPU (8 independent chains per thread, ~20 ms): the fp64-pipe roofline denominator */
 double lfb200_dfma_peak(lfb200_ctx *ctx, void *stream);
 /* device pointers of the per-column results of the last screen/test (valid

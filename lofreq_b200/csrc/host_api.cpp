@@ -151,6 +151,7 @@ struct GraphCache {
     std::vector<unsigned char> key, seen;
     cudaGraphExec_t exec = nullptr;
     bool disabled = false;
+    long long replays = 0;
     void release()
     {
         if (exec) cudaGraphExecDestroy(exec);
@@ -177,7 +178,7 @@ template <class F> static int run_graphed(GraphCache &gc, bool allowed, const st
         return 0;
     }
     if (gc.exec && key == gc.key) {
-        if (cudaGraphLaunch(gc.exec, st) == cudaSuccess) return 0;
+        if (cudaGraphLaunch(gc.exec, st) == cudaSuccess) { ++gc.replays; return 0; }
         cudaGetLastError();
         gc.disabled = true;
         enqueue();
@@ -214,6 +215,8 @@ template <class F> static int run_graphed(GraphCache &gc, bool allowed, const st
         cudaGetLastError();
         gc.disabled = true;
         enqueue();
+    } else {
+        ++gc.replays;
     }
     return 0;
 }
@@ -988,6 +991,8 @@ extern "C" int lfb200_copy_counts_device(lfb200_ctx *ctx, void *stream, int *dst
         CU(cudaMemcpyAsync(dst_dev, ctx->ws.cnt6, (size_t)ctx->cur.n_cols * 6 * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
+
+extern "C" long long lfb200_graph_replays(lfb200_ctx *ctx) { return ctx ? ctx->g_front.replays + ctx->g_test.replays : 0; }
 
 extern "C" int lfb200_last_job_counts(lfb200_ctx *ctx, long long out[4])
 {

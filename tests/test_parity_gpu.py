@@ -296,6 +296,47 @@ def test_full_size_c2_properties(caller, port_oracle):
     assert 0.005 * n < sm.n_sites < 0.02 * n
 
 
+def test_graph_replay_gives_the_same_sites():
+    """The launches of a phase are replayed as a CUDA graph once the same sequence has been queued twice in a row
+    (host_api.cpp: run_graphed).  The same resident batch through plain launches (legacy stream: never captured), through
+    the capture and through replays; a different configuration in between must not be served from the cache."""
+    import torch
+    import lofreq_b200
+    from lofreq_b200 import synth, capi
+    c = lofreq_b200.Caller()
+    n = 60_000
+    t = synth.generate_device("C2", 0, n)
+    db = c.device_batch(t)
+
+    def run(stream, **over):
+        cf = lofreq_b200.varcall_conf(**over)
+        c.screen(db, cf, stream)
+        c.test(cf, stream)
+        sites, sm = c.sites(cf, n, stream)
+        return sites.copy(), int(sm.n_sites), int(sm.n_tested), int(cf.bonf_subst)
+
+    want = run(None)
+    want_strict = run(None, sig=1e-4)
+    assert want_strict[1] <= want[1]
+    st = torch.cuda.Stream()
+    sp = st.cuda_stream
+    before = c.lib.lfb200_graph_replays(c._ctx)
+    for i in range(5):
+        got = run(sp)
+        assert got[1:] == want[1:], (i, got[1:], want[1:])
+        for f in ("col", "bonf", "lnp", "qual", "called", "status", "alt_count"):
+            assert np.array_equal(got[0][f], want[0][f]), (i, f)
+    assert c.lib.lfb200_graph_replays(c._ctx) - before >= 6          # both phases, from the second repeat on
+    got = run(sp, sig=1e-4)                                          # another configuration: plain launches again
+    assert got[1:] == want_strict[1:]
+    for f in ("col", "bonf", "lnp", "qual", "called"):
+        assert np.array_equal(got[0][f], want_strict[0][f]), f
+    got = run(sp)
+    assert got[1:] == want[1:] and np.array_equal(got[0]["lnp"], want[0]["lnp"])
+    torch.cuda.synchronize()
+    c.close()
+
+
 def _slice_out(d, lo, hi):
     return {k: (v[lo:hi] if isinstance(v, np.ndarray) else v) for k, v in d.items()}
 
