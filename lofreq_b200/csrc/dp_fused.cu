@@ -615,6 +615,40 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
                     prow[t] = ok ? make_double2(o, rq) : make_double2(0.0, 1.0);     // neutral step: the row stays as it is
                 }
             }
+        } else if (em.uniform) {
+            // the same with alignment and / or source qualities merged in (the reference's default carries BAQ): 1 / q is the
+            // product of up to four table entries, the merged probability keeps the reference's association order
+            const int o_baq = (cf.use_mq ? 2 : 1) * DP_STAGE_ROWS, o_sq = o_baq + (cf.use_baq ? DP_STAGE_ROWS : 0);
+#pragma unroll
+            for (int i0 = 0; i0 < 8; i0 += 2) {
+                int bqv[2], mqv[2], baqv[2], sqv[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int t = gl + G * (i0 + u);
+                    bqv[u] = src[t];
+                    mqv[u] = cf.use_mq ? src[DP_STAGE_ROWS + t] : 255;
+                    baqv[u] = cf.use_baq ? src[o_baq + t] : 255;
+                    sqv[u] = cf.use_sq ? src[o_sq + t] : 255;
+                }
+                double jpv[2], rqv[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    jpv[u] = merge4(s_lut[512 + sqv[u]], s_lut[256 + mqv[u]], s_lut[512 + baqv[u]], s_lut[bqv[u]]);
+                    rqv[u] = (__ldg(&lut->rbq[bqv[u]]) * __ldg(&lut->rmq[mqv[u]])) * (__ldg(&lut->raq[baqv[u]]) * __ldg(&lut->raq[sqv[u]]));
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int t = gl + G * (i0 + u);
+                    const bool ok = !dead && rbase + t < n_mine && bqv[u] >= cf.min_bq;
+                    double p, q;
+                    guard_pq(jpv[u], p, q);
+                    const double rq = rqv[u];
+                    const double o = p * s * rq;
+                    bad |= ok && !(o <= 1048576.0 && rq <= 1048576.0);
+                    qprod *= ok ? q : 1.0;
+                    prow[t] = ok ? make_double2(o, rq) : make_double2(0.0, 1.0);
+                }
+            }
         } else {
 #pragma unroll 1
             for (int i = 0; i < 8; ++i) {

@@ -311,6 +311,7 @@ static void build_lut(Lut &l)
     for (int q = 0; q < 256; ++q) {
         l.rbq[q] = 1.0 / (1.0 - l.bq[q]);
         l.rmq[q] = 1.0 / (1.0 - l.mq[q]);
+        l.raq[q] = 1.0 / (1.0 - l.aq[q]);
     }
 }
 

@@ -58,11 +58,12 @@ struct Lut {
     double bq[256];                // plain phred
     double mq[256];                // [0] = 0.5 (MQ0_ERRPROB, snpcaller.c:64), [255] = 0 (unknown -> -1 -> prob 0)
     double aq[256];                // baq / sq: [255] = 0 (-1: not available)
-    // 1 / (1 - bq[i]) and 1 / (1 - mq[i]) (inf where the probability is 1): 1 / (1 - merged probability) of a (bq, mq) pair
+    // 1 / (1 - bq[i]), 1 / (1 - mq[i]) and 1 / (1 - aq[i]) (inf where the probability is 1): 1 / (1 - merged probability) of a (bq, mq) pair
     // is their product — the step parameters of k_dp without a division (read from global memory: not part of the 768
     // doubles the kernels stage in shared memory)
     double rbq[256];
     double rmq[256];
+    double raq[256];
 };
 
 // a column (or a stand-alone snpcaller problem) the device could not rule out

@@ -200,7 +200,7 @@ __device__ XlOut xl_run(const DevConf &cf, const DevBatch &b, const Geom &g, int
                 if (w > 0 && lane == 0) edge_next = ein->v[(j + 1) & 31];
                 const double top = E[R - 1];
                 if (!is_last && lane == 31) eout->v[j] = top;
-                T = fma(top, cc.x, T * cc.y);
+                if (is_last) T = fma(top, cc.x, T * cc.y);        // warp-uniform: only the last warp owns the absorbing state
                 E[R - 1] = fma(E[R - 2], cc.x, top);
                 in_next = __shfl_up_sync(FULL, E[R - 1], 1);
 #pragma unroll
