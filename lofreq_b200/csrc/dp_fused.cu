@@ -713,16 +713,19 @@ __device__ void dp_task(const DevConf &cf, const DevBatch &b, const Workspace &w
         // software-pipelined: the parameters of read j+1 and the boundary cell for read j+1 (the top cell right
         // after its own update) are requested before the remaining R-1 cells of read j are updated
         double2 c_next = pp[0];
-        double in_next = __shfl_up_sync(FULL, E[R - 1], 1);
+        // the boundary cell travels as two 32-bit halves; the first lane of a column takes zeros instead (selected on the
+        // halves, so that the pair the DFMA reads is formed by the selects themselves)
+        int in_hi = __shfl_up_sync(FULL, __double2hiint(E[R - 1]), 1), in_lo = __shfl_up_sync(FULL, __double2loint(E[R - 1]), 1);
 #pragma unroll 4
         for (int j = 0; j < 32; ++j) {
             const double2 cc = c_next;
-            const double in = gl == 0 ? 0.0 : in_next;
+            const double in = __hiloint2double(gl == 0 ? 0 : in_hi, gl == 0 ? 0 : in_lo);
             c_next = pp[j + 1];                          // (entry SB of the row is padding)
             const double top = E[R - 1];
             T = fma(top, cc.x, T * cc.y);
             E[R - 1] = fma(E[R - 2], cc.x, top);
-            in_next = __shfl_up_sync(FULL, E[R - 1], 1);
+            in_hi = __shfl_up_sync(FULL, __double2hiint(E[R - 1]), 1);
+            in_lo = __shfl_up_sync(FULL, __double2loint(E[R - 1]), 1);
 #pragma unroll
             for (int r = R - 2; r >= 1; --r) E[r] = fma(E[r - 1], cc.x, E[r]);
             E[0] = fma(in, cc.x, E[0]);
