@@ -480,10 +480,10 @@ def run_ours(args):
     h2d_meta = 8 * (n + 1) + 16 * n + n
 
     # ---- rooflines -------------------------------------------------------------------------------
-    # HBM side (k_screen + prefix sum + k_finalize stream the quality planes): algorithmic bytes per column =
+    # HBM side (k_front + k_prune2 stream the quality planes): algorithmic bytes per column =
     # every quality byte the configuration merges + metadata in + results out, whether or not the
     # early-exit prune lets the kernels skip them (ncu `traffic` shows what is actually moved).
-    # fp64 side (k_heavy<R>, the O(depth*K) recurrence): algorithmic flops per column = 3 x cells + 12 x depth
+    # fp64 side (k_dp / k_mid / k_xl, the O(depth*K) recurrence): algorithmic flops per column = 3 x cells + 12 x depth
     # (2 mul + 1 add per cell of the reference's recurrence, 12 flops per read for the merge),
     # cells = sum_n (min(n, K-1) + 1) + (depth - K).
     peak, peak_src = measured_peaks()

@@ -978,10 +978,10 @@ extern "C" int lfb200_get_profile(lfb200_ctx *ctx, float *ms4)
 {
     if (!ctx || !ctx->profiling) return fail("profiling is off");
     CU(cudaEventSynchronize(ctx->ev[5]));
-    CU(cudaEventElapsedTime(&ms4[0], ctx->ev[0], ctx->ev[1]));   // k_screen
-    CU(cudaEventElapsedTime(&ms4[1], ctx->ev[1], ctx->ev[2]));   // k_block_counts + k_scan_blocks
-    CU(cudaEventElapsedTime(&ms4[2], ctx->ev[3], ctx->ev[4]));   // k_finalize
-    CU(cudaEventElapsedTime(&ms4[3], ctx->ev[4], ctx->ev[5]));   // k_heavy<*>
+    CU(cudaEventElapsedTime(&ms4[0], ctx->ev[0], ctx->ev[1]));   // k_front + k_scan_tiles
+    CU(cudaEventElapsedTime(&ms4[1], ctx->ev[1], ctx->ev[2]));   // (nothing any more)
+    CU(cudaEventElapsedTime(&ms4[2], ctx->ev[3], ctx->ev[4]));   // k_prune2 (alone, first, when profiling)
+    CU(cudaEventElapsedTime(&ms4[3], ctx->ev[4], ctx->ev[5]));   // k_dp<*>, k_mid, k_xl, fallbacks
     return 0;
 }
 
@@ -1081,8 +1081,8 @@ extern "C" int lfb200_call_columns(lfb200_ctx *ctx, lfb200_conf_t *conf, const l
     if (upload(ctx->in_nb, hb->num_bases, (size_t)n * 4, 0, st, &d)) return 1;
     db.num_bases = (const int *)d;
     // Quality planes: copied to the device, or — host_planes mode 1 and the plane lies in pinned (page-locked) host
-    // memory — read in place over PCIe.  The kernels touch only the reads that decide (non-reference reads in
-    // k_screen, the first few reads of a tested column in k_finalize, whole columns only for candidate sites), a
+    // memory — read in place over PCIe.  The kernels touch only the reads that decide (non-reference reads and the
+    // first few reads of a tested column in k_front / k_prune2, whole columns only for candidate sites), a
     // fraction of the bytes a bulk copy moves.  Pinned memory is mapped page-wise, so the aligned 16-byte loads
     // that straddle the end of a plane stay inside the mapping.
     auto place = [&](DevBuf &buf, const unsigned char *h, const unsigned char **out) -> int {

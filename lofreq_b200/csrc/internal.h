@@ -11,7 +11,7 @@ constexpr int NCLASS = 10;         // job lists: 0 = K <= 32 (k_mid), 1..6 = reg
                                    // column), 8 = K <= 32 columns k_mid hands back to k_heavy<1> (tail outside the untilted range)
 constexpr int CLS_XL = 7, CLS_FALLBACK = 8;
 constexpr int CLS_XLFB = 1;         // K > 2048 columns k_xl hands to k_heavy_xl (a step parameter above 2^20: rescaling after every read)
-constexpr int CLS_PRUNE2 = 9;       // K <= 8 columns still alive after the first reads of k_finalize's prune: k_prune2's input
+constexpr int CLS_PRUNE2 = 9;       // K <= 8 columns still alive after the first reads of k_front's prune: k_prune2's input
 constexpr int MAXK_WARP = 2048;    // 32 lanes * 64 cells
 
 // k_dp (dp_fused.cu): columns with 8 < K <= 2048 share a warp — G = 4, 8, 16 or 32 lanes per column, R = 8 .. 64 cells

@@ -51,7 +51,7 @@ __device__ __forceinline__ void load_raw(const DevBatch &b, long long c, RawGeom
     r.nb = b.num_bases ? __ldg(b.num_bases + c) : -1;
 }
 
-// k_screen: gates and alt counts.  Only reads that show a non-reference base decide whether a column is
+// gates and alt counts.  Only reads that show a non-reference base decide whether a column is
 // tested and what K is (snpcaller.c:418-420,489), so only those bytes are touched.  A warp takes 32
 // consecutive columns: metadata, gates and columns with at most 8 non-reference reads run lane-per-column;
 // the rare columns with more (variant sites) are then counted by the whole warp.

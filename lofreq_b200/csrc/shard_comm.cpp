@@ -4,7 +4,7 @@
 // lofreq2_call_pparallel.py:131-161).  Per batch that is a mailbox in shared host memory polled by one warp on the
 // kernels' stream (mailbox.cu: no collective, a shard waits only for the shards before it; LFB200_EXCHANGE_NCCL=1
 // selects the earlier ncclAllGather per batch instead), which leaves this shard's starting factor in device memory
-// where k_finalize reads it — no host round trip and no framework call in the path.  NCCL does the final gather of
+// where the test phase reads it (k_set_start) — no host round trip and no framework call in the path.  NCCL does the final gather of
 // the per-region counts (lfb200_comm_gathered): 2 x int64 per rank over NVLink.
 // NCCL is dlopen'ed (libnccl.so.2, the copy already loaded by the process if there is one) so that single-GPU hosts
 // need no libnccl.

@@ -7,17 +7,20 @@
 //                                           Poisson-binomial DP in log space, tail p-value per allele
 //
 // What runs here (DESIGN.md has the whole picture; dp_fused.cu, poissbin.cu, mailbox.cu, binom.cu, fisher.cu hold the rest):
-//   k_screen    gates and alt counts: only the reads showing a non-reference base are looked at; a warp takes 32
-//               columns (lane per column for few alt reads, whole warp otherwise); tested columns per tile of 256.
-//   k_front (front.cu) / k_prune2
-//               running Bonferroni factor = prefix sum over the tested flags (lofreq_call.c:794-800); the reference's
-//               early exit, one lane per column, in two stages; job lists for everything that survives.
+//   k_front (front.cu)
+//               gates and alt counts (only the reads showing a non-reference base are looked at), tested flags, the
+//               place of a column in the running Bonferroni count (lofreq_call.c:794-800), the first stage of the
+//               reference's early exit one lane per column, job lists for everything that survives.
+//   k_prune2    second stage of the early exit with the exact factor.
 //   k_mid       K <= 8 survivors: the exact distribution truncated at K, evaluated in linear space on 32 disjoint read
 //               subsets and merged by truncated convolution over warp shuffles.
-//   k_heavy<R>  one warp per column (K > 256, very deep columns, fallback list): the O(depth*K) recurrence in fp64,
-//               K cells tiled over lanes x R registers, one shuffle per read for the lane boundary.  Odds form
-//               E[k] += E[k-1]*o (one DFMA per cell), exact power-of-two rescaling, exponential tilting
-//               when the tail is further out than fp64 can hold.  k_heavy_xl: one CTA per column for K > 2048.
+//   k_dp (dp_fused.cu), k_xl (xl.cu)
+//               the O(depth*K) recurrence for 8 < K <= 2048 (several columns per warp) and K > 2048 (one CTA per column).
+//   k_heavy_all / k_heavy_xl
+//               the per-column fallbacks for what those hand back (one warp / one CTA per column): K cells tiled over
+//               lanes x R registers, one shuffle per read for the lane boundary, odds form E[k] += E[k-1]*o (one DFMA
+//               per cell), rescaling after every read if need be, exponential tilting after the fact.
+//   k_emit_sites  status / called / QUAL per site on the device, records in column order into pinned host memory.
 //   k_rank_cands  the sites in column order (a permutation), so that the host needs no sort.
 //   k_prob_jobs the same routines fed with ready-made double error probabilities (snpcaller() symbol).
 //
@@ -134,7 +137,7 @@ __device__ __forceinline__ void small_tails(const double (&P)[KV], double T, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_screen
+// read evaluation shared by k_mid and the fallbacks
 // ------------------------------------------------------------------------------------------------
 // merged error probability of a read that shows the reference base and passed the bq filter
 // (merge_srcq_mapq_baq_and_bq with the terms of absent planes dropped: x*0, +0 and *1 are exact)
@@ -239,7 +242,7 @@ __device__ __forceinline__ void mask_chunk(uint4 &v, int pos0, int n)
 
 // Full evaluation of a column with K <= KS: every lane folds the reads of its 16-byte chunks into a
 // distribution truncated at KV >= K, then the 32 distributions are merged.  Only columns that survive the
-// 32-read prune of k_finalize get here (true low-frequency variants, and the first few columns of a run
+// 32-read prune of k_prune2 get here (true low-frequency variants, and the first few columns of a run
 // whose Bonferroni factor is still small).
 template <int KV>
 __device__ __noinline__ void screen_small(const DevConf &cf, const DevBatch &b, unsigned lut_sa, const Geom &g,
@@ -289,7 +292,7 @@ __device__ __noinline__ void screen_small(const DevConf &cf, const DevBatch &b, 
 // running Bonferroni: prefix sum over tested flags, then the significance screen
 // ------------------------------------------------------------------------------------------------
 
-// exclusive scan of the per-tile counts k_screen accumulated, one block; the counts are zeroed for the next batch
+// exclusive scan of per-tile counts (the candidate marks: k_rank_cands), one block; the counts are zeroed for the next batch
 __global__ void __launch_bounds__(1024) k_scan_blocks(unsigned int *tilecount, long long *blocksum, int nb, unsigned long long *total)
 {
     __shared__ long long s_warp[32];
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(unsigned int *tilecount, l
     if (threadIdx.x == 0 && total) *total = (unsigned long long)s_carry;
 }
 
-// (2) second stage of the prune: the columns k_finalize could not rule out within PRUNE_CAP1 reads, one lane each, up to
+// (2) second stage of the prune: the columns k_front could not rule out within PRUNE_CAP1 reads, one lane each, up to
 //     PRUNE_CAP reads (from the first read again: eight reads are cheaper to redo than to carry).  The survivors (true
 //     low-frequency variants, the first columns of a run) join k_mid's job list.
 __global__ void __launch_bounds__(128) k_prune2(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b, const Lut *lut,
@@ -811,7 +814,7 @@ __device__ bool run_problem(const Src &src, const int (&cnt)[3], long long bonf,
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_mid: the columns with K <= 8 that the lane-per-column prune of k_finalize / k_prune2 could not rule out within
+// k_mid: the columns with K <= 8 that the lane-per-column prune of k_front / k_prune2 could not rule out within
 // PRUNE_CAP reads (true low-frequency variants, the first columns of a run).  At this size the recurrence over reads
 // (depth serial steps of a short row) is slower than folding the reads in parallel — every lane its 16-byte chunks into
 // a distribution truncated at 2, 4 or 8 — and merging the 32 distributions by truncated convolution.

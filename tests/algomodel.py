@@ -334,10 +334,10 @@ def model_binom(num_trials, num_success, pr):
 
 
 # ------------------------------------------------------------------------------------------------
-# packed kernels (lofreq_b200/csrc/packed.cu): what k_pk_prep / k_packed add to the arithmetic above
+# the fused recurrence kernel (lofreq_b200/csrc/dp_fused.cu: k_dp): what its tilt and lock-step form add to the arithmetic above
 # ------------------------------------------------------------------------------------------------
 def newton_tilt_fp32(p, q, K):
-    """k_pk_prep's root finder: the sums that steer it are taken in fp32 (the tolerance is |e| sqrt(d) < 0.5),
+    """k_dp's root finder (group_tilt; there on a 64-bucket histogram of the probabilities): the sums that steer it are taken in fp32 (the tolerance is |e| sqrt(d) < 0.5),
     o = p/q per read, ln s capped at 60; one accepted step ends the iteration."""
     n = int(np.sum(np.ones_like(p)))
     kt = min(float(K), n - 0.5)
@@ -366,7 +366,7 @@ def newton_tilt_fp32(p, q, K):
 
 
 def packed_column(ep, counts, bonf, sig, chunk=32):
-    """One column the way k_pk_prep + k_packed evaluate it (8 < K <= 256).  Returns
+    """One column the way k_dp evaluates it (8 < K <= 2048).  Returns
     (dead, lnp[3], ln_floor, blocks_run): dead = the conservative early exit fired, i.e. the column is insignificant."""
     counts = [int(c) for c in counts]
     K = max(counts)
