@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
     // the median override (def_alt_bq == -1) needs a warp-wide histogram: no lane-per-column path then
     const int serial_max = cf.alt_bq_mode == 2 ? 0 : 8;
     unsigned int *round_cnt = ws.counters->front_round;
+    const bool bq_only = eval_mode(cf).uniform;
 
     RawGeom nxt;
     nxt.off = 0; nxt.cnt = make_int4(0, 0, 0, 0); nxt.cov = -1; nxt.nb = -1; nxt.ref = 'N';
@@ -108,7 +109,13 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
         // column hold them wherever the column starts): requested together with its alt reads
         Chunk16 first;
         first.bq = first.mq = first.baq = first.sq = make_uint4(0, 0, 0, 0);
-        if (m_alt > 0 && cf.alt_bq_mode != 2) load_chunk8(cf, b, mg.off & ~7ll, (mg.off & ~7ll) + 8 < mg.off + mg.n, first);
+        if (m_alt > 0 && cf.alt_bq_mode != 2) {
+            const long long a8 = mg.off & ~7ll;
+            const bool hi_too = a8 + 8 < mg.off + mg.n;
+            // (uniform configurations: the first stage prunes on the base qualities alone, see lane_prune)
+            if (bq_only) first.bq = ldg8x2(b.bq + a8, hi_too);
+            else load_chunk8(cf, b, a8, hi_too, first);
+        }
         // ---- alt counts ----
         int cnt[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
         if (m_alt > 0 && m_alt <= serial_max) {
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
         const double limit = small ? cf.sig * (1.0 + 1e-9) / (double)bonf : 0.0;   // margin: borderline columns go to the host
         if (cf.alt_bq_mode != 2) {          // the median override needs a warp-wide histogram: no lane-serial prune
             // (K > KS1 cannot be ruled out within PRUNE_CAP1 reads under any real factor: listed without a walk)
-            const bool alive = lane_prune<KS1>(cf, b, s_lut, mg, K, limit, PRUNE_CAP1, small && K <= KS1, &first, false, 8);
+            const bool alive = lane_prune<KS1>(cf, b, s_lut, mg, K, limit, PRUNE_CAP1, small && K <= KS1, &first, false, 8, bq_only);
             small = small && (K > KS1 || alive);
             // one atomic per warp for the survivors' slots
             const unsigned sm_ = __ballot_sync(FULL, small);

@@ -90,7 +90,7 @@ __device__ __forceinline__ void count_alt_read(const DevConf &cf, const DevBatch
 template <int KP>
 __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b, const double *s_lut, const Geom &mg, int K,
                                            double limit, int cap_reads, bool live, const Chunk16 *first = nullptr, bool ext = false,
-                                           int first_align = 16)
+                                           int first_align = 16, bool bq_only = false)
 {
     double R[KP], T = 0.0;
 #pragma unroll
@@ -126,7 +126,11 @@ __device__ __forceinline__ bool lane_prune(const DevConf &cf, const DevBatch &b,
             }
         }
         double jp;
-        if (!dp_eval(cf, em, s_lut, mg, i, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j), byte_of(ch.sq, j), jp)) continue;
+        // bq_only (k_front, uniform configurations): the base quality alone.  Every other quality only raises a read's error
+        // probability, and the tail grows with every probability — a column ruled out on base qualities alone is ruled out.
+        if (bq_only ? !dp_eval(cf, em, s_lut, mg, i, byte_of(ch.bq, j), 255, 255, 255, jp)
+                    : !dp_eval(cf, em, s_lut, mg, i, byte_of(ch.bq, j), byte_of(ch.mq, j), byte_of(ch.baq, j), byte_of(ch.sq, j), jp))
+            continue;
         double p, q;
         guard_pq(jp, p, q);
         T = fma(R[KP - 1], p, T);
