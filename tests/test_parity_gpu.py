@@ -337,6 +337,36 @@ def test_graph_replay_gives_the_same_sites():
     c.close()
 
 
+def test_low_mapping_qualities_under_a_large_factor(caller, port_oracle):
+    """The first stage of the early exit looks at the base qualities alone (a lower bound of every read's merged error
+    probability); with poor mapping qualities the merged probabilities are far above it, so columns that this stage lets
+    through are still ruled out (or called) exactly by the later stages.  A large fixed factor makes the prune bite.
+    Also the division-free step parameters of k_dp at mq = 0 (probability 0.5), mq unknown (255) and BAQ 0..60."""
+    rng = np.random.default_rng(2024)
+    e = (np.zeros(0, int),) * 3
+    cols = []
+    for i in range(6000):
+        n = int(rng.integers(30, 400))
+        kind = rng.random()
+        k = int(rng.integers(1, 4)) if kind < 0.7 else int(rng.integers(4, 9)) if kind < 0.9 else int(rng.integers(9, min(n // 2, 120)))
+        mq_pool = rng.choice([0, 1, 3, 10, 20, 30, 60, 255], size=n, p=[.1, .05, .05, .1, .1, .1, .45, .05])
+
+        def grp(m, lo, hi, off):
+            return (rng.integers(lo, hi, m), mq_pool[off:off + m], rng.integers(0, 61, m))
+        alt_q = (25, 42) if rng.random() < 0.5 else (8, 25)
+        groups = [grp(n - k, 20, 42, 0), grp(k, alt_q[0], alt_q[1], n - k), e, e]
+        rng.shuffle(groups)
+        ref = "ACGT"[max(range(4), key=lambda g: len(groups[g][0]))]
+        cols.append(dict(ref=ref, groups=groups, gap=int(rng.integers(0, 9))))
+    b = _custom_batch(cols, pad=1)
+    for conf in (default_conf(bonf_subst=3_000_000, bonf_dynamic=0), default_conf(bonf_subst=1),
+                 default_conf(bonf_subst=3_000_000, bonf_dynamic=0, flag=2)):       # 2 = USE_MQ only
+        want = port_oracle.call_columns(b, dict(conf))
+        got = caller.call_columns(b, dict(conf))
+        compare_batch(got, want, "low mq %s" % conf)
+        assert 0 < want["called"].any(axis=1).sum() < len(cols)
+
+
 def _slice_out(d, lo, hi):
     return {k: (v[lo:hi] if isinstance(v, np.ndarray) else v) for k, v in d.items()}
 
