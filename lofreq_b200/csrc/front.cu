@@ -44,8 +44,12 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p)
     return v;
 }
 
+#ifndef LFB_FRONT_T
+#define LFB_FRONT_T 256
+#endif
+constexpr int FRONT_T = LFB_FRONT_T;      // threads per CTA = columns per unit of work (a half or a whole tile of FIN_BLOCK columns)
 #ifndef LFB_FRONT_CTAS
-#define LFB_FRONT_CTAS 3
+#define LFB_FRONT_CTAS (768 / LFB_FRONT_T)
 #endif
 constexpr int FRONT_CTAS_PER_SM = LFB_FRONT_CTAS;
 #ifndef LFB_KS1
@@ -53,16 +57,17 @@ constexpr int FRONT_CTAS_PER_SM = LFB_FRONT_CTAS;
 #endif
 constexpr int KS1 = LFB_KS1;          // largest alt count the first stage of the prune walks itself
 
-__global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
+__global__ void __launch_bounds__(FRONT_T, FRONT_CTAS_PER_SM) k_front(const __grid_constant__ DevConf cf, const __grid_constant__ DevBatch b,
                                                                         const Lut *lut, const Workspace ws)
 {
     __shared__ double s_lut[768];
-    __shared__ int s_hist[FIN_BLOCK / 32][256];
+    __shared__ int s_hist[FRONT_T / 32][256];
     __shared__ unsigned int s_round[FRONT_MAXROUNDS];     // per round of this CTA: (warps arrived << 16) + tested columns
     for (int i = threadIdx.x; i < FRONT_MAXROUNDS; i += blockDim.x) s_round[i] = 0;
     load_lut(s_lut, lut);                                 // ends with the kernel's only barrier
     const long long n = b.n_cols;
-    const long long ntiles = (n + FIN_BLOCK - 1) / FIN_BLOCK;
+    // units of FRONT_T columns; both halves of the last tile are walked (the per-warp counts of a tile are read as one word)
+    const long long ntiles = (n + FIN_BLOCK - 1) / FIN_BLOCK * (FIN_BLOCK / FRONT_T);
     const int lane = lane_id(), w = threadIdx.x >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters->bonf_start_used = cf.bonf_start;
     // the median override (def_alt_bq == -1) needs a warp-wide histogram: no lane-per-column path then
@@ -73,15 +78,15 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
     RawGeom nxt;
     nxt.off = 0; nxt.cnt = make_int4(0, 0, 0, 0); nxt.cov = -1; nxt.nb = -1; nxt.ref = 'N';
     {
-        const long long c0 = (long long)blockIdx.x * FIN_BLOCK + threadIdx.x;
+        const long long c0 = (long long)blockIdx.x * FRONT_T + threadIdx.x;
         if (c0 < n) load_raw(b, c0, nxt);
     }
     int round = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++round) {
-        const long long c = tile * FIN_BLOCK + threadIdx.x;
+        const long long c = tile * FRONT_T + threadIdx.x;
         const RawGeom raw_g = nxt;
         {
-            const long long cn = c + (long long)gridDim.x * FIN_BLOCK;
+            const long long cn = c + (long long)gridDim.x * FRONT_T;
             nxt.off = 0; nxt.cnt = make_int4(0, 0, 0, 0); nxt.cov = -1; nxt.nb = -1; nxt.ref = 'N';
             if (cn < n) load_raw(b, cn, nxt);                  // next round's metadata in flight
         }
@@ -171,11 +176,11 @@ __global__ void __launch_bounds__(FIN_BLOCK, FRONT_CTAS_PER_SM) k_front(const __
         const int lrank = t ? __popc(bal & ((2u << lane) - 1u)) : 0;      // 1-based among the tested columns of the warp
         if (c < n) ws.rank[c] = (unsigned char)lrank;
         if (lane == 0) {
-            ws.wcount[tile * (FIN_BLOCK / 32) + w] = (unsigned char)__popc(bal);
+            ws.wcount[tile * (FRONT_T / 32) + w] = (unsigned char)__popc(bal);
             if (round < FRONT_MAXROUNDS) {
                 // the warps of a CTA drift apart by whole rounds; the last one of this round hands the tile's count on
                 const unsigned v = atomicAdd(&s_round[round], (1u << 16) + (unsigned)__popc(bal)) + (1u << 16) + (unsigned)__popc(bal);
-                if ((v >> 16) == FIN_BLOCK / 32 && (v & 0xffffu)) atomicAdd(&round_cnt[round], v & 0xffffu);
+                if ((v >> 16) == FRONT_T / 32 && (v & 0xffffu)) atomicAdd(&round_cnt[round], v & 0xffffu);
             }
         }
         const long long before = (long long)__reduce_add_sync(FULL, before_l);
@@ -298,8 +303,9 @@ void launch_front(const LaunchState &ls, const DevConf &cf, const DevBatch &b, c
     cudaMemsetAsync(ws.counters, 0, sizeof(Counters), st);
     cudaMemsetAsync(ws.is_cand, 0, (size_t)nb * FIN_BLOCK, st);
     static const int front_ctas = getenv("LFB200_FRONT_CTAS") ? atoi(getenv("LFB200_FRONT_CTAS")) : FRONT_CTAS_PER_SM;
-    const int grid = nb < ls.sms * front_ctas ? nb : ls.sms * front_ctas;
-    k_front<<<grid, FIN_BLOCK, 0, st>>>(cf, b, lut, ws);
+    const int nu = nb * (FIN_BLOCK / FRONT_T);
+    const int grid = nu < ls.sms * front_ctas ? nu : ls.sms * front_ctas;
+    k_front<<<grid, FRONT_T, 0, st>>>(cf, b, lut, ws);
     k_scan_tiles<<<1, 1024, 0, st>>>(ws.wcount, ws.blocksum, nb, &ws.counters->n_tested);
 }
 

@@ -2,7 +2,7 @@
 # A/B of library builds (tools/build_variant.py) on one box: bash tools/gpu_ab_libs.sh "base f3 f5" [workload]
 mkdir -p gpurun_out
 wl=${2:-C2}
-for rep in 1 2; do
+for rep in $(seq 1 ${REPS:-2}); do
 for v in $1; do
   lib=""; [ "$v" != base ] && lib="LFB200_LIB=$PWD/lofreq_b200/lib/var_$v.so"
   env $lib timeout 300 python bench.py --workload $wl --steps ${STEPS:-100} --no-cpu --no-e2e 2>/dev/null | python -c "
