@@ -241,6 +241,17 @@ int lfb200_copy_counts_device(lfb200_ctx *ctx, void *stream, int *dst_dev);
  * out[0] k_dp (8 < K <= 2048, several columns per warp), out[1] the per-column fallback k_heavy_all (columns k_dp or
  * k_mid handed back), out[2] k_heavy_xl (K > 2048, one CTA per column), out[3] k_mid (K <= 8 survivors of the prune) */
 int lfb200_last_job_counts(lfb200_ctx *ctx, long long out[4]);
+/* The BAQ profile HMM for a batch of reads: replaces one kpa_ext_glocal() call per read (kprobaln_ext.h:38-40,
+ * kprobaln_ext.c:80-277) as bam_prob_realn_core_ext makes it (bam_md_ext.c:407) with pd == NULL — the banded glocal
+ * forward-backward that yields, per query base, the reference position / state it most probably aligns to and the
+ * phred-scaled posterior of that being wrong.  Read r: reference window ref[ref_off[r] .. ref_off[r+1]) and query
+ * query[qry_off[r] .. qry_off[r+1]) as 0..3 (4 = ambiguous), base qualities qual (NULL: Q30, as the reference assumes);
+ * d, e, bw are kpa_ext_par_t (gap open, gap extension, band width).  state[] and q[] (qry_off[n] entries each, host
+ * memory) get exactly the reference's values; reads with an empty window or query are left untouched, as the reference
+ * leaves them.  Not covered: the pd matrix of LoFreq's indel-alignment qualities (idaq, bam_md_ext.c:73). */
+int lfb200_kpa_glocal_batch(lfb200_ctx *ctx, long long n, const unsigned char *ref, const long long *ref_off,
+                            const unsigned char *query, const long long *qry_off, const unsigned char *qual, float d, float e,
+                            int bw, int *state, unsigned char *q);
 /* how many phases of this context were queued by replaying a captured CUDA graph so far (diagnostics) */
 long long lfb200_graph_replays(lfb200_ctx *ctx);
 /* measured DFMA/s of this GPU (8 independent chains per thread, ~20 ms): the fp64-pipe roofline denominator */

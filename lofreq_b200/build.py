@@ -10,8 +10,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "liblofreq_b200.so")
-SOURCES = ["snv_kernels.cu", "front.cu", "dp_fused.cu", "xl.cu", "poissbin.cu", "mailbox.cu", "binom.cu", "fisher.cu", "synth.cu", "host_api.cpp", "shard_comm.cpp"]
-HEADERS = ["internal.h", "dev_common.cuh", "screen_common.cuh", "synth_tables.h", os.path.join("..", "..", "include", "lofreq_b200.h")]
+SOURCES = ["snv_kernels.cu", "front.cu", "dp_fused.cu", "xl.cu", "poissbin.cu", "mailbox.cu", "binom.cu", "fisher.cu", "baq.cu", "synth.cu", "host_api.cpp", "shard_comm.cpp"]
+HEADERS = ["internal.h", "dev_common.cuh", "screen_common.cuh", "baq_core.cuh", "synth_tables.h", os.path.join("..", "..", "include", "lofreq_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 

@@ -90,7 +90,7 @@ VARIANT_FN = C.CFUNCTYPE(None, C.POINTER(Variant), C.c_void_p)
 SYMBOLS = ["lfb200_create", "lfb200_destroy", "lfb200_last_error", "lfb200_init_conf", "lfb200_call_columns", "lfb200_set_host_planes",
            "lfb200_screen_device", "lfb200_ntested_device", "lfb200_test_device", "lfb200_ntested_copy_device", "lfb200_test_device_from", "lfb200_bonf_start_device", "lfb200_comm_unique_id", "lfb200_comm_init", "lfb200_comm_exchange", "lfb200_comm_gathered",
            "lfb200_sites_device", "lfb200_sites_view", "lfb200_sites_buffer", "lfb200_sites_begin", "lfb200_sites_end", "lfb200_set_site_pvalues", "lfb200_site_fill_pvalues",
-           "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_dfma_peak", "lfb200_last_job_counts", "lfb200_graph_replays", "lfb200_copy_counts_device", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy", "lfb200_builder_pending", "lfb200_sb_qual_batch", "lfb200_format_snv_info", "lfb200_format_indel_info", "lfb200_format_snv_record", "lfb200_builder_add_column_strands", "lfb200_builder_on_variant",
+           "lfb200_device_results", "lfb200_set_profiling", "lfb200_get_profile", "lfb200_dfma_peak", "lfb200_last_job_counts", "lfb200_graph_replays", "lfb200_kpa_glocal_batch", "lfb200_copy_counts_device", "lfb200_builder_create", "lfb200_builder_add_column", "lfb200_builder_flush", "lfb200_builder_destroy", "lfb200_builder_pending", "lfb200_sb_qual_batch", "lfb200_format_snv_info", "lfb200_format_indel_info", "lfb200_format_snv_record", "lfb200_builder_add_column_strands", "lfb200_builder_on_variant",
            "lfb200_snpcaller", "lfb200_snpcaller_batch", "lfb200_poissbin", "lfb200_poissbin_batch", "lfb200_batch_errprobs", "lfb200_plp_to_errprobs", "lfb200_indel_tests", "lfb200_binom", "lfb200_binom_batch", "lfb200_synth_depths",
            "lfb200_synth_columns"]
 
@@ -193,6 +193,8 @@ def load():
     lib.lfb200_builder_destroy.argtypes = [vp]
     lib.lfb200_copy_counts_device.restype = C.c_int
     lib.lfb200_copy_counts_device.argtypes = [vp, vp, vp]
+    lib.lfb200_kpa_glocal_batch.restype = C.c_int
+    lib.lfb200_kpa_glocal_batch.argtypes = [vp, C.c_longlong, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_int, vp, vp]
     lib.lfb200_graph_replays.restype = C.c_longlong
     lib.lfb200_graph_replays.argtypes = [vp]
     lib.lfb200_last_job_counts.restype = C.c_int

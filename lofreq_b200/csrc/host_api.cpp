@@ -26,6 +26,7 @@
 
 #include "../../include/lofreq_b200.h"
 #include "internal.h"
+#include "baq_core.cuh"       // KpaFix (the routine itself is only ever instantiated for the device, baq.cu)
 
 using namespace lfb;
 
@@ -51,6 +52,9 @@ static int fail(const char *fmt, ...)
     } while (0)
 
 extern "C" const char *lfb200_last_error(void) { return g_err; }
+
+struct DevBuf;
+static int upload(DevBuf &buf, const void *src, size_t bytes, size_t pad, cudaStream_t st, const void **dev);
 
 // ------------------------------------------------------------------------------------------------
 // A few persistent worker threads for the long double finishing (FE flags and errno are per thread).
@@ -233,6 +237,8 @@ struct lfb200_ctx {
     DevBuf in_off, in_cnt, in_ref, in_cov, in_nb, in_bq, in_mq, in_baq, in_sq;
     // single problems
     DevBuf p_ep, p_off, p_cnt, p_bonf, p_out;
+    // BAQ HMM (lfb200_kpa_glocal_batch)
+    DevBuf k_ref, k_roff, k_qry, k_qoff, k_qual, k_state, k_q, k_f, k_b, k_s, k_fix, k_q2p;
     // pinned scratch for small D2H transfers
     Counters *h_counters = nullptr;
     Cand *h_cand = nullptr;              // pinned
@@ -443,7 +449,8 @@ extern "C" void lfb200_destroy(lfb200_ctx *ctx)
     DevBuf *bufs[] = {&ctx->w_cnt6, &ctx->w_tested, &ctx->w_bonf, &ctx->w_rank, &ctx->w_wcount, &ctx->w_blocksum, &ctx->w_jobs,
                       &ctx->w_cand, &ctx->w_counters, &ctx->w_pjobs, &ctx->w_ujobs, &ctx->w_iscand, &ctx->w_candtile, &ctx->w_candpre, &ctx->w_perm, &ctx->in_off, &ctx->in_cnt, &ctx->in_ref, &ctx->in_cov, &ctx->in_nb,
                       &ctx->in_bq, &ctx->in_mq, &ctx->in_baq, &ctx->in_sq, &ctx->p_ep, &ctx->p_off, &ctx->p_cnt,
-                      &ctx->p_bonf, &ctx->p_out};
+                      &ctx->p_bonf, &ctx->p_out, &ctx->k_ref, &ctx->k_roff, &ctx->k_qry, &ctx->k_qoff, &ctx->k_qual, &ctx->k_state, &ctx->k_q,
+                      &ctx->k_f, &ctx->k_b, &ctx->k_s, &ctx->k_fix, &ctx->k_q2p};
     for (DevBuf *b : bufs) b->release();
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -990,6 +997,93 @@ extern "C" int lfb200_copy_counts_device(lfb200_ctx *ctx, void *stream, int *dst
     if (!ctx || !ctx->have_batch) return fail("no screened batch");
     if (ctx->cur.n_cols)
         CU(cudaMemcpyAsync(dst_dev, ctx->ws.cnt6, (size_t)ctx->cur.n_cols * 6 * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BAQ HMM: kpa_ext_glocal (kprobaln_ext.h:38-40) for a batch of reads
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfb200_kpa_glocal_batch(lfb200_ctx *ctx, long long n, const unsigned char *ref, const long long *ref_off,
+                                       const unsigned char *query, const long long *qry_off, const unsigned char *qual, float d, float e,
+                                       int bw, int *state, unsigned char *q)
+{
+    if (!ctx) return fail("no context");
+    if (n < 0 || !ref_off || !qry_off || (n > 0 && (!ref || !query || !state || !q))) return fail("lfb200_kpa_glocal_batch: bad arguments");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t tot_r = (size_t)ref_off[n], tot_q = (size_t)qry_off[n];
+    // band and length of every read (kprobaln_ext.c:100-103): the scratch of a launch is sized for its widest / longest read
+    int lmax = 0, bwmax = 0;
+    for (long long r = 0; r < n; ++r) {
+        const long long lr = ref_off[r + 1] - ref_off[r], lq = qry_off[r + 1] - qry_off[r];
+        if (lr < 0 || lq < 0 || lr > 100000 || lq > 100000) return fail("lfb200_kpa_glocal_batch: read %lld has length %lld / %lld", r, lr, lq);
+        if (lr == 0 || lq == 0) continue;                      // the reference returns at once (kprobaln_ext.c:88): outputs untouched
+        int b = (int)std::max(lr, lq);
+        if (b > bw) b = bw;
+        if (b < (int)std::llabs(lr - lq)) b = (int)std::llabs(lr - lq);
+        bwmax = std::max(bwmax, b);
+        lmax = std::max(lmax, (int)lq);
+    }
+    const void *dv;
+    if (upload(ctx->k_ref, ref, tot_r, 16, st, &dv)) return 1;
+    const unsigned char *d_ref = (const unsigned char *)dv;
+    if (upload(ctx->k_roff, ref_off, (size_t)(n + 1) * 8, 0, st, &dv)) return 1;
+    const long long *d_roff = (const long long *)dv;
+    if (upload(ctx->k_qry, query, tot_q, 16, st, &dv)) return 1;
+    const unsigned char *d_qry = (const unsigned char *)dv;
+    if (upload(ctx->k_qoff, qry_off, (size_t)(n + 1) * 8, 0, st, &dv)) return 1;
+    const long long *d_qoff = (const long long *)dv;
+    const unsigned char *d_qual = nullptr;
+    if (qual) {
+        if (upload(ctx->k_qual, qual, tot_q, 16, st, &dv)) return 1;
+        d_qual = (const unsigned char *)dv;
+    }
+    float q2p[256];
+    for (int i = 0; i < 256; ++i) q2p[i] = (float)pow(10, -i / 10.);      // g_qual2prob, kprobaln_ext.c:118-120
+    if (upload(ctx->k_q2p, q2p, sizeof(q2p), 0, st, &dv)) return 1;
+    const float *d_q2p = (const float *)dv;
+    if (ctx->k_state.ensure(std::max<size_t>(tot_q, 1) * 4) || ctx->k_q.ensure(std::max<size_t>(tot_q, 1))) return fail("out of device memory");
+    // outputs of empty reads stay what the caller passed in
+    CU(cudaMemcpyAsync(ctx->k_state.p, state, tot_q * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->k_q.p, q, tot_q, cudaMemcpyHostToDevice, st));
+    const int fix_cap = 65536;
+    if (ctx->k_fix.ensure(sizeof(unsigned) * 4 + (size_t)fix_cap * sizeof(KpaFix))) return fail("out of device memory");
+    unsigned *d_nfix = (unsigned *)ctx->k_fix.p;
+    KpaFix *d_fix = (KpaFix *)((char *)ctx->k_fix.p + 16);
+    CU(cudaMemsetAsync(d_nfix, 0, 16, st));
+    const int w3 = (2 * bwmax + 1) * 3 + 6;
+    const size_t per_read = ((size_t)(lmax + 1) * w3 + 2 * (size_t)w3 + (size_t)lmax + 2) * sizeof(double);
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = std::min<size_t>(free_b / 2, (size_t)24 << 30);
+    long long chunk = (long long)std::max<size_t>(budget / std::max<size_t>(per_read, 1), 128);
+    chunk = std::min<long long>(chunk, n);
+    chunk = std::min<long long>(chunk, 1 << 20);
+    if (ctx->k_f.ensure((size_t)chunk * (lmax + 1) * w3 * 8) || ctx->k_b.ensure((size_t)chunk * 2 * w3 * 8) ||
+        ctx->k_s.ensure((size_t)chunk * (lmax + 2) * 8))
+        return fail("out of device memory for the scratch of %lld reads (%zu bytes each)", chunk, per_read);
+    for (long long r0 = 0; r0 < n; r0 += chunk) {
+        const int cnt = (int)std::min<long long>(chunk, n - r0);
+        launch_kpa_glocal(r0, cnt, d_ref, d_roff, d_qry, d_qoff, d_qual, d, e, bw, d_q2p, (double *)ctx->k_f.p, (double *)ctx->k_b.p,
+                          (double *)ctx->k_s.p, w3, (int *)ctx->k_state.p, (unsigned char *)ctx->k_q.p, d_fix, fix_cap, d_nfix, st);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(state, ctx->k_state.p, tot_q * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(q, ctx->k_q.p, tot_q, cudaMemcpyDeviceToHost, st));
+    unsigned n_fix = 0;
+    CU(cudaMemcpyAsync(&n_fix, d_nfix, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_fix > (unsigned)fix_cap) return fail("lfb200_kpa_glocal_batch: %u bases inside the rounding guard band (at most %d expected)", n_fix, fix_cap);
+    if (n_fix) {
+        // -4.343 ln(x) + .499 within 1e-9 of an integer: the truncation is decided with this libm, as the reference does
+        std::vector<KpaFix> fx(n_fix);
+        CU(cudaMemcpy(fx.data(), d_fix, (size_t)n_fix * sizeof(KpaFix), cudaMemcpyDeviceToHost));
+        for (const KpaFix &f : fx) {
+            const int k = (int)(-4.343 * log(f.x) + .499);
+            q[f.base] = (unsigned char)(k > 100 ? 99 : k);
+        }
+    }
     return 0;
 }
 

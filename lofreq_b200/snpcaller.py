@@ -201,6 +201,23 @@ class Caller:
         return int(st[0]), float(p[0]), float(q[0])
 
     # ---- host batch -----------------------------------------------------------------------
+    def kpa_glocal(self, reads, d=0.00001, e=0.4, bw=10, use_qual=True):
+        """kpa_ext_glocal (kprobaln_ext.h:38-40) for a batch of reads: reads = dict(n, ref, ref_off, query, qry_off, qual) as
+        CSR arrays (oracle.pyoracle.synth_reads has the layout); returns (state, q) per query base."""
+        tot = int(reads["qry_off"][-1])
+        state = np.zeros(max(tot, 1), np.int32)
+        q = np.zeros(max(tot, 1), np.uint8)
+
+        def p(a):
+            return a.ctypes.data_as(C.c_void_p)
+        capi.check(self.lib.lfb200_kpa_glocal_batch(self._ctx, int(reads["n"]), p(np.ascontiguousarray(reads["ref"], np.uint8)),
+                                                    p(np.ascontiguousarray(reads["ref_off"], np.int64)),
+                                                    p(np.ascontiguousarray(reads["query"], np.uint8)),
+                                                    p(np.ascontiguousarray(reads["qry_off"], np.int64)),
+                                                    p(np.ascontiguousarray(reads["qual"], np.uint8)) if use_qual else None,
+                                                    d, e, bw, p(state), p(q)))
+        return state[:tot], q[:tot]
+
     def call_columns(self, batch, conf=None, dense=True, max_sites=None):
         """batch: dict of numpy arrays (col_off, nt_cnt, ref_base, bq, mq, baq, sq, coverage), the packed
         form of plp_col_t described in include/lofreq_b200.h.  Returns a dict with the dense per-column

@@ -376,3 +376,75 @@ def have_call_oracle(adapter=False, swap=False):
 
 def have_reference():
     return os.path.exists(REF_SO)
+
+
+# ------------------------------------------------------------------------------------------------
+# BAQ HMM (kpa_ext_glocal, kprobaln_ext.c:80-277) — SURVEY.md 8f #2
+# ------------------------------------------------------------------------------------------------
+KPAREF_SO = os.path.join(HERE, "_ref", "libkparef.so")
+
+
+def have_kpa_reference():
+    return os.path.exists(KPAREF_SO)
+
+
+def synth_reads(n, seed=1, lmin=30, lmax=151, flank=10, sub=0.01, indel=0.003, n_frac=0.002):
+    """Reads the way bam_prob_realn_core_ext hands them to kpa_ext_glocal (bam_md_ext.c:380-407): a reference window of
+    the read's span plus `flank` bases on either side (0..3, 4 = ambiguous), the read with substitutions, short indels and
+    a few Ns, base qualities.  Returns CSR arrays."""
+    rng = np.random.default_rng(seed)
+    refs, qrys, quals = [], [], []
+    for _ in range(n):
+        lq = int(rng.integers(lmin, lmax))
+        core = rng.integers(0, 4, lq + 8).astype(np.uint8)
+        q = []
+        i = 0
+        while len(q) < lq and i < len(core):
+            u = rng.random()
+            if u < indel:                       # deletion from the read
+                i += int(rng.integers(1, 4))
+                continue
+            if u < 2 * indel:                   # insertion into the read
+                q.extend(rng.integers(0, 4, int(rng.integers(1, 4))).tolist())
+                continue
+            b = int(core[i])
+            if rng.random() < sub:
+                b = (b + int(rng.integers(1, 4))) % 4
+            if rng.random() < n_frac:
+                b = 4
+            q.append(b)
+            i += 1
+        q = np.array(q[:lq] if len(q) >= lq else q + rng.integers(0, 4, lq - len(q)).tolist(), np.uint8)
+        used = core[:max(i, 1)]
+        left = rng.integers(0, 4, int(rng.integers(0, flank + 1))).astype(np.uint8)
+        right = rng.integers(0, 4, int(rng.integers(0, flank + 1))).astype(np.uint8)
+        r = np.concatenate([left, used, right])
+        if rng.random() < 0.02:
+            r[int(rng.integers(0, len(r)))] = 4
+        refs.append(r); qrys.append(q)
+        quals.append(rng.integers(2, 42, len(q)).astype(np.uint8))
+    ref_off = np.concatenate([[0], np.cumsum([len(x) for x in refs])]).astype(np.int64)
+    qry_off = np.concatenate([[0], np.cumsum([len(x) for x in qrys])]).astype(np.int64)
+    return dict(n=n, ref=np.concatenate(refs), ref_off=ref_off, query=np.concatenate(qrys), qry_off=qry_off,
+                qual=np.concatenate(quals))
+
+
+class KpaRef:
+    """the reference's kpa_ext_glocal, one call per read (oracle/kpa_harness.c)"""
+
+    def __init__(self):
+        if not os.path.exists(KPAREF_SO):
+            raise RuntimeError("oracle/_ref/libkparef.so is not built (needs /root/reference: make -C oracle ref)")
+        self.lib = C.CDLL(KPAREF_SO)
+        self.lib.lfref_kpa_glocal_batch.restype = C.c_int
+
+    def glocal(self, reads, d=0.00001, e=0.4, bw=10, use_qual=True):
+        n = reads["n"]
+        tot = int(reads["qry_off"][-1])
+        state = np.zeros(tot, np.int32)
+        q = np.zeros(tot, np.uint8)
+        pr = np.zeros(n, np.int32)
+        self.lib.lfref_kpa_glocal_batch(C.c_longlong(n), _ptr(reads["ref"]), _ptr(reads["ref_off"]), _ptr(reads["query"]),
+                                        _ptr(reads["qry_off"]), _ptr(reads["qual"]) if use_qual else None, C.c_float(d),
+                                        C.c_float(e), C.c_int(bw), _ptr(state), _ptr(q), _ptr(pr))
+        return state, q, pr
