@@ -7,10 +7,11 @@
 //   best M / I cell of a row gives state[i] and q[i] = phred(1 - posterior).
 //
 // What differs from the reference is where the numbers live: the reference callocs two (l_query + 1) x (6 bw + 9) matrices
-// per read and relies on their zeros outside the band; here a cell outside a row's band is never read (ld_* return the zero
-// the reference would find), the forward matrix goes to a scratch buffer interleaved over the reads of a launch (cell c of
-// row i of read t at ((i * W3 + c) * stride + t: the threads of a warp touch consecutive addresses), and the backward
-// pass keeps two rows and folds the posterior pass into itself, so only one matrix is ever stored.
+// per read and relies on their zeros outside the band; here a cell outside a row's band is never read (the zero the
+// reference would find is supplied instead), the forward matrix goes to a scratch buffer interleaved over the reads of a
+// launch (cell c of row i of read t at ((i * W3 + c) * stride + t: the threads of a warp touch consecutive addresses),
+// rows are stored unscaled and scaled when read (no rewrite pass), and the backward pass keeps two rows and folds the
+// posterior pass into itself, so only one matrix is ever stored.
 //
 // The same source is compiled for the host by tests/test_baq_core.py (plain g++, -ffp-contract=off) to pin the arithmetic
 // against the compiled reference without a GPU; the product only ever runs the device instance.
@@ -98,14 +99,20 @@ KPA_HD int kpa_glocal_core(const uint8_t *ref0, int l_ref, const uint8_t *qry0, 
     const double bM = (double)KPA_FDIV(one_d, (float)l_ref), bI = (double)KPA_FDIV(cd, (float)l_ref);
     auto qual = [&](int i) -> double { return (double)q2p[iqual ? iqual[i - 1] : 30]; };
 
+    // Rows are stored unscaled; the reference's rescaling (row 1: a division by its sum, later rows: a multiplication by the
+    // inverse of their sum, kprobaln_ext.c:148,170; backward rows: by the inverse of the forward sum, :222) is applied when a
+    // cell is read — the same operation on the same operands gives the same bits, and a row is written once and read once
+    // instead of being rewritten in place.
+    auto fscale = [&](int i, double c, double inv) -> double { return i == 1 ? KPA_DIV(c, inv) : KPA_MUL(c, inv); };   // inv: s[1] for row 1
+
     // ---- forward
     mem.S(0) = 1.;
+    double inv_prev;                                          // scale operand of the row before the current one
     {   // row 1: from the start state
         const KpaBand r1 = kpa_band(1, bw, l_ref);
-        const int end = l_ref < bw + 1 ? l_ref : bw + 1;
         const double q1 = qual(1);
         double sum = 0.;
-        for (int k = 1; k <= end; ++k) {
+        for (int k = r1.beg; k <= r1.end; ++k) {
             const double em = KPA_MUL(kpa_emit(ref[k], query[1], q1), bM), ei = KPA_MUL(KPA_EI, bI);
             mem.F(1, kpa_u(r1.x, k, 0)) = em;
             mem.F(1, kpa_u(r1.x, k, 1)) = ei;
@@ -113,29 +120,26 @@ KPA_HD int kpa_glocal_core(const uint8_t *ref0, int l_ref, const uint8_t *qry0, 
             sum = KPA_ADD(sum, KPA_ADD(em, ei));
         }
         mem.S(1) = sum;
-        for (int k = 1; k <= end; ++k)
-            for (int s = 0; s < 3; ++s) {
-                double &c = mem.F(1, kpa_u(r1.x, k, s));
-                c = KPA_DIV(c, sum);
-            }
+        inv_prev = sum;
     }
     for (int i = 2; i <= l_query; ++i) {
         const KpaBand r = kpa_band(i, bw, l_ref), p = kpa_band(i - 1, bw, l_ref);
-        // row 1 holds positions 1 .. min(l_ref, bw + 1) (its own rule), later rows their band
-        const int pend = i - 1 == 1 ? (l_ref < bw + 1 ? l_ref : bw + 1) : p.end, pbeg = i - 1 == 1 ? 1 : p.beg;
         const double qli = qual(i);
         const int qyi = query[i];
         double sum = 0., dM = 0., dD = 0.;                  // M and D of position k - 1 of this row (zero below the band)
+        // M, I, D of position k - 1 of the row above, carried from one position to the next
+        double a0 = 0., a1 = 0., a2 = 0.;
+        if (r.beg - 1 >= p.beg && r.beg - 1 <= p.end) {
+            a0 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, r.beg - 1, 0)), inv_prev);
+            a1 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, r.beg - 1, 1)), inv_prev);
+            a2 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, r.beg - 1, 2)), inv_prev);
+        }
         for (int k = r.beg; k <= r.end; ++k) {
-            double a0 = 0., a1 = 0., a2 = 0., b0 = 0., b1 = 0.;
-            if (k - 1 >= pbeg && k - 1 <= pend) {
-                a0 = mem.F(i - 1, kpa_u(p.x, k - 1, 0));
-                a1 = mem.F(i - 1, kpa_u(p.x, k - 1, 1));
-                a2 = mem.F(i - 1, kpa_u(p.x, k - 1, 2));
-            }
-            if (k >= pbeg && k <= pend) {
-                b0 = mem.F(i - 1, kpa_u(p.x, k, 0));
-                b1 = mem.F(i - 1, kpa_u(p.x, k, 1));
+            double b0 = 0., b1 = 0., b2 = 0.;
+            if (k >= p.beg && k <= p.end) {
+                b0 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, k, 0)), inv_prev);
+                b1 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, k, 1)), inv_prev);
+                b2 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, k, 2)), inv_prev);
             }
             const double e = kpa_emit(ref[k], qyi, qli);
             const double fm = KPA_MUL(e, KPA_ADD(KPA_ADD(KPA_MUL(m0, a0), KPA_MUL(m3, a1)), KPA_MUL(m6, a2)));
@@ -147,35 +151,33 @@ KPA_HD int kpa_glocal_core(const uint8_t *ref0, int l_ref, const uint8_t *qry0, 
             sum = KPA_ADD(sum, KPA_ADD(KPA_ADD(fm, fi_), fd));
             dM = fm;
             dD = fd;
+            a0 = b0; a1 = b1; a2 = b2;
         }
         mem.S(i) = sum;
-        const double inv = KPA_DIV(1., sum);
-        for (int k = r.beg; k <= r.end; ++k)
-            for (int s = 0; s < 3; ++s) {
-                double &c = mem.F(i, kpa_u(r.x, k, s));
-                c = KPA_MUL(c, inv);
-            }
+        inv_prev = KPA_DIV(1., sum);
     }
     const KpaBand rl = kpa_band(l_query, bw, l_ref);
-    const int lbeg = l_query == 1 ? 1 : rl.beg, lend = l_query == 1 ? (l_ref < bw + 1 ? l_ref : bw + 1) : rl.end;
     {   // into the end state
         double sum = 0.;
-        for (int k = lbeg; k <= lend; ++k)
-            sum = KPA_ADD(sum, KPA_ADD(KPA_MUL(mem.F(l_query, kpa_u(rl.x, k, 0)), sM), KPA_MUL(mem.F(l_query, kpa_u(rl.x, k, 1)), sI)));
+        for (int k = rl.beg; k <= rl.end; ++k)
+            sum = KPA_ADD(sum, KPA_ADD(KPA_MUL(fscale(l_query, mem.F(l_query, kpa_u(rl.x, k, 0)), inv_prev), sM),
+                                       KPA_MUL(fscale(l_query, mem.F(l_query, kpa_u(rl.x, k, 1)), inv_prev), sI)));
         mem.S(l_query + 1) = sum;
     }
 
     // ---- backward, with the posterior of a row taken as soon as the row exists
-    auto posterior = [&](int i, int par, const KpaBand &r, int rbeg, int rend) {
+    // binv: the factor the backward row is to be read with (1 / s[i]; the last row is stored as it is: scaled == false)
+    auto posterior = [&](int i, int par, const KpaBand &r, bool scaled, double binv) {
+        const double finv = i == 1 ? mem.S(1) : KPA_DIV(1., mem.S(i));
         double sum = 0., mx = 0.;
         int max_k = -1;
-        for (int k = rbeg; k <= rend; ++k) {
-            double z = KPA_MUL(mem.F(i, kpa_u(r.x, k, 0)), mem.B(par, kpa_u(r.x, k, 0)));
-            if (z > mx) { mx = z; max_k = (k - 1) << 2 | 0; }
-            sum = KPA_ADD(sum, z);
-            z = KPA_MUL(mem.F(i, kpa_u(r.x, k, 1)), mem.B(par, kpa_u(r.x, k, 1)));
-            if (z > mx) { mx = z; max_k = (k - 1) << 2 | 1; }
-            sum = KPA_ADD(sum, z);
+        for (int k = r.beg; k <= r.end; ++k) {
+            for (int s = 0; s < 2; ++s) {
+                const double bc = mem.B(par, kpa_u(r.x, k, s));
+                const double z = KPA_MUL(fscale(i, mem.F(i, kpa_u(r.x, k, s)), finv), scaled ? KPA_MUL(bc, binv) : bc);
+                if (z > mx) { mx = z; max_k = (k - 1) << 2 | s; }
+                sum = KPA_ADD(sum, z);
+            }
         }
         mx = KPA_DIV(mx, sum);
         state[i - 1] = max_k;
@@ -205,25 +207,31 @@ KPA_HD int kpa_glocal_core(const uint8_t *ref0, int l_ref, const uint8_t *qry0, 
     {   // row l_query: from the end state
         const double sl = mem.S(l_query), sl1 = mem.S(l_query + 1);
         const double vM = KPA_DIV(KPA_DIV(sM, sl), sl1), vI = KPA_DIV(KPA_DIV(sI, sl), sl1);
-        for (int k = lbeg; k <= lend; ++k) {
+        for (int k = rl.beg; k <= rl.end; ++k) {
             mem.B(par, kpa_u(rl.x, k, 0)) = vM;
             mem.B(par, kpa_u(rl.x, k, 1)) = vI;
             mem.B(par, kpa_u(rl.x, k, 2)) = 0.;
         }
-        posterior(l_query, par, rl, lbeg, lend);
+        posterior(l_query, par, rl, false, 1.);
     }
+    bool nscaled = false;                                    // does the row below (i + 1) carry a deferred factor?
+    double ninv = 1.;
     for (int i = l_query - 1; i >= 1; --i) {
         const KpaBand r = kpa_band(i, bw, l_ref), n = kpa_band(i + 1, bw, l_ref);
-        // positions row i + 1 holds (the last row was written over [lbeg, lend], which is its band)
-        const int nbeg = (i + 1 == l_query) ? lbeg : n.beg, nend = (i + 1 == l_query) ? lend : n.end;
         const double y = i > 1 ? 1. : 0., qli1 = qual(i + 1);
         const int qyi1 = query[i + 1];
         const int np = par ^ 1;
         double dD = 0.;                                      // D of position k + 1 of this row (zero above the band)
         for (int k = r.end; k >= r.beg; --k) {
             double c11 = 0., c10i = 0.;
-            if (k + 1 >= nbeg && k + 1 <= nend) c11 = mem.B(par, kpa_u(n.x, k + 1, 0));
-            if (k >= nbeg && k <= nend) c10i = mem.B(par, kpa_u(n.x, k, 1));
+            if (k + 1 >= n.beg && k + 1 <= n.end) {
+                c11 = mem.B(par, kpa_u(n.x, k + 1, 0));
+                if (nscaled) c11 = KPA_MUL(c11, ninv);
+            }
+            if (k >= n.beg && k <= n.end) {
+                c10i = mem.B(par, kpa_u(n.x, k, 1));
+                if (nscaled) c10i = KPA_MUL(c10i, ninv);
+            }
             const double em = k >= l_ref ? 0. : kpa_emit(ref[k + 1], qyi1, qli1);
             const double e = KPA_MUL(em, c11);
             const double bm = KPA_ADD(KPA_ADD(KPA_MUL(e, m0), KPA_MUL(KPA_MUL(KPA_EI, m1), c10i)), KPA_MUL(m2, dD));
@@ -234,16 +242,10 @@ KPA_HD int kpa_glocal_core(const uint8_t *ref0, int l_ref, const uint8_t *qry0, 
             mem.B(np, kpa_u(r.x, k, 2)) = bd;
             dD = bd;
         }
-        const double inv = KPA_DIV(1., mem.S(i));
-        const int rbeg = i == 1 ? 1 : r.beg, rend = i == 1 ? (l_ref < bw + 1 ? l_ref : bw + 1) : r.end;
-        for (int k = r.beg; k <= r.end; ++k)
-            for (int s = 0; s < 3; ++s) {
-                double &c = mem.B(np, kpa_u(r.x, k, s));
-                c = KPA_MUL(c, inv);
-            }
         par = np;
-        posterior(i, par, r, r.beg, r.end);
-        (void)rbeg; (void)rend;
+        nscaled = true;
+        ninv = KPA_DIV(1., mem.S(i));
+        posterior(i, par, r, true, ninv);
     }
     return bw;
 }
