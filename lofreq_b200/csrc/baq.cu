@@ -15,6 +15,10 @@
 
 namespace lfb {
 
+#ifndef KPA_CTAS
+#define KPA_CTAS 6
+#endif
+
 struct KpaDevMem {
     double *f, *b, *s;
     size_t stride, t;
@@ -24,7 +28,7 @@ struct KpaDevMem {
     __device__ __forceinline__ double &S(int i) { return s[(size_t)i * stride + t]; }
 };
 
-__global__ void __launch_bounds__(128) k_kpa_glocal(long long r0, int n_reads, const unsigned char *ref, const long long *ref_off,
+__global__ void __launch_bounds__(128, KPA_CTAS) k_kpa_glocal(long long r0, int n_reads, const unsigned char *ref, const long long *ref_off,
                                                     const unsigned char *query, const long long *qry_off, const unsigned char *qual, float d,
                                                     float e, int bw, const float *q2p, double *f, double *b, double *s, int w3, int *state,
                                                     unsigned char *q, KpaFix *fix, int fix_cap, unsigned *n_fix)

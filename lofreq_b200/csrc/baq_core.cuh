@@ -127,20 +127,27 @@ KPA_HD int kpa_glocal_core(const uint8_t *ref0, int l_ref, const uint8_t *qry0, 
         const double qli = qual(i);
         const int qyi = query[i];
         double sum = 0., dM = 0., dD = 0.;                  // M and D of position k - 1 of this row (zero below the band)
-        // M, I, D of position k - 1 of the row above, carried from one position to the next
-        double a0 = 0., a1 = 0., a2 = 0.;
-        if (r.beg - 1 >= p.beg && r.beg - 1 <= p.end) {
-            a0 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, r.beg - 1, 0)), inv_prev);
-            a1 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, r.beg - 1, 1)), inv_prev);
-            a2 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, r.beg - 1, 2)), inv_prev);
-        }
-        for (int k = r.beg; k <= r.end; ++k) {
-            double b0 = 0., b1 = 0., b2 = 0.;
+        // M, I, D of positions k - 1 and k of the row above: carried from one position to the next, and the cells of
+        // position k + 1 are requested before the cells of position k of this row are stored (the rows live in one buffer,
+        // so the compiler would not move the loads across the stores itself)
+        // (cells outside the band of the row above come back as zeros and stay zeros under the scaling: a row's sum is
+        // positive — its insertion cells are — so the factor is finite)
+        auto above = [&](int k, double &v0, double &v1, double &v2) {
+            v0 = v1 = v2 = 0.;
             if (k >= p.beg && k <= p.end) {
-                b0 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, k, 0)), inv_prev);
-                b1 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, k, 1)), inv_prev);
-                b2 = fscale(i - 1, mem.F(i - 1, kpa_u(p.x, k, 2)), inv_prev);
+                v0 = mem.F(i - 1, kpa_u(p.x, k, 0));
+                v1 = mem.F(i - 1, kpa_u(p.x, k, 1));
+                v2 = mem.F(i - 1, kpa_u(p.x, k, 2));
             }
+        };
+        double a0, a1, a2, b0, b1, b2;
+        above(r.beg - 1, a0, a1, a2);
+        above(r.beg, b0, b1, b2);
+        a0 = fscale(i - 1, a0, inv_prev); a1 = fscale(i - 1, a1, inv_prev); a2 = fscale(i - 1, a2, inv_prev);
+        for (int k = r.beg; k <= r.end; ++k) {
+            double n0, n1, n2;
+            above(k + 1, n0, n1, n2);
+            b0 = fscale(i - 1, b0, inv_prev); b1 = fscale(i - 1, b1, inv_prev); b2 = fscale(i - 1, b2, inv_prev);
             const double e = kpa_emit(ref[k], qyi, qli);
             const double fm = KPA_MUL(e, KPA_ADD(KPA_ADD(KPA_MUL(m0, a0), KPA_MUL(m3, a1)), KPA_MUL(m6, a2)));
             const double fi_ = KPA_MUL(KPA_EI, KPA_ADD(KPA_MUL(m1, b0), KPA_MUL(m4, b1)));
@@ -152,6 +159,7 @@ KPA_HD int kpa_glocal_core(const uint8_t *ref0, int l_ref, const uint8_t *qry0, 
             dM = fm;
             dD = fd;
             a0 = b0; a1 = b1; a2 = b2;
+            b0 = n0; b1 = n1; b2 = n2;
         }
         mem.S(i) = sum;
         inv_prev = KPA_DIV(1., sum);
