@@ -179,13 +179,22 @@ KPA_HD int kpa_glocal_core(const uint8_t *ref0, int l_ref, const uint8_t *qry0, 
         const double finv = i == 1 ? mem.S(1) : KPA_DIV(1., mem.S(i));
         double sum = 0., mx = 0.;
         int max_k = -1;
+        // (the four cells of position k + 1 are requested while position k is evaluated)
+        double f0 = mem.F(i, kpa_u(r.x, r.beg, 0)), f1 = mem.F(i, kpa_u(r.x, r.beg, 1));
+        double b0 = mem.B(par, kpa_u(r.x, r.beg, 0)), b1 = mem.B(par, kpa_u(r.x, r.beg, 1));
         for (int k = r.beg; k <= r.end; ++k) {
-            for (int s = 0; s < 2; ++s) {
-                const double bc = mem.B(par, kpa_u(r.x, k, s));
-                const double z = KPA_MUL(fscale(i, mem.F(i, kpa_u(r.x, k, s)), finv), scaled ? KPA_MUL(bc, binv) : bc);
-                if (z > mx) { mx = z; max_k = (k - 1) << 2 | s; }
-                sum = KPA_ADD(sum, z);
+            double nf0 = 0., nf1 = 0., nb0 = 0., nb1 = 0.;
+            if (k < r.end) {
+                nf0 = mem.F(i, kpa_u(r.x, k + 1, 0)); nf1 = mem.F(i, kpa_u(r.x, k + 1, 1));
+                nb0 = mem.B(par, kpa_u(r.x, k + 1, 0)); nb1 = mem.B(par, kpa_u(r.x, k + 1, 1));
             }
+            double z = KPA_MUL(fscale(i, f0, finv), scaled ? KPA_MUL(b0, binv) : b0);
+            if (z > mx) { mx = z; max_k = (k - 1) << 2 | 0; }
+            sum = KPA_ADD(sum, z);
+            z = KPA_MUL(fscale(i, f1, finv), scaled ? KPA_MUL(b1, binv) : b1);
+            if (z > mx) { mx = z; max_k = (k - 1) << 2 | 1; }
+            sum = KPA_ADD(sum, z);
+            f0 = nf0; f1 = nf1; b0 = nb0; b1 = nb1;
         }
         mx = KPA_DIV(mx, sum);
         state[i - 1] = max_k;
