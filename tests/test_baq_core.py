@@ -57,6 +57,30 @@ def test_host_instance_matches_the_compiled_reference(host_lib, d, e, bw):
             assert np.array_equal(gq, wq), ("q", seed, np.argwhere(gq != wq)[:5].tolist())
 
 
+@pytest.mark.skipif(not pyoracle.have_kpa_reference(), reason="compiled reference not available")
+def test_degenerate_inputs(host_lib):
+    """qualities 0 (probability 1) and 255, reads / windows made of Ns, bands of 1 and 2, windows much longer than the read"""
+    ref = pyoracle.KpaRef()
+    rng = np.random.default_rng(99)
+    for trial in range(15):
+        r = pyoracle.synth_reads(120, seed=1000 + trial, lmin=1, lmax=60, flank=int(rng.integers(0, 30)))
+        mode = trial % 5
+        if mode == 0:
+            r["qual"][:] = 0
+        elif mode == 1:
+            r["qual"][:] = rng.choice([0, 1, 2, 93, 200, 255], len(r["qual"]))
+        elif mode == 2:
+            r["query"][:] = 4
+        elif mode == 3:
+            r["ref"][:] = 4
+        else:
+            r["qual"][:] = rng.integers(0, 256, len(r["qual"]))
+        for d, e, bw in ((0.00001, 0.4, 10), (0.5, 0.9, 2), (0.001, 0.1, 1)):
+            ws, wq, _ = ref.glocal(r, d, e, bw)
+            gs, gq, _ = _run_host(host_lib, r, d, e, bw)
+            assert np.array_equal(gs, ws) and np.array_equal(gq, wq), (trial, mode, d, e, bw)
+
+
 def test_host_instance_matches_the_golden_vectors(host_lib):
     z = np.load(GOLD)
     for i in range(int(z["n_cases"])):
