@@ -543,7 +543,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_desc(wl, n) + " per GPU (region shard = rank*cols)",
                            "cols_per_gpu": n, "depth": DEPTH.get(wl), "l2": "inputs larger than L2 (%.2f GB per step)" % (2 * total / 1e9),
-                           "planes": "bq+mq" + ("+baq" if args.baq else " (no BAQ plane: SURVEY 8d core benchmark; --baq adds it)"),
+                           "planes": "bq+mq" + ("+baq" if args.baq else " (no BAQ plane: SURVEY 8d core benchmark; --baq adds it: 4.87 G col/s in profiles/r2_bench_C2baq.json)"),
                            "value_region": "k_front (gates, counts, running Bonferroni, prune) + O(depth*K) kernels + per-site decision (status / called / QUAL) on the device + sites in column order into pinned host memory + host wait, inputs resident in HBM; long double p-value images not requested (lfb200_set_site_pvalues 0); %d contexts = batches in flight" % NC + "",
                            "tested_columns": int(n_tested), "sites": int(n_sites), "heavy_columns": int(n_heavy),
                            "sites_all_ranks": final_sites,
