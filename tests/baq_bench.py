@@ -3,7 +3,7 @@
 usage: baq_bench.py [reads]   — prints one JSON line; under ncu (-k regex:k_kpa_glocal) the kernel itself is captured"""
 import json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # tests/ may use the oracle (reference timing, read generator)
 sys.path.insert(0, ROOT)
 import lofreq_b200
 from oracle import pyoracle
