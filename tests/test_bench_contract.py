@@ -27,3 +27,32 @@ def test_reference_arm_other_ranks_stay_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1", "--ref-cols-per-proc", "500"], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """the GPU arm's lines committed under profiles/ (written on the GPU box by the round's evidence scripts): every key the
+    driver and the judge read is there, the roofline is internally consistent, the traffic comes from the committed capture"""
+    prof = os.path.join(ROOT, "profiles")
+    for wl in ("C2", "C3", "C5", "C2baq"):
+        d = json.load(open(os.path.join(prof, "r2_bench_%s.json" % wl)))
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+            assert k in d, (wl, k)
+        assert d["metric"] == "pileup_columns_per_sec" and d["unit"] == "columns/s" and d["dtype"] == "f64" and d["vs_baseline"] is None
+        assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert 0 < d["e2e"]["value"] < d["value"]
+        r = d["roofline"]
+        assert r["bound"] in ("fp64", "hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert d["clocks"]["sm_mhz"] and not d["clocks"]["reasons"]
+        assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+        # value = columns of the step / time of the step
+        assert abs(d["value"] - d["n_gpus"] * d["config"]["cols_per_gpu"] / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+
+
+def test_traffic_comes_from_the_committed_capture():
+    sys.path.insert(0, ROOT)
+    import bench
+    t = bench.ncu_traffic(["k_dp<0>"], "C2")
+    assert t and t > 1e6
+    t = bench.ncu_traffic(["k_front", "k_prune2"], "C2")
+    assert t and t > 5e7
