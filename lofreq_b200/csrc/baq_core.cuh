@@ -8,8 +8,8 @@
 //
 // What differs from the reference is where the numbers live: the reference callocs two (l_query + 1) x (6 bw + 9) matrices
 // per read and relies on their zeros outside the band; here a cell outside a row's band is never read (the zero the
-// reference would find is supplied instead), the forward matrix goes to a scratch buffer interleaved over the reads of a
-// launch (cell c of row i of read t at ((i * W3 + c) * stride + t: the threads of a warp touch consecutive addresses),
+// reference would find is supplied instead), the forward matrix goes to a scratch buffer interleaved over the 32 reads of
+// a warp (baq.cu: KpaDevMem — the threads of a warp touch consecutive addresses),
 // rows are stored unscaled and scaled when read (no rewrite pass), and the backward pass keeps two rows and folds the
 // posterior pass into itself, so only one matrix is ever stored.
 //

@@ -1060,13 +1060,14 @@ extern "C" int lfb200_kpa_glocal_batch(lfb200_ctx *ctx, long long n, const unsig
     long long chunk = (long long)std::max<size_t>(budget / std::max<size_t>(per_read, 1), 128);
     chunk = std::min<long long>(chunk, n);
     chunk = std::min<long long>(chunk, 1 << 20);
-    if (ctx->k_f.ensure((size_t)chunk * (lmax + 1) * w3 * 8) || ctx->k_b.ensure((size_t)chunk * 2 * w3 * 8) ||
-        ctx->k_s.ensure((size_t)chunk * (lmax + 2) * 8))
+    const size_t chunk32 = ((size_t)chunk + 31) / 32 * 32;             // the scratch is laid out per warp of 32 reads
+    const int rows = lmax + 1;
+    if (ctx->k_f.ensure(chunk32 * rows * w3 * 8) || ctx->k_b.ensure(chunk32 * 2 * w3 * 8) || ctx->k_s.ensure(chunk32 * (rows + 1) * 8))
         return fail("out of device memory for the scratch of %lld reads (%zu bytes each)", chunk, per_read);
     for (long long r0 = 0; r0 < n; r0 += chunk) {
         const int cnt = (int)std::min<long long>(chunk, n - r0);
         launch_kpa_glocal(r0, cnt, d_ref, d_roff, d_qry, d_qoff, d_qual, d, e, bw, d_q2p, (double *)ctx->k_f.p, (double *)ctx->k_b.p,
-                          (double *)ctx->k_s.p, w3, (int *)ctx->k_state.p, (unsigned char *)ctx->k_q.p, d_fix, fix_cap, d_nfix, st);
+                          (double *)ctx->k_s.p, w3, rows, (int *)ctx->k_state.p, (unsigned char *)ctx->k_q.p, d_fix, fix_cap, d_nfix, st);
     }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(state, ctx->k_state.p, tot_q * 4, cudaMemcpyDeviceToHost, st));

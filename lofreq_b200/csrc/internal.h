@@ -199,11 +199,11 @@ int launch_binom(long long n_prob, const int *num_trials, const int *num_success
                  int *status, cudaStream_t st);
 // fisher.cu: SB = PROB_TO_PHREDQUAL_SAFE(Fisher two-tailed p) per DP4 table (lofreq_call.c:108-125, fet.c:62-101)
 void launch_sb_qual(int sms, const int *dp4, long long n, int *sb, unsigned char *unsure, cudaStream_t st);
-// BAQ HMM (baq.cu): reads [r0, r0 + n_reads) of the batch, scratch interleaved over the launch's reads
+// BAQ HMM (baq.cu): reads [r0, r0 + n_reads) of the batch; scratch for ceil(n_reads / 32) warps of `rows` forward rows each
 struct KpaFix;
 void launch_kpa_glocal(long long r0, int n_reads, const unsigned char *ref, const long long *ref_off, const unsigned char *query,
                        const long long *qry_off, const unsigned char *qual, float d, float e, int bw, const float *q2p, double *f, double *b,
-                       double *s, int w3, int *state, unsigned char *q, KpaFix *fix, int fix_cap, unsigned *n_fix, cudaStream_t st);
+                       double *s, int w3, int rows, int *state, unsigned char *q, KpaFix *fix, int fix_cap, unsigned *n_fix, cudaStream_t st);
 int sb_qual_host(const int *dp4);
 // synth.cu
 void launch_synth_depths(int workload, long long c0, long long n, int *depth, cudaStream_t st);
